@@ -1,0 +1,185 @@
+/*
+ * ttsb.h -- C ABI of libttsb.so, the B200 (sm_100a) kernels behind the ForwardTransformer text->mel hot path
+ * of as-ideas/TransformerTTS.
+ *
+ * The reference has no FFI/plugin interface: its boundary is the Python API (model/models.py:344-642,
+ * data/audio.py:88-92).  The host-side mirror of that API lives in transformertts_b200/ and binds these entry
+ * points with ctypes (transformertts_b200/lib.py); INTEGRATION.md shows the stub a maintainer of the reference
+ * would add.  Each entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative TTSB_ERR_* otherwise; ttsb_last_error() gives the text
+ *     (thread-local);
+ *   - all pointers are CALLER-OWNED DEVICE pointers unless the name ends in _host; nothing is allocated inside;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no hidden synchronisation;
+ *   - activations are row-major (B, T, C) channels-last as in Keras; "hi/lo" pairs are the bf16 split of an fp32
+ *     tensor (x ~= hi + lo) used by the 3-pass bf16 tensor-core mode; lo pointers may be NULL in single-pass mode;
+ *   - packed weights are bf16 [N_pad, K] (K contiguous), produced from the Keras (K, N) / (k, Cin, Cout) layout by
+ *     ttsb_pack_weight.
+ */
+#ifndef TTSB_H_
+#define TTSB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTSB_OK 0
+#define TTSB_ERR_INVALID_ARGUMENT (-1)
+#define TTSB_ERR_CUDA (-2)
+#define TTSB_ERR_UNSUPPORTED (-3)
+
+#define TTSB_ABI_VERSION 1
+
+/* precision of the tensor-core products */
+#define TTSB_PREC_BF16 0   /* single bf16 pass, fp32 accumulate */
+#define TTSB_PREC_BF16X3 1 /* hi*hi + lo*hi + hi*lo, fp32 accumulate (fp32-class accuracy) */
+
+/* implementation selector (debug): tcgen05/TMA kernels, or the plain SIMT CUDA kernels kept for bring-up */
+#define TTSB_IMPL_TCGEN05 0
+#define TTSB_IMPL_SIMT 1
+
+const char* ttsb_last_error(void);
+int ttsb_abi_version(void);
+/* number of kernels this library has launched since load / since the last reset (bench.py "gpu_launches") */
+int64_t ttsb_launch_count(void);
+void ttsb_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Weight / activation preparation
+ * ------------------------------------------------------------------------------------------------------- */
+/* Keras kernel (K, N) fp32 (Conv1D (k, Cin, Cout) is the same memory with K = k*Cin) -> packed bf16 hi/lo
+ * [n_pad, K], rows >= N zero.  w_lo may be NULL. */
+int ttsb_pack_weight(const float* w_kn, int K, int N, int n_pad, void* w_hi, void* w_lo, void* stream);
+/* fp32 [n] -> bf16 hi (and lo when non-NULL) */
+int ttsb_split_bf16(const float* x, int64_t n, void* x_hi, void* x_lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Encoder prologue: Embedding + LayerNorm + scalar*PE   (model/models.py:522, model/layers.py:299-300)
+ * tokens int32 (B,T); emb (vocab,d); pe (max_pos,d) fp32; pos_scalar device scalar.
+ * ------------------------------------------------------------------------------------------------------- */
+int ttsb_embed_ln_pe_fwd(const int32_t* tokens, const float* emb, const float* gamma, const float* beta,
+                         const float* pe, const float* pos_scalar, int B, int T, int d, int vocab, float eps,
+                         float* out_f32, void* out_hi, void* out_lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM family:  Dense, dual-input Dense (concat projection) and Conv1D(k, 'same')
+ *   (model/layers.py:134-136,149 MHA projections; :93-94 FFN; :19-26 Conv1D; model/models.py:422 mel Dense)
+ *
+ *   out[b,t,:] = epilogue( bias + sum_s  A_{src[s]}[b, t + shift[s], :] @ W[koff_s : koff_s + K_s, :] )
+ *
+ * Segments: a Dense has one segment (shift 0); the concat projection has two sources; a k-tap 'same' conv has k
+ * segments over the same source with shifts -(k-1)/2 ... ; rows outside [0,T) read as zero.
+ * Epilogue (in this order): +bias, relu?, +residual?, LayerNorm over the first ln_n columns?, zero rows t >= row_len[b]?.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct ttsb_gemm_args {
+  int B, T;                 /* rows = B*T */
+  int N;                    /* logical output columns */
+  int block_n;              /* N tile (multiple of 16, <= 256); packed W has n_tiles*block_n rows */
+  int num_segments;         /* 1..4 */
+  int seg_src[4];           /* 0 or 1: which A source */
+  int seg_shift[4];         /* time shift of the source rows */
+  int seg_k[4];             /* K of the segment (multiple of 64) */
+  const void* a_hi[2];      /* bf16 (B,T,lda) sources */
+  const void* a_lo[2];      /* NULL in TTSB_PREC_BF16 */
+  int lda[2];               /* row stride in elements */
+  int a_col0[2];            /* first column of the source inside its row */
+  const void* w_hi;         /* packed bf16 [n_tiles*block_n, K_total] */
+  const void* w_lo;
+  const float* bias;        /* [N] or NULL */
+  int relu;
+  const float* residual;    /* fp32 (B,T,ld_res) or NULL */
+  int ld_res;
+  const float* ln_gamma;    /* LayerNorm params or NULL */
+  const float* ln_beta;
+  float ln_eps;
+  const int32_t* row_len;   /* [B] valid lengths or NULL */
+  float* out_f32;           /* any of the three may be NULL */
+  void* out_hi;
+  void* out_lo;
+  int ld_out;               /* row stride of all outputs, >= n_tiles*block_n, multiple of 8 */
+  /* optional transposed store: tile columns [vt_col0, vt_col0+vt_cols) go to vt_*[b][col - vt_col0][t] (row stride vt_ld) */
+  void* vt_hi;
+  void* vt_lo;
+  int vt_col0, vt_cols, vt_ld;
+  int precision;            /* TTSB_PREC_* */
+  int impl;                 /* TTSB_IMPL_* */
+} ttsb_gemm_args;
+
+int ttsb_linear_fwd(const ttsb_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused variable-length self-attention  (model/layers.py:138-147 split/merge heads, :176-195 scaled dot product)
+ *   q,k: bf16 (B,T,ld_qk) at columns q_col0 + h*dh / k_col0 + h*dh;  vT: bf16 (B, H*dh, ld_vt) (time contiguous)
+ *   out: bf16 hi/lo (B,T,ld_out), head h at columns h*dh.  Keys t >= kv_len[b] are masked (reference adds -1e9).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct ttsb_mha_args {
+  int B, T, H, dh;
+  const void* qk_hi;
+  const void* qk_lo;
+  int ld_qk, q_col0, k_col0;
+  const void* vt_hi;
+  const void* vt_lo;
+  int ld_vt;
+  const int32_t* kv_len; /* [B] */
+  void* out_hi;
+  void* out_lo;
+  int ld_out;
+  /* optional: materialise softmax weights of ONE batch row (reference returns all; its callers read item 0) */
+  float* weights_out; /* (H,T,T) fp32 or NULL */
+  int weights_batch_index;
+  int precision;
+  int impl;
+} ttsb_mha_args;
+
+int ttsb_mha_fwd(const ttsb_mha_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * StatPredictor head  Dense(C->1, relu|linear) * mask   (model/layers.py:479-485)
+ *   h fp32 (B,T,ldh) -> out fp32 (B,T)
+ * ------------------------------------------------------------------------------------------------------- */
+int ttsb_statpred_head_fwd(const float* h, int ldh, int C, const float* w, const float* bias, int relu,
+                           const int32_t* row_len, int B, int T, float* out, void* stream);
+
+/* x + relu(pitch*w + b)  (model/models.py:527-531; Dense(1->d, relu)) -> fp32 (B,T,d) */
+int ttsb_pitch_embed_add_fwd(const float* x, const float* pitch, const float* w, const float* bias, int B, int T,
+                             int d, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Length regulator  (model/models.py:532-540, model/layers.py:549-565)
+ * ------------------------------------------------------------------------------------------------------- */
+/* durations (B,Tp) fp32 * scalar -> min(max_mask) -> max(min_mask) -> round-half-even -> int32.
+ * max_mask / min_mask may be NULL.  Also writes per-row totals to out_len[B]. */
+int ttsb_durations_to_int(const float* dur, float scalar, const float* max_mask, const float* min_mask, int B, int Tp,
+                          int32_t* out_int, int32_t* out_len, void* stream);
+/* int durations (B,Tp) -> frame->phoneme index map (B,Tm) (-1 at padded frames); row totals must be <= Tm */
+int ttsb_expand_indices(const int32_t* dur_int, int B, int Tp, int Tm, int32_t* out_idx, void* stream);
+/* out[b,t,:] = idx[b,t] >= 0 ? x[b, idx[b,t], :] : 0     (Expand; fp32, d multiple of 4) */
+int ttsb_length_regulate_fwd(const float* x, const int32_t* idx, int B, int Tp, int Tm, int d, float* out, void* stream);
+/* fused Expand + decoder prologue LN + scalar*PE (model/layers.py:299-300): writes fp32 + bf16 hi/lo */
+int ttsb_expand_ln_pe_fwd(const float* x, const int32_t* idx, const float* gamma, const float* beta, const float* pe,
+                          const float* pos_scalar, int B, int Tp, int Tm, int d, float eps, float* out_f32, void* out_hi,
+                          void* out_lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * utils/spectrogram_ops.py:8-17
+ * ------------------------------------------------------------------------------------------------------- */
+int ttsb_mel_lengths(const float* mel, int B, int T, int C, float padding_value, int32_t* out, void* stream);
+int ttsb_phoneme_lengths(const int32_t* phonemes, int B, int T, int32_t padding, int32_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * STFT -> mel filterbank -> log   (data/audio.py:72-92, 209-231)
+ *   wav fp32 (n_clips, n_samples); out fp32 (n_clips, n_frames, n_mels), n_frames = 1 + n_samples/hop.
+ *   n_fft must be 1024 (the reference's config), hop 256, window = periodic Hann(1024), reflect padding.
+ *   mel_basis fp32 (n_mels, 513) dense (the kernel uses its band structure); normalizer 0 = MelGAN log(clip 1e-5),
+ *   1 = WaveRNN.
+ * ------------------------------------------------------------------------------------------------------- */
+int ttsb_stft_mel_log(const float* wav, int n_clips, int n_samples, const float* mel_basis, int n_mels,
+                      int normalizer, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTSB_H_ */

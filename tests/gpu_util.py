@@ -1,0 +1,158 @@
+"""Helpers shared by the GPU parity tests: drive single kernels of libttsb.so through the C ABI."""
+from __future__ import annotations
+
+import torch
+
+from transformertts_b200 import lib
+from transformertts_b200.model.models import _PackedLinear, _round_up
+
+DEV = 'cuda:0'
+
+
+def split_or_none(x: torch.Tensor, split: bool):
+    return lib.split_bf16(x, split)
+
+
+def run_gemm(x_list, w_kn, bias, seg_src, seg_shift, seg_k, *, precision='bf16x3', impl='tcgen05', relu=False,
+             residual=None, ln=None, row_len=None, block_n=None, single_tile=False, vt=None, want=('f32',)):
+    """x_list: fp32 (B,T,C) sources (on GPU).  Returns dict with requested outputs."""
+    split = precision == 'bf16x3'
+    B, T, _ = x_list[0].shape
+    pl = _PackedLinear(w_kn, bias, seg_k, split, single_tile=single_tile, block_n=block_n)
+    a = lib.GemmArgs()
+    a.B, a.T, a.N, a.block_n = B, T, pl.N, pl.block_n
+    a.num_segments = len(seg_k)
+    keep = []
+    for s in range(len(seg_k)):
+        a.seg_src[s], a.seg_shift[s], a.seg_k[s] = seg_src[s], seg_shift[s], seg_k[s]
+    for i, x in enumerate(x_list):
+        hi, lo = lib.split_bf16(x, split)
+        keep += [hi, lo]
+        a.a_hi[i] = hi.data_ptr()
+        a.a_lo[i] = lo.data_ptr() if lo is not None else None
+        a.lda[i] = x.shape[-1]
+        a.a_col0[i] = 0
+    a.w_hi = pl.w_hi.data_ptr()
+    a.w_lo = pl.w_lo.data_ptr() if pl.w_lo is not None else None
+    a.bias = pl.bias.data_ptr() if pl.bias is not None else None
+    a.relu = int(relu)
+    if residual is not None:
+        a.residual = residual.data_ptr()
+        a.ld_res = residual.shape[-1]
+    if ln is not None:
+        a.ln_gamma, a.ln_beta, a.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), 1e-6
+    if row_len is not None:
+        a.row_len = row_len.data_ptr()
+    out = {}
+    # poison the outputs so unwritten elements are visible
+    out_f32 = torch.full((B, T, pl.n_pad), float('nan'), device=DEV)
+    out_hi = torch.full((B, T, pl.n_pad), float('nan'), device=DEV, dtype=torch.bfloat16)
+    out_lo = torch.full((B, T, pl.n_pad), float('nan'), device=DEV, dtype=torch.bfloat16)
+    a.out_f32, a.out_hi = out_f32.data_ptr(), out_hi.data_ptr()
+    a.out_lo = out_lo.data_ptr() if split else None
+    a.ld_out = pl.n_pad
+    if vt is not None:
+        col0, cols = vt
+        ld_vt = _round_up(T, 8)
+        vt_hi = torch.full((B, cols, ld_vt), float('nan'), device=DEV, dtype=torch.bfloat16)
+        vt_lo = torch.full((B, cols, ld_vt), float('nan'), device=DEV, dtype=torch.bfloat16)
+        a.vt_hi = vt_hi.data_ptr()
+        a.vt_lo = vt_lo.data_ptr() if split else None
+        a.vt_col0, a.vt_cols, a.vt_ld = col0, cols, ld_vt
+        out['vt'] = (vt_hi, vt_lo if split else None)
+    a.precision = lib.PREC_BF16X3 if split else lib.PREC_BF16
+    a.impl = lib.IMPL_SIMT if impl == 'simt' else lib.IMPL_TCGEN05
+    lib.linear_fwd(a)
+    torch.cuda.synchronize()
+    out['f32'] = out_f32
+    out['hi'] = out_hi
+    out['lo'] = out_lo if split else None
+    out['n_pad'] = pl.n_pad
+    return out
+
+
+def ref_gemm(x_list, w_kn, bias, seg_src, seg_shift, seg_k, *, precision, relu=False, residual=None, ln=None, row_len=None):
+    """float64 CPU reference of the same contract.  In 'bf16' mode the operands are first rounded to bf16 (that is the
+    kernel's arithmetic); in 'bf16x3' mode the fp32 operands are used as they are."""
+    xs = [x.detach().cpu().double() if precision == 'bf16x3' else x.detach().cpu().bfloat16().double() for x in x_list]
+    w = w_kn.detach().cpu().reshape(-1, w_kn.shape[-1])
+    w = w.double() if precision == 'bf16x3' else w.bfloat16().double()
+    B, T, _ = xs[0].shape
+    N = w.shape[1]
+    acc = torch.zeros(B, T, N, dtype=torch.float64)
+    koff = 0
+    for s, k in enumerate(seg_k):
+        x = xs[seg_src[s]]
+        sh = seg_shift[s]
+        lo, hi = max(0, -sh), min(T, T - sh)
+        if hi > lo:
+            acc[:, lo:hi] += x[:, lo + sh:hi + sh, :k] @ w[koff:koff + k]
+        koff += k
+    if bias is not None:
+        acc += bias.detach().cpu().double()
+    if relu:
+        acc = torch.relu(acc)
+    if residual is not None:
+        acc += residual.detach().cpu().double()[..., :N]
+    if ln is not None:
+        g, b = ln[0].detach().cpu().double(), ln[1].detach().cpu().double()
+        mean = acc.mean(-1, keepdim=True)
+        var = ((acc - mean) ** 2).mean(-1, keepdim=True)
+        acc = (acc - mean) * torch.rsqrt(var + 1e-6) * g + b
+    if row_len is not None:
+        keep = torch.arange(T)[None, :] < row_len.detach().cpu()[:, None]
+        acc = acc * keep[..., None]
+    return acc
+
+
+def run_mha(q, k, v, kv_len, H, *, precision='bf16x3', impl='tcgen05', weights_b=None):
+    """q,k,v fp32 (B,T,d) on GPU -> attention output fp32 (B,T,d) (hi+lo recombined)."""
+    split = precision == 'bf16x3'
+    B, T, d = q.shape
+    dh = d // H
+    qk = torch.cat([q, k], dim=-1).contiguous()
+    qk_hi, qk_lo = lib.split_bf16(qk, split)
+    ld_vt = _round_up(T, 8)
+    vt = torch.zeros(B, d, ld_vt, device=DEV)
+    vt[:, :, :T] = v.transpose(1, 2)
+    vt_hi, vt_lo = lib.split_bf16(vt, split)
+    out_hi = torch.full((B, T, d), float('nan'), device=DEV, dtype=torch.bfloat16)
+    out_lo = torch.full((B, T, d), float('nan'), device=DEV, dtype=torch.bfloat16)
+    m = lib.MhaArgs()
+    m.B, m.T, m.H, m.dh = B, T, H, dh
+    m.qk_hi = qk_hi.data_ptr()
+    m.qk_lo = qk_lo.data_ptr() if split else None
+    m.ld_qk, m.q_col0, m.k_col0 = 2 * d, 0, d
+    m.vt_hi = vt_hi.data_ptr()
+    m.vt_lo = vt_lo.data_ptr() if split else None
+    m.ld_vt = ld_vt
+    m.kv_len = kv_len.data_ptr()
+    m.out_hi = out_hi.data_ptr()
+    m.out_lo = out_lo.data_ptr() if split else None
+    m.ld_out = d
+    wts = None
+    if weights_b is not None:
+        wts = torch.full((H, T, T), float('nan'), device=DEV)
+        m.weights_out = wts.data_ptr()
+        m.weights_batch_index = weights_b
+    m.precision = lib.PREC_BF16X3 if split else lib.PREC_BF16
+    m.impl = lib.IMPL_SIMT if impl == 'simt' else lib.IMPL_TCGEN05
+    lib.mha_fwd(m)
+    torch.cuda.synchronize()
+    out = out_hi.float() + (out_lo.float() if split else 0)
+    return out, wts
+
+
+def ref_mha(q, k, v, kv_len, H, precision):
+    """float64 CPU attention with the reference's additive -1e9 key mask (model/layers.py:176-195)."""
+    cast = (lambda t: t.detach().cpu().double()) if precision == 'bf16x3' else (lambda t: t.detach().cpu().bfloat16().double())
+    q, k, v = cast(q), cast(k), cast(v)
+    B, T, d = q.shape
+    dh = d // H
+    sp = lambda t: t.reshape(B, T, H, dh).permute(0, 2, 1, 3)
+    logits = sp(q) @ sp(k).transpose(-1, -2) / (dh ** 0.5)
+    mask = (torch.arange(T)[None, :] >= kv_len.cpu()[:, None]).double()[:, None, None, :]
+    logits = (logits.float() + (mask * -1e9).float()).double()  # fp32 add as in the reference
+    w = torch.softmax(logits, -1)
+    out = (w @ sp(v)).permute(0, 2, 1, 3).reshape(B, T, d)
+    return out, w

@@ -1,0 +1,114 @@
+"""GPU parity of the whole text->mel path through the reference-facing API (ForwardTransformer.call / predict)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import forward_oracle as fo
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / 'golden'
+MEL_TOL = 1e-3  # BASELINE.json north_star: "mel fp32 within 1e-3 abs"
+
+
+def _model(cfg_name, params, **kw):
+    from transformertts_b200.model.models import ForwardTransformer
+    m = ForwardTransformer(**fo.CONFIGS[cfg_name], **kw)
+    m.set_weights(params)
+    return m
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05'])
+def test_c1_golden_forced_durations(impl):
+    g = np.load(GOLD / 'c1_forward.npz')
+    p = fo.init_params(fo.CONFIGS['C1'], seed=7)
+    m = _model('C1', p, impl=impl)
+    out = m.call(torch.from_numpy(g['tokens']), target_durations=torch.from_numpy(g['durations'])[..., None],
+                 target_pitch=torch.from_numpy(g['pitch'])[..., None])
+    assert out['mel'].shape == (1, 250, 80)
+    assert np.abs(out['mel'].cpu().numpy() - g['mel']).max() < MEL_TOL
+    assert np.abs(out['duration'].cpu().numpy() - g['duration_pred']).max() < 1e-3
+    assert np.abs(out['pitch'].cpu().numpy() - g['pitch_pred']).max() < 1e-3
+    assert np.array_equal(out['int_durations'].cpu().numpy(), g['durations'])
+
+
+def test_c1_golden_ragged_batch_and_padding_quirks():
+    g = np.load(GOLD / 'c1_forward.npz')
+    p = fo.init_params(fo.CONFIGS['C1'], seed=7)
+    m = _model('C1', p)
+    out = m.call(torch.from_numpy(g['tokens3']), target_durations=torch.from_numpy(g['durations3']),
+                 target_pitch=torch.from_numpy(g['pitch3']))
+    mel = out['mel'].cpu().numpy()
+    assert mel.shape == g['mel3'].shape
+    assert np.abs(mel - g['mel3']).max() < MEL_TOL  # includes the conv halo frame and padded frames (= output bias)
+    lens = g['durations3'].sum(1)
+    b = int(np.argmin(lens))
+    assert np.abs(mel[b, lens[b]:] - p['out.b'].numpy()).max() < 1e-6
+    want_mask = (np.arange(mel.shape[1])[None] >= lens[:, None]).astype(np.float32)
+    assert np.array_equal(out['expanded_mask'].cpu().numpy()[:, 0, 0], want_mask)
+
+
+def test_c1_predict_api_integer_durations():
+    g = np.load(GOLD / 'c1_forward.npz')
+    p = fo.init_params(fo.CONFIGS['C1'], seed=7)
+    m = _model('C1', p)
+    out = m.predict(g['tokens'][0], encode=False)
+    got = out['int_durations'].cpu().numpy()
+    want = g['pred_int_durations']
+    # integer durations are bit-exact wherever the float duration is not within 1e-3 of a rounding boundary
+    ref_float = fo.predict(p, fo.CONFIGS['C1'], torch.from_numpy(g['tokens']))['duration'][..., 0].numpy()
+    safe = np.abs(ref_float - np.floor(ref_float) - 0.5) > 1e-3
+    assert np.array_equal(got[safe], want[safe])
+    if np.array_equal(got, want):
+        assert out['mel'].shape == g['pred_mel'].shape
+        assert np.abs(out['mel'].cpu().numpy() - g['pred_mel']).max() < MEL_TOL
+    for speed in (0.9, 1.2):
+        o = m.predict(g['tokens'][0], encode=False, speed_regulator=speed)
+        r = fo.predict(p, fo.CONFIGS['C1'], torch.from_numpy(g['tokens']), speed_regulator=speed)
+        rf = (r['duration'][..., 0] * np.float32(1.0 / speed)).numpy()
+        safe = np.abs(rf - np.floor(rf) - 0.5) > 1e-3
+        assert np.array_equal(o['int_durations'].cpu().numpy()[safe], r['int_durations'].numpy()[safe])
+
+
+@pytest.mark.parametrize('cfg_name', ['LJ256', 'LJ256-dense'])
+def test_lj256_ragged_parity(cfg_name):
+    """BASELINE configs[1] model (6+6 layers, d=256) on a small ragged batch the oracle finishes in seconds."""
+    torch.set_num_threads(8)
+    cfg = fo.CONFIGS[cfg_name]
+    p = fo.init_params(cfg, seed=7)
+    tok, dur, pit = fo.make_inputs('ragged', 3, 40, 300, seed=201)
+    ref = fo.forward_transformer_call(p, cfg, tok, dur[..., None], pit[..., None])
+    m = _model(cfg_name, p)
+    out = m.call(tok, target_durations=dur, target_pitch=pit)
+    err = (out['mel'].cpu() - ref['mel']).abs().max().item()
+    assert err < MEL_TOL, err
+    assert (out['duration'].cpu() - ref['duration']).abs().max() < 1e-3
+    assert (out['pitch'].cpu() - ref['pitch']).abs().max() < 1e-3
+    # fast mode: report (not gate) the single-pass bf16 error
+    mf = _model(cfg_name, p, precision='bf16')
+    ef = (mf.call(tok, target_durations=dur, target_pitch=pit)['mel'].cpu() - ref['mel']).abs().max().item()
+    print(f'{cfg_name}: mel max-abs-err bf16x3 {err:.2e}, bf16 {ef:.2e}')
+    assert ef < 0.25
+
+
+def test_lj256_full_size_properties():
+    """BASELINE configs[1] at full size (B=64, 128 phonemes -> 1000 frames): size-independent properties plus
+    oracle parity on a 2-row sub-batch (rows are independent)."""
+    torch.set_num_threads(8)
+    cfg = fo.CONFIGS['LJ256']
+    p = fo.init_params(cfg, seed=7)
+    tok, dur, pit = fo.make_inputs('full', 64, 128, 1000, seed=200)
+    m = _model('LJ256', p)
+    out = m.call(tok, target_durations=dur, target_pitch=pit)
+    mel = out['mel']
+    assert mel.shape == (64, 1000, 80) and torch.isfinite(mel).all()
+    assert int(out['mel_lengths'].min()) == 1000
+    # batch-permutation equivariance (rows independent)
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(0))
+    out_p = m.call(tok[perm], target_durations=dur[perm], target_pitch=pit[perm])
+    assert (out_p['mel'] - mel[perm.to(mel.device)]).abs().max() < 1e-5
+    # oracle parity on two rows
+    sel = [3, 41]
+    ref = fo.forward_transformer_call(p, cfg, tok[sel], dur[sel][..., None], pit[sel][..., None])
+    assert (mel[sel].cpu() - ref['mel']).abs().max() < MEL_TOL

@@ -1,0 +1,476 @@
+// Fused variable-length self-attention on tcgen05 (flash-style, never materialises the (B,H,T,T) tensors):
+//   per CTA one (batch row, head, 128-query tile); loop over 64-key tiles:
+//     S = Q K^T  (tcgen05.mma, fp32 in TMEM)  ->  online softmax in registers (one thread per query row, exp2 domain,
+//     keys >= kv_len masked)  ->  P (bf16 hi/lo) written to 128B-swizzled shared memory  ->  O += P V (tcgen05.mma,
+//     V^T staged by TMA from the transposed V the QKV GEMM epilogue wrote)  ->  O rescaled in TMEM only when a row
+//     maximum moved.
+// Replaces model/layers.py:123-129,138-147 (split/merge heads) and :176-195 (ScaledDotProductAttention) of the
+// reference, which materialise logits / softmax / dropout tensors of shape (B,H,T,T) in fp32.
+//
+// Masking semantics: the reference adds mask*(-1e9) to the logits of padded KEYS (layers.py:186-187); after the
+// fp32 add every such logit equals -1e9 and its softmax weight underflows to exactly 0 whenever the row has at least
+// one valid key, so skipping those keys is exact.  Rows of padded QUERIES are zeroed by the caller's row mask
+// (layers.py:229,262), so they are not computed here (written as zeros).
+#include "../../include/ttsb.h"
+#include "ttsb_common.cuh"
+#include "ttsb_host.h"
+
+namespace ttsb {
+
+constexpr int ATT_BQ = 128;
+constexpr int ATT_BKV = 64;
+constexpr int ATT_THREADS = 160;  // warps 0-3 softmax/epilogue (TMEM lane quarters 0-3), warp 4 TMA + MMA issue
+
+struct MhaKParams {
+  int B, T, H;
+  int q_col0, k_col0;
+  const int* kv_len;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  int ld_out;
+  float scale_log2;  // log2(e)/sqrt(dh)
+};
+
+template <int DH, bool kSplit>
+struct MhaCfg {
+  static constexpr int kPlanes = kSplit ? 2 : 1;
+  static constexpr int Q_BYTES = ATT_BQ * DH * 2;    // DH/64 panels of [128 x 64]
+  static constexpr int K_BYTES = ATT_BKV * DH * 2;   // DH/64 panels of [64 x 64]
+  static constexpr int V_BYTES = DH * ATT_BKV * 2;   // [DH x 64]
+  static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + kPlanes * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + kPlanes * K_BYTES;
+  static constexpr int OFF_P = OFF_V + kPlanes * V_BYTES;
+  static constexpr int OFF_BAR = OFF_P + kPlanes * P_BYTES;
+  static constexpr int kSmemBytes = OFF_BAR + 128 + 1024;
+  static constexpr int kTmemCols = (ATT_BKV + DH) <= 128 ? 128 : 256;
+  static constexpr int S_COL = 0;
+  static constexpr int O_COL = ATT_BKV;
+};
+
+template <int DH, bool kSplit>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+              const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+              const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, const MhaKParams p) {
+  using Cfg = MhaCfg<DH, kSplit>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_p = bars + 4;
+  uint64_t* bar_pv = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  int len = __ldg(p.kv_len + b);
+  len = len < 0 ? 0 : (len > p.T ? p.T : len);
+
+  if (q0 >= len) {
+    // whole query tile is padding: defined (zero) output, no tensor work
+    if (warp < 4) {
+      const int t = q0 + warp * 32 + lane;
+      if (t < p.T) {
+        const size_t o = ((size_t)b * p.T + t) * p.ld_out + h * DH;
+        for (int c = 0; c < DH; c += 8) {
+          st_global_v4(p.out_hi + o + c, 0, 0, 0, 0);
+          if (kSplit && p.out_lo) st_global_v4(p.out_lo + o + c, 0, 0, 0, 0);
+        }
+      }
+    }
+    return;
+  }
+  const int n_kv = (len + ATT_BKV - 1) / ATT_BKV;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_pv, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ===================== TMA + MMA issue thread =====================
+      uint8_t* sQ = smem + Cfg::OFF_Q;
+      uint8_t* sK = smem + Cfg::OFF_K;
+      uint8_t* sV = smem + Cfg::OFF_V;
+      uint8_t* sP = smem + Cfg::OFF_P;
+      const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BKV);
+      const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, DH);
+      const uint32_t t_s = tmem_base + Cfg::S_COL;
+      const uint32_t t_o = tmem_base + Cfg::O_COL;
+
+      mbar_arrive_expect_tx(bar_q, Cfg::kPlanes * Cfg::Q_BYTES);
+      for (int pn = 0; pn < DH / 64; ++pn) {
+        tma_load_3d(&tmQh, bar_q, sQ + pn * (ATT_BQ * 128), p.q_col0 + h * DH + pn * 64, q0, b);
+        if (kSplit) tma_load_3d(&tmQl, bar_q, sQ + Cfg::Q_BYTES + pn * (ATT_BQ * 128), p.q_col0 + h * DH + pn * 64, q0, b);
+      }
+      auto load_k = [&](int j) {
+        mbar_arrive_expect_tx(bar_k, Cfg::kPlanes * Cfg::K_BYTES);
+        for (int pn = 0; pn < DH / 64; ++pn) {
+          tma_load_3d(&tmKh, bar_k, sK + pn * (ATT_BKV * 128), p.k_col0 + h * DH + pn * 64, j * ATT_BKV, b);
+          if (kSplit) tma_load_3d(&tmKl, bar_k, sK + Cfg::K_BYTES + pn * (ATT_BKV * 128), p.k_col0 + h * DH + pn * 64, j * ATT_BKV, b);
+        }
+      };
+      auto load_v = [&](int j) {
+        mbar_arrive_expect_tx(bar_v, Cfg::kPlanes * Cfg::V_BYTES);
+        tma_load_3d(&tmVh, bar_v, sV, j * ATT_BKV, h * DH, b);
+        if (kSplit) tma_load_3d(&tmVl, bar_v, sV + Cfg::V_BYTES, j * ATT_BKV, h * DH, b);
+      };
+      load_k(0);
+      load_v(0);
+      mbar_wait(bar_q, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t ph = j & 1;
+        // ---- S = Q K^T
+        mbar_wait(bar_k, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) {
+          const uint64_t a = make_smem_desc_sw128(smem_u32(sQ + (kk / 4) * (ATT_BQ * 128))) + 2 * (kk % 4);
+          const uint64_t bb = make_smem_desc_sw128(smem_u32(sK + (kk / 4) * (ATT_BKV * 128))) + 2 * (kk % 4);
+          umma_bf16(t_s, a, bb, idesc_s, kk != 0);
+        }
+        if (kSplit) {
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) {
+            const uint64_t a = make_smem_desc_sw128(smem_u32(sQ + Cfg::Q_BYTES + (kk / 4) * (ATT_BQ * 128))) + 2 * (kk % 4);
+            const uint64_t bb = make_smem_desc_sw128(smem_u32(sK + (kk / 4) * (ATT_BKV * 128))) + 2 * (kk % 4);
+            umma_bf16(t_s, a, bb, idesc_s, 1);
+          }
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) {
+            const uint64_t a = make_smem_desc_sw128(smem_u32(sQ + (kk / 4) * (ATT_BQ * 128))) + 2 * (kk % 4);
+            const uint64_t bb = make_smem_desc_sw128(smem_u32(sK + Cfg::K_BYTES + (kk / 4) * (ATT_BKV * 128))) + 2 * (kk % 4);
+            umma_bf16(t_s, a, bb, idesc_s, 1);
+          }
+        }
+        umma_commit(bar_s);
+        // ---- V_j may be loaded once PV_{j-1} has finished reading the V buffer
+        if (j > 0) {
+          mbar_wait(bar_pv, (j - 1) & 1);
+          load_v(j);
+        }
+        // ---- K_{j+1} may be loaded once S_j has finished reading the K buffer
+        mbar_wait(bar_s, ph);
+        if (j + 1 < n_kv) load_k(j + 1);
+        // ---- O += P V
+        mbar_wait(bar_p, ph);
+        mbar_wait(bar_v, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
+          const uint64_t a = make_smem_desc_sw128(smem_u32(sP)) + 2 * kk;
+          const uint64_t bb = make_smem_desc_sw128(smem_u32(sV)) + 2 * kk;
+          umma_bf16(t_o, a, bb, idesc_o, (j | kk) != 0);
+        }
+        if (kSplit) {
+#pragma unroll
+          for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
+            const uint64_t a = make_smem_desc_sw128(smem_u32(sP + Cfg::P_BYTES)) + 2 * kk;
+            const uint64_t bb = make_smem_desc_sw128(smem_u32(sV)) + 2 * kk;
+            umma_bf16(t_o, a, bb, idesc_o, 1);
+          }
+#pragma unroll
+          for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
+            const uint64_t a = make_smem_desc_sw128(smem_u32(sP)) + 2 * kk;
+            const uint64_t bb = make_smem_desc_sw128(smem_u32(sV + Cfg::V_BYTES)) + 2 * kk;
+            umma_bf16(t_o, a, bb, idesc_o, 1);
+          }
+        }
+        umma_commit(bar_pv);
+      }
+    }
+  } else {
+    // ===================== softmax / epilogue warps: one thread per query row =====================
+    const int row = warp * 32 + lane;
+    const int tq = q0 + row;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + Cfg::S_COL;
+    const uint32_t t_o = tmem_base + lane_base + Cfg::O_COL;
+    uint8_t* sP = smem + Cfg::OFF_P;
+    float m = -INFINITY, l = 0.f;
+    uint32_t r[16];
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      float s[ATT_BKV];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < ATT_BKV / 16; ++c) {
+        tmem_ld16(t_s + c * 16, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int key = j * ATT_BKV + c * 16 + i;
+          const float v = key < len ? __uint_as_float(r[i]) * p.scale_log2 : -INFINITY;
+          s[c * 16 + i] = v;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = exp2f(m - m_new);  // first tile: exp2(-inf) = 0
+      float psum = 0.f;
+#pragma unroll
+      for (int i = 0; i < ATT_BKV; ++i) {
+        s[i] = exp2f(s[i] - m_new);
+        psum += s[i];
+      }
+      l = l * alpha + psum;
+      m = m_new;
+      if (j > 0) {
+        mbar_wait(bar_pv, (j - 1) & 1);  // O_{j-1} complete, P buffer free
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+          for (int c = 0; c < DH / 16; ++c) {
+            tmem_ld16(t_o + c * 16, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st16(t_o + c * 16, r);
+          }
+          tmem_wait_st();
+        }
+      }
+      // P -> shared memory, K-major rows of 128 B with the 128B swizzle (16-byte chunk index ^= row & 7)
+#pragma unroll
+      for (int ch = 0; ch < ATT_BKV / 8; ++ch) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(s[ch * 8 + 2 * i], h0, l0);
+          split_bf16(s[ch * 8 + 2 * i + 1], h1, l1);
+          hi[i] = pack_bf16(h0, h1);
+          lo[i] = pack_bf16(l0, l1);
+        }
+        const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(sP + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (kSplit) *reinterpret_cast<uint4*>(sP + Cfg::P_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+    }
+    // ---- epilogue: O / l -> bf16 hi/lo at columns [h*DH, (h+1)*DH)
+    mbar_wait(bar_pv, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const size_t o = ((size_t)b * p.T + (tq < p.T ? tq : 0)) * p.ld_out + h * DH;
+#pragma unroll
+    for (int c = 0; c < DH / 16; ++c) {
+      tmem_ld16(t_o + c * 16, r);
+      tmem_wait_ld();
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(__uint_as_float(r[2 * i]) * inv, h0, l0);
+        split_bf16(__uint_as_float(r[2 * i + 1]) * inv, h1, l1);
+        hi[i] = pack_bf16(h0, h1);
+        lo[i] = pack_bf16(l0, l1);
+      }
+      if (tq < p.T) {
+        st_global_v4(p.out_hi + o + c * 16, hi[0], hi[1], hi[2], hi[3]);
+        st_global_v4(p.out_hi + o + c * 16 + 8, hi[4], hi[5], hi[6], hi[7]);
+        if (kSplit && p.out_lo) {
+          st_global_v4(p.out_lo + o + c * 16, lo[0], lo[1], lo[2], lo[3]);
+          st_global_v4(p.out_lo + o + c * 16 + 8, lo[4], lo[5], lo[6], lo[7]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// SIMT bring-up kernel (one block per (b,h,query)); also produces the reference-exact attention weights
+// of one batch row on request (padded keys get logit -1e9 exactly as layers.py:186-187).
+// ----------------------------------------------------------------------------------------------------
+struct MhaSimtPtrs {
+  const __nv_bfloat16* qk_hi;
+  const __nv_bfloat16* qk_lo;
+  int ld_qk;
+  const __nv_bfloat16* vt_hi;
+  const __nv_bfloat16* vt_lo;
+  int ld_vt;
+  int dh;
+  float scale;       // 1/sqrt(dh)
+  float* weights;    // (H,T,T) or null
+  int weights_b;
+  int weights_only;  // 1: only fill weights for batch row weights_b
+};
+
+__device__ __forceinline__ float ld_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t i) {
+  float v = __bfloat162float(hi[i]);
+  if (lo) v += __bfloat162float(lo[i]);
+  return v;
+}
+
+__global__ void mha_simt_kernel(const MhaKParams p, const MhaSimtPtrs q) {
+  const int tq = blockIdx.x, h = blockIdx.y;
+  const int b = q.weights_only ? q.weights_b : blockIdx.z;
+  extern __shared__ float sm[];  // T logits + dh query + scratch
+  float* logit = sm;
+  float* qv = sm + p.T;
+  __shared__ float red[32];
+  const int len = min(max(p.kv_len[b], 0), p.T);
+  const size_t qrow = ((size_t)b * p.T + tq) * q.ld_qk;
+  for (int c = threadIdx.x; c < q.dh; c += blockDim.x) qv[c] = ld_split(q.qk_hi, q.qk_lo, qrow + p.q_col0 + h * q.dh + c);
+  __syncthreads();
+  for (int tk = threadIdx.x; tk < p.T; tk += blockDim.x) {
+    const size_t krow = ((size_t)b * p.T + tk) * q.ld_qk + p.k_col0 + h * q.dh;
+    float acc = 0.f;
+    for (int c = 0; c < q.dh; ++c) acc = fmaf(qv[c], ld_split(q.qk_hi, q.qk_lo, krow + c), acc);
+    acc = acc * q.scale;
+    if (tk >= len) acc += -1e9f;  // reference: logits += mask * -1e9
+    logit[tk] = acc;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int tk = threadIdx.x; tk < p.T; tk += blockDim.x) mx = fmaxf(mx, logit[tk]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int tk = threadIdx.x; tk < p.T; tk += blockDim.x) {
+    const float e = expf(logit[tk] - mx);
+    logit[tk] = e;
+    sum += e;
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
+  const float inv = 1.f / sum;
+  if (q.weights && b == q.weights_b) {
+    for (int tk = threadIdx.x; tk < p.T; tk += blockDim.x) q.weights[((size_t)h * p.T + tq) * p.T + tk] = logit[tk] * inv;
+  }
+  if (q.weights_only) return;
+  for (int c = threadIdx.x; c < q.dh; c += blockDim.x) {
+    const size_t vrow = ((size_t)b * p.H * q.dh + h * q.dh + c) * q.ld_vt;
+    float acc = 0.f;
+    for (int tk = 0; tk < p.T; ++tk) acc = fmaf(logit[tk], ld_split(q.vt_hi, q.vt_lo, vrow + tk), acc);
+    acc *= inv;
+    __nv_bfloat16 hi, lo;
+    split_bf16(acc, hi, lo);
+    const size_t o = ((size_t)b * p.T + tq) * p.ld_out + h * q.dh + c;
+    p.out_hi[o] = hi;
+    if (p.out_lo) p.out_lo[o] = lo;
+  }
+}
+
+template <int DH, bool kSplit>
+static int launch_tc(const ttsb_mha_args* a, const MhaKParams& p, cudaStream_t stream) {
+  using Cfg = MhaCfg<DH, kSplit>;
+  CUtensorMap tmQ[2], tmK[2], tmV[2];
+  for (int hl = 0; hl < 2; ++hl) {
+    const void* qk = hl == 0 ? a->qk_hi : (kSplit ? a->qk_lo : a->qk_hi);
+    const void* vt = hl == 0 ? a->vt_hi : (kSplit ? a->vt_lo : a->vt_hi);
+    int rc = make_tmap_bf16_3d(&tmQ[hl], qk, (uint64_t)a->ld_qk, a->T, a->B, a->ld_qk, (uint64_t)a->ld_qk * a->T, 64, ATT_BQ);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d(&tmK[hl], qk, (uint64_t)a->ld_qk, a->T, a->B, a->ld_qk, (uint64_t)a->ld_qk * a->T, 64, ATT_BKV);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d(&tmV[hl], vt, (uint64_t)a->T, (uint64_t)a->H * DH, a->B, a->ld_vt, (uint64_t)a->ld_vt * a->H * DH, 64, DH);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    TTSB_CUDA_OK(cudaFuncSetAttribute(mha_tc_kernel<DH, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((a->T + ATT_BQ - 1) / ATT_BQ, a->H, a->B);
+  mha_tc_kernel<DH, kSplit><<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tmQ[0], tmQ[1], tmK[0], tmK[1], tmV[0], tmV[1], p);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "mha_tc_kernel launch");
+}
+
+}  // namespace ttsb
+
+using namespace ttsb;
+
+extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
+  if (!a) { set_last_error("ttsb_mha_fwd: args is NULL"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->B <= 0 || a->T <= 0 || a->H <= 0) { set_last_error("ttsb_mha_fwd: B,T,H must be positive"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (!a->qk_hi || !a->vt_hi || !a->kv_len || !a->out_hi) { set_last_error("ttsb_mha_fwd: NULL tensor"); return TTSB_ERR_INVALID_ARGUMENT; }
+  const bool split = a->precision == TTSB_PREC_BF16X3;
+  if (split && (!a->qk_lo || !a->vt_lo || !a->out_lo)) { set_last_error("ttsb_mha_fwd: bf16x3 needs the lo planes"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->ld_qk % 8 || a->ld_vt % 8 || a->ld_out % 8 || a->q_col0 % 8 || a->k_col0 % 8) {
+    set_last_error("ttsb_mha_fwd: leading dimensions / column offsets must be multiples of 8");
+    return TTSB_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MhaKParams p{};
+  p.B = a->B; p.T = a->T; p.H = a->H;
+  p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.kv_len = a->kv_len;
+  p.out_hi = static_cast<__nv_bfloat16*>(a->out_hi);
+  p.out_lo = split ? static_cast<__nv_bfloat16*>(a->out_lo) : nullptr;
+  p.ld_out = a->ld_out;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)a->dh);
+
+  MhaSimtPtrs q{};
+  q.qk_hi = static_cast<const __nv_bfloat16*>(a->qk_hi);
+  q.qk_lo = split ? static_cast<const __nv_bfloat16*>(a->qk_lo) : nullptr;
+  q.ld_qk = a->ld_qk;
+  q.vt_hi = static_cast<const __nv_bfloat16*>(a->vt_hi);
+  q.vt_lo = split ? static_cast<const __nv_bfloat16*>(a->vt_lo) : nullptr;
+  q.ld_vt = a->ld_vt;
+  q.dh = a->dh;
+  q.scale = 1.f / sqrtf((float)a->dh);
+  q.weights = a->weights_out;
+  q.weights_b = a->weights_batch_index;
+  const size_t simt_smem = (size_t)(a->T + a->dh) * sizeof(float);
+
+  if (a->impl == TTSB_IMPL_SIMT) {
+    q.weights_only = 0;
+    mha_simt_kernel<<<dim3(a->T, a->H, a->B), 128, simt_smem, stream>>>(p, q);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "mha_simt_kernel launch");
+  }
+  int rc;
+  if (a->dh == 128) rc = split ? launch_tc<128, true>(a, p, stream) : launch_tc<128, false>(a, p, stream);
+  else if (a->dh == 64) rc = split ? launch_tc<64, true>(a, p, stream) : launch_tc<64, false>(a, p, stream);
+  else { set_last_error("ttsb_mha_fwd: head_dim %d not supported by the tcgen05 kernel (64, 128)", a->dh); return TTSB_ERR_UNSUPPORTED; }
+  if (rc) return rc;
+  if (a->weights_out) {
+    if (a->weights_batch_index < 0 || a->weights_batch_index >= a->B) { set_last_error("ttsb_mha_fwd: weights_batch_index out of range"); return TTSB_ERR_INVALID_ARGUMENT; }
+    q.weights_only = 1;
+    mha_simt_kernel<<<dim3(a->T, a->H, 1), 128, simt_smem, stream>>>(p, q);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "mha weights kernel launch");
+  }
+  return 0;
+}

@@ -1,0 +1,540 @@
+// Tensor-core GEMM family for the ForwardTransformer blocks (Dense / concat-projection / Conv1D 'same'):
+// persistent warp-specialised tcgen05 kernel -- TMA (3-D maps over (C,T,B), OOB rows = 'same' zero padding) ->
+// 128B-swizzled shared memory -> tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM, double buffered)
+// -> epilogue warps (tcgen05.ld, one thread per output row) fusing bias / ReLU / residual / LayerNorm / row mask and
+// writing fp32 + bf16 hi/lo copies for the next GEMM.
+//
+// Replaces, in the reference (TF2/Keras ops): model/layers.py:134-136,149 (q/k/v + concat projection),
+// :93-94 (FFN), :19-26,36-40 (Conv1D stack + residual LayerNorm), :498-524 (predictor convs), model/models.py:422.
+//
+// Precision modes: TTSB_PREC_BF16 (one product) and TTSB_PREC_BF16X3 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo), the
+// latter gives fp32-class products (needed for the 1e-3 mel parity gate) at 3x the tensor-core work.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/ttsb.h"
+#include "ttsb_common.cuh"
+#include "ttsb_host.h"
+
+namespace ttsb {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_MAX_BN = 256;
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps2-5 epilogue
+constexpr int A_TILE_BYTES = GEMM_BM * GEMM_BK * 2;      // 16 KiB
+constexpr int B_TILE_BYTES = GEMM_MAX_BN * GEMM_BK * 2;  // 32 KiB
+constexpr int TMEM_COLS = 512;
+
+struct GemmKParams {
+  int B, T, N, block_n, n_tiles, tiles_per_row, num_tiles;
+  int num_seg;
+  int seg_src[4], seg_shift[4], seg_kblocks[4];
+  const float* bias;
+  int relu;
+  const float* residual;
+  int ld_res;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  const int* row_len;
+  float* out_f32;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  int ld_out;
+  __nv_bfloat16* vt_hi;
+  __nv_bfloat16* vt_lo;
+  int vt_col0, vt_cols, vt_ld;
+};
+
+template <bool kSplit>
+struct GemmCfg {
+  static constexpr int kStages = kSplit ? 2 : 4;
+  static constexpr int kStageBytes = (kSplit ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kSmemBytes = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+};
+
+// ----------------------------------------------------------------------------------------------------
+// epilogue for one 128 x block_n accumulator tile; executed by the 4 epilogue warps (thread = one row)
+// ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_chunk(const GemmKParams& p, bool row_ok, size_t orow, int b, int t, int col0,
+                                            const float (&y)[16]) {
+  if (!row_ok) return;
+  if (p.vt_hi != nullptr && col0 >= p.vt_col0 && col0 < p.vt_col0 + p.vt_cols) {
+    // transposed store (V^T for the attention kernel): consecutive lanes hold consecutive t -> coalesced per column
+    const size_t base = ((size_t)b * p.vt_cols + (col0 - p.vt_col0)) * (size_t)p.vt_ld + t;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(y[j], hi, lo);
+      p.vt_hi[base + (size_t)j * p.vt_ld] = hi;
+      if (p.vt_lo) p.vt_lo[base + (size_t)j * p.vt_ld] = lo;
+    }
+    return;
+  }
+  const size_t o = orow * (size_t)p.ld_out + col0;
+  if (p.out_f32) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      *reinterpret_cast<float4*>(p.out_f32 + o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+  }
+  if (p.out_hi) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(y[2 * j], h0, l0);
+      split_bf16(y[2 * j + 1], h1, l1);
+      h[j] = pack_bf16(h0, h1);
+      l[j] = pack_bf16(l0, l1);
+    }
+    st_global_v4(p.out_hi + o, h[0], h[1], h[2], h[3]);
+    st_global_v4(p.out_hi + o + 8, h[4], h[5], h[6], h[7]);
+    if (p.out_lo) {
+      st_global_v4(p.out_lo + o, l[0], l[1], l[2], l[3]);
+      st_global_v4(p.out_lo + o + 8, l[4], l[5], l[6], l[7]);
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t taddr, int b, int t0, int n0, int lane_row) {
+  const int t = t0 + lane_row;
+  const bool row_ok = t < p.T;
+  const bool row_keep = row_ok && (p.row_len == nullptr || t < __ldg(p.row_len + b));
+  const size_t orow = (size_t)b * p.T + (row_ok ? t : 0);
+  const int ncols = min(p.block_n, p.N - n0);  // logical columns in this tile
+  uint32_t r[16];
+  float y[16];
+
+  if (p.gamma == nullptr) {
+    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      tmem_ld16(taddr + c0, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = c0 + j;
+        float v = __uint_as_float(r[j]);
+        if (c < ncols) {
+          if (p.bias) v += __ldg(p.bias + n0 + c);
+          if (p.relu) v = fmaxf(v, 0.f);
+          if (p.residual && row_ok) v += __ldg(p.residual + orow * (size_t)p.ld_res + n0 + c);
+        } else {
+          v = 0.f;
+        }
+        y[j] = row_keep ? v : 0.f;
+      }
+      store_chunk(p, row_ok, orow, b, t, n0 + c0, y);
+    }
+    return;
+  }
+
+  // ---- LayerNorm epilogue (single N tile): pass 1 builds v = acc + bias (+relu) (+residual) and parks it in TMEM
+  const float inv_n = 1.f / (float)ncols;
+  float sum = 0.f;
+  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+    tmem_ld16(taddr + c0, r);
+    tmem_wait_ld();
+    float res[16];
+    if (p.residual && row_ok) {
+      const float4* rp = reinterpret_cast<const float4*>(p.residual + orow * (size_t)p.ld_res + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 q = (c0 + 4 * j < ncols) ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        res[4 * j] = q.x; res[4 * j + 1] = q.y; res[4 * j + 2] = q.z; res[4 * j + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) res[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = c0 + j;
+      float v = __uint_as_float(r[j]);
+      if (c < ncols) {
+        if (p.bias) v += __ldg(p.bias + c);
+        if (p.relu) v = fmaxf(v, 0.f);
+        v += res[j];
+      } else {
+        v = 0.f;
+      }
+      sum += v;
+      r[j] = __float_as_uint(v);
+    }
+    tmem_st16(taddr + c0, r);
+  }
+  tmem_wait_st();
+  const float mean = sum * inv_n;
+  float ssq = 0.f;
+  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+    tmem_ld16(taddr + c0, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float dlt = (c0 + j < ncols) ? (__uint_as_float(r[j]) - mean) : 0.f;
+      ssq += dlt * dlt;
+    }
+  }
+  const float rstd = rsqrtf(ssq * inv_n + p.eps);
+  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+    tmem_ld16(taddr + c0, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = c0 + j;
+      float v = 0.f;
+      if (c < ncols) v = (__uint_as_float(r[j]) - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c);
+      y[j] = row_keep ? v : 0.f;
+    }
+    store_chunk(p, row_ok, orow, b, t, c0, y);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// kernel
+// ----------------------------------------------------------------------------------------------------
+template <bool kSplit>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant__ CUtensorMap tmA0l,
+               const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
+               const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const GemmKParams p) {
+  using Cfg = GemmCfg<kSplit>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOffset);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0h);
+    tma_prefetch_desc(&tmWh);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full + s, 1);
+      mbar_init(tmem_empty + s, 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t stage_tx = (kSplit ? 2u : 1u) * (uint32_t)(A_TILE_BYTES + p.block_n * GEMM_BK * 2);
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int b = m_tile / p.tiles_per_row;
+      const int t0 = (m_tile % p.tiles_per_row) * GEMM_BM;
+      const int n0 = n_tile * p.block_n;
+      int kglob = 0;
+      for (int s = 0; s < p.num_seg; ++s) {
+        const CUtensorMap* mh = p.seg_src[s] == 0 ? &tmA0h : &tmA1h;
+        const CUtensorMap* ml = p.seg_src[s] == 0 ? &tmA0l : &tmA1l;
+        for (int kb = 0; kb < p.seg_kblocks[s]; ++kb, ++kglob) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(full_bar + stage, stage_tx);
+          tma_load_3d(mh, full_bar + stage, st, kb * GEMM_BK, t0 + p.seg_shift[s], b);
+          tma_load_2d(&tmWh, full_bar + stage, st + A_TILE_BYTES, kglob * GEMM_BK, n0);
+          if (kSplit) {
+            uint8_t* st2 = st + A_TILE_BYTES + B_TILE_BYTES;
+            tma_load_3d(ml, full_bar + stage, st2, kb * GEMM_BK, t0 + p.seg_shift[s], b);
+            tma_load_2d(&tmWl, full_bar + stage, st2 + A_TILE_BYTES, kglob * GEMM_BK, n0);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_bf16(GEMM_BM, p.block_n);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int total_kb = 0;
+    for (int s = 0; s < p.num_seg; ++s) total_kb += p.seg_kblocks[s];
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * GEMM_MAX_BN;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint64_t a_hi = make_smem_desc_sw128(st);
+        const uint64_t b_hi = make_smem_desc_sw128(st + A_TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
+          umma_bf16(d_tmem, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (kb | kk) != 0);
+        }
+        if (kSplit) {
+          const uint64_t a_lo = make_smem_desc_sw128(st + A_TILE_BYTES + B_TILE_BYTES);
+          const uint64_t b_lo = make_smem_desc_sw128(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < GEMM_BK / 16; ++kk) umma_bf16(d_tmem, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
+#pragma unroll
+          for (int kk = 0; kk < GEMM_BK / 16; ++kk) umma_bf16(d_tmem, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1);
+        }
+        umma_commit(empty_bar + stage);  // frees the smem stage once these MMAs have read it
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full + acc);  // accumulator complete
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int b = m_tile / p.tiles_per_row;
+      const int t0 = (m_tile % p.tiles_per_row) * GEMM_BM;
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GEMM_MAX_BN;
+      epilogue_tile(p, taddr, b, t0, n_tile * p.block_n, quarter * 32 + lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// SIMT bring-up kernel: same contract, plain loads, one block per output row.  Not a fast path.
+// ----------------------------------------------------------------------------------------------------
+struct GemmSimtPtrs {
+  const __nv_bfloat16* a_hi[2];
+  const __nv_bfloat16* a_lo[2];
+  int lda[2];
+  const __nv_bfloat16* w_hi;
+  const __nv_bfloat16* w_lo;
+  int k_total;
+};
+
+__global__ void gemm_simt_kernel(const GemmKParams p, const GemmSimtPtrs q) {
+  const int row = blockIdx.x;
+  const int b = row / p.T, t = row % p.T;
+  const int n_alloc = p.n_tiles * p.block_n;
+  extern __shared__ float srow[];  // n_alloc values + 2 scratch
+  for (int n = threadIdx.x; n < n_alloc; n += blockDim.x) {
+    float acc = 0.f;
+    if (n < p.N) {
+      int koff = 0;
+      for (int s = 0; s < p.num_seg; ++s) {
+        const int src = p.seg_src[s];
+        const int ts = t + p.seg_shift[s];
+        const int K = p.seg_kblocks[s] * GEMM_BK;
+        if (ts >= 0 && ts < p.T) {
+          const __nv_bfloat16* ah = q.a_hi[src] + ((size_t)b * p.T + ts) * q.lda[src];
+          const __nv_bfloat16* al = q.a_lo[src] ? q.a_lo[src] + ((size_t)b * p.T + ts) * q.lda[src] : nullptr;
+          const __nv_bfloat16* wh = q.w_hi + (size_t)n * q.k_total + koff;
+          const __nv_bfloat16* wl = q.w_lo ? q.w_lo + (size_t)n * q.k_total + koff : nullptr;
+          for (int k = 0; k < K; ++k) {
+            const float a1 = __bfloat162float(ah[k]);
+            const float w1 = __bfloat162float(wh[k]);
+            acc = fmaf(a1, w1, acc);
+            if (al) acc = fmaf(__bfloat162float(al[k]), w1, acc);
+            if (wl) acc = fmaf(a1, __bfloat162float(wl[k]), acc);
+          }
+        }
+        koff += K;
+      }
+      if (p.bias) acc += p.bias[n];
+      if (p.relu) acc = fmaxf(acc, 0.f);
+      if (p.residual) acc += p.residual[(size_t)row * p.ld_res + n];
+    }
+    srow[n] = acc;
+  }
+  __syncthreads();
+  const bool keep = p.row_len == nullptr || t < p.row_len[b];
+  float mean = 0.f, rstd = 1.f;
+  if (p.gamma) {
+    float* scratch = srow + n_alloc;
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int n = 0; n < p.N; ++n) s += srow[n];
+      const float m = s / p.N;
+      float v = 0.f;
+      for (int n = 0; n < p.N; ++n) v += (srow[n] - m) * (srow[n] - m);
+      scratch[0] = m;
+      scratch[1] = rsqrtf(v / p.N + p.eps);
+    }
+    __syncthreads();
+    mean = scratch[0];
+    rstd = scratch[1];
+  }
+  for (int n = threadIdx.x; n < n_alloc; n += blockDim.x) {
+    float v = srow[n];
+    if (n < p.N) {
+      if (p.gamma) v = (v - mean) * rstd * p.gamma[n] + p.beta[n];
+    } else {
+      v = 0.f;
+    }
+    if (!keep) v = 0.f;
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    if (p.vt_hi && n >= p.vt_col0 && n < p.vt_col0 + p.vt_cols) {
+      const size_t o = ((size_t)b * p.vt_cols + (n - p.vt_col0)) * (size_t)p.vt_ld + t;
+      p.vt_hi[o] = hi;
+      if (p.vt_lo) p.vt_lo[o] = lo;
+      continue;
+    }
+    const size_t o = (size_t)row * p.ld_out + n;
+    if (p.out_f32) p.out_f32[o] = v;
+    if (p.out_hi) p.out_hi[o] = hi;
+    if (p.out_lo) p.out_lo[o] = lo;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// host
+// ----------------------------------------------------------------------------------------------------
+static int validate(const ttsb_gemm_args* a, int* k_total_out) {
+  if (!a) { set_last_error("ttsb_linear_fwd: args is NULL"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->B <= 0 || a->T <= 0 || a->N <= 0) { set_last_error("ttsb_linear_fwd: B,T,N must be positive"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->block_n < 16 || a->block_n > GEMM_MAX_BN || a->block_n % 16) {
+    set_last_error("ttsb_linear_fwd: block_n=%d must be a multiple of 16 in [16,256]", a->block_n);
+    return TTSB_ERR_INVALID_ARGUMENT;
+  }
+  if (a->num_segments < 1 || a->num_segments > 4) { set_last_error("ttsb_linear_fwd: num_segments out of range"); return TTSB_ERR_INVALID_ARGUMENT; }
+  int kt = 0;
+  for (int s = 0; s < a->num_segments; ++s) {
+    if (a->seg_k[s] <= 0 || a->seg_k[s] % GEMM_BK) { set_last_error("ttsb_linear_fwd: seg_k must be a positive multiple of 64"); return TTSB_ERR_INVALID_ARGUMENT; }
+    const int src = a->seg_src[s];
+    if (src < 0 || src > 1 || !a->a_hi[src]) { set_last_error("ttsb_linear_fwd: bad segment source"); return TTSB_ERR_INVALID_ARGUMENT; }
+    if (a->precision == TTSB_PREC_BF16X3 && !a->a_lo[src]) { set_last_error("ttsb_linear_fwd: bf16x3 needs a_lo"); return TTSB_ERR_INVALID_ARGUMENT; }
+    if (a->lda[src] % 8 || a->a_col0[src] % 8) { set_last_error("ttsb_linear_fwd: lda/a_col0 must be multiples of 8"); return TTSB_ERR_INVALID_ARGUMENT; }
+    kt += a->seg_k[s];
+  }
+  if (!a->w_hi || (a->precision == TTSB_PREC_BF16X3 && !a->w_lo)) { set_last_error("ttsb_linear_fwd: missing packed weights"); return TTSB_ERR_INVALID_ARGUMENT; }
+  const int n_tiles = (a->N + a->block_n - 1) / a->block_n;
+  if (a->ld_out < n_tiles * a->block_n || a->ld_out % 8) {
+    set_last_error("ttsb_linear_fwd: ld_out=%d must be >= %d and a multiple of 8", a->ld_out, n_tiles * a->block_n);
+    return TTSB_ERR_INVALID_ARGUMENT;
+  }
+  if (a->ln_gamma && (n_tiles != 1 || !a->ln_beta)) { set_last_error("ttsb_linear_fwd: LayerNorm epilogue needs N <= block_n and beta"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->residual && (a->ld_res % 4)) { set_last_error("ttsb_linear_fwd: ld_res must be a multiple of 4"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->vt_hi && (a->vt_col0 % a->block_n || a->vt_cols % 16)) { set_last_error("ttsb_linear_fwd: vt_col0 must be tile aligned"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->precision != TTSB_PREC_BF16 && a->precision != TTSB_PREC_BF16X3) { set_last_error("ttsb_linear_fwd: unknown precision"); return TTSB_ERR_INVALID_ARGUMENT; }
+  *k_total_out = kt;
+  return 0;
+}
+
+}  // namespace ttsb
+
+using namespace ttsb;
+
+extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
+  int k_total = 0;
+  int rc = validate(a, &k_total);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const bool split = a->precision == TTSB_PREC_BF16X3;
+
+  GemmKParams p{};
+  p.B = a->B; p.T = a->T; p.N = a->N; p.block_n = a->block_n;
+  p.n_tiles = (a->N + a->block_n - 1) / a->block_n;
+  p.tiles_per_row = (a->T + GEMM_BM - 1) / GEMM_BM;
+  p.num_tiles = a->B * p.tiles_per_row * p.n_tiles;
+  p.num_seg = a->num_segments;
+  int src_k[2] = {0, 0};
+  for (int s = 0; s < a->num_segments; ++s) {
+    p.seg_src[s] = a->seg_src[s];
+    p.seg_shift[s] = a->seg_shift[s];
+    p.seg_kblocks[s] = a->seg_k[s] / GEMM_BK;
+    if (a->seg_k[s] > src_k[a->seg_src[s]]) src_k[a->seg_src[s]] = a->seg_k[s];
+  }
+  p.bias = a->bias; p.relu = a->relu; p.residual = a->residual; p.ld_res = a->ld_res;
+  p.gamma = a->ln_gamma; p.beta = a->ln_beta; p.eps = a->ln_eps; p.row_len = a->row_len;
+  p.out_f32 = a->out_f32;
+  p.out_hi = static_cast<__nv_bfloat16*>(a->out_hi);
+  p.out_lo = split ? static_cast<__nv_bfloat16*>(a->out_lo) : nullptr;
+  p.ld_out = a->ld_out;
+  p.vt_hi = static_cast<__nv_bfloat16*>(a->vt_hi);
+  p.vt_lo = split ? static_cast<__nv_bfloat16*>(a->vt_lo) : nullptr;
+  p.vt_col0 = a->vt_col0; p.vt_cols = a->vt_cols; p.vt_ld = a->vt_ld;
+
+  if (a->impl == TTSB_IMPL_SIMT) {
+    GemmSimtPtrs q{};
+    for (int i = 0; i < 2; ++i) {
+      q.a_hi[i] = a->a_hi[i] ? static_cast<const __nv_bfloat16*>(a->a_hi[i]) + a->a_col0[i] : nullptr;
+      q.a_lo[i] = (split && a->a_lo[i]) ? static_cast<const __nv_bfloat16*>(a->a_lo[i]) + a->a_col0[i] : nullptr;
+      q.lda[i] = a->lda[i];
+    }
+    q.w_hi = static_cast<const __nv_bfloat16*>(a->w_hi);
+    q.w_lo = split ? static_cast<const __nv_bfloat16*>(a->w_lo) : nullptr;
+    q.k_total = k_total;
+    const int n_alloc = p.n_tiles * p.block_n;
+    gemm_simt_kernel<<<a->B * a->T, 256, (n_alloc + 2) * sizeof(float), stream>>>(p, q);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "gemm_simt_kernel launch");
+  }
+
+  // tensor maps: activations as (C, T, B) boxes of (64, 128, 1); weights as (K_total, N_pad) boxes of (64, block_n)
+  CUtensorMap tmA[2][2], tmW[2];
+  for (int i = 0; i < 2; ++i) {
+    const int use = a->a_hi[i] ? i : 0;  // unused slots alias source 0 so the kernel params stay valid
+    const int kext = src_k[use] > 0 ? src_k[use] : GEMM_BK;
+    for (int h = 0; h < 2; ++h) {
+      const void* base = h == 0 ? a->a_hi[use] : (split ? a->a_lo[use] : a->a_hi[use]);
+      rc = make_tmap_bf16_3d(&tmA[i][h], static_cast<const __nv_bfloat16*>(base) + a->a_col0[use], kext, a->T, a->B,
+                             (uint64_t)a->lda[use], (uint64_t)a->lda[use] * a->T, GEMM_BK, GEMM_BM);
+      if (rc) return rc;
+    }
+  }
+  for (int h = 0; h < 2; ++h) {
+    const void* base = h == 0 ? a->w_hi : (split ? a->w_lo : a->w_hi);
+    rc = make_tmap_bf16_2d(&tmW[h], base, k_total, p.n_tiles * p.block_n, (uint64_t)k_total, GEMM_BK, p.block_n);
+    if (rc) return rc;
+  }
+
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (split) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true>::kSmemBytes));
+      attr_set = true;
+    }
+    gemm_tc_kernel<true><<<grid, GEMM_THREADS, GemmCfg<true>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false>::kSmemBytes));
+      attr_set = true;
+    }
+    gemm_tc_kernel<false><<<grid, GEMM_THREADS, GemmCfg<false>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p);
+  }
+  count_launch();
+  return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
+}

@@ -1,0 +1,19 @@
+// Host-side helpers shared by the C-ABI translation units (error text, launch counter, TMA descriptor encode).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ttsb {
+void set_last_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+void count_launch();
+int num_sms();
+
+// bf16 tensor (dim0 contiguous, dim1 rows, dim2 batches); strides in ELEMENTS; 128-byte swizzle; OOB reads give zeros.
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1,
+                      uint64_t stride2, uint32_t box0, uint32_t box1);
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1, uint32_t box0,
+                      uint32_t box1);
+}  // namespace ttsb

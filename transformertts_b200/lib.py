@@ -1,0 +1,189 @@
+"""ctypes binding of libttsb.so (include/ttsb.h).  There is no CPU fallback: if the library is missing or a call
+fails, a TtsbError is raised."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+PREC_BF16 = 0
+PREC_BF16X3 = 1
+IMPL_TCGEN05 = 0
+IMPL_SIMT = 1
+
+_LIB_PATH = Path(__file__).resolve().parent / 'libttsb.so'
+_lib = None
+
+EXPORTS = [
+    'ttsb_last_error', 'ttsb_abi_version', 'ttsb_launch_count', 'ttsb_reset_launch_count', 'ttsb_pack_weight',
+    'ttsb_split_bf16', 'ttsb_embed_ln_pe_fwd', 'ttsb_linear_fwd', 'ttsb_mha_fwd', 'ttsb_statpred_head_fwd',
+    'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
+    'ttsb_expand_ln_pe_fwd', 'ttsb_mel_lengths', 'ttsb_phoneme_lengths', 'ttsb_stft_mel_log',
+]
+
+
+class TtsbError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ('B', C.c_int), ('T', C.c_int), ('N', C.c_int), ('block_n', C.c_int), ('num_segments', C.c_int),
+        ('seg_src', C.c_int * 4), ('seg_shift', C.c_int * 4), ('seg_k', C.c_int * 4),
+        ('a_hi', C.c_void_p * 2), ('a_lo', C.c_void_p * 2), ('lda', C.c_int * 2), ('a_col0', C.c_int * 2),
+        ('w_hi', C.c_void_p), ('w_lo', C.c_void_p), ('bias', C.c_void_p), ('relu', C.c_int),
+        ('residual', C.c_void_p), ('ld_res', C.c_int), ('ln_gamma', C.c_void_p), ('ln_beta', C.c_void_p),
+        ('ln_eps', C.c_float), ('row_len', C.c_void_p), ('out_f32', C.c_void_p), ('out_hi', C.c_void_p),
+        ('out_lo', C.c_void_p), ('ld_out', C.c_int), ('vt_hi', C.c_void_p), ('vt_lo', C.c_void_p),
+        ('vt_col0', C.c_int), ('vt_cols', C.c_int), ('vt_ld', C.c_int), ('precision', C.c_int), ('impl', C.c_int),
+    ]
+
+
+class MhaArgs(C.Structure):
+    _fields_ = [
+        ('B', C.c_int), ('T', C.c_int), ('H', C.c_int), ('dh', C.c_int),
+        ('qk_hi', C.c_void_p), ('qk_lo', C.c_void_p), ('ld_qk', C.c_int), ('q_col0', C.c_int), ('k_col0', C.c_int),
+        ('vt_hi', C.c_void_p), ('vt_lo', C.c_void_p), ('ld_vt', C.c_int), ('kv_len', C.c_void_p),
+        ('out_hi', C.c_void_p), ('out_lo', C.c_void_p), ('ld_out', C.c_int),
+        ('weights_out', C.c_void_p), ('weights_batch_index', C.c_int), ('precision', C.c_int), ('impl', C.c_int),
+    ]
+
+
+def library_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load libttsb.so (built in-tree by transformertts_b200.build).  Raises TtsbError when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise TtsbError(f'{_LIB_PATH} not found -- run `python -m transformertts_b200.build` (no CPU fallback exists)')
+    lib = C.CDLL(str(_LIB_PATH))
+    lib.ttsb_last_error.restype = C.c_char_p
+    lib.ttsb_launch_count.restype = C.c_int64
+    lib.ttsb_reset_launch_count.restype = None
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise TtsbError(f'libttsb.so does not export {name}')
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise TtsbError(f'{what} failed ({rc}): {load().ttsb_last_error().decode()}')
+
+
+def ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise TtsbError('libttsb expects CUDA tensors')
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load().ttsb_launch_count())
+
+
+def reset_launch_count():
+    load().ttsb_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# thin typed wrappers (shapes are taken from the tensors; all tensors must be contiguous)
+# ------------------------------------------------------------------------------------------------------------
+def pack_weight(w_kn: torch.Tensor, n_pad: int, split: bool):
+    """Keras (K,N) fp32 kernel (Conv1D (k,Cin,Cout) is reshaped to (k*Cin, Cout)) -> bf16 hi/lo [n_pad, K]."""
+    w2 = w_kn.reshape(-1, w_kn.shape[-1]).contiguous().float()
+    K, N = w2.shape
+    hi = torch.empty((n_pad, K), dtype=torch.bfloat16, device=w2.device)
+    lo = torch.empty_like(hi) if split else None
+    _check(load().ttsb_pack_weight(ptr(w2), K, N, n_pad, ptr(hi), ptr(lo), _stream()), 'ttsb_pack_weight')
+    return hi, lo
+
+
+def split_bf16(x: torch.Tensor, split: bool):
+    x = x.contiguous().float()
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi) if split else None
+    _check(load().ttsb_split_bf16(ptr(x), C.c_int64(x.numel()), ptr(hi), ptr(lo), _stream()), 'ttsb_split_bf16')
+    return hi, lo
+
+
+def linear_fwd(args: GemmArgs):
+    _check(load().ttsb_linear_fwd(C.byref(args), _stream()), 'ttsb_linear_fwd')
+
+
+def mha_fwd(args: MhaArgs):
+    _check(load().ttsb_mha_fwd(C.byref(args), _stream()), 'ttsb_mha_fwd')
+
+
+def embed_ln_pe_fwd(tokens, emb, gamma, beta, pe, pos_scalar, eps, out_f32, out_hi, out_lo):
+    B, T = tokens.shape
+    vocab, d = emb.shape
+    _check(load().ttsb_embed_ln_pe_fwd(ptr(tokens), ptr(emb), ptr(gamma), ptr(beta), ptr(pe), ptr(pos_scalar), B, T, d,
+                                       vocab, C.c_float(eps), ptr(out_f32), ptr(out_hi), ptr(out_lo), _stream()),
+           'ttsb_embed_ln_pe_fwd')
+
+
+def expand_ln_pe_fwd(x, idx, gamma, beta, pe, pos_scalar, eps, out_f32, out_hi, out_lo):
+    B, Tp, d = x.shape
+    Tm = idx.shape[1]
+    _check(load().ttsb_expand_ln_pe_fwd(ptr(x), ptr(idx), ptr(gamma), ptr(beta), ptr(pe), ptr(pos_scalar), B, Tp, Tm, d,
+                                        C.c_float(eps), ptr(out_f32), ptr(out_hi), ptr(out_lo), _stream()),
+           'ttsb_expand_ln_pe_fwd')
+
+
+def length_regulate_fwd(x, idx, out):
+    B, Tp, d = x.shape
+    Tm = idx.shape[1]
+    _check(load().ttsb_length_regulate_fwd(ptr(x), ptr(idx), B, Tp, Tm, d, ptr(out), _stream()), 'ttsb_length_regulate_fwd')
+
+
+def durations_to_int(dur, scalar, max_mask, min_mask, out_int, out_len):
+    B, Tp = dur.shape
+    _check(load().ttsb_durations_to_int(ptr(dur), C.c_float(scalar), ptr(max_mask), ptr(min_mask), B, Tp, ptr(out_int),
+                                        ptr(out_len), _stream()), 'ttsb_durations_to_int')
+
+
+def expand_indices(dur_int, Tm, out_idx):
+    B, Tp = dur_int.shape
+    _check(load().ttsb_expand_indices(ptr(dur_int), B, Tp, Tm, ptr(out_idx), _stream()), 'ttsb_expand_indices')
+
+
+def statpred_head_fwd(h, C_in, w, bias, relu, row_len, out):
+    B, T, ldh = h.shape
+    _check(load().ttsb_statpred_head_fwd(ptr(h), ldh, C_in, ptr(w), ptr(bias), int(relu), ptr(row_len), B, T, ptr(out),
+                                         _stream()), 'ttsb_statpred_head_fwd')
+
+
+def pitch_embed_add_fwd(x, pitch, w, bias, out):
+    B, T, d = x.shape
+    _check(load().ttsb_pitch_embed_add_fwd(ptr(x), ptr(pitch), ptr(w), ptr(bias), B, T, d, ptr(out), _stream()),
+           'ttsb_pitch_embed_add_fwd')
+
+
+def mel_lengths(mel, padding_value, out):
+    B, T, Cc = mel.shape
+    _check(load().ttsb_mel_lengths(ptr(mel), B, T, Cc, C.c_float(padding_value), ptr(out), _stream()), 'ttsb_mel_lengths')
+
+
+def phoneme_lengths(ph, padding, out):
+    B, T = ph.shape
+    _check(load().ttsb_phoneme_lengths(ptr(ph), B, T, int(padding), ptr(out), _stream()), 'ttsb_phoneme_lengths')
+
+
+def stft_mel_log(wav, mel_basis, normalizer, out):
+    n_clips, n_samples = wav.shape
+    n_mels = mel_basis.shape[0]
+    _check(load().ttsb_stft_mel_log(ptr(wav), n_clips, n_samples, ptr(mel_basis), n_mels, int(normalizer), ptr(out),
+                                    _stream()), 'ttsb_stft_mel_log')

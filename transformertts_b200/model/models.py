@@ -1,0 +1,567 @@
+"""ForwardTransformer: host-side mirror of the reference's text->mel model (model/models.py:344-642) over torch CUDA
+tensors, executing every layer through libttsb.so (hand-written sm_100a kernels, include/ttsb.h).
+
+Same constructor arguments, methods and output dictionary as the reference class; tensors are torch.Tensor instead of
+tf.Tensor.  There is no CPU / eager-PyTorch fallback: without the CUDA library the model raises TtsbError.
+
+Parameter names (flat dict, Keras layouts -- Dense (in,out), Conv1D (k,in,out)):
+  embedding; {encoder,decoder}.ln.{gamma,beta}; {..}.pos_scalar;
+  {..}.b{i}.{wq,wk,wv,wo}.{w,b}; {..}.b{i}.ln1.{gamma,beta}; dense block: ffn1/ffn2.{w,b}; conv block: conv{j}.{w,b};
+  {..}.b{i}.ln2.{gamma,beta}; {dur_pred,pitch_pred}.conv{j}.{w,b} / .ln{j}.{gamma,beta} / .out.{w,b};
+  pitch_embed.{w,b}; out.{w,b}
+"""
+from __future__ import annotations
+
+import math
+from pathlib import Path
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import lib
+from .transformer_utils import mask_from_lengths, positional_encoding
+
+LN_EPS = 1e-6  # reference: model/layers.py:27,96,207,295,508
+DEFAULT_VOCAB = 127  # 126 phoneme/punctuation symbols + pad id 0 (reference: data/text/tokenizer.py:17-20)
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _pick_block_n(N: int, need_single_tile: bool) -> int:
+    n16 = _round_up(N, 16)
+    if n16 <= 256:
+        return n16
+    if need_single_tile:
+        raise lib.TtsbError(f'LayerNorm-epilogue GEMM needs N <= 256 (got {N}); model dimension 384 is not supported yet')
+    for bn in range(256, 15, -16):
+        if n16 % bn == 0:
+            return bn
+    return 256
+
+
+class _PackedLinear:
+    """One GEMM of the family in include/ttsb.h: packed bf16 weights + bias + static shape info."""
+
+    def __init__(self, w_kn: torch.Tensor, bias: Optional[torch.Tensor], seg_k: List[int], split: bool, single_tile: bool = False,
+                 block_n: Optional[int] = None):
+        K, N = w_kn.reshape(-1, w_kn.shape[-1]).shape
+        assert sum(seg_k) == K, (seg_k, K)
+        self.N = N
+        self.K = K
+        self.seg_k = seg_k
+        self.block_n = block_n or _pick_block_n(N, single_tile)
+        self.n_tiles = (N + self.block_n - 1) // self.block_n
+        self.n_pad = self.n_tiles * self.block_n
+        self.w_hi, self.w_lo = lib.pack_weight(w_kn, self.n_pad, split)
+        self.bias = bias.contiguous().float() if bias is not None else None
+
+
+class ForwardTransformer:
+    def __init__(self,
+                 encoder_model_dimension: int,
+                 decoder_model_dimension: int,
+                 dropout_rate: float,
+                 decoder_num_heads: list,
+                 encoder_num_heads: list,
+                 encoder_max_position_encoding: int,
+                 decoder_max_position_encoding: int,
+                 encoder_dense_blocks: int,
+                 decoder_dense_blocks: int,
+                 duration_conv_filters: list,
+                 pitch_conv_filters: list,
+                 duration_kernel_size: int,
+                 pitch_kernel_size: int,
+                 predictors_dropout: float,
+                 mel_channels: int,
+                 phoneme_language: str = 'en-us',
+                 with_stress: bool = True,
+                 model_breathing: bool = False,
+                 transposed_attn_convs: bool = True,
+                 encoder_attention_conv_filters: list = None,
+                 decoder_attention_conv_filters: list = None,
+                 encoder_attention_conv_kernel: int = None,
+                 decoder_attention_conv_kernel: int = None,
+                 encoder_feed_forward_dimension: int = None,
+                 decoder_feed_forward_dimension: int = None,
+                 debug=False,
+                 **kwargs):
+        # same config bookkeeping as the reference (model/models.py:453-462): ctor args + extra yaml keys
+        loc = dict(locals())
+        self.config = {k: v for k, v in loc.items() if k not in ('self', 'kwargs', '__class__')}
+        self.config.update(kwargs)
+        if encoder_model_dimension != decoder_model_dimension:
+            raise ValueError('Expand feeds the encoder output to the decoder: model dimensions must match')
+        self.mel_channels = int(mel_channels)
+        self.vocab_size = int(kwargs.get('vocab_size', DEFAULT_VOCAB))
+        self.alphabet = kwargs.get('alphabet')
+        self.device = torch.device(kwargs.get('device', 'cuda:0'))
+        # numerics of the tensor-core products: 'bf16x3' meets the 1e-3 mel parity gate, 'bf16' is the fast mode
+        self.precision = kwargs.get('precision', 'bf16x3')
+        self.impl = kwargs.get('impl', 'tcgen05')
+        self.return_attention_weights = bool(kwargs.get('return_attention_weights', False))
+        self.debug = debug
+        self._stacks = {}
+        for name in ('encoder', 'decoder'):
+            d = int(self.config[f'{name}_model_dimension'])
+            heads = list(self.config[f'{name}_num_heads'])
+            n_dense = int(self.config[f'{name}_dense_blocks'])
+            self._stacks[name] = dict(
+                d=d, heads=heads, n_dense=n_dense, ffn=self.config.get(f'{name}_feed_forward_dimension'),
+                filters=[int(f) for f in (self.config.get(f'{name}_attention_conv_filters') or [])],
+                kernel=self.config.get(f'{name}_attention_conv_kernel'),
+                max_pos=int(self.config[f'{name}_max_position_encoding']))
+        self.weights: Dict[str, torch.Tensor] = {}
+        self._packed = None
+        self.optimizer = None
+        self.loss_weights = [1., 1., 3.]
+        self._init_weights(seed=int(kwargs.get('seed', 42)))
+
+    # ------------------------------------------------------------------------------------------------
+    # parameters
+    # ------------------------------------------------------------------------------------------------
+    def _param_shapes(self) -> Dict[str, tuple]:
+        c = self.config
+        shapes = {}
+        d_enc = self._stacks['encoder']['d']
+        shapes['embedding'] = (self.vocab_size, d_enc)
+        for name, st in self._stacks.items():
+            d = st['d']
+            shapes[f'{name}.ln.gamma'] = (d,)
+            shapes[f'{name}.ln.beta'] = (d,)
+            shapes[f'{name}.pos_scalar'] = ()
+            for i, _ in enumerate(st['heads']):
+                pre = f'{name}.b{i}.'
+                for w in ('wq', 'wk', 'wv'):
+                    shapes[pre + w + '.w'] = (d, d)
+                    shapes[pre + w + '.b'] = (d,)
+                shapes[pre + 'wo.w'] = (2 * d, d)
+                shapes[pre + 'wo.b'] = (d,)
+                shapes[pre + 'ln1.gamma'] = (d,)
+                shapes[pre + 'ln1.beta'] = (d,)
+                if i < st['n_dense']:
+                    F = int(st['ffn'])
+                    shapes[pre + 'ffn1.w'] = (d, F)
+                    shapes[pre + 'ffn1.b'] = (F,)
+                    shapes[pre + 'ffn2.w'] = (F, d)
+                    shapes[pre + 'ffn2.b'] = (d,)
+                else:
+                    cin = d
+                    for j, f in enumerate(st['filters']):
+                        shapes[pre + f'conv{j}.w'] = (int(st['kernel']), cin, f)
+                        shapes[pre + f'conv{j}.b'] = (f,)
+                        cin = f
+                shapes[pre + 'ln2.gamma'] = (d,)
+                shapes[pre + 'ln2.beta'] = (d,)
+        for name, filt, k in (('dur_pred', c['duration_conv_filters'], c['duration_kernel_size']),
+                              ('pitch_pred', c['pitch_conv_filters'], c['pitch_kernel_size'])):
+            cin = d_enc
+            for j, f in enumerate(filt):
+                shapes[f'{name}.conv{j}.w'] = (int(k), cin, int(f))
+                shapes[f'{name}.conv{j}.b'] = (int(f),)
+                shapes[f'{name}.ln{j}.gamma'] = (int(f),)
+                shapes[f'{name}.ln{j}.beta'] = (int(f),)
+                cin = int(f)
+            shapes[f'{name}.out.w'] = (cin, 1)
+            shapes[f'{name}.out.b'] = (1,)
+        shapes['pitch_embed.w'] = (1, d_enc)
+        shapes['pitch_embed.b'] = (d_enc,)
+        shapes['out.w'] = (self._stacks['decoder']['d'], self.mel_channels)
+        shapes['out.b'] = (self.mel_channels,)
+        return shapes
+
+    def _init_weights(self, seed: int):
+        """Keras defaults the reference relies on: glorot_uniform kernels, zero biases, LayerNorm (1,0),
+        Embedding uniform(-0.05, 0.05), pos_encoding_scalar 1.0 (model/layers.py:282)."""
+        g = torch.Generator(device='cpu').manual_seed(seed)
+        w = {}
+        for name, shape in self._param_shapes().items():
+            if name == 'embedding':
+                t = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+            elif name.endswith('.gamma') or name.endswith('pos_scalar'):
+                t = torch.ones(shape)
+            elif name.endswith('.beta') or name.endswith('.b'):
+                t = torch.zeros(shape)
+            else:  # kernels
+                if len(shape) == 3:
+                    fan_in, fan_out = shape[0] * shape[1], shape[0] * shape[2]
+                else:
+                    fan_in, fan_out = shape
+                lim = math.sqrt(6.0 / (fan_in + fan_out))
+                t = (torch.rand(shape, generator=g) * 2 - 1) * lim
+            w[name] = t
+        self.set_weights(w)
+
+    def set_weights(self, weights: Dict[str, torch.Tensor]):
+        shapes = self._param_shapes()
+        missing = set(shapes) - set(weights)
+        if missing:
+            raise KeyError(f'missing parameters: {sorted(missing)[:5]} ...')
+        for name, shape in shapes.items():
+            t = torch.as_tensor(weights[name]).detach().to(torch.float32)
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError(f'{name}: expected shape {shape}, got {tuple(t.shape)}')
+            self.weights[name] = t.to(self.device).contiguous()
+        self._packed = None
+
+    def get_weights(self) -> Dict[str, torch.Tensor]:
+        return {k: v.detach().clone() for k, v in self.weights.items()}
+
+    @property
+    def trainable_variables(self) -> List[torch.Tensor]:
+        return [self.weights[k] for k in self._param_shapes()]
+
+    def build_model_weights(self) -> None:
+        """Reference builds Keras variables with a dummy call (model/models.py:597-598); here they exist already."""
+        self._prepare()
+
+    # ------------------------------------------------------------------------------------------------
+    # operand preparation (packed bf16 weights, PE tables)
+    # ------------------------------------------------------------------------------------------------
+    @property
+    def _split(self) -> bool:
+        return self.precision == 'bf16x3'
+
+    @property
+    def _prec(self) -> int:
+        return lib.PREC_BF16X3 if self._split else lib.PREC_BF16
+
+    @property
+    def _impl(self) -> int:
+        return lib.IMPL_SIMT if self.impl == 'simt' else lib.IMPL_TCGEN05
+
+    def _prepare(self):
+        if self._packed is not None and self._packed['precision'] == self.precision:
+            return self._packed
+        lib.load()
+        W = self.weights
+        sp = self._split
+        P = {'precision': self.precision}
+        for name, st in self._stacks.items():
+            d = st['d']
+            P[f'{name}.pe'] = positional_encoding(st['max_pos'], d)[0].to(self.device).contiguous()
+            for i, _ in enumerate(st['heads']):
+                pre = f'{name}.b{i}.'
+                wqkv = torch.cat([W[pre + 'wq.w'], W[pre + 'wk.w'], W[pre + 'wv.w']], dim=1)
+                bqkv = torch.cat([W[pre + 'wq.b'], W[pre + 'wk.b'], W[pre + 'wv.b']])
+                bn = d if d <= 256 else d // 2
+                P[pre + 'qkv'] = _PackedLinear(wqkv, bqkv, [d], sp, block_n=bn)
+                P[pre + 'wo'] = _PackedLinear(W[pre + 'wo.w'], W[pre + 'wo.b'], [d, d], sp, single_tile=True)
+                if i < st['n_dense']:
+                    P[pre + 'ffn1'] = _PackedLinear(W[pre + 'ffn1.w'], W[pre + 'ffn1.b'], [d], sp)
+                    P[pre + 'ffn2'] = _PackedLinear(W[pre + 'ffn2.w'], W[pre + 'ffn2.b'], [int(st['ffn'])], sp, single_tile=True)
+                else:
+                    cin = d
+                    nconv = len(st['filters'])
+                    for j, f in enumerate(st['filters']):
+                        P[pre + f'conv{j}'] = _PackedLinear(W[pre + f'conv{j}.w'], W[pre + f'conv{j}.b'],
+                                                            [cin] * int(st['kernel']), sp, single_tile=(j == nconv - 1))
+                        cin = f
+        d_enc = self._stacks['encoder']['d']
+        for name, filt, k in (('dur_pred', self.config['duration_conv_filters'], self.config['duration_kernel_size']),
+                              ('pitch_pred', self.config['pitch_conv_filters'], self.config['pitch_kernel_size'])):
+            cin = d_enc
+            for j, f in enumerate(filt):
+                P[f'{name}.conv{j}'] = _PackedLinear(W[f'{name}.conv{j}.w'], W[f'{name}.conv{j}.b'], [cin] * int(k), sp,
+                                                     single_tile=True)
+                cin = int(f)
+        P['out'] = _PackedLinear(W['out.w'], W['out.b'], [self._stacks['decoder']['d']], sp)
+        self._packed = P
+        return P
+
+    # ------------------------------------------------------------------------------------------------
+    # kernels
+    # ------------------------------------------------------------------------------------------------
+    def _act(self, B, T, C, f32=True):
+        """Allocate an activation triple (fp32, bf16 hi, bf16 lo)."""
+        dev = self.device
+        f = torch.empty((B, T, C), dtype=torch.float32, device=dev) if f32 else None
+        hi = torch.empty((B, T, C), dtype=torch.bfloat16, device=dev)
+        lo = torch.empty((B, T, C), dtype=torch.bfloat16, device=dev) if self._split else None
+        return f, hi, lo
+
+    def _gemm(self, pl: _PackedLinear, B, T, srcs, seg_src, seg_shift, relu=False, residual=None, ln=None, row_len=None,
+              out_f32=None, out_hi=None, out_lo=None, ld_out=None, vt=None):
+        a = lib.GemmArgs()
+        a.B, a.T, a.N, a.block_n = B, T, pl.N, pl.block_n
+        a.num_segments = len(pl.seg_k)
+        for s, k in enumerate(pl.seg_k):
+            a.seg_src[s] = seg_src[s]
+            a.seg_shift[s] = seg_shift[s]
+            a.seg_k[s] = k
+        for i, (hi, lo, ld, col0) in enumerate(srcs):
+            a.a_hi[i] = hi.data_ptr()
+            a.a_lo[i] = lo.data_ptr() if lo is not None else None
+            a.lda[i] = ld
+            a.a_col0[i] = col0
+        a.w_hi = pl.w_hi.data_ptr()
+        a.w_lo = pl.w_lo.data_ptr() if pl.w_lo is not None else None
+        a.bias = pl.bias.data_ptr() if pl.bias is not None else None
+        a.relu = int(relu)
+        if residual is not None:
+            a.residual = residual.data_ptr()
+            a.ld_res = residual.shape[-1]
+        if ln is not None:
+            a.ln_gamma = ln[0].data_ptr()
+            a.ln_beta = ln[1].data_ptr()
+            a.ln_eps = LN_EPS
+        a.row_len = row_len.data_ptr() if row_len is not None else None
+        a.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+        a.out_hi = out_hi.data_ptr() if out_hi is not None else None
+        a.out_lo = out_lo.data_ptr() if out_lo is not None else None
+        a.ld_out = ld_out if ld_out is not None else pl.n_pad
+        if vt is not None:
+            vt_hi, vt_lo, col0, cols, ld = vt
+            a.vt_hi = vt_hi.data_ptr()
+            a.vt_lo = vt_lo.data_ptr() if vt_lo is not None else None
+            a.vt_col0, a.vt_cols, a.vt_ld = col0, cols, ld
+        a.precision = self._prec
+        a.impl = self._impl
+        lib.linear_fwd(a)
+
+    def _conv_shifts(self, k: int) -> List[int]:
+        return [j - (k - 1) // 2 for j in range(k)]
+
+    def _block(self, P, name: str, i: int, x, lens, B: int, T: int, attn_out: Optional[dict], key: str):
+        """One SelfAttentionDenseBlock / SelfAttentionConvBlock (reference: model/layers.py:214-264)."""
+        st = self._stacks[name]
+        d, H = st['d'], st['heads'][i]
+        dh = d // H
+        pre = f'{name}.b{i}.'
+        W = self.weights
+        x_f, x_hi, x_lo = x
+        dev = self.device
+        # --- q,k,v projections: one GEMM, V written transposed for the attention kernel
+        qkv = P[pre + 'qkv']
+        ld_vt = _round_up(T, 8)
+        qk_hi = torch.empty((B, T, qkv.n_pad), dtype=torch.bfloat16, device=dev)
+        qk_lo = torch.empty_like(qk_hi) if self._split else None
+        vt_hi = torch.empty((B, d, ld_vt), dtype=torch.bfloat16, device=dev)
+        vt_lo = torch.empty_like(vt_hi) if self._split else None
+        self._gemm(qkv, B, T, [(x_hi, x_lo, d, 0)], [0], [0], out_hi=qk_hi, out_lo=qk_lo, vt=(vt_hi, vt_lo, 2 * d, d, ld_vt))
+        # --- fused attention
+        _, at_hi, at_lo = self._act(B, T, d, f32=False)
+        m = lib.MhaArgs()
+        m.B, m.T, m.H, m.dh = B, T, H, dh
+        m.qk_hi = qk_hi.data_ptr()
+        m.qk_lo = qk_lo.data_ptr() if qk_lo is not None else None
+        m.ld_qk, m.q_col0, m.k_col0 = qkv.n_pad, 0, d
+        m.vt_hi = vt_hi.data_ptr()
+        m.vt_lo = vt_lo.data_ptr() if vt_lo is not None else None
+        m.ld_vt = ld_vt
+        m.kv_len = lens.data_ptr()
+        m.out_hi = at_hi.data_ptr()
+        m.out_lo = at_lo.data_ptr() if at_lo is not None else None
+        m.ld_out = d
+        wts = None
+        if attn_out is not None and self.return_attention_weights:
+            wts = torch.empty((1, H, T, T), dtype=torch.float32, device=dev)
+            m.weights_out = wts.data_ptr()
+            m.weights_batch_index = 0
+        m.precision = self._prec
+        m.impl = self._impl
+        lib.mha_fwd(m)
+        if attn_out is not None:
+            attn_out[key] = wts
+        # --- output projection on concat([x, attn]) + residual + LayerNorm + row mask
+        y = self._act(B, T, d)
+        self._gemm(P[pre + 'wo'], B, T, [(x_hi, x_lo, d, 0), (at_hi, at_lo, d, 0)], [0, 1], [0, 0], residual=x_f,
+                   ln=(W[pre + 'ln1.gamma'], W[pre + 'ln1.beta']), row_len=lens, out_f32=y[0], out_hi=y[1], out_lo=y[2])
+        z = self._act(B, T, d)
+        if i < st['n_dense']:
+            F = int(st['ffn'])
+            _, h_hi, h_lo = self._act(B, T, P[pre + 'ffn1'].n_pad, f32=False)
+            self._gemm(P[pre + 'ffn1'], B, T, [(y[1], y[2], d, 0)], [0], [0], relu=True, out_hi=h_hi, out_lo=h_lo)
+            self._gemm(P[pre + 'ffn2'], B, T, [(h_hi, h_lo, P[pre + 'ffn1'].n_pad, 0)], [0], [0], residual=y[0],
+                       ln=(W[pre + 'ln2.gamma'], W[pre + 'ln2.beta']), row_len=lens, out_f32=z[0], out_hi=z[1], out_lo=z[2])
+        else:
+            k = int(st['kernel'])
+            shifts = self._conv_shifts(k)
+            h_hi, h_lo, ld = y[1], y[2], d
+            n = len(st['filters'])
+            for j in range(n - 1):
+                pl = P[pre + f'conv{j}']
+                _, o_hi, o_lo = self._act(B, T, pl.n_pad, f32=False)
+                self._gemm(pl, B, T, [(h_hi, h_lo, ld, 0)], [0] * k, shifts, relu=True, out_hi=o_hi, out_lo=o_lo)
+                h_hi, h_lo, ld = o_hi, o_lo, pl.n_pad
+            self._gemm(P[pre + f'conv{n - 1}'], B, T, [(h_hi, h_lo, ld, 0)], [0] * k, shifts, residual=y[0],
+                       ln=(W[pre + 'ln2.gamma'], W[pre + 'ln2.beta']), row_len=lens, out_f32=z[0], out_hi=z[1], out_lo=z[2])
+        return z
+
+    def _stat_predictor(self, P, name: str, x, lens, B: int, T: int, relu_head: bool):
+        """StatPredictor (reference: model/layers.py:463-524).  The input is already zero at padded rows."""
+        W = self.weights
+        filt = self.config['duration_conv_filters' if name == 'dur_pred' else 'pitch_conv_filters']
+        k = int(self.config['duration_kernel_size' if name == 'dur_pred' else 'pitch_kernel_size'])
+        shifts = self._conv_shifts(k)
+        _, h_hi, h_lo = x
+        ld = x[1].shape[-1]
+        h_f = None
+        for j, f in enumerate(filt):
+            pl = P[f'{name}.conv{j}']
+            h_f, o_hi, o_lo = self._act(B, T, pl.n_pad)
+            self._gemm(pl, B, T, [(h_hi, h_lo, ld, 0)], [0] * k, shifts, relu=True,
+                       ln=(W[f'{name}.ln{j}.gamma'], W[f'{name}.ln{j}.beta']), out_f32=h_f, out_hi=o_hi, out_lo=o_lo)
+            h_hi, h_lo, ld = o_hi, o_lo, pl.n_pad
+        out = torch.empty((B, T), dtype=torch.float32, device=self.device)
+        lib.statpred_head_fwd(h_f, int(filt[-1]), W[f'{name}.out.w'].reshape(-1).contiguous(), W[f'{name}.out.b'], relu_head, lens, out)
+        return out
+
+    # ------------------------------------------------------------------------------------------------
+    # reference API
+    # ------------------------------------------------------------------------------------------------
+    def call(self, x, target_durations=None, target_pitch=None, training=False, durations_scalar=1.,
+             max_durations_mask=None, min_durations_mask=None):
+        """reference: model/models.py:518-550.  x int (B,Tp) with trailing pad id 0; targets (B,Tp,1) or (B,Tp)."""
+        if training:
+            raise lib.TtsbError('training=True goes through train_step (dropout + backward); call() is inference-only')
+        P = self._prepare()
+        W = self.weights
+        dev = self.device
+        x = torch.as_tensor(x).to(device=dev, dtype=torch.int32).contiguous()
+        if x.dim() != 2:
+            raise ValueError('input tokens must have shape (batch, length)')
+        B, Tp = x.shape
+        d = self._stacks['encoder']['d']
+        # encoder padding -> per-row valid lengths (count of non-zero ids; batches are padded at the end)
+        enc_len = torch.empty((B,), dtype=torch.int32, device=dev)
+        lib.phoneme_lengths(x, 0, enc_len)
+        h = self._act(B, Tp, d)
+        lib.embed_ln_pe_fwd(x, W['embedding'], W['encoder.ln.gamma'], W['encoder.ln.beta'], P['encoder.pe'],
+                            W['encoder.pos_scalar'].reshape(1), LN_EPS, h[0], h[1], h[2])
+        enc_attn, dec_attn = {}, {}
+        for i in range(len(self._stacks['encoder']['heads'])):
+            h = self._block(P, 'encoder', i, h, enc_len, B, Tp, enc_attn, self._attn_key('encoder', i))
+        durations = self._stat_predictor(P, 'dur_pred', h, enc_len, B, Tp, relu_head=True)
+        pitch = self._stat_predictor(P, 'pitch_pred', h, enc_len, B, Tp, relu_head=False)
+        if target_pitch is not None:
+            src_pitch = torch.as_tensor(target_pitch).to(device=dev, dtype=torch.float32).reshape(B, Tp).contiguous()
+        else:
+            src_pitch = pitch
+        h_pe = torch.empty((B, Tp, d), dtype=torch.float32, device=dev)
+        lib.pitch_embed_add_fwd(h[0], src_pitch, W['pitch_embed.w'].reshape(-1).contiguous(), W['pitch_embed.b'], h_pe)
+        if target_durations is not None:
+            use_dur = torch.as_tensor(target_durations).to(device=dev, dtype=torch.float32).reshape(B, Tp).contiguous()
+            scalar = 1.0
+        else:
+            use_dur = durations
+            scalar = float(durations_scalar)
+        mx = torch.as_tensor(max_durations_mask).to(device=dev, dtype=torch.float32).contiguous() if max_durations_mask is not None else None
+        mn = torch.as_tensor(min_durations_mask).to(device=dev, dtype=torch.float32).contiguous() if min_durations_mask is not None else None
+        dur_int = torch.empty((B, Tp), dtype=torch.int32, device=dev)
+        dec_len = torch.empty((B,), dtype=torch.int32, device=dev)
+        lib.durations_to_int(use_dur, scalar, mx, mn, dur_int, dec_len)
+        Tm = int(dec_len.max().item())  # output shape is data dependent (as in the reference): one host sync
+        if int(dur_int.min().item()) < 0:
+            raise ValueError('negative duration')
+        dd = self._stacks['decoder']['d']
+        if Tm == 0:
+            mel = torch.zeros((B, 0, self.mel_channels), dtype=torch.float32, device=dev)
+        else:
+            idx = torch.empty((B, Tm), dtype=torch.int32, device=dev)
+            lib.expand_indices(dur_int, Tm, idx)
+            m = self._act(B, Tm, dd)
+            lib.expand_ln_pe_fwd(h_pe, idx, W['decoder.ln.gamma'], W['decoder.ln.beta'], P['decoder.pe'],
+                                 W['decoder.pos_scalar'].reshape(1), LN_EPS, m[0], m[1], m[2])
+            for i in range(len(self._stacks['decoder']['heads'])):
+                m = self._block(P, 'decoder', i, m, dec_len, B, Tm, dec_attn, self._attn_key('decoder', i))
+            mel = torch.empty((B, Tm, self.mel_channels), dtype=torch.float32, device=dev)
+            self._gemm(P['out'], B, Tm, [(m[1], m[2], dd, 0)], [0], [0], out_f32=mel, ld_out=self.mel_channels)
+        return {'mel': mel,
+                'duration': durations[..., None],
+                'pitch': pitch[..., None],
+                'expanded_mask': mask_from_lengths(dec_len, Tm),
+                'encoder_attention': enc_attn,
+                'decoder_attention': dec_attn,
+                'int_durations': dur_int,
+                'mel_lengths': dec_len}
+
+    __call__ = call
+
+    def _attn_key(self, name: str, i: int) -> str:
+        n_dense = self._stacks[name]['n_dense']
+        cname = name.capitalize()
+        if i < n_dense:
+            return f'{cname}_DenseBlock{i + 1}_SelfAttention'
+        return f'{cname}_ConvBlock{i - n_dense + 1}_SelfAttention'
+
+    def forward(self, input_sequence, durations_scalar):
+        """reference: model/models.py:509-512."""
+        return self.call(input_sequence, target_durations=None, target_pitch=None, training=False,
+                         durations_scalar=durations_scalar, max_durations_mask=None, min_durations_mask=None)
+
+    def encode_text(self, text):
+        tp = getattr(self, 'text_pipeline', None)
+        if tp is None:
+            raise NotImplementedError('text encoding needs the espeak phonemizer, which is outside the text->mel hot path; '
+                                      'pass token ids with encode=False or attach a text_pipeline')
+        return tp(text)
+
+    def _duration_mask(self, encoded: np.ndarray, table: Optional[dict], default: float) -> torch.Tensor:
+        """reference: model/models.py:579-595 (per-phoneme max / min duration)."""
+        mask = np.full(encoded.shape, default, dtype=np.float32)
+        if table is not None:
+            tok = self.text_pipeline.tokenizer
+            for sym, val in table.items():
+                mask[encoded == tok(sym)[0]] = val
+        return torch.from_numpy(mask)
+
+    def predict(self, inp, encode=True, speed_regulator=1., phoneme_max_duration=None, phoneme_min_duration=None,
+                max_durations_mask=None, min_durations_mask=None, phoneme_durations=None, phoneme_pitch=None):
+        """reference: model/models.py:559-577 (passed max/min masks are overwritten by the per-phoneme ones, as there)."""
+        if encode:
+            inp = self.encode_text(inp)
+        inp = torch.as_tensor(np.asarray(inp) if not torch.is_tensor(inp) else inp)
+        if inp.dim() < 2:
+            inp = inp[None]
+        inp = inp.to(torch.int32)
+        host = inp.cpu().numpy()
+        nz = host != 0
+        if (nz[:, 1:] & ~nz[:, :-1]).any():
+            raise ValueError('pad id 0 inside a sequence: batches must be padded at the end')
+        duration_scalar = float(np.float32(1. / speed_regulator))
+        max_mask = self._duration_mask(host, phoneme_max_duration, float('inf'))
+        min_mask = self._duration_mask(host, phoneme_min_duration, 0.0)
+        out = self.call(inp, target_durations=phoneme_durations, target_pitch=phoneme_pitch, training=False,
+                        durations_scalar=duration_scalar, max_durations_mask=max_mask, min_durations_mask=min_mask)
+        out['mel'] = out['mel'].squeeze()
+        return out
+
+    # ------------------------------------------------------------------------------------------------
+    # persistence (reference: model/models.py:600-638 -- config.yaml + weights file in one directory)
+    # ------------------------------------------------------------------------------------------------
+    def save_model(self, path: str):
+        import yaml
+        path = Path(path)
+        path.mkdir(parents=True, exist_ok=True)
+        cfg = {k: v for k, v in self.config.items() if k != 'device'}
+        if self.alphabet is not None:
+            cfg['alphabet'] = self.alphabet
+        cfg['step'] = self.step
+        with open(path / 'config.yaml', 'w') as f:
+            yaml.safe_dump(cfg, f)
+        torch.save({k: v.cpu() for k, v in self.weights.items()}, path / 'model_weights.pt')
+
+    @classmethod
+    def load_model(cls, path):
+        import yaml
+        path = Path(path)
+        with open(path / 'config.yaml', 'r') as f:
+            config = yaml.safe_load(f)
+        model = cls.from_config(config)
+        model.set_weights(torch.load(path / 'model_weights.pt', map_location='cpu'))
+        return model
+
+    @classmethod
+    def from_config(cls, config: dict, custom_objects=None):
+        return cls(**config)
+
+    @property
+    def step(self) -> int:
+        return int(self.optimizer.iterations) if self.optimizer is not None else 0
+
+    def set_constants(self, learning_rate: float = None, **kwargs):
+        if learning_rate is not None and self.optimizer is not None:
+            self.optimizer.lr = float(learning_rate)
