@@ -1,0 +1,45 @@
+"""CPU tests of the host-side logic (no GPU): tile selection, parameter inventory, config handling, tables."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import forward_oracle as fo
+
+
+def test_block_n_selection():
+    from transformertts_b200.model.models import _pick_block_n
+    assert _pick_block_n(768, False) == 256
+    assert _pick_block_n(1024, False) == 256
+    assert _pick_block_n(1536, False) == 256
+    assert _pick_block_n(226, True) == 240
+    assert _pick_block_n(80, False) == 80
+    assert _pick_block_n(128, True) == 128
+    with pytest.raises(Exception):
+        _pick_block_n(384, True)
+
+
+def test_positional_encoding_matches_oracle_bitwise():
+    from transformertts_b200.model.transformer_utils import positional_encoding
+    for n, d in ((2000, 256), (300, 128)):
+        assert torch.equal(positional_encoding(n, d), fo.positional_encoding(n, d))
+
+
+def test_masks_mirror_reference_semantics():
+    from transformertts_b200.model import transformer_utils as tu
+    seq = torch.tensor([[3, 4, 0, 0], [1, 2, 3, 4]])
+    assert torch.equal(tu.create_encoder_padding_mask(seq), fo.create_encoder_padding_mask(seq))
+    mel = torch.zeros(2, 5, 3)
+    mel[0, :2] = 1
+    mel[1, :5] = -1
+    assert torch.equal(tu.create_mel_padding_mask(mel), fo.create_mel_padding_mask(mel))
+    assert torch.equal(tu.mask_from_lengths(torch.tensor([2, 5]), 5), fo.create_mel_padding_mask(mel))
+    assert tu.create_look_ahead_mask(3).tolist() == [[0, 1, 1], [0, 0, 1], [0, 0, 0]]
+
+
+def test_scheduling_and_losses_mirror_reference():
+    from transformertts_b200.utils.scheduling import piecewise_linear_schedule, reduction_schedule
+    sched = [[0, 1.0e-4], [100, 5.0e-5], [200, 1.0e-5]]
+    assert piecewise_linear_schedule(0, sched) == pytest.approx(1e-4)
+    assert piecewise_linear_schedule(50, sched) == pytest.approx(7.5e-5)
+    assert piecewise_linear_schedule(1000, sched) == pytest.approx(1e-5)
+    assert reduction_schedule(90000, [[0, 10], [80000, 5], [100000, 2]]) == 5

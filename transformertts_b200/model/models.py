@@ -115,6 +115,7 @@ class ForwardTransformer:
                 max_pos=int(self.config[f'{name}_max_position_encoding']))
         self.weights: Dict[str, torch.Tensor] = {}
         self._packed = None
+        self._prof = None  # bench.py: {tag: [(start_event, end_event, flops)]} for tagged GEMM launches
         self.optimizer = None
         self.loss_weights = [1., 1., 3.]
         self._init_weights(seed=int(kwargs.get('seed', 42)))
@@ -283,7 +284,12 @@ class ForwardTransformer:
         return f, hi, lo
 
     def _gemm(self, pl: _PackedLinear, B, T, srcs, seg_src, seg_shift, relu=False, residual=None, ln=None, row_len=None,
-              out_f32=None, out_hi=None, out_lo=None, ld_out=None, vt=None):
+              out_f32=None, out_hi=None, out_lo=None, ld_out=None, vt=None, tag=None):
+        prof = self._prof
+        if prof is not None and tag is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         a = lib.GemmArgs()
         a.B, a.T, a.N, a.block_n = B, T, pl.N, pl.block_n
         a.num_segments = len(pl.seg_k)
@@ -320,6 +326,9 @@ class ForwardTransformer:
         a.precision = self._prec
         a.impl = self._impl
         lib.linear_fwd(a)
+        if prof is not None and tag is not None:
+            e1.record()
+            prof.setdefault(tag, []).append((e0, e1, 2.0 * B * T * pl.K * pl.N))
 
     def _conv_shifts(self, k: int) -> List[int]:
         return [j - (k - 1) // 2 for j in range(k)]
@@ -384,10 +393,12 @@ class ForwardTransformer:
             for j in range(n - 1):
                 pl = P[pre + f'conv{j}']
                 _, o_hi, o_lo = self._act(B, T, pl.n_pad, f32=False)
-                self._gemm(pl, B, T, [(h_hi, h_lo, ld, 0)], [0] * k, shifts, relu=True, out_hi=o_hi, out_lo=o_lo)
+                self._gemm(pl, B, T, [(h_hi, h_lo, ld, 0)], [0] * k, shifts, relu=True, out_hi=o_hi, out_lo=o_lo,
+                           tag=f'{name}.conv{j}')
                 h_hi, h_lo, ld = o_hi, o_lo, pl.n_pad
             self._gemm(P[pre + f'conv{n - 1}'], B, T, [(h_hi, h_lo, ld, 0)], [0] * k, shifts, residual=y[0],
-                       ln=(W[pre + 'ln2.gamma'], W[pre + 'ln2.beta']), row_len=lens, out_f32=z[0], out_hi=z[1], out_lo=z[2])
+                       ln=(W[pre + 'ln2.gamma'], W[pre + 'ln2.beta']), row_len=lens, out_f32=z[0], out_hi=z[1], out_lo=z[2],
+                       tag=f'{name}.conv{n - 1}')
         return z
 
     def _stat_predictor(self, P, name: str, x, lens, B: int, T: int, relu_head: bool):
