@@ -36,6 +36,7 @@ extern "C" {
 /* precision of the tensor-core products */
 #define TTSB_PREC_BF16 0   /* single bf16 pass, fp32 accumulate */
 #define TTSB_PREC_BF16X3 1 /* hi*hi + lo*hi + hi*lo, fp32 accumulate (fp32-class accuracy) */
+#define TTSB_PREC_FP16 2   /* ttsb_mha_fwd only: single IEEE fp16 pass (11-bit mantissa), q/k/vT hold fp16 */
 
 /* implementation selector (debug): tcgen05/TMA kernels, or the plain SIMT CUDA kernels kept for bring-up */
 #define TTSB_IMPL_TCGEN05 0
@@ -88,11 +89,11 @@ typedef struct ttsb_gemm_args {
   int a_col0[2];            /* first column of the source inside its row */
   const void* w_hi;         /* packed bf16 [n_tiles*block_n, K_total] */
   const void* w_lo;
-  const float* bias;        /* [N] or NULL */
+  const float* bias;        /* [n_tiles*block_n] (zero padded past N) or NULL */
   int relu;
   const float* residual;    /* fp32 (B,T,ld_res) or NULL */
   int ld_res;
-  const float* ln_gamma;    /* LayerNorm params or NULL */
+  const float* ln_gamma;    /* LayerNorm params [block_n] (padded) or NULL */
   const float* ln_beta;
   float ln_eps;
   const int32_t* row_len;   /* [B] valid lengths or NULL */
@@ -104,6 +105,7 @@ typedef struct ttsb_gemm_args {
   void* vt_hi;
   void* vt_lo;
   int vt_col0, vt_cols, vt_ld;
+  int out_fp16;             /* 1: out_hi / vt_hi receive IEEE fp16 (single plane) instead of bf16 hi/lo */
   int precision;            /* TTSB_PREC_* */
   int impl;                 /* TTSB_IMPL_* */
 } ttsb_gemm_args;
@@ -113,7 +115,9 @@ int ttsb_linear_fwd(const ttsb_gemm_args* args, void* stream);
 /* ---------------------------------------------------------------------------------------------------------
  * Fused variable-length self-attention  (model/layers.py:138-147 split/merge heads, :176-195 scaled dot product)
  *   q,k: bf16 (B,T,ld_qk) at columns q_col0 + h*dh / k_col0 + h*dh;  vT: bf16 (B, H*dh, ld_vt) (time contiguous)
- *   out: bf16 hi/lo (B,T,ld_out), head h at columns h*dh.  Keys t >= kv_len[b] are masked (reference adds -1e9).
+ *   out: bf16 hi (and lo when out_lo != NULL) (B,T,ld_out), head h at columns h*dh.  Keys t >= kv_len[b] are masked
+ *   (the reference adds -1e9).  precision TTSB_PREC_FP16: qk_hi / vt_hi hold IEEE fp16 (written by ttsb_linear_fwd
+ *   with out_fp16 = 1), one tensor-core pass.
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct ttsb_mha_args {
   int B, T, H, dh;

@@ -40,7 +40,10 @@ def run_gemm(x_list, w_kn, bias, seg_src, seg_shift, seg_k, *, precision='bf16x3
         a.residual = residual.data_ptr()
         a.ld_res = residual.shape[-1]
     if ln is not None:
-        a.ln_gamma, a.ln_beta, a.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), 1e-6
+        from transformertts_b200.model.models import _pad_vec
+        g_pad, b_pad = _pad_vec(ln[0], pl.n_pad), _pad_vec(ln[1], pl.n_pad)
+        keep += [g_pad, b_pad]
+        a.ln_gamma, a.ln_beta, a.ln_eps = g_pad.data_ptr(), b_pad.data_ptr(), 1e-6
     if row_len is not None:
         a.row_len = row_len.data_ptr()
     out = {}
@@ -105,17 +108,23 @@ def ref_gemm(x_list, w_kn, bias, seg_src, seg_shift, seg_k, *, precision, relu=F
     return acc
 
 
+def _to16(x, precision, split):
+    if precision == 'fp16':
+        return x.contiguous().half(), None
+    return lib.split_bf16(x, split)
+
+
 def run_mha(q, k, v, kv_len, H, *, precision='bf16x3', impl='tcgen05', weights_b=None):
     """q,k,v fp32 (B,T,d) on GPU -> attention output fp32 (B,T,d) (hi+lo recombined)."""
     split = precision == 'bf16x3'
     B, T, d = q.shape
     dh = d // H
     qk = torch.cat([q, k], dim=-1).contiguous()
-    qk_hi, qk_lo = lib.split_bf16(qk, split)
+    qk_hi, qk_lo = _to16(qk, precision, split)
     ld_vt = _round_up(T, 8)
     vt = torch.zeros(B, d, ld_vt, device=DEV)
     vt[:, :, :T] = v.transpose(1, 2)
-    vt_hi, vt_lo = lib.split_bf16(vt, split)
+    vt_hi, vt_lo = _to16(vt, precision, split)
     out_hi = torch.full((B, T, d), float('nan'), device=DEV, dtype=torch.bfloat16)
     out_lo = torch.full((B, T, d), float('nan'), device=DEV, dtype=torch.bfloat16)
     m = lib.MhaArgs()
@@ -128,24 +137,25 @@ def run_mha(q, k, v, kv_len, H, *, precision='bf16x3', impl='tcgen05', weights_b
     m.ld_vt = ld_vt
     m.kv_len = kv_len.data_ptr()
     m.out_hi = out_hi.data_ptr()
-    m.out_lo = out_lo.data_ptr() if split else None
+    m.out_lo = out_lo.data_ptr()
     m.ld_out = d
     wts = None
     if weights_b is not None:
         wts = torch.full((H, T, T), float('nan'), device=DEV)
         m.weights_out = wts.data_ptr()
         m.weights_batch_index = weights_b
-    m.precision = lib.PREC_BF16X3 if split else lib.PREC_BF16
+    m.precision = {'bf16x3': lib.PREC_BF16X3, 'bf16': lib.PREC_BF16, 'fp16': lib.PREC_FP16}[precision]
     m.impl = lib.IMPL_SIMT if impl == 'simt' else lib.IMPL_TCGEN05
     lib.mha_fwd(m)
     torch.cuda.synchronize()
-    out = out_hi.float() + (out_lo.float() if split else 0)
+    out = out_hi.float() + out_lo.float()
     return out, wts
 
 
 def ref_mha(q, k, v, kv_len, H, precision):
     """float64 CPU attention with the reference's additive -1e9 key mask (model/layers.py:176-195)."""
-    cast = (lambda t: t.detach().cpu().double()) if precision == 'bf16x3' else (lambda t: t.detach().cpu().bfloat16().double())
+    cast = {'bf16x3': lambda t: t.detach().cpu().double(), 'bf16': lambda t: t.detach().cpu().bfloat16().double(),
+            'fp16': lambda t: t.detach().cpu().half().double()}[precision]
     q, k, v = cast(q), cast(k), cast(v)
     B, T, d = q.shape
     dh = d // H

@@ -11,6 +11,8 @@
 // fp32 add every such logit equals -1e9 and its softmax weight underflows to exactly 0 whenever the row has at least
 // one valid key, so skipping those keys is exact.  Rows of padded QUERIES are zeroed by the caller's row mask
 // (layers.py:229,262), so they are not computed here (written as zeros).
+#include <cuda_fp16.h>
+
 #include "../../include/ttsb.h"
 #include "ttsb_common.cuh"
 #include "ttsb_host.h"
@@ -49,7 +51,7 @@ struct MhaCfg {
   static constexpr int O_COL = ATT_BKV;
 };
 
-template <int DH, bool kSplit>
+template <int DH, bool kSplit, bool kF16>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
               const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
@@ -82,7 +84,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
         const size_t o = ((size_t)b * p.T + t) * p.ld_out + h * DH;
         for (int c = 0; c < DH; c += 8) {
           st_global_v4(p.out_hi + o + c, 0, 0, 0, 0);
-          if (kSplit && p.out_lo) st_global_v4(p.out_lo + o + c, 0, 0, 0, 0);
+          if (p.out_lo) st_global_v4(p.out_lo + o + c, 0, 0, 0, 0);
         }
       }
     }
@@ -115,8 +117,8 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
       uint8_t* sK = smem + Cfg::OFF_K;
       uint8_t* sV = smem + Cfg::OFF_V;
       uint8_t* sP = smem + Cfg::OFF_P;
-      const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BKV);
-      const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, DH);
+      const uint32_t idesc_s = kF16 ? make_idesc_f16(ATT_BQ, ATT_BKV) : make_idesc_bf16(ATT_BQ, ATT_BKV);
+      const uint32_t idesc_o = kF16 ? make_idesc_f16(ATT_BQ, DH) : make_idesc_bf16(ATT_BQ, DH);
       const uint32_t t_s = tmem_base + Cfg::S_COL;
       const uint32_t t_o = tmem_base + Cfg::O_COL;
 
@@ -259,11 +261,17 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(s[ch * 8 + 2 * i], h0, l0);
-          split_bf16(s[ch * 8 + 2 * i + 1], h1, l1);
-          hi[i] = pack_bf16(h0, h1);
-          lo[i] = pack_bf16(l0, l1);
+          if (kF16) {
+            const __half2 hh = __floats2half2_rn(s[ch * 8 + 2 * i], s[ch * 8 + 2 * i + 1]);
+            hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+            lo[i] = 0;
+          } else {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(s[ch * 8 + 2 * i], h0, l0);
+            split_bf16(s[ch * 8 + 2 * i + 1], h1, l1);
+            hi[i] = pack_bf16(h0, h1);
+            lo[i] = pack_bf16(l0, l1);
+          }
         }
         const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
         *reinterpret_cast<uint4*>(sP + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -295,7 +303,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
       if (tq < p.T) {
         st_global_v4(p.out_hi + o + c * 16, hi[0], hi[1], hi[2], hi[3]);
         st_global_v4(p.out_hi + o + c * 16 + 8, hi[4], hi[5], hi[6], hi[7]);
-        if (kSplit && p.out_lo) {
+        if (p.out_lo) {
           st_global_v4(p.out_lo + o + c * 16, lo[0], lo[1], lo[2], lo[3]);
           st_global_v4(p.out_lo + o + c * 16 + 8, lo[4], lo[5], lo[6], lo[7]);
         }
@@ -324,13 +332,15 @@ struct MhaSimtPtrs {
   const __nv_bfloat16* vt_lo;
   int ld_vt;
   int dh;
+  int f16;           // operands hold IEEE fp16 bit patterns
   float scale;       // 1/sqrt(dh)
   float* weights;    // (H,T,T) or null
   int weights_b;
   int weights_only;  // 1: only fill weights for batch row weights_b
 };
 
-__device__ __forceinline__ float ld_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t i) {
+__device__ __forceinline__ float ld_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t i, int f16 = 0) {
+  if (f16) return __half2float(reinterpret_cast<const __half*>(hi)[i]);
   float v = __bfloat162float(hi[i]);
   if (lo) v += __bfloat162float(lo[i]);
   return v;
@@ -345,12 +355,12 @@ __global__ void mha_simt_kernel(const MhaKParams p, const MhaSimtPtrs q) {
   __shared__ float red[32];
   const int len = min(max(p.kv_len[b], 0), p.T);
   const size_t qrow = ((size_t)b * p.T + tq) * q.ld_qk;
-  for (int c = threadIdx.x; c < q.dh; c += blockDim.x) qv[c] = ld_split(q.qk_hi, q.qk_lo, qrow + p.q_col0 + h * q.dh + c);
+  for (int c = threadIdx.x; c < q.dh; c += blockDim.x) qv[c] = ld_split(q.qk_hi, q.qk_lo, qrow + p.q_col0 + h * q.dh + c, q.f16);
   __syncthreads();
   for (int tk = threadIdx.x; tk < p.T; tk += blockDim.x) {
     const size_t krow = ((size_t)b * p.T + tk) * q.ld_qk + p.k_col0 + h * q.dh;
     float acc = 0.f;
-    for (int c = 0; c < q.dh; ++c) acc = fmaf(qv[c], ld_split(q.qk_hi, q.qk_lo, krow + c), acc);
+    for (int c = 0; c < q.dh; ++c) acc = fmaf(qv[c], ld_split(q.qk_hi, q.qk_lo, krow + c, q.f16), acc);
     acc = acc * q.scale;
     if (tk >= len) acc += -1e9f;  // reference: logits += mask * -1e9
     logit[tk] = acc;
@@ -383,7 +393,7 @@ __global__ void mha_simt_kernel(const MhaKParams p, const MhaSimtPtrs q) {
   for (int c = threadIdx.x; c < q.dh; c += blockDim.x) {
     const size_t vrow = ((size_t)b * p.H * q.dh + h * q.dh + c) * q.ld_vt;
     float acc = 0.f;
-    for (int tk = 0; tk < p.T; ++tk) acc = fmaf(logit[tk], ld_split(q.vt_hi, q.vt_lo, vrow + tk), acc);
+    for (int tk = 0; tk < p.T; ++tk) acc = fmaf(logit[tk], ld_split(q.vt_hi, q.vt_lo, vrow + tk, q.f16), acc);
     acc *= inv;
     __nv_bfloat16 hi, lo;
     split_bf16(acc, hi, lo);
@@ -393,7 +403,7 @@ __global__ void mha_simt_kernel(const MhaKParams p, const MhaSimtPtrs q) {
   }
 }
 
-template <int DH, bool kSplit>
+template <int DH, bool kSplit, bool kF16>
 static int launch_tc(const ttsb_mha_args* a, const MhaKParams& p, cudaStream_t stream) {
   using Cfg = MhaCfg<DH, kSplit>;
   CUtensorMap tmQ[2], tmK[2], tmV[2];
@@ -409,11 +419,11 @@ static int launch_tc(const ttsb_mha_args* a, const MhaKParams& p, cudaStream_t s
   }
   static bool attr_set = false;
   if (!attr_set) {
-    TTSB_CUDA_OK(cudaFuncSetAttribute(mha_tc_kernel<DH, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    TTSB_CUDA_OK(cudaFuncSetAttribute(mha_tc_kernel<DH, kSplit, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   dim3 grid((a->T + ATT_BQ - 1) / ATT_BQ, a->H, a->B);
-  mha_tc_kernel<DH, kSplit><<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tmQ[0], tmQ[1], tmK[0], tmK[1], tmV[0], tmV[1], p);
+  mha_tc_kernel<DH, kSplit, kF16><<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tmQ[0], tmQ[1], tmK[0], tmK[1], tmV[0], tmV[1], p);
   count_launch();
   return check_cuda(cudaGetLastError(), "mha_tc_kernel launch");
 }
@@ -427,6 +437,7 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   if (a->B <= 0 || a->T <= 0 || a->H <= 0) { set_last_error("ttsb_mha_fwd: B,T,H must be positive"); return TTSB_ERR_INVALID_ARGUMENT; }
   if (!a->qk_hi || !a->vt_hi || !a->kv_len || !a->out_hi) { set_last_error("ttsb_mha_fwd: NULL tensor"); return TTSB_ERR_INVALID_ARGUMENT; }
   const bool split = a->precision == TTSB_PREC_BF16X3;
+  const bool f16 = a->precision == TTSB_PREC_FP16;
   if (split && (!a->qk_lo || !a->vt_lo || !a->out_lo)) { set_last_error("ttsb_mha_fwd: bf16x3 needs the lo planes"); return TTSB_ERR_INVALID_ARGUMENT; }
   if (a->ld_qk % 8 || a->ld_vt % 8 || a->ld_out % 8 || a->q_col0 % 8 || a->k_col0 % 8) {
     set_last_error("ttsb_mha_fwd: leading dimensions / column offsets must be multiples of 8");
@@ -437,7 +448,7 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   p.B = a->B; p.T = a->T; p.H = a->H;
   p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.kv_len = a->kv_len;
   p.out_hi = static_cast<__nv_bfloat16*>(a->out_hi);
-  p.out_lo = split ? static_cast<__nv_bfloat16*>(a->out_lo) : nullptr;
+  p.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);  // optional second plane of the OUTPUT (consumer may be bf16x3)
   p.ld_out = a->ld_out;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)a->dh);
 
@@ -450,6 +461,7 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   q.ld_vt = a->ld_vt;
   q.dh = a->dh;
   q.scale = 1.f / sqrtf((float)a->dh);
+  q.f16 = f16 ? 1 : 0;
   q.weights = a->weights_out;
   q.weights_b = a->weights_batch_index;
   const size_t simt_smem = (size_t)(a->T + a->dh) * sizeof(float);
@@ -461,8 +473,8 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
     return check_cuda(cudaGetLastError(), "mha_simt_kernel launch");
   }
   int rc;
-  if (a->dh == 128) rc = split ? launch_tc<128, true>(a, p, stream) : launch_tc<128, false>(a, p, stream);
-  else if (a->dh == 64) rc = split ? launch_tc<64, true>(a, p, stream) : launch_tc<64, false>(a, p, stream);
+  if (a->dh == 128) rc = split ? launch_tc<128, true, false>(a, p, stream) : (f16 ? launch_tc<128, false, true>(a, p, stream) : launch_tc<128, false, false>(a, p, stream));
+  else if (a->dh == 64) rc = split ? launch_tc<64, true, false>(a, p, stream) : (f16 ? launch_tc<64, false, true>(a, p, stream) : launch_tc<64, false, false>(a, p, stream));
   else { set_last_error("ttsb_mha_fwd: head_dim %d not supported by the tcgen05 kernel (64, 128)", a->dh); return TTSB_ERR_UNSUPPORTED; }
   if (rc) return rc;
   if (a->weights_out) {

@@ -13,6 +13,8 @@
 #include <stdio.h>
 
 #include "../../include/ttsb.h"
+#include <cuda_fp16.h>
+
 #include "ttsb_common.cuh"
 #include "ttsb_host.h"
 
@@ -21,7 +23,8 @@ namespace ttsb {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_MAX_BN = 256;
-constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps2-5 epilogue
+constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps2-9 epilogue (2 per TMEM lane quarter)
+constexpr int GEMM_EPI_WARPS = 8;
 constexpr int A_TILE_BYTES = GEMM_BM * GEMM_BK * 2;      // 16 KiB
 constexpr int B_TILE_BYTES = GEMM_MAX_BN * GEMM_BK * 2;  // 32 KiB
 constexpr int TMEM_COLS = 512;
@@ -45,6 +48,7 @@ struct GemmKParams {
   __nv_bfloat16* vt_hi;
   __nv_bfloat16* vt_lo;
   int vt_col0, vt_cols, vt_ld;
+  int h16;  // 1: out_hi / vt_hi receive IEEE fp16 instead of bf16 (single plane; operands of the fp16 attention)
 };
 
 template <bool kSplit>
@@ -52,24 +56,58 @@ struct GemmCfg {
   static constexpr int kStages = kSplit ? 2 : 4;
   static constexpr int kStageBytes = (kSplit ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES);
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kSmemBytes = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int kRedOffset = kBarOffset + 256;          // LayerNorm pair-exchange scratch: [2 acc][2][2][128] floats
+  static constexpr int kSmemBytes = kRedOffset + 4096 + 1024;  // + alignment slack
 };
 
 // ----------------------------------------------------------------------------------------------------
-// epilogue for one 128 x block_n accumulator tile; executed by the 4 epilogue warps (thread = one row)
+// Epilogue for one 128 x block_n accumulator tile.  8 epilogue warps: warp (quarter, half) owns TMEM lanes
+// [32*quarter, +32) (thread = one output row) and the lower / upper half of the tile's 16-column chunks, so two warps
+// per SM sub-partition interleave and hide each other's latencies.  Per-column vectors (bias, gamma, beta) are read
+// as warp-uniform float4 loads (buffers are padded to n_pad by the host).
 // ----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_chunk(const GemmKParams& p, bool row_ok, size_t orow, int b, int t, int col0,
-                                            const float (&y)[16]) {
-  if (!row_ok) return;
+__device__ __forceinline__ void ldg16(const float* __restrict__ p, float (&v)[16]) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 f = __ldg(q + j);
+    v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+  }
+}
+
+// bf16 hi (and lo = bf16(y - hi)) of 16 floats, packed pairwise with cvt.rn.bf16x2
+__device__ __forceinline__ void pack_hi_lo(const float (&y)[16], uint32_t (&h)[8], uint32_t (&l)[8], bool want_lo) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+  }
+  if (want_lo) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float f0 = __uint_as_float(h[j] << 16), f1 = __uint_as_float(h[j] & 0xffff0000u);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(y[2 * j] - f0, y[2 * j + 1] - f1);
+      l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_chunk(const GemmKParams& p, size_t orow, int b, int t, int col0, const float (&y)[16]) {
   if (p.vt_hi != nullptr && col0 >= p.vt_col0 && col0 < p.vt_col0 + p.vt_cols) {
     // transposed store (V^T for the attention kernel): consecutive lanes hold consecutive t -> coalesced per column
     const size_t base = ((size_t)b * p.vt_cols + (col0 - p.vt_col0)) * (size_t)p.vt_ld + t;
+    if (p.h16) {
+      __half* dst = reinterpret_cast<__half*>(p.vt_hi);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      __nv_bfloat16 hi, lo;
-      split_bf16(y[j], hi, lo);
-      p.vt_hi[base + (size_t)j * p.vt_ld] = hi;
-      if (p.vt_lo) p.vt_lo[base + (size_t)j * p.vt_ld] = lo;
+      for (int j = 0; j < 16; ++j) dst[base + (size_t)j * p.vt_ld] = __float2half_rn(y[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(y[j], hi, lo);
+        p.vt_hi[base + (size_t)j * p.vt_ld] = hi;
+        if (p.vt_lo) p.vt_lo[base + (size_t)j * p.vt_ld] = lo;
+      }
     }
     return;
   }
@@ -81,50 +119,75 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, bool row_ok, s
   }
   if (p.out_hi) {
     uint32_t h[8], l[8];
+    if (p.h16) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(y[2 * j], h0, l0);
-      split_bf16(y[2 * j + 1], h1, l1);
-      h[j] = pack_bf16(h0, h1);
-      l[j] = pack_bf16(l0, l1);
+      for (int j = 0; j < 8; ++j) {
+        const __half2 hh = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+        h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+    } else {
+      pack_hi_lo(y, h, l, p.out_lo != nullptr);
     }
     st_global_v4(p.out_hi + o, h[0], h[1], h[2], h[3]);
     st_global_v4(p.out_hi + o + 8, h[4], h[5], h[6], h[7]);
-    if (p.out_lo) {
+    if (p.out_lo && !p.h16) {
       st_global_v4(p.out_lo + o, l[0], l[1], l[2], l[3]);
       st_global_v4(p.out_lo + o + 8, l[4], l[5], l[6], l[7]);
     }
   }
 }
 
-__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t taddr, int b, int t0, int n0, int lane_row) {
-  const int t = t0 + lane_row;
+// exchange of per-row partial sums between the two warps that share a lane quarter
+__device__ __forceinline__ float pair_sum(float part, float* red, int half, int row, int quarter) {
+  red[half * GEMM_BM + row] = part;
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+  return part + red[(half ^ 1) * GEMM_BM + row];
+}
+
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t taddr, int b, int t0, int n0, int row, int half,
+                                              int quarter, float* red /* [2][2][128] for this accumulator stage */) {
+  const int t = t0 + row;
   const bool row_ok = t < p.T;
   const bool row_keep = row_ok && (p.row_len == nullptr || t < __ldg(p.row_len + b));
   const size_t orow = (size_t)b * p.T + (row_ok ? t : 0);
   const int ncols = min(p.block_n, p.N - n0);  // logical columns in this tile
+  const bool partial = ncols < p.block_n;
+  const int nch = p.block_n >> 4;
+  const int ch_begin = half ? (nch + 1) >> 1 : 0;
+  const int ch_end = half ? nch : (nch + 1) >> 1;
   uint32_t r[16];
-  float y[16];
+  float y[16], aux[16];
 
   if (p.gamma == nullptr) {
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+      const int c0 = ch << 4;
       tmem_ld16(taddr + c0, r);
+      if (p.bias) ldg16(p.bias + n0 + c0, aux);
       tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int c = c0 + j;
-        float v = __uint_as_float(r[j]);
-        if (c < ncols) {
-          if (p.bias) v += __ldg(p.bias + n0 + c);
-          if (p.relu) v = fmaxf(v, 0.f);
-          if (p.residual && row_ok) v += __ldg(p.residual + orow * (size_t)p.ld_res + n0 + c);
-        } else {
-          v = 0.f;
-        }
-        y[j] = row_keep ? v : 0.f;
+      for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[j] += aux[j];
       }
-      store_chunk(p, row_ok, orow, b, t, n0 + c0, y);
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+      }
+      if (p.residual && row_ok) {
+        ldg16(p.residual + orow * (size_t)p.ld_res + n0 + c0, aux);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[j] += aux[j];
+      }
+      if (partial) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[j] = (c0 + j < ncols) ? y[j] : 0.f;
+      }
+      if (!row_keep) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[j] = 0.f;
+      }
+      if (row_ok) store_chunk(p, orow, b, t, n0 + c0, y);
     }
     return;
   }
@@ -132,61 +195,77 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
   // ---- LayerNorm epilogue (single N tile): pass 1 builds v = acc + bias (+relu) (+residual) and parks it in TMEM
   const float inv_n = 1.f / (float)ncols;
   float sum = 0.f;
-  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+  for (int ch = ch_begin; ch < ch_end; ++ch) {
+    const int c0 = ch << 4;
     tmem_ld16(taddr + c0, r);
+    if (p.bias) ldg16(p.bias + c0, aux);
     tmem_wait_ld();
-    float res[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]);
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] += aux[j];
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+    }
     if (p.residual && row_ok) {
-      const float4* rp = reinterpret_cast<const float4*>(p.residual + orow * (size_t)p.ld_res + c0);
+      ldg16(p.residual + orow * (size_t)p.ld_res + c0, aux);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 q = (c0 + 4 * j < ncols) ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        res[4 * j] = q.x; res[4 * j + 1] = q.y; res[4 * j + 2] = q.z; res[4 * j + 3] = q.w;
-      }
-    } else {
+      for (int j = 0; j < 16; ++j) y[j] += aux[j];
+    }
+    if (partial) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) res[j] = 0.f;
+      for (int j = 0; j < 16; ++j) y[j] = (c0 + j < ncols) ? y[j] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int c = c0 + j;
-      float v = __uint_as_float(r[j]);
-      if (c < ncols) {
-        if (p.bias) v += __ldg(p.bias + c);
-        if (p.relu) v = fmaxf(v, 0.f);
-        v += res[j];
-      } else {
-        v = 0.f;
-      }
-      sum += v;
-      r[j] = __float_as_uint(v);
+      sum += y[j];
+      r[j] = __float_as_uint(y[j]);
     }
     tmem_st16(taddr + c0, r);
   }
   tmem_wait_st();
-  const float mean = sum * inv_n;
+  const float mean = pair_sum(sum, red, half, row, quarter) * inv_n;
   float ssq = 0.f;
-  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+  for (int ch = ch_begin; ch < ch_end; ++ch) {
+    const int c0 = ch << 4;
     tmem_ld16(taddr + c0, r);
     tmem_wait_ld();
+    if (partial) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float dlt = (c0 + j < ncols) ? (__uint_as_float(r[j]) - mean) : 0.f;
-      ssq += dlt * dlt;
+      for (int j = 0; j < 16; ++j) {
+        const float dlt = (c0 + j < ncols) ? (__uint_as_float(r[j]) - mean) : 0.f;
+        ssq += dlt * dlt;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float dlt = __uint_as_float(r[j]) - mean;
+        ssq += dlt * dlt;
+      }
     }
   }
-  const float rstd = rsqrtf(ssq * inv_n + p.eps);
-  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+  const float rstd = rsqrtf(pair_sum(ssq, red + 2 * GEMM_BM, half, row, quarter) * inv_n + p.eps);
+  for (int ch = ch_begin; ch < ch_end; ++ch) {
+    const int c0 = ch << 4;
     tmem_ld16(taddr + c0, r);
+    float bt[16];
+    ldg16(p.gamma + c0, aux);
+    ldg16(p.beta + c0, bt);
     tmem_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int c = c0 + j;
-      float v = 0.f;
-      if (c < ncols) v = (__uint_as_float(r[j]) - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c);
-      y[j] = row_keep ? v : 0.f;
+    for (int j = 0; j < 16; ++j) y[j] = (__uint_as_float(r[j]) - mean) * rstd * aux[j] + bt[j];
+    if (partial) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = (c0 + j < ncols) ? y[j] : 0.f;
     }
-    store_chunk(p, row_ok, orow, b, t, c0, y);
+    if (!row_keep) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = 0.f;
+    }
+    if (row_ok) store_chunk(p, orow, b, t, c0, y);
   }
 }
 
@@ -219,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full + s, 1);
-      mbar_init(tmem_empty + s, 4);
+      mbar_init(tmem_empty + s, GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -302,7 +381,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     }
   } else if (warp >= 2) {
     // ===================== epilogue warps =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which half of the tile's column chunks
+    float* red_all = reinterpret_cast<float*>(smem + Cfg::kRedOffset);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -313,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GEMM_MAX_BN;
-      epilogue_tile(p, taddr, b, t0, n_tile * p.block_n, quarter * 32 + lane);
+      epilogue_tile(p, taddr, b, t0, n_tile * p.block_n, quarter * 32 + lane, half, quarter, red_all + acc * (4 * GEMM_BM));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
@@ -404,6 +485,7 @@ __global__ void gemm_simt_kernel(const GemmKParams p, const GemmSimtPtrs q) {
     if (!keep) v = 0.f;
     __nv_bfloat16 hi, lo;
     split_bf16(v, hi, lo);
+    if (p.h16) hi = __ushort_as_bfloat16(__half_as_ushort(__float2half_rn(v)));  // same 16-bit slot, fp16 payload
     if (p.vt_hi && n >= p.vt_col0 && n < p.vt_col0 + p.vt_cols) {
       const size_t o = ((size_t)b * p.vt_cols + (n - p.vt_col0)) * (size_t)p.vt_ld + t;
       p.vt_hi[o] = hi;
@@ -484,6 +566,8 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
   p.vt_hi = static_cast<__nv_bfloat16*>(a->vt_hi);
   p.vt_lo = split ? static_cast<__nv_bfloat16*>(a->vt_lo) : nullptr;
   p.vt_col0 = a->vt_col0; p.vt_cols = a->vt_cols; p.vt_ld = a->vt_ld;
+  p.h16 = a->out_fp16 ? 1 : 0;
+  if (p.h16) { p.out_lo = nullptr; p.vt_lo = nullptr; }
 
   if (a->impl == TTSB_IMPL_SIMT) {
     GemmSimtPtrs q{};

@@ -134,6 +134,10 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_
          | ((N >> 3) << 17)   // n_dim
          | ((M >> 4) << 24);  // m_dim
 }
+// Same with IEEE fp16 operands (a_format = b_format = 0).
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {

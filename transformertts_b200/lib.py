@@ -10,6 +10,7 @@ import torch
 
 PREC_BF16 = 0
 PREC_BF16X3 = 1
+PREC_FP16 = 2
 IMPL_TCGEN05 = 0
 IMPL_SIMT = 1
 
@@ -37,7 +38,8 @@ class GemmArgs(C.Structure):
         ('residual', C.c_void_p), ('ld_res', C.c_int), ('ln_gamma', C.c_void_p), ('ln_beta', C.c_void_p),
         ('ln_eps', C.c_float), ('row_len', C.c_void_p), ('out_f32', C.c_void_p), ('out_hi', C.c_void_p),
         ('out_lo', C.c_void_p), ('ld_out', C.c_int), ('vt_hi', C.c_void_p), ('vt_lo', C.c_void_p),
-        ('vt_col0', C.c_int), ('vt_cols', C.c_int), ('vt_ld', C.c_int), ('precision', C.c_int), ('impl', C.c_int),
+        ('vt_col0', C.c_int), ('vt_cols', C.c_int), ('vt_ld', C.c_int), ('out_fp16', C.c_int), ('precision', C.c_int),
+        ('impl', C.c_int),
     ]
 
 
