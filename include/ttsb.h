@@ -106,6 +106,7 @@ typedef struct ttsb_gemm_args {
   void* vt_lo;
   int vt_col0, vt_cols, vt_ld;
   int out_fp16;             /* 1: out_hi / vt_hi receive IEEE fp16 (single plane) instead of bf16 hi/lo */
+  float* out_preln;         /* optional fp32 (B,T,ld_out): value before the LayerNorm (saved for the backward pass) */
   int precision;            /* TTSB_PREC_* */
   int impl;                 /* TTSB_IMPL_* */
 } ttsb_gemm_args;
@@ -139,6 +140,88 @@ typedef struct ttsb_mha_args {
 } ttsb_mha_args;
 
 int ttsb_mha_fwd(const ttsb_mha_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Training-step GEMMs (single-pass bf16, fp32 accumulate) -- gradients of the layers above
+ *
+ * ttsb_bgemm: per-(batch row b, head h) products  out_z[m][n] = alpha * sum_k A_z[m][k] * B_z[n][k]  where both operands
+ *   are activations: S = Q K^T, O = P V, dP = dO V^T, dQ = dS K, dK = dS^T Q, dV = P^T dO (model/layers.py:179-193 and
+ *   its gradient).  Each operand is a bf16 tensor described as (dim0 contiguous = K axis, dim1 = rows, dim2 = batches)
+ *   with element strides; the tile origin of problem z=(b,h) is (k + h*h_col, row + h*h_row, z_batch ? z : b).
+ * ttsb_wgrad: weight gradients  dW[seg*Cin + c][n] += sum_{b,t} Xt[b][c][t + shift_seg] * Gt[b][n][t]  for Dense (1
+ *   segment), concat-Dense (2 sources) and Conv1D (k segments); Xt / Gt are the time-transposed bf16 copies
+ *   (B, C, ld_t) produced by ttsb_transpose_bf16; dW is fp32 in the Keras (K, N) layout and is ACCUMULATED into.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct ttsb_bgemm_args {
+  int B, H, M, N, K;
+  const void* a;
+  long long a_dim0, a_dim1, a_dim2, a_stride1, a_stride2;
+  int a_h_col, a_h_row, a_z_batch;
+  const void* b;
+  long long b_dim0, b_dim1, b_dim2, b_stride1, b_stride2;
+  int b_h_col, b_h_row, b_z_batch;
+  float alpha;
+  float* out_f32;            /* either or both */
+  void* out_bf16;
+  int ld_out;                /* row stride (elements), multiple of 8 */
+  long long out_batch_stride;/* elements between consecutive z (or b when out_by_b) */
+  int out_h_col;             /* column offset per head */
+  int out_by_b;              /* 1: output batch index is b (heads side by side in the columns) */
+  int out_cols;              /* writable columns per row of one problem (multiple of 16); columns >= N are written 0 */
+  const int32_t* row_len;    /* optional [B]: rows m >= row_len[b] are written as zeros */
+  const int32_t* col_len;    /* optional [B]: columns n >= col_len[b] are written as zeros */
+} ttsb_bgemm_args;
+
+int ttsb_bgemm(const ttsb_bgemm_args* args, void* stream);
+
+typedef struct ttsb_wgrad_args {
+  int B, T, Cin, N;
+  int num_segments;
+  int seg_src[4];
+  int seg_shift[4];
+  const void* xt[2];         /* bf16 (B, xt_rows[i], ld_t); the first Cin rows of each batch are used */
+  int xt_rows[2];
+  const void* gt;            /* bf16 (B, gt_rows, ld_t); the first N rows are used */
+  int gt_rows;
+  int ld_t;                  /* row stride of the transposed tensors (multiple of 8) */
+  float* dw;                 /* fp32 (num_segments*Cin, N), accumulated */
+} ttsb_wgrad_args;
+
+int ttsb_wgrad(const ttsb_wgrad_args* args, void* stream);
+
+/* bf16 (B,T,ld_src)[:, :, col0:col0+C] -> (B, dst_rows >= C, ld_t >= T) time-transposed copy for ttsb_wgrad / ttsb_bgemm;
+ * colsum (optional, fp32 [C]) accumulates the column sums = bias gradient of a Dense/Conv1D whose output grad this is. */
+int ttsb_transpose_bf16(const void* src, int B, int T, int ld_src, int col0, int C, void* dst, int dst_rows, int ld_t,
+                        float* colsum, void* stream);
+/* Row softmax of materialised, pre-scaled scores S fp32 (B*H, T, ld) with key masking (model/layers.py:186-192) and
+ * attention dropout: P_pre = softmax, P_drop = dropout(P_pre) (pass the same pointer twice when drop_p == 0). */
+int ttsb_softmax_fwd(const float* S, int B, int H, int T, int Tk, int ld, const int32_t* kv_len, float drop_p,
+                     uint32_t seed, uint32_t site, void* P_pre, void* P_drop, void* stream);
+int ttsb_softmax_bwd(const void* P_pre, const float* dP, int B, int H, int T, int Tk, int ld, const int32_t* kv_len,
+                     float scale, float drop_p, uint32_t seed, uint32_t site, void* dS, void* stream);
+/* LayerNorm backward from the saved pre-norm values u (keras LayerNormalization, model/layers.py:27,96,207,295,508). */
+int ttsb_layernorm_bwd(const float* dz, const float* u, const float* gamma, int B, int T, int C, int ld, float eps,
+                       const int32_t* row_len, int relu_mask, float pre_drop_p, uint32_t pre_site, float post_drop_p,
+                       uint32_t post_site, uint32_t seed, float* du, void* g_bf16, float* dgamma, float* dbeta, void* stream);
+int ttsb_relu_bwd(void* dy_bf16, const void* h_bf16, int64_t n, void* stream);
+int ttsb_cast_bf16(const float* x, int64_t n, float drop_p, uint32_t seed, uint32_t site, void* out_bf16, void* stream);
+/* fp32 (rows, C) -> bf16 (rows, ld_out >= C) with zero padding columns */
+int ttsb_cast_bf16_pad(const float* x, int64_t rows, int C, void* out_bf16, int ld_out, void* stream);
+/* mean |pred - target| over ALL elements of pred[:, :Tt] (utils/losses.py:41-49 as called with mask=None), added to
+ * *loss_out; grad = weight * sign(pred - target) / numel (zero for rows >= Tt). */
+int ttsb_mae_loss(const float* pred, int B, int Tp, int Tt, int C, const float* target_f32, const int32_t* target_i32,
+                  float weight, float* loss_out, float* grad, void* stream);
+int ttsb_expand_bwd(const float* dm, const int32_t* dur_int, int B, int Tp, int Tm, int d, float* dx, void* stream);
+int ttsb_embedding_bwd(const float* dx, const int32_t* tokens, int B, int T, int d, int vocab, float* demb, void* stream);
+int ttsb_pe_scalar_bwd(const float* g, const float* pe, int B, int T, int d, float* dscalar, void* stream);
+int ttsb_pitch_embed_bwd(const float* g, const float* pitch, const float* w, const float* bias, int B, int T, int d,
+                         float* dw, float* db, void* stream);
+int ttsb_statpred_head_bwd(const float* gout, const float* out, const float* h, int ldh, int C, const float* w, int relu,
+                           const int32_t* row_len, int B, int T, float* dh, float* dw, float* db, void* stream);
+/* Keras/TF-2.2 Adam (utils/training_config_manager.py:102-106): theta -= lr_t * m / (sqrt(v) + eps) with
+ * lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) computed by the caller; grad is multiplied by grad_scale first. */
+int ttsb_adam_tf_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
+                      float eps, float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * StatPredictor head  Dense(C->1, relu|linear) * mask   (model/layers.py:479-485)

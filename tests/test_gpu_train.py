@@ -1,0 +1,235 @@
+"""GPU parity of the training step: gradient kernels one by one, then loss / gradients / Adam of the whole
+ForwardTransformer against torch autograd on the CPU oracle (dropout off; the forward runs in single-pass bf16, so
+gradients are compared per tensor with a relative tolerance)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import forward_oracle as fo
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _lib():
+    from transformertts_b200 import lib
+    lib.load()
+    return lib
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def test_transpose_with_column_sums():
+    lib = _lib()
+    g = torch.Generator().manual_seed(0)
+    B, T, C = 3, 203, 300
+    x = torch.randn(B, T, 320, generator=g).bfloat16().to(DEV)
+    ld_t = 208
+    dst = torch.zeros(B, C, ld_t, dtype=torch.bfloat16, device=DEV)
+    cs = torch.zeros(C, device=DEV)
+    lib.transpose_bf16(x, B, T, 320, 16, C, dst, C, ld_t, cs)
+    torch.cuda.synchronize()
+    ref = x[:, :, 16:16 + C].transpose(1, 2)
+    assert torch.equal(dst[:, :, :T], ref)
+    assert _rel(cs, x[:, :, 16:16 + C].float().sum((0, 1))) < 1e-5
+
+
+def test_wgrad_conv_and_concat():
+    """dW of Conv1D(k=3,'same') and of the concat projection against x^T g on the CPU."""
+    lib = _lib()
+    from transformertts_b200.model.training import TrainEngine
+    g = torch.Generator().manual_seed(1)
+    B, T, Cin, N = 5, 333, 256, 226
+    x = torch.randn(B, T, Cin, generator=g).bfloat16()
+    gy = torch.randn(B, T, N, generator=g).bfloat16()
+    ld_t = 336
+
+    def tr(t):
+        out = torch.zeros(t.shape[0], t.shape[2], ld_t, dtype=torch.bfloat16)
+        out[:, :, :T] = t.transpose(1, 2)
+        return out.to(DEV)
+
+    xt, gt = tr(x), tr(gy)
+    dw = torch.zeros(3 * Cin, N, device=DEV)
+    a = lib.WgradArgs()
+    a.B, a.T, a.Cin, a.N, a.num_segments = B, T, Cin, N, 3
+    for s, sh in enumerate((-1, 0, 1)):
+        a.seg_src[s], a.seg_shift[s] = 0, sh
+    a.xt[0], a.xt_rows[0] = xt.data_ptr(), Cin
+    a.gt, a.gt_rows, a.ld_t, a.dw = gt.data_ptr(), N, ld_t, dw.data_ptr()
+    lib.wgrad(a)
+    torch.cuda.synchronize()
+    xd, gd = x.double(), gy.double()
+    ref = torch.zeros(3, Cin, N, dtype=torch.float64)
+    for tap, sh in enumerate((-1, 0, 1)):
+        lo, hi = max(0, -sh), min(T, T - sh)
+        ref[tap] = torch.einsum('btc,btn->cn', xd[:, lo + sh:hi + sh], gd[:, lo:hi])
+    assert _rel(dw.view(3, Cin, N), ref) < 1e-4
+    # two sources (concat projection), accumulate on top of existing values
+    x2 = torch.randn(B, T, Cin, generator=g).bfloat16()
+    dw2 = torch.ones(2 * Cin, N, device=DEV)
+    a2 = lib.WgradArgs()
+    a2.B, a2.T, a2.Cin, a2.N, a2.num_segments = B, T, Cin, N, 2
+    a2.seg_src[0], a2.seg_src[1] = 0, 1
+    x2t = tr(x2)
+    a2.xt[0], a2.xt[1], a2.xt_rows[0], a2.xt_rows[1] = xt.data_ptr(), x2t.data_ptr(), Cin, Cin
+    a2.gt, a2.gt_rows, a2.ld_t, a2.dw = gt.data_ptr(), N, ld_t, dw2.data_ptr()
+    lib.wgrad(a2)
+    torch.cuda.synchronize()
+    ref2 = 1 + torch.cat([torch.einsum('btc,btn->cn', xd, gd), torch.einsum('btc,btn->cn', x2.double(), gd)])
+    assert _rel(dw2, ref2) < 1e-4
+
+
+@pytest.mark.parametrize('H,dh,T', [(2, 128, 200), (2, 64, 333)])
+def test_attention_train_path_forward_and_backward(H, dh, T):
+    """S = QK^T, softmax, O = PV and the five gradient GEMMs, through TrainEngine helpers on a standalone block."""
+    lib = _lib()
+    from transformertts_b200.model.training import TrainEngine
+    from transformertts_b200.model.models import _round_up
+    g = torch.Generator().manual_seed(2)
+    B, d = 3, H * dh
+    qkv = torch.randn(B, T, 3 * d, generator=g).bfloat16()
+    dO = torch.randn(B, T, d, generator=g).bfloat16()
+    lens = torch.tensor([T, T // 2, 70], dtype=torch.int32)
+    eng = TrainEngine.__new__(TrainEngine)
+    eng.dev = torch.device(DEV)
+    qkv_d, dO_d, lens_d = qkv.to(DEV), dO.to(DEV), lens.to(DEV)
+    Z, ldp = B * H, _round_up(T, 16)
+    S = torch.empty(Z, T, ldp, device=DEV)
+    eng._bgemm(B, H, T, T, dh, qkv_d, (3 * d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 0), qkv_d, (2 * d, T, B), (3 * d, 3 * d * T),
+               (dh, 0, 0, d), alpha=1.0 / math.sqrt(dh), out_f32=S, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
+    P = torch.empty(Z, T, ldp, dtype=torch.bfloat16, device=DEV)
+    lib.softmax_fwd(S, B, H, T, T, ldp, lens_d, 0.0, 0, 0, P, P)
+    vT, ld8 = eng._transpose(qkv_d, B, T, 3 * d, 2 * d, d)
+    attn = torch.empty(B, T, d, dtype=torch.bfloat16, device=DEV)
+    eng._bgemm(B, H, T, dh, T, P, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), vT, (T, d, B), (ld8, d * ld8), (0, dh, 0, 0),
+               out_bf16=attn, ld_out=d, out_batch_stride=T * d, out_h_col=dh, out_by_b=1, out_cols=dh)
+    torch.cuda.synchronize()
+    # reference with autograd (fp64) on the bf16 inputs
+    x = qkv.double().requires_grad_(True)
+    q, k, v = [t.reshape(B, T, H, dh).permute(0, 2, 1, 3) for t in x.split(d, dim=-1)]
+    logits = q @ k.transpose(-1, -2) / math.sqrt(dh)
+    mask = torch.arange(T)[None, :] >= lens[:, None]
+    logits = logits.masked_fill(mask[:, None, None, :], float('-inf'))
+    w = torch.softmax(logits, -1)
+    o = (w @ v).permute(0, 2, 1, 3).reshape(B, T, d)
+    keep = (~mask)[..., None].double()
+    (o * keep * dO.double()).sum().backward()
+    for b in range(B):
+        n = int(lens[b])
+        assert _rel(attn[b, :n], o[b, :n]) < 1e-2
+        assert _rel(P.view(B, H, T, ldp)[b, :, :n, :T].float(), w[b, :, :n]) < 1e-2
+    # backward
+    dO_m = (dO.double() * keep).bfloat16().to(DEV)  # rows of padded queries carry zero gradient (row mask upstream)
+    dP = torch.empty(Z, T, ldp, device=DEV)
+    eng._bgemm(B, H, T, T, dh, dO_m, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv_d, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
+               out_f32=dP, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
+    dS = torch.empty(Z, T, ldp, dtype=torch.bfloat16, device=DEV)
+    lib.softmax_bwd(P, dP, B, H, T, T, ldp, lens_d, 1.0 / math.sqrt(dh), 0.0, 0, 0, dS)
+    qkT, _ = eng._transpose(qkv_d, B, T, 3 * d, 0, 2 * d)
+    dST, _ = eng._transpose(dS, Z, T, ldp, 0, T)
+    PT, _ = eng._transpose(P, Z, T, ldp, 0, T)
+    daT, _ = eng._transpose(dO_m, B, T, d, 0, d)
+    dqkv = torch.full((B, T, 3 * d), float('nan'), dtype=torch.bfloat16, device=DEV)
+    common = dict(out_bf16=dqkv, ld_out=3 * d, out_batch_stride=T * 3 * d, out_h_col=dh, out_by_b=1, out_cols=dh)
+    eng._bgemm(B, H, T, dh, T, dS, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), qkT, (T, d, B), (ld8, 2 * d * ld8), (0, dh, 0, d * ld8), out_ptr_off=0, **common)
+    eng._bgemm(B, H, T, dh, T, dST, (T, T, Z), (ld8, T * ld8), (0, 0, 1, 0), qkT, (T, d, B), (ld8, 2 * d * ld8), (0, dh, 0, 0), out_ptr_off=d, **common)
+    eng._bgemm(B, H, T, dh, T, PT, (T, T, Z), (ld8, T * ld8), (0, 0, 1, 0), daT, (T, d, B), (ld8, d * ld8), (0, dh, 0, 0), out_ptr_off=2 * d, **common)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dqkv.float()).all()
+    assert _rel(dqkv.float(), x.grad) < 3e-2
+
+
+def test_layernorm_bwd_and_small_ops():
+    lib = _lib()
+    g = torch.Generator().manual_seed(3)
+    B, T, C, ld = 4, 77, 226, 256
+    u = torch.zeros(B, T, ld)
+    u[..., :C] = torch.relu(torch.randn(B, T, C, generator=g))
+    dz = torch.zeros(B, T, ld)
+    dz[..., :C] = torch.randn(B, T, C, generator=g)
+    gamma = torch.zeros(ld)
+    gamma[:C] = 1 + 0.1 * torch.randn(C, generator=g)
+    lens = torch.tensor([77, 30, 0, 50], dtype=torch.int32)
+    uu = u[..., :C].double().requires_grad_(True)
+    gg = gamma[:C].double().requires_grad_(True)
+    bb = torch.zeros(C, dtype=torch.float64, requires_grad=True)
+    keep = (torch.arange(T)[None] < lens[:, None])[..., None].double()
+    y = fo.layer_norm(uu, gg, bb) * keep
+    (y * dz[..., :C].double()).sum().backward()
+    du = torch.full((B, T, ld), float('nan'), device=DEV)
+    gb = torch.full((B, T, ld), float('nan'), dtype=torch.bfloat16, device=DEV)
+    dg, db = torch.zeros(ld, device=DEV), torch.zeros(ld, device=DEV)
+    lib.layernorm_bwd(dz.to(DEV), u.to(DEV), gamma.to(DEV), B, T, C, ld, 1e-6, lens.to(DEV), True, du, gb, dg, db)
+    torch.cuda.synchronize()
+    assert _rel(du[..., :C], uu.grad) < 1e-4 and torch.count_nonzero(du[..., C:]) == 0
+    assert _rel(dg[:C], gg.grad) < 1e-4 and _rel(db[:C], bb.grad) < 1e-4
+    assert _rel(gb[..., :C].float(), uu.grad * (u[..., :C] > 0)) < 1e-2
+    # MAE loss + gradient (unmasked mean over all elements, int targets)
+    pred = torch.randn(3, 20, 1, generator=g)
+    tgt = torch.randint(0, 5, (3, 20), generator=g, dtype=torch.int32)
+    loss = torch.zeros(1, device=DEV)
+    grad = torch.empty(3, 20, device=DEV)
+    lib.mae_loss(pred.to(DEV), 3, 20, 20, 1, tgt.to(DEV), 3.0, loss, grad)
+    torch.cuda.synchronize()
+    ref = fo.masked_mean_absolute_error(tgt[..., None], pred)
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert _rel(grad, 3.0 * torch.sign(pred[..., 0] - tgt) / 60) < 1e-6
+    # Adam (Keras form)
+    p, gr = torch.randn(1000, generator=g), torch.randn(1000, generator=g) * 1e-3
+    m0, v0 = torch.zeros(1000), torch.zeros(1000)
+    pd, md, vd = p.to(DEV), m0.to(DEV), v0.to(DEV)
+    pr = p.clone()
+    for step in (1, 2, 3):
+        lr_t = 1e-4 * math.sqrt(1 - 0.98 ** step) / (1 - 0.9 ** step)
+        lib.adam_tf_step(pd, gr.to(DEV), md, vd, lr_t, 0.9, 0.98, 1e-9)
+        fo.adam_tf_step(pr, gr, m0, v0, step, 1e-4)
+    torch.cuda.synchronize()
+    assert (pd.cpu() - pr).abs().max() < 1e-7
+
+
+@pytest.mark.parametrize('cfg_name,B,Tp,Tm', [('C1', 3, 24, 150), ('LJ256', 2, 32, 260)])
+def test_train_step_loss_grads_and_adam(cfg_name, B, Tp, Tm):
+    """One deterministic training step (dropout off): loss, every parameter gradient and the Adam update vs the
+    oracle (torch autograd on the restated fp32 graph).  The GPU forward/backward is single-pass bf16."""
+    torch.set_num_threads(8)
+    from transformertts_b200.model.models import ForwardTransformer
+    from transformertts_b200.model.training import Adam
+    cfg = fo.CONFIGS[cfg_name]
+    p = fo.init_params(cfg, seed=7)
+    tok, dur, pit = fo.make_inputs('ragged', B, Tp, Tm, seed=301)
+    mel_tgt = fo.make_mel_targets(dur, 80, seed=302)
+    ref_out, ref_g = fo.loss_and_grads(p, cfg, tok, mel_tgt, dur, pit)
+    model = ForwardTransformer(**cfg, train_dropout=False)
+    model.set_weights(p)
+    model._compile(Adam(1e-4))
+    eng = model._get_engine()
+    out = eng.forward_backward(tok, mel_tgt, dur, pit, training=True)
+    torch.cuda.synchronize()
+    assert abs(out['loss'].item() - ref_out['loss'].item()) < 2e-2 * abs(ref_out['loss'].item())
+    for k in ('mel', 'duration', 'pitch'):
+        assert abs(out['losses'][k].item() - ref_out['losses'][k].item()) < 2e-2 * abs(ref_out['losses'][k].item()) + 1e-4
+    worst = []
+    for name, gref in ref_g.items():
+        rel = _rel(eng.g[name], gref)
+        worst.append((rel, name))
+    worst.sort(reverse=True)
+    print('worst gradient relative errors:', worst[:6])
+    assert worst[0][0] < 0.08, worst[:6]
+    # Adam: the update applied to the flat buffer equals the oracle formula on the same gradients
+    w0 = eng.flat_w.clone()
+    g0 = eng.flat_g.clone()
+    eng.apply_adam(model.optimizer)
+    torch.cuda.synchronize()
+    m_ref, v_ref, w_ref = torch.zeros_like(w0).cpu(), torch.zeros_like(w0).cpu(), w0.cpu().clone()
+    fo.adam_tf_step(w_ref, g0.cpu(), m_ref, v_ref, 1, 1e-4)
+    assert (eng.flat_w.cpu() - w_ref).abs().max() < 1e-7
+    assert model.step == 1
+    # a second full step runs (weights were re-packed) and lowers nothing to NaN
+    out2 = model.train_step(tok, mel_tgt, dur, pit)
+    assert math.isfinite(out2['loss'].item())

@@ -1,0 +1,353 @@
+// Batched / reduction GEMMs of the training step on tcgen05 (single-pass bf16, fp32 accumulate in TMEM).
+// Same pipeline as gemm_tc.cu (TMA -> 128B-swizzled smem ring -> tcgen05.mma -> 8 epilogue warps), different tiling:
+//
+//  mode BATCHED : out[z][m][n] = alpha * sum_k A_z[m][k] * B_z[n][k]        z = (batch row b, head h)
+//                 both operands come from activations (per-(b,h) B operand), e.g. S = Q K^T, O = P V, dP = dO V^T,
+//                 dQ = dS K, dK = dS^T Q, dV = P^T dO of the attention forward/backward (model/layers.py:176-195 and
+//                 its gradient), each operand addressed through a 3-D TMA map with per-head column/row offsets.
+//  mode WGRAD   : dW[seg*Cin + c][n] += sum_b sum_t X^T[b][c][t + shift_seg] * G^T[b][n][t]
+//                 weight gradients of Dense / concat-Dense / Conv1D (k taps = k segments), reduction over all B*T
+//                 rows split across CTAs, partial tiles added with fp32 red.global.add (Keras (K,N) layout).
+#include <cuda_fp16.h>
+
+#include "../../include/ttsb.h"
+#include "ttsb_common.cuh"
+#include "ttsb_host.h"
+
+namespace ttsb {
+
+constexpr int BG_BM = 128;
+constexpr int BG_BK = 64;
+constexpr int BG_MAX_BN = 256;
+constexpr int BG_THREADS = 320;
+constexpr int BG_STAGES = 4;
+constexpr int BG_A_BYTES = BG_BM * BG_BK * 2;
+constexpr int BG_B_BYTES = BG_MAX_BN * BG_BK * 2;
+constexpr int BG_STAGE_BYTES = BG_A_BYTES + BG_B_BYTES;
+constexpr int BG_BAR_OFFSET = BG_STAGES * BG_STAGE_BYTES;
+constexpr int BG_SMEM_BYTES = BG_BAR_OFFSET + 256 + 1024;
+
+struct BgOperand {
+  int h_col;    // added to coordinate 0 (contiguous dim) per head
+  int h_row;    // added to coordinate 1 per head
+  int z_batch;  // 1: coordinate 2 = z (b*H + h); 0: coordinate 2 = b
+};
+
+struct BgParams {
+  int mode;  // 0 batched, 1 wgrad
+  // batched
+  int Z, H, M, N, K;  // per-z problem: M x N x K
+  BgOperand opA, opB;
+  float alpha;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  int ld_out;                 // row stride (elements)
+  long long out_z_stride;     // stride between z (or b when out_by_b) problems
+  int out_h_col;              // column offset per head
+  int out_by_b;               // 1: batch index of the output is b (heads side by side in columns)
+  int out_cols;               // writable columns of one problem's row (multiple of 16)
+  const int* row_len;         // optional [B]: rows m >= len[b] are written as zero
+  const int* col_len;         // optional [B]: columns n >= len[b] are written as zero
+  // wgrad
+  int B, T, Cin, num_seg, seg_src[4], seg_shift[4], splits, b_per_split;
+  float* dw;                  // fp32 (num_seg*Cin, N) accumulated with atomics
+  // common
+  int block_n, n_tiles, m_tiles, num_tiles;
+};
+
+__global__ void __launch_bounds__(BG_THREADS, 1)
+bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmB, const BgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BG_BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + BG_STAGES;
+  uint64_t* tmem_full = empty_bar + BG_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < BG_STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full + s, 1);
+      mbar_init(tmem_empty + s, 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t stage_tx = (uint32_t)(BG_A_BYTES + p.block_n * BG_BK * 2);
+  const int t_chunks = (p.T + BG_BK - 1) / BG_BK;
+
+  // number of k-blocks of a tile (uniform across roles)
+  auto tile_kblocks = [&](int tile) -> int {
+    if (p.mode == 0) return (p.K + BG_BK - 1) / BG_BK;
+    const int split = tile % p.splits;
+    const int b0 = split * p.b_per_split;
+    const int nb = min(p.b_per_split, p.B - b0);
+    return nb > 0 ? nb * t_chunks : 0;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      if (p.mode == 0) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = (tile / p.n_tiles) % p.m_tiles;
+        const int z = tile / (p.n_tiles * p.m_tiles);
+        const int b = z / p.H, h = z % p.H;
+        const int m0 = m_tile * BG_BM, n0 = n_tile * p.block_n;
+        const int kbs = (p.K + BG_BK - 1) / BG_BK;
+        for (int kb = 0; kb < kbs; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* st = smem + stage * BG_STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar + stage, stage_tx);
+          tma_load_3d(&tmA0, full_bar + stage, st, kb * BG_BK + h * p.opA.h_col, m0 + h * p.opA.h_row, p.opA.z_batch ? z : b);
+          tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES, kb * BG_BK + h * p.opB.h_col, n0 + h * p.opB.h_row,
+                      p.opB.z_batch ? z : b);
+          if (++stage == BG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      } else {
+        int r = tile;
+        const int split = r % p.splits; r /= p.splits;
+        const int n_tile = r % p.n_tiles; r /= p.n_tiles;
+        const int m_tile = r % p.m_tiles; r /= p.m_tiles;
+        const int seg = r;
+        const CUtensorMap* mA = p.seg_src[seg] == 0 ? &tmA0 : &tmA1;
+        const int c0 = m_tile * BG_BM, n0 = n_tile * p.block_n;
+        const int b0 = split * p.b_per_split;
+        const int b1 = min(b0 + p.b_per_split, p.B);
+        for (int b = b0; b < b1; ++b) {
+          for (int tc = 0; tc < t_chunks; ++tc) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            uint8_t* st = smem + stage * BG_STAGE_BYTES;
+            mbar_arrive_expect_tx(full_bar + stage, stage_tx);
+            tma_load_3d(mA, full_bar + stage, st, tc * BG_BK + p.seg_shift[seg], c0, b);
+            tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES, tc * BG_BK, n0, b);
+            if (++stage == BG_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_bf16(BG_BM, p.block_n);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int kbs = tile_kblocks(tile);
+      if (kbs == 0) continue;
+      mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BG_MAX_BN;
+      for (int kb = 0; kb < kbs; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + stage * BG_STAGE_BYTES);
+        const uint64_t a = make_smem_desc_sw128(st);
+        const uint64_t b = make_smem_desc_sw128(st + BG_A_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BG_BK / 16; ++kk) umma_bf16(d_tmem, a + 2 * kk, b + 2 * kk, idesc, (kb | kk) != 0);
+        umma_commit(empty_bar + stage);
+        if (++stage == BG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int nch = p.block_n >> 4;
+    const int ch_begin = half ? (nch + 1) >> 1 : 0;
+    const int ch_end = half ? nch : (nch + 1) >> 1;
+    uint32_t r[16];
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      if (tile_kblocks(tile) == 0) continue;
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BG_MAX_BN;
+      if (p.mode == 0) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = (tile / p.n_tiles) % p.m_tiles;
+        const int z = tile / (p.n_tiles * p.m_tiles);
+        const int b = z / p.H, h = z % p.H;
+        const int m = m_tile * BG_BM + row;
+        const int n0 = n_tile * p.block_n;
+        const bool row_ok = m < p.M;
+        const bool row_keep = row_ok && (p.row_len == nullptr || m < __ldg(p.row_len + b));
+        const int clen = p.col_len ? __ldg(p.col_len + b) : p.N;
+        const size_t o = (size_t)(p.out_by_b ? b : z) * (size_t)p.out_z_stride + (size_t)(row_ok ? m : 0) * p.ld_out + h * p.out_h_col + n0;
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          const int c0 = ch << 4;
+          __syncwarp();
+          tmem_ld16(taddr + c0, r);
+          tmem_wait_ld();
+          if (row_ok && n0 + c0 < p.out_cols) {  // out_cols (multiple of 16) bounds the writable part of the row
+            float y[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + c0 + j;
+              y[j] = (row_keep && n < clen && n < p.N) ? __uint_as_float(r[j]) * p.alpha : 0.f;
+            }
+            if (p.out_f32) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(p.out_f32 + o + c0 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            }
+            if (p.out_bf16) {
+              uint32_t hh[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 v = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                hh[j] = *reinterpret_cast<const uint32_t*>(&v);
+              }
+              st_global_v4(p.out_bf16 + o + c0, hh[0], hh[1], hh[2], hh[3]);
+              st_global_v4(p.out_bf16 + o + c0 + 8, hh[4], hh[5], hh[6], hh[7]);
+            }
+          }
+        }
+      } else {
+        int rr = tile / p.splits;
+        const int n_tile = rr % p.n_tiles; rr /= p.n_tiles;
+        const int m_tile = rr % p.m_tiles; rr /= p.m_tiles;
+        const int seg = rr;
+        const int c = m_tile * BG_BM + row;
+        const int n0 = n_tile * p.block_n;
+        const bool row_ok = c < p.Cin;
+        float* dst = p.dw + ((size_t)seg * p.Cin + (row_ok ? c : 0)) * p.N + n0;
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          const int c0 = ch << 4;
+          __syncwarp();
+          tmem_ld16(taddr + c0, r);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c0 + j < p.N) atomicAdd(dst + c0 + j, __uint_as_float(r[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const BgParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TTSB_CUDA_OK(cudaFuncSetAttribute(bgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  bgemm_tc_kernel<<<grid, BG_THREADS, BG_SMEM_BYTES, stream>>>(a0, a1, b, p);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "bgemm_tc_kernel launch");
+}
+
+static int pick_block_n(int N) {
+  const int n16 = (N + 15) / 16 * 16;
+  return n16 < BG_MAX_BN ? n16 : BG_MAX_BN;
+}
+
+}  // namespace ttsb
+
+using namespace ttsb;
+
+extern "C" int ttsb_bgemm(const ttsb_bgemm_args* a, void* stream_v) {
+  if (!a) { set_last_error("ttsb_bgemm: args is NULL"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->B <= 0 || a->H <= 0 || a->M <= 0 || a->N <= 0 || a->K <= 0) { set_last_error("ttsb_bgemm: non-positive dimension"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (!a->a || !a->b || (!a->out_f32 && !a->out_bf16)) { set_last_error("ttsb_bgemm: NULL tensor"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->ld_out % 8 || a->out_cols % 16 || a->out_cols <= 0) { set_last_error("ttsb_bgemm: ld_out must be a multiple of 8 and out_cols of 16"); return TTSB_ERR_INVALID_ARGUMENT; }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  BgParams p{};
+  p.mode = 0;
+  p.Z = a->B * a->H; p.H = a->H; p.M = a->M; p.N = a->N; p.K = a->K;
+  p.opA = {a->a_h_col, a->a_h_row, a->a_z_batch};
+  p.opB = {a->b_h_col, a->b_h_row, a->b_z_batch};
+  p.alpha = a->alpha;
+  p.out_f32 = a->out_f32;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
+  p.ld_out = a->ld_out; p.out_z_stride = a->out_batch_stride; p.out_h_col = a->out_h_col; p.out_by_b = a->out_by_b; p.out_cols = a->out_cols;
+  p.row_len = a->row_len; p.col_len = a->col_len;
+  p.block_n = pick_block_n(a->N);
+  p.n_tiles = (a->N + p.block_n - 1) / p.block_n;
+  p.m_tiles = (a->M + BG_BM - 1) / BG_BM;
+  p.num_tiles = p.Z * p.m_tiles * p.n_tiles;
+  p.T = 1;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_3d(&tmA, a->a, (uint64_t)a->a_dim0, (uint64_t)a->a_dim1, (uint64_t)a->a_dim2, (uint64_t)a->a_stride1,
+                             (uint64_t)a->a_stride2, BG_BK, BG_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tmB, a->b, (uint64_t)a->b_dim0, (uint64_t)a->b_dim1, (uint64_t)a->b_dim2, (uint64_t)a->b_stride1,
+                         (uint64_t)a->b_stride2, BG_BK, p.block_n);
+  if (rc) return rc;
+  return launch(tmA, tmA, tmB, p, stream);
+}
+
+extern "C" int ttsb_wgrad(const ttsb_wgrad_args* a, void* stream_v) {
+  if (!a) { set_last_error("ttsb_wgrad: args is NULL"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->B <= 0 || a->T <= 0 || a->Cin <= 0 || a->N <= 0 || a->num_segments < 1 || a->num_segments > 4) {
+    set_last_error("ttsb_wgrad: bad dimensions");
+    return TTSB_ERR_INVALID_ARGUMENT;
+  }
+  if (!a->xt[0] || !a->gt || !a->dw || a->ld_t % 8) { set_last_error("ttsb_wgrad: NULL tensor or ld_t not a multiple of 8"); return TTSB_ERR_INVALID_ARGUMENT; }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  BgParams p{};
+  p.mode = 1;
+  p.B = a->B; p.T = a->T; p.Cin = a->Cin; p.N = a->N; p.num_seg = a->num_segments; p.H = 1;
+  for (int s = 0; s < a->num_segments; ++s) {
+    p.seg_src[s] = a->seg_src[s];
+    p.seg_shift[s] = a->seg_shift[s];
+    if (a->seg_src[s] < 0 || a->seg_src[s] > 1 || !a->xt[a->seg_src[s]]) { set_last_error("ttsb_wgrad: bad segment source"); return TTSB_ERR_INVALID_ARGUMENT; }
+  }
+  p.dw = a->dw;
+  p.block_n = pick_block_n(a->N);
+  p.n_tiles = (a->N + p.block_n - 1) / p.block_n;
+  p.m_tiles = (a->Cin + BG_BM - 1) / BG_BM;
+  const int base_tiles = a->num_segments * p.m_tiles * p.n_tiles;
+  int splits = (2 * num_sms() + base_tiles - 1) / base_tiles;
+  if (splits > a->B) splits = a->B;
+  if (splits < 1) splits = 1;
+  p.b_per_split = (a->B + splits - 1) / splits;
+  p.splits = (a->B + p.b_per_split - 1) / p.b_per_split;
+  p.num_tiles = base_tiles * p.splits;
+  CUtensorMap tmA[2], tmB;
+  for (int i = 0; i < 2; ++i) {
+    const void* base = a->xt[i] ? a->xt[i] : a->xt[0];
+    int rc = make_tmap_bf16_3d(&tmA[i], base, (uint64_t)a->T, (uint64_t)a->Cin, (uint64_t)a->B, (uint64_t)a->ld_t,
+                               (uint64_t)a->ld_t * a->xt_rows[a->xt[i] ? i : 0], BG_BK, BG_BM);
+    if (rc) return rc;
+  }
+  int rc = make_tmap_bf16_3d(&tmB, a->gt, (uint64_t)a->T, (uint64_t)a->N, (uint64_t)a->B, (uint64_t)a->ld_t,
+                             (uint64_t)a->ld_t * a->gt_rows, BG_BK, p.block_n);
+  if (rc) return rc;
+  return launch(tmA[0], tmA[1], tmB, p, stream);
+}

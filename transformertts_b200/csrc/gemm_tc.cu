@@ -48,6 +48,7 @@ struct GemmKParams {
   __nv_bfloat16* vt_hi;
   __nv_bfloat16* vt_lo;
   int vt_col0, vt_cols, vt_ld;
+  float* out_preln;  // optional fp32 (B,T,ld_out): the pre-LayerNorm value (saved for the backward pass)
   int h16;  // 1: out_hi / vt_hi receive IEEE fp16 instead of bf16 (single plane; operands of the fp16 attention)
 };
 
@@ -161,6 +162,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
   if (p.gamma == nullptr) {
     for (int ch = ch_begin; ch < ch_end; ++ch) {
       const int c0 = ch << 4;
+      __syncwarp();
       tmem_ld16(taddr + c0, r);
       if (p.bias) ldg16(p.bias + n0 + c0, aux);
       tmem_wait_ld();
@@ -197,6 +199,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
   float sum = 0.f;
   for (int ch = ch_begin; ch < ch_end; ++ch) {
     const int c0 = ch << 4;
+    __syncwarp();
     tmem_ld16(taddr + c0, r);
     if (p.bias) ldg16(p.bias + c0, aux);
     tmem_wait_ld();
@@ -224,6 +227,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
       sum += y[j];
       r[j] = __float_as_uint(y[j]);
     }
+    if (p.out_preln && row_ok) {
+      float* dst = p.out_preln + orow * (size_t)p.ld_out + c0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+    }
     tmem_st16(taddr + c0, r);
   }
   tmem_wait_st();
@@ -231,6 +239,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
   float ssq = 0.f;
   for (int ch = ch_begin; ch < ch_end; ++ch) {
     const int c0 = ch << 4;
+    __syncwarp();
     tmem_ld16(taddr + c0, r);
     tmem_wait_ld();
     if (partial) {
@@ -250,6 +259,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
   const float rstd = rsqrtf(pair_sum(ssq, red + 2 * GEMM_BM, half, row, quarter) * inv_n + p.eps);
   for (int ch = ch_begin; ch < ch_end; ++ch) {
     const int c0 = ch << 4;
+    __syncwarp();
     tmem_ld16(taddr + c0, r);
     float bt[16];
     ldg16(p.gamma + c0, aux);
@@ -471,6 +481,8 @@ __global__ void gemm_simt_kernel(const GemmKParams p, const GemmSimtPtrs q) {
       scratch[0] = m;
       scratch[1] = rsqrtf(v / p.N + p.eps);
     }
+    if (p.out_preln)
+      for (int n = threadIdx.x; n < n_alloc; n += blockDim.x) p.out_preln[(size_t)row * p.ld_out + n] = n < p.N ? srow[n] : 0.f;
     __syncthreads();
     mean = scratch[0];
     rstd = scratch[1];
@@ -567,6 +579,7 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
   p.vt_lo = split ? static_cast<__nv_bfloat16*>(a->vt_lo) : nullptr;
   p.vt_col0 = a->vt_col0; p.vt_cols = a->vt_cols; p.vt_ld = a->vt_ld;
   p.h16 = a->out_fp16 ? 1 : 0;
+  p.out_preln = a->out_preln;
   if (p.h16) { p.out_lo = nullptr; p.vt_lo = nullptr; }
 
   if (a->impl == TTSB_IMPL_SIMT) {

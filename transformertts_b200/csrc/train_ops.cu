@@ -1,0 +1,519 @@
+// Bandwidth-bound kernels of the training step (reference: ForwardTransformer._train_step, model/models.py:464-482,
+// losses utils/losses.py:41-70, Adam utils/training_config_manager.py:102-106): time-transposes feeding the weight-
+// gradient GEMMs (with fused bias-gradient column sums), softmax forward/backward on materialised score rows,
+// LayerNorm backward, ReLU masks, loss + its gradient, length-regulator / embedding / head backward, fused Adam.
+// All are coalesced row kernels; reductions across rows use shared-memory partials + fp32 atomics.
+#include <cuda_fp16.h>
+
+#include "../../include/ttsb.h"
+#include "ttsb_common.cuh"
+#include "ttsb_host.h"
+
+namespace ttsb {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Stateless dropout decision: keep element `idx` of dropout site `site` with probability 1-p (32-bit mix of a
+// 64-bit counter; the same function regenerates the mask in the backward pass).
+__device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t site, uint64_t idx, uint32_t thresh) {
+  uint32_t x = (uint32_t)idx * 0x9E3779B1u ^ (uint32_t)(idx >> 32) * 0x85EBCA77u ^ seed * 0xC2B2AE3Du ^ site * 0x27D4EB2Fu;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x >= thresh;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bf16 (B, T, ld_src)[:, :, col0:col0+C]  ->  (B, C, ld_t) ; optional fp32 column sums (bias gradients)
+// ------------------------------------------------------------------------------------------------
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int T, int ld_src, int col0, int C,
+                                      __nv_bfloat16* __restrict__ dst, int dst_rows, int ld_t, float* colsum) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 256 threads: 64 x 4
+  for (int r = ty; r < 64; r += 4) {
+    const int t = t0 + r, c = c0 + tx;
+    tile[r][tx] = (t < T && c < C) ? src[((size_t)b * T + t) * ld_src + col0 + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int r = ty; r < 64; r += 4) {
+    const int c = c0 + r, t = t0 + tx;
+    if (c < C && t < T) dst[((size_t)b * dst_rows + c) * ld_t + t] = tile[tx][r];
+  }
+  if (colsum != nullptr && ty == 0) {
+    const int c = c0 + tx;
+    if (c < C) {
+      float s = 0.f;
+      for (int r = 0; r < 64; ++r) s += __bfloat162float(tile[r][tx]);
+      atomicAdd(colsum + c, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax over materialised score rows (training attention):  S fp32 (Z, T, ld) already scaled by 1/sqrt(dh)
+// ------------------------------------------------------------------------------------------------
+__global__ void softmax_fwd_kernel(const float* __restrict__ S, int Z, int H, int T, int Tk, int ld, const int* __restrict__ kv_len,
+                                   float drop_p, uint32_t seed, uint32_t site, __nv_bfloat16* __restrict__ P_pre,
+                                   __nv_bfloat16* __restrict__ P_drop) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= Z * T) return;
+  const int lane = threadIdx.x & 31;
+  const int z = row / T, t = row % T, b = z / H;
+  const int len = min(max(__ldg(kv_len + b), 0), Tk);
+  const size_t base = (size_t)row * ld;
+  const bool live = t < len;  // padded query rows are masked downstream: write zeros
+  float mx = -INFINITY;
+  if (live)
+    for (int k = lane; k < len; k += 32) mx = fmaxf(mx, S[base + k]);
+  mx = wmax(mx);
+  float sum = 0.f;
+  if (live)
+    for (int k = lane; k < len; k += 32) sum += __expf(S[base + k] - mx);
+  sum = wsum(sum);
+  const float inv = live ? 1.f / sum : 0.f;
+  const uint32_t thresh = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (int k = lane; k < ld; k += 32) {
+    float pv = (live && k < len) ? __expf(S[base + k] - mx) * inv : 0.f;
+    P_pre[base + k] = __float2bfloat16_rn(pv);
+    if (P_drop != P_pre) {
+      const bool keep = drop_p <= 0.f || dropout_keep(seed, site, base + k, thresh);
+      P_drop[base + k] = __float2bfloat16_rn(keep ? pv * keep_scale : 0.f);
+    }
+  }
+}
+
+// dS = scale * P_pre * (dPp - sum_k P_pre dPp),  dPp = dP * keep/(1-p)
+__global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P_pre, const float* __restrict__ dP, int Z, int H, int T, int Tk,
+                                   int ld, const int* __restrict__ kv_len, float scale, float drop_p, uint32_t seed, uint32_t site,
+                                   __nv_bfloat16* __restrict__ dS) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= Z * T) return;
+  const int lane = threadIdx.x & 31;
+  const int z = row / T, t = row % T, b = z / H;
+  const int len = min(max(__ldg(kv_len + b), 0), Tk);
+  const size_t base = (size_t)row * ld;
+  const bool live = t < len;
+  const uint32_t thresh = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float dot = 0.f;
+  if (live)
+    for (int k = lane; k < len; k += 32) {
+      const bool keep = drop_p <= 0.f || dropout_keep(seed, site, base + k, thresh);
+      const float g = keep ? dP[base + k] * keep_scale : 0.f;
+      dot += __bfloat162float(P_pre[base + k]) * g;
+    }
+  dot = wsum(dot);
+  for (int k = lane; k < ld; k += 32) {
+    float v = 0.f;
+    if (live && k < len) {
+      const bool keep = drop_p <= 0.f || dropout_keep(seed, site, base + k, thresh);
+      const float g = keep ? dP[base + k] * keep_scale : 0.f;
+      v = scale * __bfloat162float(P_pre[base + k]) * (g - dot);
+    }
+    dS[base + k] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward (Keras non-fused forward: y = (u-mean)*rsqrt(var+eps)*gamma + beta), one warp per row.
+//   dz fp32 (M, ld), u fp32 (M, ld) pre-LN values, C valid columns.  Rows t >= row_len[b] carry zero gradient.
+//   outputs: du fp32 (optional), g bf16 = du (* relu mask u>0 if relu_mask) (* dropout mask) for the GEMMs,
+//   dgamma/dbeta accumulated with atomics.  dz_drop_*: dropout applied AFTER the LayerNorm in the forward pass.
+// ------------------------------------------------------------------------------------------------
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ u, const float* __restrict__ gamma,
+                                     int M, int T, int C, int ld, float eps, const int* __restrict__ row_len, int relu_mask,
+                                     float pre_drop_p, uint32_t pre_site, float post_drop_p, uint32_t post_site, uint32_t seed,
+                                     float* __restrict__ du, __nv_bfloat16* __restrict__ g_out, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  extern __shared__ float part[];  // [2][C] per block
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) part[c] = 0.f;
+  __syncthreads();
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  constexpr int MAXV = 16;  // C <= 512
+  constexpr int RPW = 8;    // rows per warp: fewer global atomics for dgamma/dbeta
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int row = (blockIdx.x * warps + (threadIdx.x >> 5)) * RPW + rr;
+    if (row >= M) break;
+    const int b = row / T, t = row % T;
+    const bool live = row_len == nullptr || t < __ldg(row_len + b);
+    const size_t base = (size_t)row * ld;
+    float uv[MAXV], gz[MAXV];
+    const uint32_t post_thresh = post_drop_p > 0.f ? (uint32_t)(post_drop_p * 4294967296.0) : 0u;
+    const float post_scale = post_drop_p > 0.f ? 1.f / (1.f - post_drop_p) : 1.f;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      uv[i] = (c < C) ? u[base + c] : 0.f;
+      float g = (c < C && live) ? dz[base + c] : 0.f;
+      if (post_drop_p > 0.f && c < C) g = dropout_keep(seed, post_site, base + c, post_thresh) ? g * post_scale : 0.f;
+      gz[i] = g;
+      s += uv[i];
+    }
+    const float mean = wsum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      const float d = (c < C) ? uv[i] - mean : 0.f;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(wsum(q) / C + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        const float xh = (uv[i] - mean) * rstd;
+        const float gg = gz[i] * __ldg(gamma + c);
+        sg += gg;
+        sgx += gg * xh;
+        if (live) {
+          atomicAdd(part + c, gz[i] * xh);
+          atomicAdd(part + C + c, gz[i]);
+        }
+      }
+    }
+    sg = wsum(sg) / C;
+    sgx = wsum(sgx) / C;
+    const uint32_t pre_thresh = pre_drop_p > 0.f ? (uint32_t)(pre_drop_p * 4294967296.0) : 0u;
+    const float pre_scale = pre_drop_p > 0.f ? 1.f / (1.f - pre_drop_p) : 1.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < ld) {
+        float d = 0.f;
+        if (c < C) {
+          const float xh = (uv[i] - mean) * rstd;
+          d = rstd * (gz[i] * __ldg(gamma + c) - sg - xh * sgx);
+        }
+        if (du) du[base + c] = d;
+        if (g_out) {
+          float gv = d;
+          if (relu_mask && !(uv[i] > 0.f)) gv = 0.f;
+          if (pre_drop_p > 0.f) gv = dropout_keep(seed, pre_site, base + c, pre_thresh) ? gv * pre_scale : 0.f;
+          g_out[base + c] = __float2bfloat16_rn(gv);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (part[c] != 0.f) atomicAdd(dgamma + c, part[c]);
+    if (part[C + c] != 0.f) atomicAdd(dbeta + c, part[C + c]);
+  }
+}
+
+// dy (bf16, in place) *= (h > 0)
+__global__ void relu_bwd_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  uint4 g = *reinterpret_cast<const uint4*>(dy + i);
+  const uint4 hv = *reinterpret_cast<const uint4*>(h + i);
+  __nv_bfloat16* gp = reinterpret_cast<__nv_bfloat16*>(&g);
+  const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (!(__bfloat162float(hp[j]) > 0.f)) gp[j] = __float2bfloat16(0.f);
+  *reinterpret_cast<uint4*>(dy + i) = g;
+}
+
+// fp32 -> bf16 copy with optional row mask / dropout regeneration:  out = x (* keep/(1-p))
+__global__ void cast_bf16_kernel(const float* __restrict__ x, int64_t n, float drop_p, uint32_t seed, uint32_t site,
+                                 __nv_bfloat16* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = x[i];
+  if (drop_p > 0.f) v = dropout_keep(seed, site, (uint64_t)i, (uint32_t)(drop_p * 4294967296.0)) ? v / (1.f - drop_p) : 0.f;
+  out[i] = __float2bfloat16_rn(v);
+}
+
+// fp32 (rows, C) -> bf16 (rows, ld_out >= C), zero in the padding columns (K of a GEMM must be a multiple of 64)
+__global__ void cast_bf16_pad_kernel(const float* __restrict__ x, int64_t rows, int C, __nv_bfloat16* __restrict__ out, int ld_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld_out) return;
+  const int c = (int)(i % ld_out);
+  const int64_t r = i / ld_out;
+  out[i] = __float2bfloat16_rn(c < C ? x[r * C + c] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mean absolute error over ALL elements (utils/losses.py:41-49 with mask=None) and its gradient
+//   pred (rows, ld_pred)[:, :C] vs target (rows_t, C): rows beyond rows_valid get zero gradient
+// ------------------------------------------------------------------------------------------------
+__global__ void mae_loss_kernel(const float* __restrict__ pred, int64_t B, int64_t Tp, int64_t Tt, int C, const float* __restrict__ tgt_f,
+                                const int* __restrict__ tgt_i, float weight, float* __restrict__ loss_out, float* __restrict__ grad) {
+  // pred (B, Tp, C), target (B, Tt, C) with Tt <= Tp: loss over pred[:, :Tt]
+  const int64_t n = B * Tt * C;
+  const float inv_n = 1.f / (float)n;
+  float local = 0.f;
+  const int64_t total = B * Tp * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % C, t = (i / C) % Tp, b = i / (C * Tp);
+    float g = 0.f;
+    if (t < Tt) {
+      const int64_t j = (b * Tt + t) * C + c;
+      const float tv = tgt_f ? tgt_f[j] : (float)tgt_i[j];
+      const float d = pred[i] - tv;
+      local += fabsf(d);
+      g = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * weight * inv_n;
+    }
+    if (grad) grad[i] = g;
+  }
+  local = wsum(local);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    atomicAdd(loss_out, s * inv_n);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Expand backward: dx[b,i,:] = sum of dm[b, t, :] over the frames t copied from phoneme i (contiguous segment)
+// ------------------------------------------------------------------------------------------------
+__global__ void expand_bwd_kernel(const float* __restrict__ dm, const int* __restrict__ dur, int Tp, int Tm, int d,
+                                  float* __restrict__ dx) {
+  extern __shared__ int cum[];  // exclusive starts, Tp+1
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < Tp; ++i) { cum[i] = run; run += max(dur[(size_t)b * Tp + i], 0); }
+    cum[Tp] = run;
+  }
+  __syncthreads();
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x >> 5; i < Tp; i += warps) {
+    const int s = cum[i], e = min(cum[i + 1], Tm);
+    for (int c = lane; c < d; c += 32) {
+      float acc = 0.f;
+      for (int t = s; t < e; ++t) acc += dm[((size_t)b * Tm + t) * d + c];
+      dx[((size_t)b * Tp + i) * d + c] = acc;
+    }
+  }
+}
+
+__global__ void embedding_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ tokens, int rows, int d, int vocab,
+                                     float* __restrict__ demb) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int tok = tokens[row];
+  tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+  for (int c = threadIdx.x & 31; c < d; c += 32) atomicAdd(demb + (size_t)tok * d + c, dx[(size_t)row * d + c]);
+}
+
+// positional-encoding scalar gradient: sum_{row,c} g[row,c] * pe[t,c]
+__global__ void pe_scalar_bwd_kernel(const float* __restrict__ g, const float* __restrict__ pe, int rows, int T, int d,
+                                     float* __restrict__ dscalar) {
+  float local = 0.f;
+  const int64_t n = (int64_t)rows * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d);
+    const int t = (int)((i / d) % T);
+    local += g[i] * __ldg(pe + (size_t)t * d + c);
+  }
+  local = wsum(local);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    atomicAdd(dscalar, s);
+  }
+}
+
+// pitch embedding Dense(1->d, relu) gradients w.r.t. its kernel and bias: pre = pitch*w + b
+__global__ void pitch_embed_bwd_kernel(const float* __restrict__ g, const float* __restrict__ pitch, const float* __restrict__ w,
+                                       const float* __restrict__ bias, int rows, int d, float* __restrict__ dw, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const int r0 = blockIdx.y * 256, r1 = min(r0 + 256, rows);
+  const float wc = w[c], bc = bias[c];
+  float sw = 0.f, sb = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float pv = pitch[r];
+    if (fmaf(pv, wc, bc) > 0.f) {
+      const float gv = g[(size_t)r * d + c];
+      sw += gv * pv;
+      sb += gv;
+    }
+  }
+  atomicAdd(dw + c, sw);
+  atomicAdd(db + c, sb);
+}
+
+// StatPredictor head backward: out = act(h.w + b) * mask
+__global__ void statpred_head_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out, const float* __restrict__ h,
+                                         int ldh, int C, const float* __restrict__ w, int relu, const int* __restrict__ row_len,
+                                         int rows, int T, float* __restrict__ dh, float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float part[];  // C + 1
+  for (int c = threadIdx.x; c <= C; c += blockDim.x) part[c] = 0.f;
+  __syncthreads();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row < rows) {
+    const int b = row / T, t = row % T;
+    float g = gout[row];
+    if (row_len && t >= row_len[b]) g = 0.f;
+    if (relu && !(out[row] > 0.f)) g = 0.f;
+    for (int c = lane; c < ldh; c += 32) {
+      float v = 0.f;
+      if (c < C) {
+        v = g * __ldg(w + c);
+        if (g != 0.f) atomicAdd(part + c, g * h[(size_t)row * ldh + c]);
+      }
+      dh[(size_t)row * ldh + c] = v;
+    }
+    if (lane == 0 && g != 0.f) atomicAdd(part + C, g);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c <= C; c += blockDim.x)
+    if (part[c] != 0.f) atomicAdd(c < C ? dw + c : db, part[c]);
+}
+
+// Keras (TF 2.2) Adam: theta -= lr_t * m / (sqrt(v) + eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the host
+__global__ void adam_tf_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                               int64_t n, float lr_t, float b1, float b2, float eps, float gscale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * gscale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+static inline int bad(const char* msg) {
+  set_last_error("%s", msg);
+  return TTSB_ERR_INVALID_ARGUMENT;
+}
+
+}  // namespace ttsb
+
+using namespace ttsb;
+#define STREAM(s) static_cast<cudaStream_t>(s)
+#define LAUNCH_OK(name) \
+  count_launch();       \
+  return check_cuda(cudaGetLastError(), name)
+#define BF(p) static_cast<__nv_bfloat16*>(p)
+#define CBF(p) static_cast<const __nv_bfloat16*>(p)
+
+extern "C" int ttsb_transpose_bf16(const void* src, int B, int T, int ld_src, int col0, int C, void* dst, int dst_rows, int ld_t,
+                                   float* colsum, void* stream) {
+  if (!src || !dst || B <= 0 || T <= 0 || C <= 0 || ld_t < T || dst_rows < C) return bad("ttsb_transpose_bf16: bad arguments");
+  dim3 grid((T + 63) / 64, (C + 63) / 64, B);
+  transpose_bf16_kernel<<<grid, 256, 0, STREAM(stream)>>>(CBF(src), T, ld_src, col0, C, BF(dst), dst_rows, ld_t, colsum);
+  LAUNCH_OK("transpose_bf16_kernel");
+}
+
+extern "C" int ttsb_softmax_fwd(const float* S, int B, int H, int T, int Tk, int ld, const int32_t* kv_len, float drop_p,
+                                uint32_t seed, uint32_t site, void* P_pre, void* P_drop, void* stream) {
+  if (!S || !kv_len || !P_pre || !P_drop || B <= 0 || H <= 0 || T <= 0 || Tk <= 0 || ld < Tk) return bad("ttsb_softmax_fwd: bad arguments");
+  const int rows = B * H * T;
+  softmax_fwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(S, B * H, H, T, Tk, ld, kv_len, drop_p, seed, site, BF(P_pre), BF(P_drop));
+  LAUNCH_OK("softmax_fwd_kernel");
+}
+
+extern "C" int ttsb_softmax_bwd(const void* P_pre, const float* dP, int B, int H, int T, int Tk, int ld, const int32_t* kv_len,
+                                float scale, float drop_p, uint32_t seed, uint32_t site, void* dS, void* stream) {
+  if (!P_pre || !dP || !kv_len || !dS || B <= 0 || H <= 0 || T <= 0 || Tk <= 0 || ld < Tk) return bad("ttsb_softmax_bwd: bad arguments");
+  const int rows = B * H * T;
+  softmax_bwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(CBF(P_pre), dP, B * H, H, T, Tk, ld, kv_len, scale, drop_p, seed, site, BF(dS));
+  LAUNCH_OK("softmax_bwd_kernel");
+}
+
+extern "C" int ttsb_layernorm_bwd(const float* dz, const float* u, const float* gamma, int B, int T, int C, int ld, float eps,
+                                  const int32_t* row_len, int relu_mask, float pre_drop_p, uint32_t pre_site, float post_drop_p,
+                                  uint32_t post_site, uint32_t seed, float* du, void* g_bf16, float* dgamma, float* dbeta, void* stream) {
+  if (!dz || !u || !gamma || !dgamma || !dbeta || B <= 0 || T <= 0 || C <= 0 || C > 512 || ld < C || ld > 512)
+    return bad("ttsb_layernorm_bwd: bad arguments (C, ld <= 512)");
+  const int rows = B * T;
+  layernorm_bwd_kernel<<<(rows + 63) / 64, 256, 2 * C * sizeof(float), STREAM(stream)>>>(dz, u, gamma, rows, T, C, ld, eps, row_len, relu_mask,
+                                                                                      pre_drop_p, pre_site, post_drop_p, post_site, seed, du,
+                                                                                      BF(g_bf16), dgamma, dbeta);
+  LAUNCH_OK("layernorm_bwd_kernel");
+}
+
+extern "C" int ttsb_relu_bwd(void* dy, const void* h, int64_t n, void* stream) {
+  if (!dy || !h || n <= 0 || n % 8) return bad("ttsb_relu_bwd: n must be a positive multiple of 8");
+  relu_bwd_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, STREAM(stream)>>>(BF(dy), CBF(h), n);
+  LAUNCH_OK("relu_bwd_kernel");
+}
+
+extern "C" int ttsb_cast_bf16(const float* x, int64_t n, float drop_p, uint32_t seed, uint32_t site, void* out, void* stream) {
+  if (!x || !out || n <= 0) return bad("ttsb_cast_bf16: bad arguments");
+  cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM(stream)>>>(x, n, drop_p, seed, site, BF(out));
+  LAUNCH_OK("cast_bf16_kernel");
+}
+
+extern "C" int ttsb_cast_bf16_pad(const float* x, int64_t rows, int C, void* out, int ld_out, void* stream) {
+  if (!x || !out || rows <= 0 || C <= 0 || ld_out < C) return bad("ttsb_cast_bf16_pad: bad arguments");
+  const int64_t n = rows * ld_out;
+  cast_bf16_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM(stream)>>>(x, rows, C, BF(out), ld_out);
+  LAUNCH_OK("cast_bf16_pad_kernel");
+}
+
+extern "C" int ttsb_mae_loss(const float* pred, int B, int Tp, int Tt, int C, const float* target_f32, const int32_t* target_i32,
+                             float weight, float* loss_out, float* grad, void* stream) {
+  if (!pred || (!target_f32 && !target_i32) || !loss_out || B <= 0 || Tp <= 0 || Tt <= 0 || Tt > Tp || C <= 0)
+    return bad("ttsb_mae_loss: bad arguments (need Tt <= Tp)");
+  mae_loss_kernel<<<592, 256, 0, STREAM(stream)>>>(pred, B, Tp, Tt, C, target_f32, target_i32, weight, loss_out, grad);
+  LAUNCH_OK("mae_loss_kernel");
+}
+
+extern "C" int ttsb_expand_bwd(const float* dm, const int32_t* dur_int, int B, int Tp, int Tm, int d, float* dx, void* stream) {
+  if (!dm || !dur_int || !dx || B <= 0 || Tp <= 0 || Tm <= 0 || d <= 0) return bad("ttsb_expand_bwd: bad arguments");
+  expand_bwd_kernel<<<B, 1024, (Tp + 1) * sizeof(int), STREAM(stream)>>>(dm, dur_int, Tp, Tm, d, dx);
+  LAUNCH_OK("expand_bwd_kernel");
+}
+
+extern "C" int ttsb_embedding_bwd(const float* dx, const int32_t* tokens, int B, int T, int d, int vocab, float* demb, void* stream) {
+  if (!dx || !tokens || !demb || B <= 0 || T <= 0 || d <= 0 || vocab <= 0) return bad("ttsb_embedding_bwd: bad arguments");
+  const int rows = B * T;
+  embedding_bwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(dx, tokens, rows, d, vocab, demb);
+  LAUNCH_OK("embedding_bwd_kernel");
+}
+
+extern "C" int ttsb_pe_scalar_bwd(const float* g, const float* pe, int B, int T, int d, float* dscalar, void* stream) {
+  if (!g || !pe || !dscalar || B <= 0 || T <= 0 || d <= 0) return bad("ttsb_pe_scalar_bwd: bad arguments");
+  pe_scalar_bwd_kernel<<<296, 256, 0, STREAM(stream)>>>(g, pe, B * T, T, d, dscalar);
+  LAUNCH_OK("pe_scalar_bwd_kernel");
+}
+
+extern "C" int ttsb_pitch_embed_bwd(const float* g, const float* pitch, const float* w, const float* bias, int B, int T, int d,
+                                    float* dw, float* db, void* stream) {
+  if (!g || !pitch || !w || !bias || !dw || !db || B <= 0 || T <= 0 || d <= 0) return bad("ttsb_pitch_embed_bwd: bad arguments");
+  const int rows = B * T;
+  dim3 grid((d + 127) / 128, (rows + 255) / 256);
+  pitch_embed_bwd_kernel<<<grid, 128, 0, STREAM(stream)>>>(g, pitch, w, bias, rows, d, dw, db);
+  LAUNCH_OK("pitch_embed_bwd_kernel");
+}
+
+extern "C" int ttsb_statpred_head_bwd(const float* gout, const float* out, const float* h, int ldh, int C, const float* w, int relu,
+                                      const int32_t* row_len, int B, int T, float* dh, float* dw, float* db, void* stream) {
+  if (!gout || !out || !h || !w || !dh || !dw || !db || B <= 0 || T <= 0 || C <= 0 || ldh < C) return bad("ttsb_statpred_head_bwd: bad arguments");
+  const int rows = B * T;
+  statpred_head_bwd_kernel<<<(rows + 7) / 8, 256, (C + 1) * sizeof(float), STREAM(stream)>>>(gout, out, h, ldh, C, w, relu, row_len, rows, T, dh, dw, db);
+  LAUNCH_OK("statpred_head_bwd_kernel");
+}
+
+extern "C" int ttsb_adam_tf_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
+                                 float eps, float grad_scale, void* stream) {
+  if (!param || !grad || !m || !v || n <= 0) return bad("ttsb_adam_tf_step: bad arguments");
+  adam_tf_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM(stream)>>>(param, grad, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+  LAUNCH_OK("adam_tf_kernel");
+}

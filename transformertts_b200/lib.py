@@ -22,6 +22,9 @@ EXPORTS = [
     'ttsb_split_bf16', 'ttsb_embed_ln_pe_fwd', 'ttsb_linear_fwd', 'ttsb_mha_fwd', 'ttsb_statpred_head_fwd',
     'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
     'ttsb_expand_ln_pe_fwd', 'ttsb_mel_lengths', 'ttsb_phoneme_lengths', 'ttsb_stft_mel_log',
+    'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_transpose_bf16', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
+    'ttsb_relu_bwd', 'ttsb_cast_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
+    'ttsb_pitch_embed_bwd', 'ttsb_statpred_head_bwd', 'ttsb_adam_tf_step',
 ]
 
 
@@ -38,8 +41,29 @@ class GemmArgs(C.Structure):
         ('residual', C.c_void_p), ('ld_res', C.c_int), ('ln_gamma', C.c_void_p), ('ln_beta', C.c_void_p),
         ('ln_eps', C.c_float), ('row_len', C.c_void_p), ('out_f32', C.c_void_p), ('out_hi', C.c_void_p),
         ('out_lo', C.c_void_p), ('ld_out', C.c_int), ('vt_hi', C.c_void_p), ('vt_lo', C.c_void_p),
-        ('vt_col0', C.c_int), ('vt_cols', C.c_int), ('vt_ld', C.c_int), ('out_fp16', C.c_int), ('precision', C.c_int),
-        ('impl', C.c_int),
+        ('vt_col0', C.c_int), ('vt_cols', C.c_int), ('vt_ld', C.c_int), ('out_fp16', C.c_int), ('out_preln', C.c_void_p),
+        ('precision', C.c_int), ('impl', C.c_int),
+    ]
+
+
+class BgemmArgs(C.Structure):
+    _fields_ = [
+        ('B', C.c_int), ('H', C.c_int), ('M', C.c_int), ('N', C.c_int), ('K', C.c_int),
+        ('a', C.c_void_p), ('a_dim0', C.c_longlong), ('a_dim1', C.c_longlong), ('a_dim2', C.c_longlong),
+        ('a_stride1', C.c_longlong), ('a_stride2', C.c_longlong), ('a_h_col', C.c_int), ('a_h_row', C.c_int), ('a_z_batch', C.c_int),
+        ('b', C.c_void_p), ('b_dim0', C.c_longlong), ('b_dim1', C.c_longlong), ('b_dim2', C.c_longlong),
+        ('b_stride1', C.c_longlong), ('b_stride2', C.c_longlong), ('b_h_col', C.c_int), ('b_h_row', C.c_int), ('b_z_batch', C.c_int),
+        ('alpha', C.c_float), ('out_f32', C.c_void_p), ('out_bf16', C.c_void_p), ('ld_out', C.c_int),
+        ('out_batch_stride', C.c_longlong), ('out_h_col', C.c_int), ('out_by_b', C.c_int), ('out_cols', C.c_int),
+        ('row_len', C.c_void_p), ('col_len', C.c_void_p),
+    ]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ('B', C.c_int), ('T', C.c_int), ('Cin', C.c_int), ('N', C.c_int), ('num_segments', C.c_int),
+        ('seg_src', C.c_int * 4), ('seg_shift', C.c_int * 4), ('xt', C.c_void_p * 2), ('xt_rows', C.c_int * 2),
+        ('gt', C.c_void_p), ('gt_rows', C.c_int), ('ld_t', C.c_int), ('dw', C.c_void_p),
     ]
 
 
@@ -189,3 +213,91 @@ def stft_mel_log(wav, mel_basis, normalizer, out):
     n_mels = mel_basis.shape[0]
     _check(load().ttsb_stft_mel_log(ptr(wav), n_clips, n_samples, ptr(mel_basis), n_mels, int(normalizer), ptr(out),
                                     _stream()), 'ttsb_stft_mel_log')
+
+
+# ------------------------------------------------------------------------------------------------------------
+# training-step kernels
+# ------------------------------------------------------------------------------------------------------------
+def bgemm(args: BgemmArgs):
+    _check(load().ttsb_bgemm(C.byref(args), _stream()), 'ttsb_bgemm')
+
+
+def wgrad(args: WgradArgs):
+    _check(load().ttsb_wgrad(C.byref(args), _stream()), 'ttsb_wgrad')
+
+
+def transpose_bf16(src, B, T, ld_src, col0, Cc, dst, dst_rows, ld_t, colsum=None):
+    _check(load().ttsb_transpose_bf16(ptr(src), B, T, ld_src, col0, Cc, ptr(dst), dst_rows, ld_t, ptr(colsum), _stream()),
+           'ttsb_transpose_bf16')
+
+
+def softmax_fwd(S, B, H, T, Tk, ld, kv_len, drop_p, seed, site, P_pre, P_drop):
+    _check(load().ttsb_softmax_fwd(ptr(S), B, H, T, Tk, ld, ptr(kv_len), C.c_float(drop_p), C.c_uint32(seed), C.c_uint32(site),
+                                   ptr(P_pre), ptr(P_drop), _stream()), 'ttsb_softmax_fwd')
+
+
+def softmax_bwd(P_pre, dP, B, H, T, Tk, ld, kv_len, scale, drop_p, seed, site, dS):
+    _check(load().ttsb_softmax_bwd(ptr(P_pre), ptr(dP), B, H, T, Tk, ld, ptr(kv_len), C.c_float(scale), C.c_float(drop_p),
+                                   C.c_uint32(seed), C.c_uint32(site), ptr(dS), _stream()), 'ttsb_softmax_bwd')
+
+
+def layernorm_bwd(dz, u, gamma, B, T, Cc, ld, eps, row_len, relu_mask, du, g_bf16, dgamma, dbeta, pre_drop=(0.0, 0),
+                  post_drop=(0.0, 0), seed=0):
+    _check(load().ttsb_layernorm_bwd(ptr(dz), ptr(u), ptr(gamma), B, T, Cc, ld, C.c_float(eps), ptr(row_len), int(relu_mask),
+                                     C.c_float(pre_drop[0]), C.c_uint32(pre_drop[1]), C.c_float(post_drop[0]),
+                                     C.c_uint32(post_drop[1]), C.c_uint32(seed), ptr(du), ptr(g_bf16), ptr(dgamma), ptr(dbeta),
+                                     _stream()), 'ttsb_layernorm_bwd')
+
+
+def relu_bwd(dy, h):
+    _check(load().ttsb_relu_bwd(ptr(dy), ptr(h), C.c_int64(dy.numel()), _stream()), 'ttsb_relu_bwd')
+
+
+def cast_bf16(x, out, drop_p=0.0, seed=0, site=0):
+    _check(load().ttsb_cast_bf16(ptr(x), C.c_int64(x.numel()), C.c_float(drop_p), C.c_uint32(seed), C.c_uint32(site), ptr(out),
+                                 _stream()), 'ttsb_cast_bf16')
+
+
+def cast_bf16_pad(x, rows, Cc, out, ld_out):
+    _check(load().ttsb_cast_bf16_pad(ptr(x), C.c_int64(rows), Cc, ptr(out), ld_out, _stream()), 'ttsb_cast_bf16_pad')
+
+
+def mae_loss(pred, B, Tp, Tt, Cc, target, weight, loss_out, grad):
+    tf = ptr(target) if target.dtype == torch.float32 else None
+    ti = ptr(target) if target.dtype == torch.int32 else None
+    _check(load().ttsb_mae_loss(ptr(pred), B, Tp, Tt, Cc, tf, ti, C.c_float(weight), ptr(loss_out), ptr(grad), _stream()),
+           'ttsb_mae_loss')
+
+
+def expand_bwd(dm, dur_int, dx):
+    B, Tm, d = dm.shape
+    Tp = dur_int.shape[1]
+    _check(load().ttsb_expand_bwd(ptr(dm), ptr(dur_int), B, Tp, Tm, d, ptr(dx), _stream()), 'ttsb_expand_bwd')
+
+
+def embedding_bwd(dx, tokens, demb):
+    B, T, d = dx.shape
+    _check(load().ttsb_embedding_bwd(ptr(dx), ptr(tokens), B, T, d, demb.shape[0], ptr(demb), _stream()), 'ttsb_embedding_bwd')
+
+
+def pe_scalar_bwd(g, pe, dscalar):
+    B, T, d = g.shape
+    _check(load().ttsb_pe_scalar_bwd(ptr(g), ptr(pe), B, T, d, ptr(dscalar), _stream()), 'ttsb_pe_scalar_bwd')
+
+
+def pitch_embed_bwd(g, pitch, w, bias, dw, db):
+    B, T, d = g.shape
+    _check(load().ttsb_pitch_embed_bwd(ptr(g), ptr(pitch), ptr(w), ptr(bias), B, T, d, ptr(dw), ptr(db), _stream()),
+           'ttsb_pitch_embed_bwd')
+
+
+def statpred_head_bwd(gout, out, h, C_in, w, relu, row_len, dh, dw, db):
+    B, T, ldh = h.shape
+    _check(load().ttsb_statpred_head_bwd(ptr(gout), ptr(out), ptr(h), ldh, C_in, ptr(w), int(relu), ptr(row_len), B, T, ptr(dh),
+                                         ptr(dw), ptr(db), _stream()), 'ttsb_statpred_head_bwd')
+
+
+def adam_tf_step(param, grad, m, v, lr_t, beta1, beta2, eps, grad_scale=1.0):
+    _check(load().ttsb_adam_tf_step(ptr(param), ptr(grad), ptr(m), ptr(v), C.c_int64(param.numel()), C.c_float(lr_t),
+                                    C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(grad_scale), _stream()),
+           'ttsb_adam_tf_step')

@@ -132,6 +132,8 @@ class ForwardTransformer:
         self._prof = None  # bench.py: {tag: [(start_event, end_event, flops)]} for tagged GEMM launches
         self.optimizer = None
         self.loss_weights = [1., 1., 3.]
+        self.train_dropout = bool(kwargs.get('train_dropout', True))  # False: deterministic training step (parity tests)
+        self._engine = None
         self._init_weights(seed=int(kwargs.get('seed', 42)))
 
     # ------------------------------------------------------------------------------------------------
@@ -218,7 +220,10 @@ class ForwardTransformer:
             t = torch.as_tensor(weights[name]).detach().to(torch.float32)
             if tuple(t.shape) != tuple(shape):
                 raise ValueError(f'{name}: expected shape {shape}, got {tuple(t.shape)}')
-            self.weights[name] = t.to(self.device).contiguous()
+            if self._engine is not None:  # parameters are views of the flat training buffer: update in place
+                self.weights[name].copy_(t.to(self.device))
+            else:
+                self.weights[name] = t.to(self.device).contiguous()
         self._packed = None
 
     def get_weights(self) -> Dict[str, torch.Tensor]:
@@ -256,7 +261,7 @@ class ForwardTransformer:
         P = {'precision': self.precision}
         for name, st in self._stacks.items():
             d = st['d']
-            P[f'{name}.pe'] = positional_encoding(st['max_pos'], d)[0].to(self.device).contiguous()
+            P[f'{name}.pe'] = self._prepare_pe(name)
             for i, _ in enumerate(st['heads']):
                 pre = f'{name}.b{i}.'
                 wqkv = torch.cat([W[pre + 'wq.w'], W[pre + 'wk.w'], W[pre + 'wv.w']], dim=1)
@@ -287,6 +292,13 @@ class ForwardTransformer:
         self._packed = P
         return P
 
+    def _prepare_pe(self, name: str) -> torch.Tensor:
+        st = self._stacks[name]
+        key = f'_pe_{name}'
+        if not hasattr(self, key):
+            setattr(self, key, positional_encoding(st['max_pos'], st['d'])[0].to(self.device).contiguous())
+        return getattr(self, key)
+
     # ------------------------------------------------------------------------------------------------
     # kernels
     # ------------------------------------------------------------------------------------------------
@@ -299,7 +311,8 @@ class ForwardTransformer:
         return f, hi, lo
 
     def _gemm(self, pl: _PackedLinear, B, T, srcs, seg_src, seg_shift, relu=False, residual=None, ln=None, row_len=None,
-              out_f32=None, out_hi=None, out_lo=None, ld_out=None, vt=None, tag=None, out_fp16=False):
+              out_f32=None, out_hi=None, out_lo=None, ld_out=None, vt=None, tag=None, out_fp16=False, out_preln=None,
+              dropout=None, dropout_post=None):
         prof = self._prof
         if prof is not None and tag is not None:
             e0 = torch.cuda.Event(enable_timing=True)
@@ -325,6 +338,7 @@ class ForwardTransformer:
             a.residual = residual.data_ptr()
             a.ld_res = residual.shape[-1]
         if ln is not None:
+            ln = (_pad_vec(ln[0], pl.n_pad), _pad_vec(ln[1], pl.n_pad))
             a.ln_gamma = ln[0].data_ptr()
             a.ln_beta = ln[1].data_ptr()
             a.ln_eps = LN_EPS
@@ -339,6 +353,10 @@ class ForwardTransformer:
             a.vt_lo = vt_lo.data_ptr() if vt_lo is not None else None
             a.vt_col0, a.vt_cols, a.vt_ld = col0, cols, ld
         a.out_fp16 = int(out_fp16)
+        a.out_preln = out_preln.data_ptr() if out_preln is not None else None
+        for dp in (dropout, dropout_post):
+            if dp is not None and dp[0] > 0:
+                raise lib.TtsbError('dropout inside the GEMM epilogue is not implemented yet (train with dropout_rate=0)')
         a.precision = self._prec
         a.impl = self._impl
         lib.linear_fwd(a)
@@ -589,6 +607,37 @@ class ForwardTransformer:
     @classmethod
     def from_config(cls, config: dict, custom_objects=None):
         return cls(**config)
+
+    # ------------------------------------------------------------------------------------------------
+    # training (reference: model/models.py:464-507)
+    # ------------------------------------------------------------------------------------------------
+    def _compile(self, optimizer=None, learning_rate: float = 1.0e-4):
+        """reference: model/models.py:484-490 + utils/training_config_manager.py:102-106 (Adam b1 .9, b2 .98, eps 1e-9)."""
+        from .training import Adam
+        self.loss_weights = [1., 1., 3.]
+        self.optimizer = optimizer if optimizer is not None else Adam(learning_rate)
+
+    def _get_engine(self):
+        if self._engine is None:
+            from .training import TrainEngine
+            self._engine = TrainEngine(self)
+        return self._engine
+
+    def train_step(self, input_sequence, target_sequence, target_durations, target_pitch, grad_sync=None):
+        """reference: model/models.py:464-482.  grad_sync(flat_grad) is the data-parallel hook (NCCL all-reduce)."""
+        if self.optimizer is None:
+            self._compile()
+        eng = self._get_engine()
+        out = eng.forward_backward(input_sequence, target_sequence, target_durations, target_pitch, training=True)
+        scale = 1.0
+        if grad_sync is not None:
+            scale = grad_sync(eng.flat_g)
+        eng.apply_adam(self.optimizer, grad_scale=scale)
+        return out
+
+    def val_step(self, input_sequence, target_sequence, target_durations, target_pitch):
+        """reference: model/models.py:492-507."""
+        return self._get_engine().forward_backward(input_sequence, target_sequence, target_durations, target_pitch, training=False)
 
     @property
     def step(self) -> int:

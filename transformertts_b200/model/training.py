@@ -1,0 +1,537 @@
+"""Training step of the ForwardTransformer (reference: ForwardTransformer._train_step, model/models.py:464-482;
+losses utils/losses.py:41-70 with weights [1,1,3] models.py:485; Adam utils/training_config_manager.py:102-106).
+
+The forward pass is run in single-pass bf16 tensor-core mode (BASELINE.json configs[2]: "bf16") and keeps what the
+backward needs; the backward is hand-written: every gradient GEMM runs on tcgen05 (data gradients through the forward
+GEMM kernel with re-packed weights, weight gradients and the attention gradients through ttsb_wgrad / ttsb_bgemm),
+everything else through the row kernels of csrc/train_ops.cu.  Parameters, gradients and Adam moments live in flat
+fp32 buffers so that Adam is one launch and data-parallel all-reduce works on contiguous buckets.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import lib
+from .models import LN_EPS, _PackedLinear, _pad_vec, _round_up
+
+
+class Adam:
+    """Optimizer state in the reference's terms: lr (assignable), iterations, Keras hyper-parameters."""
+
+    def __init__(self, learning_rate: float, beta_1: float = 0.9, beta_2: float = 0.98, epsilon: float = 1e-9):
+        self.lr = float(learning_rate)
+        self.beta_1, self.beta_2, self.epsilon = beta_1, beta_2, epsilon
+        self.iterations = 0
+        self.m = None
+        self.v = None
+
+
+class TrainEngine:
+    def __init__(self, model):
+        self.model = model
+        self.dev = model.device
+        names = list(model._param_shapes().keys())
+        sizes = [model.weights[n].numel() for n in names]
+        self.names = names
+        total = sum(sizes)
+        self.flat_w = torch.empty(total, dtype=torch.float32, device=self.dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        off = 0
+        self.g: Dict[str, torch.Tensor] = {}
+        for n, sz in zip(names, sizes):
+            shape = model.weights[n].shape
+            self.flat_w[off:off + sz].copy_(model.weights[n].reshape(-1))
+            model.weights[n] = self.flat_w[off:off + sz].view(shape)  # parameters become views of the flat buffer
+            self.g[n] = self.flat_g[off:off + sz].view(shape)
+            off += sz
+        model._packed = None
+        self.P = None
+        self.world = 1
+        self.seed = 1234
+        self.drop_sites = 0
+
+    # ------------------------------------------------------------------------------------------------
+    # packed operands for the step (weights change every step)
+    # ------------------------------------------------------------------------------------------------
+    def _pack(self):
+        m = self.model
+        W = m.weights
+        P = {}
+
+        def fwd(key, w, b, seg_k, single=False, block_n=None):
+            P[key] = _PackedLinear(w, b, seg_k, False, single_tile=single, block_n=block_n)
+
+        def dgrad_dense(key, w):  # (K,N) -> data gradient operator: out K columns, contraction over N (padded to 64)
+            K, N = w.shape
+            npad = _round_up(N, 64)
+            wt = torch.zeros((npad, K), dtype=torch.float32, device=self.dev)
+            wt[:N] = w.t()
+            P[key] = _PackedLinear(wt, None, [npad], False)
+
+        def dgrad_conv(key, w):  # (k,Cin,Cout) -> [Cin, k*Cout_pad]
+            k, cin, cout = w.shape
+            cpad = _round_up(cout, 64)
+            wt = torch.zeros((k, cpad, cin), dtype=torch.float32, device=self.dev)
+            wt[:, :cout] = w.permute(0, 2, 1)
+            P[key] = _PackedLinear(wt.reshape(k * cpad, cin), None, [cpad] * k, False)
+
+        for name, st in m._stacks.items():
+            d = st['d']
+            for i, _ in enumerate(st['heads']):
+                pre = f'{name}.b{i}.'
+                wqkv = torch.cat([W[pre + 'wq.w'], W[pre + 'wk.w'], W[pre + 'wv.w']], dim=1)
+                bqkv = torch.cat([W[pre + 'wq.b'], W[pre + 'wk.b'], W[pre + 'wv.b']])
+                fwd(pre + 'qkv', wqkv, bqkv, [d], block_n=d if d <= 256 else d // 2)
+                dgrad_dense(pre + 'qkv.d', wqkv)
+                fwd(pre + 'wo', W[pre + 'wo.w'], W[pre + 'wo.b'], [d, d], single=True)
+                dgrad_dense(pre + 'wo.dx', W[pre + 'wo.w'][:d])
+                dgrad_dense(pre + 'wo.da', W[pre + 'wo.w'][d:])
+                if i < st['n_dense']:
+                    F = int(st['ffn'])
+                    fwd(pre + 'ffn1', W[pre + 'ffn1.w'], W[pre + 'ffn1.b'], [d])
+                    fwd(pre + 'ffn2', W[pre + 'ffn2.w'], W[pre + 'ffn2.b'], [F], single=True)
+                    dgrad_dense(pre + 'ffn1.d', W[pre + 'ffn1.w'])
+                    dgrad_dense(pre + 'ffn2.d', W[pre + 'ffn2.w'])
+                else:
+                    cin = d
+                    n = len(st['filters'])
+                    for j, f in enumerate(st['filters']):
+                        fwd(pre + f'conv{j}', W[pre + f'conv{j}.w'], W[pre + f'conv{j}.b'], [cin] * int(st['kernel']), single=(j == n - 1))
+                        dgrad_conv(pre + f'conv{j}.d', W[pre + f'conv{j}.w'])
+                        cin = f
+        d_enc = m._stacks['encoder']['d']
+        for name, filt, k in (('dur_pred', m.config['duration_conv_filters'], m.config['duration_kernel_size']),
+                              ('pitch_pred', m.config['pitch_conv_filters'], m.config['pitch_kernel_size'])):
+            cin = d_enc
+            for j, f in enumerate(filt):
+                bn = _round_up(int(f), 64)  # 226 -> 256 columns so the next contraction is a multiple of 64
+                fwd(f'{name}.conv{j}', W[f'{name}.conv{j}.w'], W[f'{name}.conv{j}.b'], [cin] * int(k), single=True, block_n=bn)
+                P[f'{name}.ln{j}'] = (_pad_vec(W[f'{name}.ln{j}.gamma'], bn), _pad_vec(W[f'{name}.ln{j}.beta'], bn))
+                dgrad_conv(f'{name}.conv{j}.d', W[f'{name}.conv{j}.w'])
+                cin = int(f)
+        fwd('out', W['out.w'], W['out.b'], [m._stacks['decoder']['d']])
+        dgrad_dense('out.d', W['out.w'])
+        for name, st in m._stacks.items():
+            P[f'{name}.pe'] = m._prepare_pe(name)
+        self.P = P
+        return P
+
+    # ------------------------------------------------------------------------------------------------
+    # small helpers
+    # ------------------------------------------------------------------------------------------------
+    def _bf(self, *shape):
+        return torch.empty(shape, dtype=torch.bfloat16, device=self.dev)
+
+    def _f32(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.dev)
+
+    def _transpose(self, src, B, T, ld_src, col0, C, colsum=None):
+        ld_t = _round_up(T, 8)
+        dst = self._bf(B, C, ld_t)
+        lib.transpose_bf16(src, B, T, ld_src, col0, C, dst, C, ld_t, colsum)
+        return dst, ld_t
+
+    def _wgrad(self, xts: List[torch.Tensor], gt, B, T, Cin, N, segs, ld_t, dw):
+        a = lib.WgradArgs()
+        a.B, a.T, a.Cin, a.N = B, T, Cin, N
+        a.num_segments = len(segs)
+        for s, (src, shift) in enumerate(segs):
+            a.seg_src[s], a.seg_shift[s] = src, shift
+        for i, xt in enumerate(xts):
+            a.xt[i] = xt.data_ptr()
+            a.xt_rows[i] = xt.shape[1]
+        a.gt = gt.data_ptr()
+        a.gt_rows = gt.shape[1]
+        a.ld_t = ld_t
+        a.dw = dw.data_ptr()
+        lib.wgrad(a)
+
+    def _bgemm(self, B, H, M, N, K, a, a_dims, a_strides, a_off, b, b_dims, b_strides, b_off, alpha=1.0, out_f32=None, out_bf16=None,
+               ld_out=0, out_batch_stride=0, out_h_col=0, out_by_b=0, out_cols=0, out_ptr_off=0, row_len=None, col_len=None):
+        g = lib.BgemmArgs()
+        g.B, g.H, g.M, g.N, g.K = B, H, M, N, K
+        g.a = a.data_ptr() + 2 * a_off[3]
+        g.a_dim0, g.a_dim1, g.a_dim2 = a_dims
+        g.a_stride1, g.a_stride2 = a_strides
+        g.a_h_col, g.a_h_row, g.a_z_batch = a_off[:3]
+        g.b = b.data_ptr() + 2 * b_off[3]
+        g.b_dim0, g.b_dim1, g.b_dim2 = b_dims
+        g.b_stride1, g.b_stride2 = b_strides
+        g.b_h_col, g.b_h_row, g.b_z_batch = b_off[:3]
+        g.alpha = alpha
+        if out_f32 is not None:
+            g.out_f32 = out_f32.data_ptr() + 4 * out_ptr_off
+        if out_bf16 is not None:
+            g.out_bf16 = out_bf16.data_ptr() + 2 * out_ptr_off
+        g.ld_out, g.out_batch_stride, g.out_h_col, g.out_by_b, g.out_cols = ld_out, out_batch_stride, out_h_col, out_by_b, out_cols
+        g.row_len = row_len.data_ptr() if row_len is not None else None
+        g.col_len = col_len.data_ptr() if col_len is not None else None
+        lib.bgemm(g)
+
+    # ------------------------------------------------------------------------------------------------
+    # one self-attention block: forward (saving) and backward
+    # ------------------------------------------------------------------------------------------------
+    def _block_fwd(self, name, i, x_f, x_bf, lens, B, T):
+        m, P, W = self.model, self.P, self.model.weights
+        st = m._stacks[name]
+        d, H = st['d'], st['heads'][i]
+        dh = d // H
+        pre = f'{name}.b{i}.'
+        c = {'x_f': x_f, 'x_bf': x_bf, 'T': T}
+        qkv = self._bf(B, T, 3 * d)
+        m._gemm(P[pre + 'qkv'], B, T, [(x_bf, None, d, 0)], [0], [0], out_hi=qkv, ld_out=3 * d)
+        ldp = _round_up(T, 16)
+        Z = B * H
+        S = self._f32(Z, T, ldp)
+        self._bgemm(B, H, T, T, dh, qkv, (3 * d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 0), qkv, (2 * d, T, B), (3 * d, 3 * d * T),
+                    (dh, 0, 0, d), alpha=1.0 / math.sqrt(dh), out_f32=S, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
+        P_pre = self._bf(Z, T, ldp)
+        rate = self.drop_rate
+        P_drop = self._bf(Z, T, ldp) if rate > 0 else P_pre
+        site_p = self._site()
+        lib.softmax_fwd(S, B, H, T, T, ldp, lens, rate, self.seed, site_p, P_pre, P_drop)
+        del S
+        vT, ld8 = self._transpose(qkv, B, T, 3 * d, 2 * d, d)
+        attn = self._bf(B, T, d)
+        self._bgemm(B, H, T, dh, T, P_drop, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), vT, (T, d, B), (ld8, d * ld8), (0, dh, 0, 0),
+                    out_bf16=attn, ld_out=d, out_batch_stride=T * d, out_h_col=dh, out_by_b=1, out_cols=dh)
+        y_f, y_bf, u1 = self._f32(B, T, d), self._bf(B, T, d), self._f32(B, T, d)
+        site_o = self._site()
+        m._gemm(P[pre + 'wo'], B, T, [(x_bf, None, d, 0), (attn, None, d, 0)], [0, 1], [0, 0], residual=x_f,
+                ln=(W[pre + 'ln1.gamma'], W[pre + 'ln1.beta']), row_len=lens, out_f32=y_f, out_hi=y_bf, out_preln=u1,
+                dropout=(rate, site_o))
+        z_f, z_bf, u2 = self._f32(B, T, d), self._bf(B, T, d), self._f32(B, T, d)
+        site_c = self._site()
+        if i < st['n_dense']:
+            F = int(st['ffn'])
+            h = self._bf(B, T, F)
+            m._gemm(P[pre + 'ffn1'], B, T, [(y_bf, None, d, 0)], [0], [0], relu=True, out_hi=h, ld_out=F)
+            m._gemm(P[pre + 'ffn2'], B, T, [(h, None, F, 0)], [0], [0], residual=y_f, ln=(W[pre + 'ln2.gamma'], W[pre + 'ln2.beta']),
+                    row_len=lens, out_f32=z_f, out_hi=z_bf, out_preln=u2, dropout=(rate, site_c))
+            hs = [h]
+        else:
+            k = int(st['kernel'])
+            shifts = m._conv_shifts(k)
+            hs = []
+            cur, ld = y_bf, d
+            n = len(st['filters'])
+            for j in range(n - 1):
+                f = st['filters'][j]
+                h = self._bf(B, T, f)
+                m._gemm(P[pre + f'conv{j}'], B, T, [(cur, None, ld, 0)], [0] * k, shifts, relu=True, out_hi=h, ld_out=f)
+                hs.append(h)
+                cur, ld = h, f
+            m._gemm(P[pre + f'conv{n - 1}'], B, T, [(cur, None, ld, 0)], [0] * k, shifts, residual=y_f,
+                    ln=(W[pre + 'ln2.gamma'], W[pre + 'ln2.beta']), row_len=lens, out_f32=z_f, out_hi=z_bf, out_preln=u2,
+                    dropout=(rate, site_c))
+        c.update(qkv=qkv, P_pre=P_pre, P_drop=P_drop, attn=attn, y_f=y_f, y_bf=y_bf, u1=u1, u2=u2, hs=hs, ldp=ldp,
+                 sites=(site_p, site_o, site_c))
+        return z_f, z_bf, c
+
+    def _block_bwd(self, name, i, c, dz, lens, B):
+        m, P, W, G = self.model, self.P, self.model.weights, self.g
+        st = m._stacks[name]
+        d, H = st['d'], st['heads'][i]
+        dh = d // H
+        T = c['T']
+        pre = f'{name}.b{i}.'
+        rate = self.drop_rate
+        site_p, site_o, site_c = c['sites']
+        Z = B * H
+        # ---- LayerNorm 2 (+ row mask) ; the branch gradient carries the branch dropout mask
+        du2, g2 = self._f32(B, T, d), self._bf(B, T, d)
+        lib.layernorm_bwd(dz, c['u2'], W[pre + 'ln2.gamma'], B, T, d, d, LN_EPS, lens, False, du2, g2, G[pre + 'ln2.gamma'],
+                          G[pre + 'ln2.beta'], pre_drop=(rate, site_c), seed=self.seed)
+        if i < st['n_dense']:
+            F = int(st['ffn'])
+            h = c['hs'][0]
+            g2T, ld8 = self._transpose(g2, B, T, d, 0, d, colsum=G[pre + 'ffn2.b'])
+            hT, _ = self._transpose(h, B, T, F, 0, F)
+            self._wgrad([hT], g2T, B, T, F, d, [(0, 0)], ld8, G[pre + 'ffn2.w'])
+            dh_ = self._bf(B, T, F)
+            m._gemm(P[pre + 'ffn2.d'], B, T, [(g2, None, d, 0)], [0], [0], out_hi=dh_, ld_out=F)
+            lib.relu_bwd(dh_, h)
+            dhT, _ = self._transpose(dh_, B, T, F, 0, F, colsum=G[pre + 'ffn1.b'])
+            yT, _ = self._transpose(c['y_bf'], B, T, d, 0, d)
+            self._wgrad([yT], dhT, B, T, d, F, [(0, 0)], ld8, G[pre + 'ffn1.w'])
+            dy = self._f32(B, T, d)
+            m._gemm(P[pre + 'ffn1.d'], B, T, [(dh_, None, F, 0)], [0], [0], residual=du2, out_f32=dy, ld_out=d)
+        else:
+            k = int(st['kernel'])
+            shifts = m._conv_shifts(k)
+            dshifts = [-s for s in shifts]
+            n = len(st['filters'])
+            inputs = [c['y_bf']] + c['hs']  # input of conv j
+            in_dims = [d] + list(st['filters'][:-1])
+            g_cur, g_dim = g2, d
+            ld8 = _round_up(T, 8)
+            for j in range(n - 1, -1, -1):
+                cin = in_dims[j]
+                gT, _ = self._transpose(g_cur, B, T, g_cur.shape[-1], 0, g_dim, colsum=G[pre + f'conv{j}.b'])
+                xT, _ = self._transpose(inputs[j], B, T, cin, 0, cin)
+                self._wgrad([xT], gT, B, T, cin, g_dim, [(0, s) for s in shifts], ld8, G[pre + f'conv{j}.w'])
+                kpad = _round_up(g_dim, 64)
+                assert g_cur.shape[-1] == kpad, 'gradient operand must be padded to the packed contraction width'
+                if j > 0:
+                    dx_ = self._bf(B, T, cin)
+                    m._gemm(P[pre + f'conv{j}.d'], B, T, [(g_cur, None, kpad, 0)], [0] * k, dshifts, out_hi=dx_, ld_out=cin)
+                    lib.relu_bwd(dx_, inputs[j])
+                    g_cur, g_dim = dx_, cin
+                else:
+                    dy = self._f32(B, T, d)
+                    m._gemm(P[pre + 'conv0.d'], B, T, [(g_cur, None, kpad, 0)], [0] * k, dshifts, residual=du2, out_f32=dy, ld_out=d)
+        # ---- LayerNorm 1
+        du1, g1 = self._f32(B, T, d), self._bf(B, T, d)
+        lib.layernorm_bwd(dy, c['u1'], W[pre + 'ln1.gamma'], B, T, d, d, LN_EPS, lens, False, du1, g1, G[pre + 'ln1.gamma'],
+                          G[pre + 'ln1.beta'], pre_drop=(rate, site_o), seed=self.seed)
+        g1T, ld8 = self._transpose(g1, B, T, d, 0, d, colsum=G[pre + 'wo.b'])
+        xT, _ = self._transpose(c['x_bf'], B, T, d, 0, d)
+        aT, _ = self._transpose(c['attn'], B, T, d, 0, d)
+        self._wgrad([xT, aT], g1T, B, T, d, d, [(0, 0), (1, 0)], ld8, G[pre + 'wo.w'])
+        dattn = self._bf(B, T, d)
+        m._gemm(P[pre + 'wo.da'], B, T, [(g1, None, d, 0)], [0], [0], out_hi=dattn, ld_out=d)
+        dx_acc = self._f32(B, T, d)
+        m._gemm(P[pre + 'wo.dx'], B, T, [(g1, None, d, 0)], [0], [0], residual=du1, out_f32=dx_acc, ld_out=d)
+        # ---- attention backward on the materialised probabilities
+        qkv, ldp = c['qkv'], c['ldp']
+        dP = self._f32(Z, T, ldp)
+        self._bgemm(B, H, T, T, dh, dattn, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
+                    out_f32=dP, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
+        dS = self._bf(Z, T, ldp)
+        lib.softmax_bwd(c['P_pre'], dP, B, H, T, T, ldp, lens, 1.0 / math.sqrt(dh), rate, self.seed, site_p, dS)
+        del dP
+        qkT, _ = self._transpose(qkv, B, T, 3 * d, 0, 2 * d)           # rows [0,d) = Q^T, [d,2d) = K^T
+        dST, _ = self._transpose(dS, Z, T, ldp, 0, T)                   # (Z, Tk, ld8)
+        PT, _ = self._transpose(c['P_drop'], Z, T, ldp, 0, T)
+        daT, _ = self._transpose(dattn, B, T, d, 0, d)
+        dqkv = self._bf(B, T, 3 * d)
+        common = dict(out_bf16=dqkv, ld_out=3 * d, out_batch_stride=T * 3 * d, out_h_col=dh, out_by_b=1, out_cols=dh)
+        # dQ = dS K : A = dS (Z,T,Tk), B = K^T rows d + h*dh
+        self._bgemm(B, H, T, dh, T, dS, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), qkT, (T, d, B), (ld8, 2 * d * ld8), (0, dh, 0, d * ld8),
+                    out_ptr_off=0, **common)
+        # dK = dS^T Q : A = dS^T (Z,Tk,T), B = Q^T rows h*dh
+        self._bgemm(B, H, T, dh, T, dST, (T, T, Z), (ld8, T * ld8), (0, 0, 1, 0), qkT, (T, d, B), (ld8, 2 * d * ld8), (0, dh, 0, 0),
+                    out_ptr_off=d, **common)
+        # dV = P^T dO : A = P_drop^T (Z,Tk,T), B = dO^T rows h*dh
+        self._bgemm(B, H, T, dh, T, PT, (T, T, Z), (ld8, T * ld8), (0, 0, 1, 0), daT, (T, d, B), (ld8, d * ld8), (0, dh, 0, 0),
+                    out_ptr_off=2 * d, **common)
+        # ---- q/k/v projections
+        bq = self._tmp_zero(3 * d)
+        dqkvT, _ = self._transpose(dqkv, B, T, 3 * d, 0, 3 * d, colsum=bq)
+        wq = self._tmp_zero(d * 3 * d).view(d, 3 * d)
+        self._wgrad([xT], dqkvT, B, T, d, 3 * d, [(0, 0)], ld8, wq)
+        for n_, nm in enumerate(('wq', 'wk', 'wv')):
+            G[pre + nm + '.w'].add_(wq[:, n_ * d:(n_ + 1) * d])
+            G[pre + nm + '.b'].add_(bq[n_ * d:(n_ + 1) * d])
+        dx = self._f32(B, T, d)
+        m._gemm(P[pre + 'qkv.d'], B, T, [(dqkv, None, 3 * d, 0)], [0], [0], residual=dx_acc, out_f32=dx, ld_out=d)
+        return dx
+
+    def _tmp_zero(self, n):
+        return torch.zeros(n, dtype=torch.float32, device=self.dev)
+
+    def _site(self):
+        self.drop_sites += 1
+        return self.drop_sites
+
+    # ------------------------------------------------------------------------------------------------
+    # predictors
+    # ------------------------------------------------------------------------------------------------
+    def _pred_fwd(self, name, x_bf, lens, B, T, relu_head):
+        m, P, W = self.model, self.P, self.model.weights
+        filt = m.config['duration_conv_filters' if name == 'dur_pred' else 'pitch_conv_filters']
+        k = int(m.config['duration_kernel_size' if name == 'dur_pred' else 'pitch_kernel_size'])
+        shifts = m._conv_shifts(k)
+        rate = float(m.config.get('predictors_dropout', 0.0)) if self.use_dropout else 0.0
+        cur, ld = x_bf, x_bf.shape[-1]
+        us, outs, sites = [], [], []
+        h_f = None
+        for j, f in enumerate(filt):
+            pl = P[f'{name}.conv{j}']
+            h_f, o_bf, u = self._f32(B, T, pl.n_pad), self._bf(B, T, pl.n_pad), self._f32(B, T, pl.n_pad)
+            site = self._site()
+            m._gemm(pl, B, T, [(cur, None, ld, 0)], [0] * k, shifts, relu=True, ln=P[f'{name}.ln{j}'], out_f32=h_f, out_hi=o_bf,
+                    out_preln=u, dropout_post=(rate, site))
+            us.append(u)
+            outs.append(o_bf)
+            sites.append(site)
+            cur, ld = o_bf, pl.n_pad
+        out = self._f32(B, T)
+        lib.statpred_head_fwd(h_f, int(filt[-1]), W[f'{name}.out.w'].reshape(-1), W[f'{name}.out.b'], relu_head, lens, out)
+        return out, dict(us=us, outs=outs, h_f=h_f, x_bf=x_bf, sites=sites, rate=rate, out=out, relu=relu_head)
+
+    def _pred_bwd(self, name, c, gout, lens, B, T, xT_enc, ld8, dx_acc):
+        """Returns the accumulated encoder-output gradient (fp32)."""
+        m, P, W, G = self.model, self.P, self.model.weights, self.g
+        filt = [int(f) for f in m.config['duration_conv_filters' if name == 'dur_pred' else 'pitch_conv_filters']]
+        k = int(m.config['duration_kernel_size' if name == 'dur_pred' else 'pitch_kernel_size'])
+        shifts = m._conv_shifts(k)
+        dshifts = [-s for s in shifts]
+        d_enc = m._stacks['encoder']['d']
+        ldh = c['h_f'].shape[-1]
+        dh = self._f32(B, T, ldh)
+        lib.statpred_head_bwd(gout, c['out'], c['h_f'], filt[-1], W[f'{name}.out.w'].reshape(-1), c['relu'], lens, dh,
+                              G[f'{name}.out.w'].view(-1), G[f'{name}.out.b'])
+        dz = dh
+        n = len(filt)
+        for j in range(n - 1, -1, -1):
+            C = filt[j]
+            ld = c['us'][j].shape[-1]
+            gam = _pad_vec(W[f'{name}.ln{j}.gamma'], ld)
+            dg, db = self._tmp_zero(ld), self._tmp_zero(ld)
+            g_bf = self._bf(B, T, ld)
+            lib.layernorm_bwd(dz, c['us'][j], gam, B, T, C, ld, LN_EPS, None, True, None, g_bf, dg, db,
+                              post_drop=(c['rate'], c['sites'][j]), seed=self.seed)
+            G[f'{name}.ln{j}.gamma'].add_(dg[:C])
+            G[f'{name}.ln{j}.beta'].add_(db[:C])
+            cin = d_enc if j == 0 else filt[j - 1]
+            gT, _ = self._transpose(g_bf, B, T, ld, 0, C, colsum=G[f'{name}.conv{j}.b'])
+            if j == 0:
+                xT = xT_enc
+            else:
+                xT, _ = self._transpose(c['outs'][j - 1], B, T, c['outs'][j - 1].shape[-1], 0, cin)
+            self._wgrad([xT], gT, B, T, cin, C, [(0, s) for s in shifts], ld8, G[f'{name}.conv{j}.w'])
+            if j > 0:
+                ldn = c['us'][j - 1].shape[-1]
+                dz = self._f32(B, T, ldn)
+                m._gemm(P[f'{name}.conv{j}.d'], B, T, [(g_bf, None, ld, 0)], [0] * k, dshifts, out_f32=dz, ld_out=ldn)
+            else:
+                out = self._f32(B, T, d_enc)
+                m._gemm(P[f'{name}.conv0.d'], B, T, [(g_bf, None, ld, 0)], [0] * k, dshifts, residual=dx_acc, out_f32=out, ld_out=d_enc)
+                return out
+
+    # ------------------------------------------------------------------------------------------------
+    # full step
+    # ------------------------------------------------------------------------------------------------
+    def forward_backward(self, phonemes, mel_tgt, dur_tgt, pitch_tgt, training=True):
+        m, W, G = self.model, self.model.weights, self.g
+        dev = self.dev
+        self.use_dropout = training and m.train_dropout
+        self.drop_rate = float(m.config.get('dropout_rate', 0.0)) if self.use_dropout else 0.0
+        self.drop_sites = 0
+        saved_precision = m.precision
+        m.precision = 'bf16'
+        try:
+            P = self._pack()
+            x = torch.as_tensor(phonemes).to(device=dev, dtype=torch.int32).contiguous()
+            mel_tgt = torch.as_tensor(mel_tgt).to(device=dev, dtype=torch.float32).contiguous()
+            dur_tgt = torch.as_tensor(dur_tgt).to(device=dev, dtype=torch.int32).contiguous()
+            pitch_tgt = torch.as_tensor(pitch_tgt).to(device=dev, dtype=torch.float32).contiguous()
+            B, Tp = x.shape
+            d = m._stacks['encoder']['d']
+            enc_len = torch.empty((B,), dtype=torch.int32, device=dev)
+            lib.phoneme_lengths(x, 0, enc_len)
+            # ---- encoder prologue (embedding rows are kept as the LayerNorm input for the backward pass)
+            e_rows = self._f32(1, B * Tp, d)
+            lib.length_regulate_fwd(W['embedding'].view(1, -1, d), x.view(1, -1), e_rows)
+            h_f, h_bf = self._f32(B, Tp, d), self._bf(B, Tp, d)
+            site_e = self._site()
+            lib.embed_ln_pe_fwd(x, W['embedding'], W['encoder.ln.gamma'], W['encoder.ln.beta'], P['encoder.pe'],
+                                W['encoder.pos_scalar'].reshape(1), LN_EPS, h_f, h_bf, None)
+            h_f, h_bf = self._prologue_dropout(h_f, h_bf, site_e)
+            enc_ctx = []
+            for i in range(len(m._stacks['encoder']['heads'])):
+                h_f, h_bf, c = self._block_fwd('encoder', i, h_f, h_bf, enc_len, B, Tp)
+                enc_ctx.append(c)
+            dur_out, dur_ctx = self._pred_fwd('dur_pred', h_bf, enc_len, B, Tp, True)
+            pit_out, pit_ctx = self._pred_fwd('pitch_pred', h_bf, enc_len, B, Tp, False)
+            h_pe = self._f32(B, Tp, d)
+            pw = W['pitch_embed.w'].reshape(-1)
+            lib.pitch_embed_add_fwd(h_f, pitch_tgt, pw, W['pitch_embed.b'], h_pe)
+            dur_int = torch.empty((B, Tp), dtype=torch.int32, device=dev)
+            dec_len = torch.empty((B,), dtype=torch.int32, device=dev)
+            lib.durations_to_int(dur_tgt.float(), 1.0, None, None, dur_int, dec_len)
+            Tm = int(dec_len.max().item())
+            mel_len = mel_tgt.shape[1]
+            if Tm < mel_len:
+                raise ValueError(f'durations expand to {Tm} frames but the target has {mel_len}')
+            idx = torch.empty((B, Tm), dtype=torch.int32, device=dev)
+            lib.expand_indices(dur_int, Tm, idx)
+            dd = m._stacks['decoder']['d']
+            expanded = self._f32(B, Tm, dd)
+            lib.length_regulate_fwd(h_pe, idx, expanded)
+            m_f, m_bf = self._f32(B, Tm, dd), self._bf(B, Tm, dd)
+            site_d = self._site()
+            lib.expand_ln_pe_fwd(h_pe, idx, W['decoder.ln.gamma'], W['decoder.ln.beta'], P['decoder.pe'],
+                                 W['decoder.pos_scalar'].reshape(1), LN_EPS, m_f, m_bf, None)
+            m_f, m_bf = self._prologue_dropout(m_f, m_bf, site_d)
+            dec_ctx = []
+            for i in range(len(m._stacks['decoder']['heads'])):
+                m_f, m_bf, c = self._block_fwd('decoder', i, m_f, m_bf, dec_len, B, Tm)
+                dec_ctx.append(c)
+            mel = self._f32(B, Tm, m.mel_channels)
+            m._gemm(P['out'], B, Tm, [(m_bf, None, dd, 0)], [0], [0], out_f32=mel, ld_out=m.mel_channels)
+            # ---- losses (utils/losses.py:41-70, weights [1,1,3]) and their gradients
+            losses = torch.zeros(3, dtype=torch.float32, device=dev)
+            wts = m.loss_weights
+            dmel = self._f32(B, Tm, m.mel_channels)
+            ddur, dpit = self._f32(B, Tp), self._f32(B, Tp)
+            lib.mae_loss(mel, B, Tm, mel_len, m.mel_channels, mel_tgt, wts[0], losses[0:1], dmel)
+            lib.mae_loss(dur_out, B, Tp, Tp, 1, dur_tgt, wts[1], losses[1:2], ddur)
+            lib.mae_loss(pit_out, B, Tp, Tp, 1, pitch_tgt, wts[2], losses[2:3], dpit)
+            out = {'mel': mel, 'duration': dur_out[..., None], 'pitch': pit_out[..., None],
+                   'expanded_mask': None, 'encoder_attention': {}, 'decoder_attention': {},
+                   'losses': {'mel': losses[0], 'duration': losses[1], 'pitch': losses[2]},
+                   'loss': wts[0] * losses[0] + wts[1] * losses[1] + wts[2] * losses[2], 'mel_lengths': dec_len}
+            if not training:
+                return out
+            # =============================== backward ===============================
+            self.flat_g.zero_()
+            C = m.mel_channels
+            kpad = _round_up(C, 64)
+            g = self._bf(B, Tm, kpad)
+            lib.cast_bf16_pad(dmel, B * Tm, C, g, kpad)
+            gT, ld8m = self._transpose(g, B, Tm, kpad, 0, C, colsum=G['out.b'])
+            mT, _ = self._transpose(m_bf, B, Tm, dd, 0, dd)
+            self._wgrad([mT], gT, B, Tm, dd, C, [(0, 0)], ld8m, G['out.w'])
+            dz = self._f32(B, Tm, dd)
+            m._gemm(P['out.d'], B, Tm, [(g, None, kpad, 0)], [0], [0], out_f32=dz, ld_out=dd)
+            for i in range(len(dec_ctx) - 1, -1, -1):
+                dz = self._block_bwd('decoder', i, dec_ctx[i], dz, dec_len, B)
+                dec_ctx[i] = None
+            d_exp = self._prologue_bwd('decoder', dz, expanded, dec_len, B, Tm, site_d)
+            dh_pe = self._f32(B, Tp, d)
+            lib.expand_bwd(d_exp, dur_int, dh_pe)
+            lib.pitch_embed_bwd(dh_pe, pitch_tgt, pw, W['pitch_embed.b'], G['pitch_embed.w'].view(-1), G['pitch_embed.b'])
+            # predictors read the encoder output; their input gradient is accumulated onto dh_pe
+            xT_enc, ld8p = self._transpose(h_bf, B, Tp, d, 0, d)
+            acc = self._pred_bwd('dur_pred', dur_ctx, ddur, enc_len, B, Tp, xT_enc, ld8p, dh_pe)
+            acc = self._pred_bwd('pitch_pred', pit_ctx, dpit, enc_len, B, Tp, xT_enc, ld8p, acc)
+            dz = acc
+            for i in range(len(enc_ctx) - 1, -1, -1):
+                dz = self._block_bwd('encoder', i, enc_ctx[i], dz, enc_len, B)
+                enc_ctx[i] = None
+            de = self._prologue_bwd('encoder', dz, e_rows.view(B, Tp, d), enc_len, B, Tp, site_e)
+            lib.embedding_bwd(de, x, G['embedding'])
+            return out
+        finally:
+            m.precision = saved_precision
+
+    def _prologue_dropout(self, x_f, x_bf, site):
+        """Dropout after LayerNorm + PE of a stack (model/layers.py:301)."""
+        if self.drop_rate <= 0:
+            return x_f, x_bf
+        raise lib.TtsbError('stack-prologue dropout is not implemented yet (use dropout_rate=0)')
+
+    def _prologue_bwd(self, name, g, u, lens, B, T, site):
+        m, W, G = self.model, self.model.weights, self.g
+        d = m._stacks[name]['d']
+        lib.pe_scalar_bwd(g, self.P[f'{name}.pe'], G[f'{name}.pos_scalar'].view(1))
+        du = self._f32(B, T, d)
+        lib.layernorm_bwd(g, u.contiguous(), W[f'{name}.ln.gamma'], B, T, d, d, LN_EPS, None, False, du, None,
+                          G[f'{name}.ln.gamma'], G[f'{name}.ln.beta'])
+        return du
+
+    # ------------------------------------------------------------------------------------------------
+    def apply_adam(self, opt: Adam, grad_scale: float = 1.0):
+        if opt.m is None:
+            opt.m = torch.zeros_like(self.flat_w)
+            opt.v = torch.zeros_like(self.flat_w)
+        opt.iterations += 1
+        t = opt.iterations
+        lr_t = opt.lr * math.sqrt(1.0 - opt.beta_2 ** t) / (1.0 - opt.beta_1 ** t)
+        lib.adam_tf_step(self.flat_w, self.flat_g, opt.m, opt.v, lr_t, opt.beta_1, opt.beta_2, opt.epsilon, grad_scale)
+        self.model._packed = None
