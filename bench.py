@@ -129,6 +129,86 @@ def cpu_reference_line(args, rank, world):
             'note': 'TF2 reference cannot be installed offline (no tensorflow wheel); oracle/ is its CPU restatement'}
 
 
+def train_bench(args, rank, world, dev, cfg, params):
+    """BASELINE configs[2]: LJ256 training step (fwd + bwd + Adam, dropout 0.1, bf16 tensor-core products), batch 32 per
+    GPU, 128 phonemes -> 1000 frames, gradients all-reduced with NCCL (sum, scaled 1/N inside the Adam kernel)."""
+    import torch.distributed as dist
+    from oracle import forward_oracle as fo
+    from transformertts_b200 import lib
+    from transformertts_b200.model.models import ForwardTransformer
+    from transformertts_b200.model.training import Adam
+    Bt = 32
+    model = ForwardTransformer(**cfg, device=str(dev), train_dropout=True)
+    model.set_weights(params)
+    model._compile(Adam(1e-4))
+    eng = model._get_engine()
+    eng.rank = rank
+    tok, dur, pit = fo.make_inputs('full', Bt, TP, TM, seed=300 + rank)
+    mel = fo.make_mel_targets(dur, cfg['mel_channels'], seed=400 + rank)
+    tok_d, dur_d, pit_d, mel_d = tok.to(dev), dur.to(dev), pit.to(dev), mel.to(dev)
+
+    def sync(flat_g):
+        if world > 1:
+            dist.all_reduce(flat_g, op=dist.ReduceOp.SUM)
+            return 1.0 / world
+        return 1.0
+
+    def step():
+        return model.train_step(tok_d, mel_d, dur_d, pit_d, grad_sync=sync)
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = lib.launch_count()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    # end to end: host batch (pinned) -> device every step, loss read back every step (as train_tts.py:151-158 does)
+    tok_h, dur_h, pit_h, mel_h = tok.pin_memory(), dur.pin_memory(), pit.pin_memory(), mel.pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o = model.train_step(tok_h.to(dev, non_blocking=True), mel_h.to(dev, non_blocking=True), dur_h.to(dev, non_blocking=True),
+                             pit_h.to(dev, non_blocking=True), grad_sync=sync)
+        loss_val = float(o['loss'])
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    peak_tf, _, peak_src = _peaks()
+    flops = 3.0 * fo.forward_flops(cfg, [TP] * Bt, [TM] * Bt)
+    if rank == 0:
+        sps = args.steps / (ms * 1e-3)
+        line = {'metric': 'train_steps_per_sec', 'value': sps, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                'config': {'workload': 'C3: LJ256 training step (fwd+bwd+Adam, dropout 0.1, MAE losses [1,1,3]), 32 rows/GPU, 128 phonemes -> 1000 frames',
+                           'model': CFG_NAME, 'global_batch': Bt * world, 'seq_len': TM, 'parallelism': f'dp{world} (NCCL all-reduce of the flat gradient)',
+                           'l2': 'per-step working set exceeds the 126 MB L2'},
+                'frames_per_sec': sps * Bt * TM * world,
+                'e2e': {'value': args.steps / float(dt.item()), 'unit': 'steps/s', 'h2d_bytes_per_step': int(tok.numel() * 4 + dur.numel() * 4 + pit.numel() * 4 + mel.numel() * 4),
+                        'd2h_bytes_per_step': 4},
+                'gpu_launches': int(launches), 'clocks': clocks, 'loss': loss_val,
+                'roofline': {'bound': 'tensor', 'achieved': flops * world / (ms / args.steps * 1e-3) / 1e12 / world, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                             'frac': flops / (ms / args.steps * 1e-3) / 1e12 / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                             'kernel': 'whole step (3x forward algorithmic FLOPs per GPU)'},
+                'cpu_baseline': None}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -137,6 +217,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help="'train': BASELINE configs[2] (fwd+bwd+Adam, bf16, batch 32/GPU, NCCL data parallel)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -163,6 +245,11 @@ def main():
 
     cfg = fo.CONFIGS[CFG_NAME]
     params = fo.init_params(cfg, seed=7)  # random-init weights of the named architecture
+    if args.mode == 'train':
+        train_bench(args, rank, world, dev, cfg, params)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     model = ForwardTransformer(**cfg, device=str(dev), precision=args.precision)
     model.set_weights(params)
     tok, dur, pit = _inputs(200 + rank)  # per-rank shard of the synthetic batch (weak scaling: 64 rows per GPU)

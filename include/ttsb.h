@@ -107,6 +107,10 @@ typedef struct ttsb_gemm_args {
   int vt_col0, vt_cols, vt_ld;
   int out_fp16;             /* 1: out_hi / vt_hi receive IEEE fp16 (single plane) instead of bf16 hi/lo */
   float* out_preln;         /* optional fp32 (B,T,ld_out): value before the LayerNorm (saved for the backward pass) */
+  /* training dropout (keras semantics, stateless mask from (seed, site, element index)): drop_pre on the GEMM output
+   * after bias/ReLU and before the residual add; drop_post on the LayerNorm output */
+  float drop_pre_p, drop_post_p;
+  uint32_t drop_pre_site, drop_post_site, drop_seed;
   int precision;            /* TTSB_PREC_* */
   int impl;                 /* TTSB_IMPL_* */
 } ttsb_gemm_args;
@@ -148,9 +152,10 @@ int ttsb_mha_fwd(const ttsb_mha_args* args, void* stream);
  *   are activations: S = Q K^T, O = P V, dP = dO V^T, dQ = dS K, dK = dS^T Q, dV = P^T dO (model/layers.py:179-193 and
  *   its gradient).  Each operand is a bf16 tensor described as (dim0 contiguous = K axis, dim1 = rows, dim2 = batches)
  *   with element strides; the tile origin of problem z=(b,h) is (k + h*h_col, row + h*h_row, z_batch ? z : b).
- * ttsb_wgrad: weight gradients  dW[seg*Cin + c][n] += sum_{b,t} Xt[b][c][t + shift_seg] * Gt[b][n][t]  for Dense (1
- *   segment), concat-Dense (2 sources) and Conv1D (k segments); Xt / Gt are the time-transposed bf16 copies
- *   (B, C, ld_t) produced by ttsb_transpose_bf16; dW is fp32 in the Keras (K, N) layout and is ACCUMULATED into.
+ * ttsb_wgrad: weight gradients  dW[seg*Cin + c][n] += sum_{b,t} Xt_seg[b][c][t] * Gt[b][n][t]  for Dense (1 segment),
+ *   concat-Dense (2 segments = the two sources) and Conv1D (k segments = the k tap-shifted copies of the input);
+ *   Xt_seg / Gt are time-transposed bf16 copies (B, C, ld_t) produced by ttsb_transpose_bf16; dW is fp32 in the Keras
+ *   (K, N) layout and is ACCUMULATED into.
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct ttsb_bgemm_args {
   int B, H, M, N, K;
@@ -176,11 +181,9 @@ int ttsb_bgemm(const ttsb_bgemm_args* args, void* stream);
 
 typedef struct ttsb_wgrad_args {
   int B, T, Cin, N;
-  int num_segments;
-  int seg_src[4];
-  int seg_shift[4];
-  const void* xt[2];         /* bf16 (B, xt_rows[i], ld_t); the first Cin rows of each batch are used */
-  int xt_rows[2];
+  int num_segments;          /* 1..4 */
+  const void* xt[4];         /* per segment: bf16 (B, xt_rows[s], ld_t); the first Cin rows of each batch are used */
+  int xt_rows[4];
   const void* gt;            /* bf16 (B, gt_rows, ld_t); the first N rows are used */
   int gt_rows;
   int ld_t;                  /* row stride of the transposed tensors (multiple of 8) */
@@ -189,10 +192,12 @@ typedef struct ttsb_wgrad_args {
 
 int ttsb_wgrad(const ttsb_wgrad_args* args, void* stream);
 
-/* bf16 (B,T,ld_src)[:, :, col0:col0+C] -> (B, dst_rows >= C, ld_t >= T) time-transposed copy for ttsb_wgrad / ttsb_bgemm;
+/* bf16 (B,T,ld_src)[:, :, col0:col0+C] -> (B, dst_rows >= C, ld_t >= T) time-transposed copy for ttsb_wgrad / ttsb_bgemm:
+ * dst[b][c][t] = src[b][t + t_shift][c] (zero outside [0,T); the conv taps of ttsb_wgrad use pre-shifted copies because a
+ * TMA box cannot start at an unaligned element of the contiguous dimension);
  * colsum (optional, fp32 [C]) accumulates the column sums = bias gradient of a Dense/Conv1D whose output grad this is. */
 int ttsb_transpose_bf16(const void* src, int B, int T, int ld_src, int col0, int C, void* dst, int dst_rows, int ld_t,
-                        float* colsum, void* stream);
+                        float* colsum, int t_shift, void* stream);
 /* Row softmax of materialised, pre-scaled scores S fp32 (B*H, T, ld) with key masking (model/layers.py:186-192) and
  * attention dropout: P_pre = softmax, P_drop = dropout(P_pre) (pass the same pointer twice when drop_p == 0). */
 int ttsb_softmax_fwd(const float* S, int B, int H, int T, int Tk, int ld, const int32_t* kv_len, float drop_p,
@@ -213,7 +218,17 @@ int ttsb_mae_loss(const float* pred, int B, int Tp, int Tt, int C, const float* 
                   float weight, float* loss_out, float* grad, void* stream);
 int ttsb_expand_bwd(const float* dm, const int32_t* dur_int, int B, int Tp, int Tm, int d, float* dx, void* stream);
 int ttsb_embedding_bwd(const float* dx, const int32_t* tokens, int B, int T, int d, int vocab, float* demb, void* stream);
-int ttsb_pe_scalar_bwd(const float* g, const float* pe, int B, int T, int d, float* dscalar, void* stream);
+/* d(pos_encoding_scalar) = sum dropout(g) * PE[t]; (drop_p, seed, site) regenerate the prologue dropout mask */
+int ttsb_pe_scalar_bwd(const float* g, const float* pe, int B, int T, int d, float drop_p, uint32_t seed, uint32_t site,
+                       float* dscalar, void* stream);
+/* training variants of the two stack prologues: keras Dropout after LayerNorm + PE (model/layers.py:301) */
+int ttsb_embed_ln_pe_train_fwd(const int32_t* tokens, const float* emb, const float* gamma, const float* beta,
+                               const float* pe, const float* pos_scalar, int B, int T, int d, int vocab, float eps,
+                               float drop_p, uint32_t seed, uint32_t site, float* out_f32, void* out_hi, void* out_lo,
+                               void* stream);
+int ttsb_expand_ln_pe_train_fwd(const float* x, const int32_t* idx, const float* gamma, const float* beta, const float* pe,
+                                const float* pos_scalar, int B, int Tp, int Tm, int d, float eps, float drop_p, uint32_t seed,
+                                uint32_t site, float* out_f32, void* out_hi, void* out_lo, void* stream);
 int ttsb_pitch_embed_bwd(const float* g, const float* pitch, const float* w, const float* bias, int B, int T, int d,
                          float* dw, float* db, void* stream);
 int ttsb_statpred_head_bwd(const float* gout, const float* out, const float* h, int ldh, int C, const float* w, int relu,

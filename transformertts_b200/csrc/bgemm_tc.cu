@@ -5,7 +5,7 @@
 //                 both operands come from activations (per-(b,h) B operand), e.g. S = Q K^T, O = P V, dP = dO V^T,
 //                 dQ = dS K, dK = dS^T Q, dV = P^T dO of the attention forward/backward (model/layers.py:176-195 and
 //                 its gradient), each operand addressed through a 3-D TMA map with per-head column/row offsets.
-//  mode WGRAD   : dW[seg*Cin + c][n] += sum_b sum_t X^T[b][c][t + shift_seg] * G^T[b][n][t]
+//  mode WGRAD   : dW[seg*Cin + c][n] += sum_b sum_t X^T_seg[b][c][t] * G^T[b][n][t]
 //                 weight gradients of Dense / concat-Dense / Conv1D (k taps = k segments), reduction over all B*T
 //                 rows split across CTAs, partial tiles added with fp32 red.global.add (Keras (K,N) layout).
 #include <cuda_fp16.h>
@@ -49,7 +49,7 @@ struct BgParams {
   const int* row_len;         // optional [B]: rows m >= len[b] are written as zero
   const int* col_len;         // optional [B]: columns n >= len[b] are written as zero
   // wgrad
-  int B, T, Cin, num_seg, seg_src[4], seg_shift[4], splits, b_per_split;
+  int B, T, Cin, num_seg, splits, b_per_split;
   float* dw;                  // fp32 (num_seg*Cin, N) accumulated with atomics
   // common
   int block_n, n_tiles, m_tiles, num_tiles;
@@ -57,6 +57,7 @@ struct BgParams {
 
 __global__ void __launch_bounds__(BG_THREADS, 1)
 bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                 const __grid_constant__ CUtensorMap tmB, const BgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -127,7 +128,7 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const int n_tile = r % p.n_tiles; r /= p.n_tiles;
         const int m_tile = r % p.m_tiles; r /= p.m_tiles;
         const int seg = r;
-        const CUtensorMap* mA = p.seg_src[seg] == 0 ? &tmA0 : &tmA1;
+        const CUtensorMap* mA = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
         const int c0 = m_tile * BG_BM, n0 = n_tile * p.block_n;
         const int b0 = split * p.b_per_split;
         const int b1 = min(b0 + p.b_per_split, p.B);
@@ -136,7 +137,7 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* st = smem + stage * BG_STAGE_BYTES;
             mbar_arrive_expect_tx(full_bar + stage, stage_tx);
-            tma_load_3d(mA, full_bar + stage, st, tc * BG_BK + p.seg_shift[seg], c0, b);
+            tma_load_3d(mA, full_bar + stage, st, tc * BG_BK, c0, b);
             tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES, tc * BG_BK, n0, b);
             if (++stage == BG_STAGES) { stage = 0; phase ^= 1; }
           }
@@ -260,14 +261,14 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
 }
 
-static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const BgParams& p, cudaStream_t stream) {
+static int launch(const CUtensorMap* a, const CUtensorMap& b, const BgParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     TTSB_CUDA_OK(cudaFuncSetAttribute(bgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMEM_BYTES));
     attr_set = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  bgemm_tc_kernel<<<grid, BG_THREADS, BG_SMEM_BYTES, stream>>>(a0, a1, b, p);
+  bgemm_tc_kernel<<<grid, BG_THREADS, BG_SMEM_BYTES, stream>>>(a[0], a[1], a[2], a[3], b, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "bgemm_tc_kernel launch");
 }
@@ -309,7 +310,8 @@ extern "C" int ttsb_bgemm(const ttsb_bgemm_args* a, void* stream_v) {
   rc = make_tmap_bf16_3d(&tmB, a->b, (uint64_t)a->b_dim0, (uint64_t)a->b_dim1, (uint64_t)a->b_dim2, (uint64_t)a->b_stride1,
                          (uint64_t)a->b_stride2, BG_BK, p.block_n);
   if (rc) return rc;
-  return launch(tmA, tmA, tmB, p, stream);
+  CUtensorMap tmAs[4] = {tmA, tmA, tmA, tmA};
+  return launch(tmAs, tmB, p, stream);
 }
 
 extern "C" int ttsb_wgrad(const ttsb_wgrad_args* a, void* stream_v) {
@@ -323,11 +325,8 @@ extern "C" int ttsb_wgrad(const ttsb_wgrad_args* a, void* stream_v) {
   BgParams p{};
   p.mode = 1;
   p.B = a->B; p.T = a->T; p.Cin = a->Cin; p.N = a->N; p.num_seg = a->num_segments; p.H = 1;
-  for (int s = 0; s < a->num_segments; ++s) {
-    p.seg_src[s] = a->seg_src[s];
-    p.seg_shift[s] = a->seg_shift[s];
-    if (a->seg_src[s] < 0 || a->seg_src[s] > 1 || !a->xt[a->seg_src[s]]) { set_last_error("ttsb_wgrad: bad segment source"); return TTSB_ERR_INVALID_ARGUMENT; }
-  }
+  for (int s = 0; s < a->num_segments; ++s)
+    if (!a->xt[s]) { set_last_error("ttsb_wgrad: NULL segment source"); return TTSB_ERR_INVALID_ARGUMENT; }
   p.dw = a->dw;
   p.block_n = pick_block_n(a->N);
   p.n_tiles = (a->N + p.block_n - 1) / p.block_n;
@@ -339,15 +338,15 @@ extern "C" int ttsb_wgrad(const ttsb_wgrad_args* a, void* stream_v) {
   p.b_per_split = (a->B + splits - 1) / splits;
   p.splits = (a->B + p.b_per_split - 1) / p.b_per_split;
   p.num_tiles = base_tiles * p.splits;
-  CUtensorMap tmA[2], tmB;
-  for (int i = 0; i < 2; ++i) {
-    const void* base = a->xt[i] ? a->xt[i] : a->xt[0];
-    int rc = make_tmap_bf16_3d(&tmA[i], base, (uint64_t)a->T, (uint64_t)a->Cin, (uint64_t)a->B, (uint64_t)a->ld_t,
-                               (uint64_t)a->ld_t * a->xt_rows[a->xt[i] ? i : 0], BG_BK, BG_BM);
+  CUtensorMap tmA[4], tmB;
+  for (int i = 0; i < 4; ++i) {
+    const int use = (i < a->num_segments) ? i : 0;
+    int rc = make_tmap_bf16_3d(&tmA[i], a->xt[use], (uint64_t)a->T, (uint64_t)a->Cin, (uint64_t)a->B, (uint64_t)a->ld_t,
+                               (uint64_t)a->ld_t * a->xt_rows[use], BG_BK, BG_BM);
     if (rc) return rc;
   }
   int rc = make_tmap_bf16_3d(&tmB, a->gt, (uint64_t)a->T, (uint64_t)a->N, (uint64_t)a->B, (uint64_t)a->ld_t,
                              (uint64_t)a->ld_t * a->gt_rows, BG_BK, p.block_n);
   if (rc) return rc;
-  return launch(tmA[0], tmA[1], tmB, p, stream);
+  return launch(tmA, tmB, p, stream);
 }

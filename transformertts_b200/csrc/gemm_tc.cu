@@ -49,6 +49,8 @@ struct GemmKParams {
   __nv_bfloat16* vt_lo;
   int vt_col0, vt_cols, vt_ld;
   float* out_preln;  // optional fp32 (B,T,ld_out): the pre-LayerNorm value (saved for the backward pass)
+  float drop_pre_p, drop_post_p;  // training dropout: on the GEMM output before the residual add / on the LayerNorm output
+  uint32_t drop_pre_site, drop_post_site, drop_seed;
   int h16;  // 1: out_hi / vt_hi receive IEEE fp16 instead of bf16 (single plane; operands of the fp16 attention)
 };
 
@@ -138,6 +140,13 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, size_t orow, i
   }
 }
 
+__device__ __forceinline__ void apply_dropout16(float (&y)[16], float p, uint32_t seed, uint32_t site, uint64_t elem0) {
+  const uint32_t thresh = dropout_thresh(p);
+  const float ks = 1.f / (1.f - p);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) y[j] = dropout_keep(seed, site, elem0 + j, thresh) ? y[j] * ks : 0.f;
+}
+
 // exchange of per-row partial sums between the two warps that share a lane quarter
 __device__ __forceinline__ float pair_sum(float part, float* red, int half, int row, int quarter) {
   red[half * GEMM_BM + row] = part;
@@ -176,6 +185,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
 #pragma unroll
         for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
       }
+      if (p.drop_pre_p > 0.f) apply_dropout16(y, p.drop_pre_p, p.drop_seed, p.drop_pre_site, orow * (uint64_t)p.ld_out + n0 + c0);
       if (p.residual && row_ok) {
         ldg16(p.residual + orow * (size_t)p.ld_res + n0 + c0, aux);
 #pragma unroll
@@ -213,6 +223,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
 #pragma unroll
       for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
     }
+    if (p.drop_pre_p > 0.f) apply_dropout16(y, p.drop_pre_p, p.drop_seed, p.drop_pre_site, orow * (uint64_t)p.ld_out + c0);
     if (p.residual && row_ok) {
       ldg16(p.residual + orow * (size_t)p.ld_res + c0, aux);
 #pragma unroll
@@ -267,6 +278,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
     tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; ++j) y[j] = (__uint_as_float(r[j]) - mean) * rstd * aux[j] + bt[j];
+    if (p.drop_post_p > 0.f) apply_dropout16(y, p.drop_post_p, p.drop_seed, p.drop_post_site, orow * (uint64_t)p.ld_out + c0);
     if (partial) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) y[j] = (c0 + j < ncols) ? y[j] : 0.f;
@@ -580,6 +592,16 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
   p.vt_col0 = a->vt_col0; p.vt_cols = a->vt_cols; p.vt_ld = a->vt_ld;
   p.h16 = a->out_fp16 ? 1 : 0;
   p.out_preln = a->out_preln;
+  p.drop_pre_p = a->drop_pre_p; p.drop_post_p = a->drop_post_p;
+  p.drop_pre_site = a->drop_pre_site; p.drop_post_site = a->drop_post_site; p.drop_seed = a->drop_seed;
+  if (a->drop_pre_p < 0.f || a->drop_pre_p >= 1.f || a->drop_post_p < 0.f || a->drop_post_p >= 1.f) {
+    set_last_error("ttsb_linear_fwd: dropout rates must be in [0,1)");
+    return TTSB_ERR_INVALID_ARGUMENT;
+  }
+  if ((a->drop_pre_p > 0.f || a->drop_post_p > 0.f) && a->impl == TTSB_IMPL_SIMT) {
+    set_last_error("ttsb_linear_fwd: dropout is only implemented in the tcgen05 kernel");
+    return TTSB_ERR_UNSUPPORTED;
+  }
   if (p.h16) { p.out_lo = nullptr; p.vt_lo = nullptr; }
 
   if (a->impl == TTSB_IMPL_SIMT) {

@@ -19,7 +19,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // LayerNorm (Keras non-fused: biased variance, rsqrt(var+eps)) of a row held as float4 fragments, + scalar*pe, store.
 __device__ __forceinline__ void ln_pe_store(float4 (&v)[ROW_MAX_V4], int nv, int d, int lane, const float* gamma,
                                             const float* beta, float eps, const float* pe_row, float scalar, float* out_f32,
-                                            __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+                                            __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, float drop_p = 0.f, uint32_t seed = 0,
+                                            uint32_t site = 0, uint64_t elem0 = 0) {
+  const uint32_t thresh = dropout_thresh(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < ROW_MAX_V4; ++i)
@@ -45,6 +48,12 @@ __device__ __forceinline__ void ln_pe_store(float4 (&v)[ROW_MAX_V4], int nv, int
       y.y = (v[i].y - mean) * rstd * g.y + bt.y + scalar * pe.y;
       y.z = (v[i].z - mean) * rstd * g.z + bt.z + scalar * pe.z;
       y.w = (v[i].w - mean) * rstd * g.w + bt.w + scalar * pe.w;
+      if (drop_p > 0.f) {  // keras Dropout after LayerNorm + PE (model/layers.py:301), training only
+        y.x = dropout_keep(seed, site, elem0 + c0 + 0, thresh) ? y.x * keep_scale : 0.f;
+        y.y = dropout_keep(seed, site, elem0 + c0 + 1, thresh) ? y.y * keep_scale : 0.f;
+        y.z = dropout_keep(seed, site, elem0 + c0 + 2, thresh) ? y.z * keep_scale : 0.f;
+        y.w = dropout_keep(seed, site, elem0 + c0 + 3, thresh) ? y.w * keep_scale : 0.f;
+      }
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + c0) = y;
       if (out_hi) {
         __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
@@ -58,7 +67,8 @@ __device__ __forceinline__ void ln_pe_store(float4 (&v)[ROW_MAX_V4], int nv, int
 
 __global__ void embed_ln_pe_kernel(const int* __restrict__ tokens, const float* __restrict__ emb, const float* gamma,
                                    const float* beta, const float* pe, const float* pos_scalar, int rows, int T, int d,
-                                   int vocab, float eps, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+                                   int vocab, float eps, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                                   float drop_p, uint32_t seed, uint32_t site) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -74,12 +84,13 @@ __global__ void embed_ln_pe_kernel(const int* __restrict__ tokens, const float* 
   }
   const size_t o = (size_t)row * d;
   ln_pe_store(v, nv, d, lane, gamma, beta, eps, pe + (size_t)t * d, __ldg(pos_scalar), out_f32 ? out_f32 + o : nullptr,
-              out_hi ? out_hi + o : nullptr, out_lo ? out_lo + o : nullptr);
+              out_hi ? out_hi + o : nullptr, out_lo ? out_lo + o : nullptr, drop_p, seed, site, (uint64_t)o);
 }
 
 __global__ void expand_ln_pe_kernel(const float* __restrict__ x, const int* __restrict__ idx, const float* gamma,
                                     const float* beta, const float* pe, const float* pos_scalar, int B, int Tp, int Tm, int d,
-                                    float eps, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+                                    float eps, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, float drop_p,
+                                    uint32_t seed, uint32_t site) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B * Tm) return;
   const int lane = threadIdx.x & 31;
@@ -95,7 +106,7 @@ __global__ void expand_ln_pe_kernel(const float* __restrict__ x, const int* __re
   }
   const size_t o = (size_t)row * d;
   ln_pe_store(v, nv, d, lane, gamma, beta, eps, pe + (size_t)t * d, __ldg(pos_scalar), out_f32 ? out_f32 + o : nullptr,
-              out_hi ? out_hi + o : nullptr, out_lo ? out_lo + o : nullptr);
+              out_hi ? out_hi + o : nullptr, out_lo ? out_lo + o : nullptr, drop_p, seed, site, (uint64_t)o);
 }
 
 // Expand (model/layers.py:549-565) as a gather: 16-byte vectorised, one warp per output frame.
@@ -288,6 +299,7 @@ static inline int bad(const char* msg) {
 
 using namespace ttsb;
 #define STREAM(s) static_cast<cudaStream_t>(s)
+
 #define LAUNCH_OK(name)  \
   count_launch();        \
   return check_cuda(cudaGetLastError(), name)
@@ -308,29 +320,42 @@ extern "C" int ttsb_split_bf16(const float* x, int64_t n, void* x_hi, void* x_lo
   LAUNCH_OK("split_bf16_kernel");
 }
 
-extern "C" int ttsb_embed_ln_pe_fwd(const int32_t* tokens, const float* emb, const float* gamma, const float* beta,
-                                    const float* pe, const float* pos_scalar, int B, int T, int d, int vocab, float eps,
-                                    float* out_f32, void* out_hi, void* out_lo, void* stream) {
+extern "C" int ttsb_embed_ln_pe_train_fwd(const int32_t* tokens, const float* emb, const float* gamma, const float* beta,
+                                          const float* pe, const float* pos_scalar, int B, int T, int d, int vocab, float eps,
+                                          float drop_p, uint32_t seed, uint32_t site, float* out_f32, void* out_hi, void* out_lo,
+                                          void* stream) {
   if (!tokens || !emb || !gamma || !beta || !pe || !pos_scalar) return bad("ttsb_embed_ln_pe_fwd: NULL input");
   if (B <= 0 || T <= 0 || d <= 0 || d % 4 || d > 128 * ROW_MAX_V4 || vocab <= 0) return bad("ttsb_embed_ln_pe_fwd: need d % 4 == 0, d <= 512");
   const int rows = B * T;
   embed_ln_pe_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(tokens, emb, gamma, beta, pe, pos_scalar, rows, T, d, vocab, eps,
                                                                 out_f32, static_cast<__nv_bfloat16*>(out_hi),
-                                                                static_cast<__nv_bfloat16*>(out_lo));
+                                                                static_cast<__nv_bfloat16*>(out_lo), drop_p, seed, site);
   LAUNCH_OK("embed_ln_pe_kernel");
 }
 
-extern "C" int ttsb_expand_ln_pe_fwd(const float* x, const int32_t* idx, const float* gamma, const float* beta, const float* pe,
-                                     const float* pos_scalar, int B, int Tp, int Tm, int d, float eps, float* out_f32, void* out_hi,
-                                     void* out_lo, void* stream) {
+extern "C" int ttsb_embed_ln_pe_fwd(const int32_t* tokens, const float* emb, const float* gamma, const float* beta,
+                                    const float* pe, const float* pos_scalar, int B, int T, int d, int vocab, float eps,
+                                    float* out_f32, void* out_hi, void* out_lo, void* stream) {
+  return ttsb_embed_ln_pe_train_fwd(tokens, emb, gamma, beta, pe, pos_scalar, B, T, d, vocab, eps, 0.f, 0u, 0u, out_f32, out_hi, out_lo, stream);
+}
+
+extern "C" int ttsb_expand_ln_pe_train_fwd(const float* x, const int32_t* idx, const float* gamma, const float* beta, const float* pe,
+                                           const float* pos_scalar, int B, int Tp, int Tm, int d, float eps, float drop_p, uint32_t seed,
+                                           uint32_t site, float* out_f32, void* out_hi, void* out_lo, void* stream) {
   if (!x || !idx || !gamma || !beta || !pe || !pos_scalar) return bad("ttsb_expand_ln_pe_fwd: NULL input");
   if (B <= 0 || Tp <= 0 || Tm < 0 || d <= 0 || d % 4 || d > 128 * ROW_MAX_V4) return bad("ttsb_expand_ln_pe_fwd: need d % 4 == 0, d <= 512");
   if (Tm == 0) return 0;
   const int rows = B * Tm;
   expand_ln_pe_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(x, idx, gamma, beta, pe, pos_scalar, B, Tp, Tm, d, eps, out_f32,
                                                                  static_cast<__nv_bfloat16*>(out_hi),
-                                                                 static_cast<__nv_bfloat16*>(out_lo));
+                                                                 static_cast<__nv_bfloat16*>(out_lo), drop_p, seed, site);
   LAUNCH_OK("expand_ln_pe_kernel");
+}
+
+extern "C" int ttsb_expand_ln_pe_fwd(const float* x, const int32_t* idx, const float* gamma, const float* beta, const float* pe,
+                                     const float* pos_scalar, int B, int Tp, int Tm, int d, float eps, float* out_f32, void* out_hi,
+                                     void* out_lo, void* stream) {
+  return ttsb_expand_ln_pe_train_fwd(x, idx, gamma, beta, pe, pos_scalar, B, Tp, Tm, d, eps, 0.f, 0u, 0u, out_f32, out_hi, out_lo, stream);
 }
 
 extern "C" int ttsb_length_regulate_fwd(const float* x, const int32_t* idx, int B, int Tp, int Tm, int d, float* out, void* stream) {

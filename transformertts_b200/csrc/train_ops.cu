@@ -22,26 +22,18 @@ __device__ __forceinline__ float wmax(float v) {
   return v;
 }
 
-// Stateless dropout decision: keep element `idx` of dropout site `site` with probability 1-p (32-bit mix of a
-// 64-bit counter; the same function regenerates the mask in the backward pass).
-__device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t site, uint64_t idx, uint32_t thresh) {
-  uint32_t x = (uint32_t)idx * 0x9E3779B1u ^ (uint32_t)(idx >> 32) * 0x85EBCA77u ^ seed * 0xC2B2AE3Du ^ site * 0x27D4EB2Fu;
-  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-  return x >= thresh;
-}
-
 // ------------------------------------------------------------------------------------------------
 // bf16 (B, T, ld_src)[:, :, col0:col0+C]  ->  (B, C, ld_t) ; optional fp32 column sums (bias gradients)
 // ------------------------------------------------------------------------------------------------
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int T, int ld_src, int col0, int C,
-                                      __nv_bfloat16* __restrict__ dst, int dst_rows, int ld_t, float* colsum) {
+                                      __nv_bfloat16* __restrict__ dst, int dst_rows, int ld_t, float* colsum, int t_shift) {
   __shared__ __nv_bfloat16 tile[64][66];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 256 threads: 64 x 4
   for (int r = ty; r < 64; r += 4) {
-    const int t = t0 + r, c = c0 + tx;
-    tile[r][tx] = (t < T && c < C) ? src[((size_t)b * T + t) * ld_src + col0 + c] : __float2bfloat16(0.f);
+    const int t = t0 + r + t_shift, c = c0 + tx;  // dst[b][c][t'] = src[b][t' + t_shift][c], zero outside [0,T)
+    tile[r][tx] = (t >= 0 && t < T && c < C) ? src[((size_t)b * T + t) * ld_src + col0 + c] : __float2bfloat16(0.f);
   }
   __syncthreads();
   for (int r = ty; r < 64; r += 4) {
@@ -316,13 +308,17 @@ __global__ void embedding_bwd_kernel(const float* __restrict__ dx, const int* __
 
 // positional-encoding scalar gradient: sum_{row,c} g[row,c] * pe[t,c]
 __global__ void pe_scalar_bwd_kernel(const float* __restrict__ g, const float* __restrict__ pe, int rows, int T, int d,
-                                     float* __restrict__ dscalar) {
+                                     float drop_p, uint32_t seed, uint32_t site, float* __restrict__ dscalar) {
+  const uint32_t thresh = dropout_thresh(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float local = 0.f;
   const int64_t n = (int64_t)rows * d;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % d);
     const int t = (int)((i / d) % T);
-    local += g[i] * __ldg(pe + (size_t)t * d + c);
+    float gv = g[i];
+    if (drop_p > 0.f) gv = dropout_keep(seed, site, (uint64_t)i, thresh) ? gv * keep_scale : 0.f;
+    local += gv * __ldg(pe + (size_t)t * d + c);
   }
   local = wsum(local);
   __shared__ float red[32];
@@ -413,10 +409,10 @@ using namespace ttsb;
 #define CBF(p) static_cast<const __nv_bfloat16*>(p)
 
 extern "C" int ttsb_transpose_bf16(const void* src, int B, int T, int ld_src, int col0, int C, void* dst, int dst_rows, int ld_t,
-                                   float* colsum, void* stream) {
+                                   float* colsum, int t_shift, void* stream) {
   if (!src || !dst || B <= 0 || T <= 0 || C <= 0 || ld_t < T || dst_rows < C) return bad("ttsb_transpose_bf16: bad arguments");
   dim3 grid((T + 63) / 64, (C + 63) / 64, B);
-  transpose_bf16_kernel<<<grid, 256, 0, STREAM(stream)>>>(CBF(src), T, ld_src, col0, C, BF(dst), dst_rows, ld_t, colsum);
+  transpose_bf16_kernel<<<grid, 256, 0, STREAM(stream)>>>(CBF(src), T, ld_src, col0, C, BF(dst), dst_rows, ld_t, colsum, t_shift);
   LAUNCH_OK("transpose_bf16_kernel");
 }
 
@@ -488,9 +484,10 @@ extern "C" int ttsb_embedding_bwd(const float* dx, const int32_t* tokens, int B,
   LAUNCH_OK("embedding_bwd_kernel");
 }
 
-extern "C" int ttsb_pe_scalar_bwd(const float* g, const float* pe, int B, int T, int d, float* dscalar, void* stream) {
+extern "C" int ttsb_pe_scalar_bwd(const float* g, const float* pe, int B, int T, int d, float drop_p, uint32_t seed, uint32_t site,
+                                  float* dscalar, void* stream) {
   if (!g || !pe || !dscalar || B <= 0 || T <= 0 || d <= 0) return bad("ttsb_pe_scalar_bwd: bad arguments");
-  pe_scalar_bwd_kernel<<<296, 256, 0, STREAM(stream)>>>(g, pe, B * T, T, d, dscalar);
+  pe_scalar_bwd_kernel<<<296, 256, 0, STREAM(stream)>>>(g, pe, B * T, T, d, drop_p, seed, site, dscalar);
   LAUNCH_OK("pe_scalar_bwd_kernel");
 }
 

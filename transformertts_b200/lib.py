@@ -24,7 +24,8 @@ EXPORTS = [
     'ttsb_expand_ln_pe_fwd', 'ttsb_mel_lengths', 'ttsb_phoneme_lengths', 'ttsb_stft_mel_log',
     'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_transpose_bf16', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
     'ttsb_relu_bwd', 'ttsb_cast_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
-    'ttsb_pitch_embed_bwd', 'ttsb_statpred_head_bwd', 'ttsb_adam_tf_step',
+    'ttsb_pitch_embed_bwd', 'ttsb_statpred_head_bwd', 'ttsb_adam_tf_step', 'ttsb_embed_ln_pe_train_fwd',
+    'ttsb_expand_ln_pe_train_fwd',
 ]
 
 
@@ -42,7 +43,8 @@ class GemmArgs(C.Structure):
         ('ln_eps', C.c_float), ('row_len', C.c_void_p), ('out_f32', C.c_void_p), ('out_hi', C.c_void_p),
         ('out_lo', C.c_void_p), ('ld_out', C.c_int), ('vt_hi', C.c_void_p), ('vt_lo', C.c_void_p),
         ('vt_col0', C.c_int), ('vt_cols', C.c_int), ('vt_ld', C.c_int), ('out_fp16', C.c_int), ('out_preln', C.c_void_p),
-        ('precision', C.c_int), ('impl', C.c_int),
+        ('drop_pre_p', C.c_float), ('drop_post_p', C.c_float), ('drop_pre_site', C.c_uint32), ('drop_post_site', C.c_uint32),
+        ('drop_seed', C.c_uint32), ('precision', C.c_int), ('impl', C.c_int),
     ]
 
 
@@ -62,7 +64,7 @@ class BgemmArgs(C.Structure):
 class WgradArgs(C.Structure):
     _fields_ = [
         ('B', C.c_int), ('T', C.c_int), ('Cin', C.c_int), ('N', C.c_int), ('num_segments', C.c_int),
-        ('seg_src', C.c_int * 4), ('seg_shift', C.c_int * 4), ('xt', C.c_void_p * 2), ('xt_rows', C.c_int * 2),
+        ('xt', C.c_void_p * 4), ('xt_rows', C.c_int * 4),
         ('gt', C.c_void_p), ('gt_rows', C.c_int), ('ld_t', C.c_int), ('dw', C.c_void_p),
     ]
 
@@ -153,20 +155,20 @@ def mha_fwd(args: MhaArgs):
     _check(load().ttsb_mha_fwd(C.byref(args), _stream()), 'ttsb_mha_fwd')
 
 
-def embed_ln_pe_fwd(tokens, emb, gamma, beta, pe, pos_scalar, eps, out_f32, out_hi, out_lo):
+def embed_ln_pe_fwd(tokens, emb, gamma, beta, pe, pos_scalar, eps, out_f32, out_hi, out_lo, drop=(0.0, 0, 0)):
     B, T = tokens.shape
     vocab, d = emb.shape
-    _check(load().ttsb_embed_ln_pe_fwd(ptr(tokens), ptr(emb), ptr(gamma), ptr(beta), ptr(pe), ptr(pos_scalar), B, T, d,
-                                       vocab, C.c_float(eps), ptr(out_f32), ptr(out_hi), ptr(out_lo), _stream()),
-           'ttsb_embed_ln_pe_fwd')
+    _check(load().ttsb_embed_ln_pe_train_fwd(ptr(tokens), ptr(emb), ptr(gamma), ptr(beta), ptr(pe), ptr(pos_scalar), B, T, d,
+                                             vocab, C.c_float(eps), C.c_float(drop[0]), C.c_uint32(drop[1]), C.c_uint32(drop[2]),
+                                             ptr(out_f32), ptr(out_hi), ptr(out_lo), _stream()), 'ttsb_embed_ln_pe_fwd')
 
 
-def expand_ln_pe_fwd(x, idx, gamma, beta, pe, pos_scalar, eps, out_f32, out_hi, out_lo):
+def expand_ln_pe_fwd(x, idx, gamma, beta, pe, pos_scalar, eps, out_f32, out_hi, out_lo, drop=(0.0, 0, 0)):
     B, Tp, d = x.shape
     Tm = idx.shape[1]
-    _check(load().ttsb_expand_ln_pe_fwd(ptr(x), ptr(idx), ptr(gamma), ptr(beta), ptr(pe), ptr(pos_scalar), B, Tp, Tm, d,
-                                        C.c_float(eps), ptr(out_f32), ptr(out_hi), ptr(out_lo), _stream()),
-           'ttsb_expand_ln_pe_fwd')
+    _check(load().ttsb_expand_ln_pe_train_fwd(ptr(x), ptr(idx), ptr(gamma), ptr(beta), ptr(pe), ptr(pos_scalar), B, Tp, Tm, d,
+                                              C.c_float(eps), C.c_float(drop[0]), C.c_uint32(drop[1]), C.c_uint32(drop[2]),
+                                              ptr(out_f32), ptr(out_hi), ptr(out_lo), _stream()), 'ttsb_expand_ln_pe_fwd')
 
 
 def length_regulate_fwd(x, idx, out):
@@ -226,8 +228,8 @@ def wgrad(args: WgradArgs):
     _check(load().ttsb_wgrad(C.byref(args), _stream()), 'ttsb_wgrad')
 
 
-def transpose_bf16(src, B, T, ld_src, col0, Cc, dst, dst_rows, ld_t, colsum=None):
-    _check(load().ttsb_transpose_bf16(ptr(src), B, T, ld_src, col0, Cc, ptr(dst), dst_rows, ld_t, ptr(colsum), _stream()),
+def transpose_bf16(src, B, T, ld_src, col0, Cc, dst, dst_rows, ld_t, colsum=None, t_shift=0):
+    _check(load().ttsb_transpose_bf16(ptr(src), B, T, ld_src, col0, Cc, ptr(dst), dst_rows, ld_t, ptr(colsum), int(t_shift), _stream()),
            'ttsb_transpose_bf16')
 
 
@@ -280,9 +282,10 @@ def embedding_bwd(dx, tokens, demb):
     _check(load().ttsb_embedding_bwd(ptr(dx), ptr(tokens), B, T, d, demb.shape[0], ptr(demb), _stream()), 'ttsb_embedding_bwd')
 
 
-def pe_scalar_bwd(g, pe, dscalar):
+def pe_scalar_bwd(g, pe, dscalar, drop=(0.0, 0, 0)):
     B, T, d = g.shape
-    _check(load().ttsb_pe_scalar_bwd(ptr(g), ptr(pe), B, T, d, ptr(dscalar), _stream()), 'ttsb_pe_scalar_bwd')
+    _check(load().ttsb_pe_scalar_bwd(ptr(g), ptr(pe), B, T, d, C.c_float(drop[0]), C.c_uint32(drop[1]), C.c_uint32(drop[2]),
+                                     ptr(dscalar), _stream()), 'ttsb_pe_scalar_bwd')
 
 
 def pitch_embed_bwd(g, pitch, w, bias, dw, db):

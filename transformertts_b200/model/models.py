@@ -134,6 +134,7 @@ class ForwardTransformer:
         self.loss_weights = [1., 1., 3.]
         self.train_dropout = bool(kwargs.get('train_dropout', True))  # False: deterministic training step (parity tests)
         self._engine = None
+        self._drop_seed = 0
         self._init_weights(seed=int(kwargs.get('seed', 42)))
 
     # ------------------------------------------------------------------------------------------------
@@ -354,9 +355,11 @@ class ForwardTransformer:
             a.vt_col0, a.vt_cols, a.vt_ld = col0, cols, ld
         a.out_fp16 = int(out_fp16)
         a.out_preln = out_preln.data_ptr() if out_preln is not None else None
-        for dp in (dropout, dropout_post):
-            if dp is not None and dp[0] > 0:
-                raise lib.TtsbError('dropout inside the GEMM epilogue is not implemented yet (train with dropout_rate=0)')
+        if dropout is not None and dropout[0] > 0:
+            a.drop_pre_p, a.drop_pre_site = dropout[0], dropout[1]
+        if dropout_post is not None and dropout_post[0] > 0:
+            a.drop_post_p, a.drop_post_site = dropout_post[0], dropout_post[1]
+        a.drop_seed = self._drop_seed
         a.precision = self._prec
         a.impl = self._impl
         lib.linear_fwd(a)

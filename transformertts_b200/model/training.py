@@ -35,22 +35,25 @@ class TrainEngine:
         self.dev = model.device
         names = list(model._param_shapes().keys())
         sizes = [model.weights[n].numel() for n in names]
+        padded = [_round_up(sz, 8) for sz in sizes]  # every parameter starts 32-byte aligned (kernels use float4 loads)
         self.names = names
-        total = sum(sizes)
-        self.flat_w = torch.empty(total, dtype=torch.float32, device=self.dev)
+        total = sum(padded)
+        self.flat_w = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.dev)
         off = 0
         self.g: Dict[str, torch.Tensor] = {}
-        for n, sz in zip(names, sizes):
+        for n, sz, psz in zip(names, sizes, padded):
             shape = model.weights[n].shape
             self.flat_w[off:off + sz].copy_(model.weights[n].reshape(-1))
             model.weights[n] = self.flat_w[off:off + sz].view(shape)  # parameters become views of the flat buffer
             self.g[n] = self.flat_g[off:off + sz].view(shape)
-            off += sz
+            off += psz
         model._packed = None
         self.P = None
         self.world = 1
+        self.base_seed = 1234
         self.seed = 1234
+        self.rank = 0
         self.drop_sites = 0
 
     # ------------------------------------------------------------------------------------------------
@@ -128,18 +131,21 @@ class TrainEngine:
     def _f32(self, *shape):
         return torch.empty(shape, dtype=torch.float32, device=self.dev)
 
-    def _transpose(self, src, B, T, ld_src, col0, C, colsum=None):
+    def _transpose(self, src, B, T, ld_src, col0, C, colsum=None, t_shift=0):
         ld_t = _round_up(T, 8)
         dst = self._bf(B, C, ld_t)
-        lib.transpose_bf16(src, B, T, ld_src, col0, C, dst, C, ld_t, colsum)
+        lib.transpose_bf16(src, B, T, ld_src, col0, C, dst, C, ld_t, colsum, t_shift)
         return dst, ld_t
 
-    def _wgrad(self, xts: List[torch.Tensor], gt, B, T, Cin, N, segs, ld_t, dw):
+    def _transpose_taps(self, src, B, T, ld_src, C, shifts):
+        """One time-transposed copy per conv tap: xt_s[b][c][t] = src[b][t + s][c]."""
+        return [self._transpose(src, B, T, ld_src, 0, C, t_shift=s)[0] for s in shifts]
+
+    def _wgrad(self, xts: List[torch.Tensor], gt, B, T, Cin, N, ld_t, dw):
+        """xts: one transposed source per segment (conv: one per tap; concat projection: one per input)."""
         a = lib.WgradArgs()
         a.B, a.T, a.Cin, a.N = B, T, Cin, N
-        a.num_segments = len(segs)
-        for s, (src, shift) in enumerate(segs):
-            a.seg_src[s], a.seg_shift[s] = src, shift
+        a.num_segments = len(xts)
         for i, xt in enumerate(xts):
             a.xt[i] = xt.data_ptr()
             a.xt_rows[i] = xt.shape[1]
@@ -250,13 +256,13 @@ class TrainEngine:
             h = c['hs'][0]
             g2T, ld8 = self._transpose(g2, B, T, d, 0, d, colsum=G[pre + 'ffn2.b'])
             hT, _ = self._transpose(h, B, T, F, 0, F)
-            self._wgrad([hT], g2T, B, T, F, d, [(0, 0)], ld8, G[pre + 'ffn2.w'])
+            self._wgrad([hT], g2T, B, T, F, d, ld8, G[pre + 'ffn2.w'])
             dh_ = self._bf(B, T, F)
             m._gemm(P[pre + 'ffn2.d'], B, T, [(g2, None, d, 0)], [0], [0], out_hi=dh_, ld_out=F)
             lib.relu_bwd(dh_, h)
             dhT, _ = self._transpose(dh_, B, T, F, 0, F, colsum=G[pre + 'ffn1.b'])
             yT, _ = self._transpose(c['y_bf'], B, T, d, 0, d)
-            self._wgrad([yT], dhT, B, T, d, F, [(0, 0)], ld8, G[pre + 'ffn1.w'])
+            self._wgrad([yT], dhT, B, T, d, F, ld8, G[pre + 'ffn1.w'])
             dy = self._f32(B, T, d)
             m._gemm(P[pre + 'ffn1.d'], B, T, [(dh_, None, F, 0)], [0], [0], residual=du2, out_f32=dy, ld_out=d)
         else:
@@ -271,8 +277,9 @@ class TrainEngine:
             for j in range(n - 1, -1, -1):
                 cin = in_dims[j]
                 gT, _ = self._transpose(g_cur, B, T, g_cur.shape[-1], 0, g_dim, colsum=G[pre + f'conv{j}.b'])
-                xT, _ = self._transpose(inputs[j], B, T, cin, 0, cin)
-                self._wgrad([xT], gT, B, T, cin, g_dim, [(0, s) for s in shifts], ld8, G[pre + f'conv{j}.w'])
+                xTs = self._transpose_taps(inputs[j], B, T, cin, cin, shifts)
+                self._wgrad(xTs, gT, B, T, cin, g_dim, ld8, G[pre + f'conv{j}.w'])
+                del xTs
                 kpad = _round_up(g_dim, 64)
                 assert g_cur.shape[-1] == kpad, 'gradient operand must be padded to the packed contraction width'
                 if j > 0:
@@ -290,7 +297,7 @@ class TrainEngine:
         g1T, ld8 = self._transpose(g1, B, T, d, 0, d, colsum=G[pre + 'wo.b'])
         xT, _ = self._transpose(c['x_bf'], B, T, d, 0, d)
         aT, _ = self._transpose(c['attn'], B, T, d, 0, d)
-        self._wgrad([xT, aT], g1T, B, T, d, d, [(0, 0), (1, 0)], ld8, G[pre + 'wo.w'])
+        self._wgrad([xT, aT], g1T, B, T, d, d, ld8, G[pre + 'wo.w'])
         dattn = self._bf(B, T, d)
         m._gemm(P[pre + 'wo.da'], B, T, [(g1, None, d, 0)], [0], [0], out_hi=dattn, ld_out=d)
         dx_acc = self._f32(B, T, d)
@@ -322,7 +329,7 @@ class TrainEngine:
         bq = self._tmp_zero(3 * d)
         dqkvT, _ = self._transpose(dqkv, B, T, 3 * d, 0, 3 * d, colsum=bq)
         wq = self._tmp_zero(d * 3 * d).view(d, 3 * d)
-        self._wgrad([xT], dqkvT, B, T, d, 3 * d, [(0, 0)], ld8, wq)
+        self._wgrad([xT], dqkvT, B, T, d, 3 * d, ld8, wq)
         for n_, nm in enumerate(('wq', 'wk', 'wv')):
             G[pre + nm + '.w'].add_(wq[:, n_ * d:(n_ + 1) * d])
             G[pre + nm + '.b'].add_(bq[n_ * d:(n_ + 1) * d])
@@ -389,11 +396,10 @@ class TrainEngine:
             G[f'{name}.ln{j}.beta'].add_(db[:C])
             cin = d_enc if j == 0 else filt[j - 1]
             gT, _ = self._transpose(g_bf, B, T, ld, 0, C, colsum=G[f'{name}.conv{j}.b'])
-            if j == 0:
-                xT = xT_enc
-            else:
-                xT, _ = self._transpose(c['outs'][j - 1], B, T, c['outs'][j - 1].shape[-1], 0, cin)
-            self._wgrad([xT], gT, B, T, cin, C, [(0, s) for s in shifts], ld8, G[f'{name}.conv{j}.w'])
+            src = c['x_bf'] if j == 0 else c['outs'][j - 1]
+            xTs = self._transpose_taps(src, B, T, src.shape[-1], cin, shifts)
+            self._wgrad(xTs, gT, B, T, cin, C, ld8, G[f'{name}.conv{j}.w'])
+            del xTs
             if j > 0:
                 ldn = c['us'][j - 1].shape[-1]
                 dz = self._f32(B, T, ldn)
@@ -412,6 +418,8 @@ class TrainEngine:
         self.use_dropout = training and m.train_dropout
         self.drop_rate = float(m.config.get('dropout_rate', 0.0)) if self.use_dropout else 0.0
         self.drop_sites = 0
+        self.seed = (self.base_seed * 2654435761 + (m.optimizer.iterations if m.optimizer else 0) * 40503 + self.rank * 97) & 0x7fffffff
+        m._drop_seed = self.seed
         saved_precision = m.precision
         m.precision = 'bf16'
         try:
@@ -430,8 +438,7 @@ class TrainEngine:
             h_f, h_bf = self._f32(B, Tp, d), self._bf(B, Tp, d)
             site_e = self._site()
             lib.embed_ln_pe_fwd(x, W['embedding'], W['encoder.ln.gamma'], W['encoder.ln.beta'], P['encoder.pe'],
-                                W['encoder.pos_scalar'].reshape(1), LN_EPS, h_f, h_bf, None)
-            h_f, h_bf = self._prologue_dropout(h_f, h_bf, site_e)
+                                W['encoder.pos_scalar'].reshape(1), LN_EPS, h_f, h_bf, None, drop=(self.drop_rate, self.seed, site_e))
             enc_ctx = []
             for i in range(len(m._stacks['encoder']['heads'])):
                 h_f, h_bf, c = self._block_fwd('encoder', i, h_f, h_bf, enc_len, B, Tp)
@@ -456,8 +463,7 @@ class TrainEngine:
             m_f, m_bf = self._f32(B, Tm, dd), self._bf(B, Tm, dd)
             site_d = self._site()
             lib.expand_ln_pe_fwd(h_pe, idx, W['decoder.ln.gamma'], W['decoder.ln.beta'], P['decoder.pe'],
-                                 W['decoder.pos_scalar'].reshape(1), LN_EPS, m_f, m_bf, None)
-            m_f, m_bf = self._prologue_dropout(m_f, m_bf, site_d)
+                                 W['decoder.pos_scalar'].reshape(1), LN_EPS, m_f, m_bf, None, drop=(self.drop_rate, self.seed, site_d))
             dec_ctx = []
             for i in range(len(m._stacks['decoder']['heads'])):
                 m_f, m_bf, c = self._block_fwd('decoder', i, m_f, m_bf, dec_len, B, Tm)
@@ -486,7 +492,7 @@ class TrainEngine:
             lib.cast_bf16_pad(dmel, B * Tm, C, g, kpad)
             gT, ld8m = self._transpose(g, B, Tm, kpad, 0, C, colsum=G['out.b'])
             mT, _ = self._transpose(m_bf, B, Tm, dd, 0, dd)
-            self._wgrad([mT], gT, B, Tm, dd, C, [(0, 0)], ld8m, G['out.w'])
+            self._wgrad([mT], gT, B, Tm, dd, C, ld8m, G['out.w'])
             dz = self._f32(B, Tm, dd)
             m._gemm(P['out.d'], B, Tm, [(g, None, kpad, 0)], [0], [0], out_f32=dz, ld_out=dd)
             for i in range(len(dec_ctx) - 1, -1, -1):
@@ -510,19 +516,13 @@ class TrainEngine:
         finally:
             m.precision = saved_precision
 
-    def _prologue_dropout(self, x_f, x_bf, site):
-        """Dropout after LayerNorm + PE of a stack (model/layers.py:301)."""
-        if self.drop_rate <= 0:
-            return x_f, x_bf
-        raise lib.TtsbError('stack-prologue dropout is not implemented yet (use dropout_rate=0)')
-
     def _prologue_bwd(self, name, g, u, lens, B, T, site):
         m, W, G = self.model, self.model.weights, self.g
         d = m._stacks[name]['d']
-        lib.pe_scalar_bwd(g, self.P[f'{name}.pe'], G[f'{name}.pos_scalar'].view(1))
+        lib.pe_scalar_bwd(g, self.P[f'{name}.pe'], G[f'{name}.pos_scalar'].view(1), drop=(self.drop_rate, self.seed, site))
         du = self._f32(B, T, d)
         lib.layernorm_bwd(g, u.contiguous(), W[f'{name}.ln.gamma'], B, T, d, d, LN_EPS, None, False, du, None,
-                          G[f'{name}.ln.gamma'], G[f'{name}.ln.beta'])
+                          G[f'{name}.ln.gamma'], G[f'{name}.ln.beta'], post_drop=(self.drop_rate, site), seed=self.seed)
         return du
 
     # ------------------------------------------------------------------------------------------------
