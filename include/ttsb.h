@@ -101,11 +101,7 @@ typedef struct ttsb_gemm_args {
   void* out_hi;
   void* out_lo;
   int ld_out;               /* row stride of all outputs, >= n_tiles*block_n, multiple of 8 */
-  /* optional transposed store: tile columns [vt_col0, vt_col0+vt_cols) go to vt_*[b][col - vt_col0][t] (row stride vt_ld) */
-  void* vt_hi;
-  void* vt_lo;
-  int vt_col0, vt_cols, vt_ld;
-  int out_fp16;             /* 1: out_hi / vt_hi receive IEEE fp16 (single plane) instead of bf16 hi/lo */
+  int out_fp16;             /* 1: out_hi receives IEEE fp16 (single plane) instead of bf16 hi/lo */
   float* out_preln;         /* optional fp32 (B,T,ld_out): value before the LayerNorm (saved for the backward pass) */
   /* training dropout (keras semantics, stateless mask from (seed, site, element index)): drop_pre on the GEMM output
    * after bias/ReLU and before the residual add; drop_post on the LayerNorm output */
@@ -119,19 +115,16 @@ int ttsb_linear_fwd(const ttsb_gemm_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused variable-length self-attention  (model/layers.py:138-147 split/merge heads, :176-195 scaled dot product)
- *   q,k: bf16 (B,T,ld_qk) at columns q_col0 + h*dh / k_col0 + h*dh;  vT: bf16 (B, H*dh, ld_vt) (time contiguous)
+ *   q,k,v: bf16 (B,T,ld_qk) at columns q_col0 + h*dh / k_col0 + h*dh / v_col0 + h*dh of one buffer (the QKV GEMM output)
  *   out: bf16 hi (and lo when out_lo != NULL) (B,T,ld_out), head h at columns h*dh.  Keys t >= kv_len[b] are masked
- *   (the reference adds -1e9).  precision TTSB_PREC_FP16: qk_hi / vt_hi hold IEEE fp16 (written by ttsb_linear_fwd
+ *   (the reference adds -1e9).  precision TTSB_PREC_FP16: qk_hi holds IEEE fp16 (written by ttsb_linear_fwd
  *   with out_fp16 = 1), one tensor-core pass.
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct ttsb_mha_args {
   int B, T, H, dh;
   const void* qk_hi;
   const void* qk_lo;
-  int ld_qk, q_col0, k_col0;
-  const void* vt_hi;
-  const void* vt_lo;
-  int ld_vt;
+  int ld_qk, q_col0, k_col0, v_col0;
   const int32_t* kv_len; /* [B] */
   void* out_hi;
   void* out_lo;
@@ -150,21 +143,24 @@ int ttsb_mha_fwd(const ttsb_mha_args* args, void* stream);
  *
  * ttsb_bgemm: per-(batch row b, head h) products  out_z[m][n] = alpha * sum_k A_z[m][k] * B_z[n][k]  where both operands
  *   are activations: S = Q K^T, O = P V, dP = dO V^T, dQ = dS K, dK = dS^T Q, dV = P^T dO (model/layers.py:179-193 and
- *   its gradient).  Each operand is a bf16 tensor described as (dim0 contiguous = K axis, dim1 = rows, dim2 = batches)
- *   with element strides; the tile origin of problem z=(b,h) is (k + h*h_col, row + h*h_row, z_batch ? z : b).
- * ttsb_wgrad: weight gradients  dW[seg*Cin + c][n] += sum_{b,t} Xt_seg[b][c][t] * Gt[b][n][t]  for Dense (1 segment),
- *   concat-Dense (2 segments = the two sources) and Conv1D (k segments = the k tap-shifted copies of the input);
- *   Xt_seg / Gt are time-transposed bf16 copies (B, C, ld_t) produced by ttsb_transpose_bf16; dW is fp32 in the Keras
- *   (K, N) layout and is ACCUMULATED into.
+ *   its gradient).  Each operand is a bf16 tensor described as (dim0 contiguous, dim1 rows, dim2 batches) with element
+ *   strides.  K-major operand (x_mn_major = 0): dim0 is the contraction axis, dim1 the M (or N) axis; MN-major operand
+ *   (x_mn_major = 1): dim0 is the M (or N) axis, dim1 the contraction axis -- so a transposed operand (P^T, dS^T, dO^T,
+ *   V^T, K^T) is the SAME tensor read MN-major and no transposed copies exist.  The tile origin of problem z = (b,h) is
+ *   (c0 + h*h_col, c1 + h*h_row, z_batch ? z : b).
+ * ttsb_wgrad: weight gradients  dW[seg*Cin + c][n] += sum_{b,t} X_seg[b][t + shift_seg][c] * G[b][t][n]  for Dense
+ *   (1 segment), concat-Dense (2 sources) and Conv1D (k segments with the tap shifts); X and G are the row-major bf16
+ *   activations / output gradients (B, T, ld) read MN-major; dW is fp32 in the Keras (K, N) layout and is ACCUMULATED
+ *   into.
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct ttsb_bgemm_args {
   int B, H, M, N, K;
   const void* a;
   long long a_dim0, a_dim1, a_dim2, a_stride1, a_stride2;
-  int a_h_col, a_h_row, a_z_batch;
+  int a_h_col, a_h_row, a_z_batch, a_mn_major;
   const void* b;
   long long b_dim0, b_dim1, b_dim2, b_stride1, b_stride2;
-  int b_h_col, b_h_row, b_z_batch;
+  int b_h_col, b_h_row, b_z_batch, b_mn_major;
   float alpha;
   float* out_f32;            /* either or both */
   void* out_bf16;
@@ -182,22 +178,17 @@ int ttsb_bgemm(const ttsb_bgemm_args* args, void* stream);
 typedef struct ttsb_wgrad_args {
   int B, T, Cin, N;
   int num_segments;          /* 1..4 */
-  const void* xt[4];         /* per segment: bf16 (B, xt_rows[s], ld_t); the first Cin rows of each batch are used */
-  int xt_rows[4];
-  const void* gt;            /* bf16 (B, gt_rows, ld_t); the first N rows are used */
-  int gt_rows;
-  int ld_t;                  /* row stride of the transposed tensors (multiple of 8) */
+  int seg_src[4];            /* which x source */
+  int seg_shift[4];          /* time shift of the source rows (conv taps); rows outside [0,T) read as zero */
+  const void* x[2];          /* bf16 (B, T, ldx[i]); the first Cin columns are used */
+  int ldx[2];
+  const void* g;             /* bf16 (B, T, ldg); the first N columns are used */
+  int ldg;
   float* dw;                 /* fp32 (num_segments*Cin, N), accumulated */
 } ttsb_wgrad_args;
 
 int ttsb_wgrad(const ttsb_wgrad_args* args, void* stream);
 
-/* bf16 (B,T,ld_src)[:, :, col0:col0+C] -> (B, dst_rows >= C, ld_t >= T) time-transposed copy for ttsb_wgrad / ttsb_bgemm:
- * dst[b][c][t] = src[b][t + t_shift][c] (zero outside [0,T); the conv taps of ttsb_wgrad use pre-shifted copies because a
- * TMA box cannot start at an unaligned element of the contiguous dimension);
- * colsum (optional, fp32 [C]) accumulates the column sums = bias gradient of a Dense/Conv1D whose output grad this is. */
-int ttsb_transpose_bf16(const void* src, int B, int T, int ld_src, int col0, int C, void* dst, int dst_rows, int ld_t,
-                        float* colsum, int t_shift, void* stream);
 /* Row softmax of materialised, pre-scaled scores S fp32 (B*H, T, ld) with key masking (model/layers.py:186-192) and
  * attention dropout: P_pre = softmax, P_drop = dropout(P_pre) (pass the same pointer twice when drop_p == 0). */
 int ttsb_softmax_fwd(const float* S, int B, int H, int T, int Tk, int ld, const int32_t* kv_len, float drop_p,
@@ -207,9 +198,11 @@ int ttsb_softmax_bwd(const void* P_pre, const float* dP, int B, int H, int T, in
 /* LayerNorm backward from the saved pre-norm values u (keras LayerNormalization, model/layers.py:27,96,207,295,508). */
 int ttsb_layernorm_bwd(const float* dz, const float* u, const float* gamma, int B, int T, int C, int ld, float eps,
                        const int32_t* row_len, int relu_mask, float pre_drop_p, uint32_t pre_site, float post_drop_p,
-                       uint32_t post_site, uint32_t seed, float* du, void* g_bf16, float* dgamma, float* dbeta, void* stream);
+                       uint32_t post_site, uint32_t seed, float* du, void* g_bf16, float* dgamma, float* dbeta, float* dbias,
+                       void* stream);
+/* column sums of bf16 (rows, ld)[:, :C] accumulated into fp32 out[C] (bias gradients) */
+int ttsb_colsum_bf16(const void* x, int64_t rows, int C, int ld, float* out, void* stream);
 int ttsb_relu_bwd(void* dy_bf16, const void* h_bf16, int64_t n, void* stream);
-int ttsb_cast_bf16(const float* x, int64_t n, float drop_p, uint32_t seed, uint32_t site, void* out_bf16, void* stream);
 /* fp32 (rows, C) -> bf16 (rows, ld_out >= C) with zero padding columns */
 int ttsb_cast_bf16_pad(const float* x, int64_t rows, int C, void* out_bf16, int ld_out, void* stream);
 /* mean |pred - target| over ALL elements of pred[:, :Tt] (utils/losses.py:41-49 as called with mask=None), added to

@@ -14,7 +14,7 @@ def split_or_none(x: torch.Tensor, split: bool):
 
 
 def run_gemm(x_list, w_kn, bias, seg_src, seg_shift, seg_k, *, precision='bf16x3', impl='tcgen05', relu=False,
-             residual=None, ln=None, row_len=None, block_n=None, single_tile=False, vt=None, want=('f32',)):
+             residual=None, ln=None, row_len=None, block_n=None, single_tile=False, out_fp16=False):
     """x_list: fp32 (B,T,C) sources (on GPU).  Returns dict with requested outputs."""
     split = precision == 'bf16x3'
     B, T, _ = x_list[0].shape
@@ -54,15 +54,7 @@ def run_gemm(x_list, w_kn, bias, seg_src, seg_shift, seg_k, *, precision='bf16x3
     a.out_f32, a.out_hi = out_f32.data_ptr(), out_hi.data_ptr()
     a.out_lo = out_lo.data_ptr() if split else None
     a.ld_out = pl.n_pad
-    if vt is not None:
-        col0, cols = vt
-        ld_vt = _round_up(T, 8)
-        vt_hi = torch.full((B, cols, ld_vt), float('nan'), device=DEV, dtype=torch.bfloat16)
-        vt_lo = torch.full((B, cols, ld_vt), float('nan'), device=DEV, dtype=torch.bfloat16)
-        a.vt_hi = vt_hi.data_ptr()
-        a.vt_lo = vt_lo.data_ptr() if split else None
-        a.vt_col0, a.vt_cols, a.vt_ld = col0, cols, ld_vt
-        out['vt'] = (vt_hi, vt_lo if split else None)
+    a.out_fp16 = int(out_fp16)
     a.precision = lib.PREC_BF16X3 if split else lib.PREC_BF16
     a.impl = lib.IMPL_SIMT if impl == 'simt' else lib.IMPL_TCGEN05
     lib.linear_fwd(a)
@@ -119,22 +111,15 @@ def run_mha(q, k, v, kv_len, H, *, precision='bf16x3', impl='tcgen05', weights_b
     split = precision == 'bf16x3'
     B, T, d = q.shape
     dh = d // H
-    qk = torch.cat([q, k], dim=-1).contiguous()
+    qk = torch.cat([q, k, v], dim=-1).contiguous()
     qk_hi, qk_lo = _to16(qk, precision, split)
-    ld_vt = _round_up(T, 8)
-    vt = torch.zeros(B, d, ld_vt, device=DEV)
-    vt[:, :, :T] = v.transpose(1, 2)
-    vt_hi, vt_lo = _to16(vt, precision, split)
     out_hi = torch.full((B, T, d), float('nan'), device=DEV, dtype=torch.bfloat16)
     out_lo = torch.full((B, T, d), float('nan'), device=DEV, dtype=torch.bfloat16)
     m = lib.MhaArgs()
     m.B, m.T, m.H, m.dh = B, T, H, dh
     m.qk_hi = qk_hi.data_ptr()
     m.qk_lo = qk_lo.data_ptr() if split else None
-    m.ld_qk, m.q_col0, m.k_col0 = 2 * d, 0, d
-    m.vt_hi = vt_hi.data_ptr()
-    m.vt_lo = vt_lo.data_ptr() if split else None
-    m.ld_vt = ld_vt
+    m.ld_qk, m.q_col0, m.k_col0, m.v_col0 = 3 * d, 0, d, 2 * d
     m.kv_len = kv_len.data_ptr()
     m.out_hi = out_hi.data_ptr()
     m.out_lo = out_lo.data_ptr()

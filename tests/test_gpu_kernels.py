@@ -165,23 +165,22 @@ def _tol(precision):
 
 @pytest.mark.parametrize('impl', IMPLS)
 @pytest.mark.parametrize('precision', PRECS)
-def test_gemm_qkv_with_transposed_v(impl, precision):
-    """Dense d -> 3d with bias; last third stored transposed (V^T) for the attention kernel."""
+def test_gemm_qkv_projection(impl, precision):
+    """Dense d -> 3d with bias into one (B,T,3d) buffer: bf16 hi/lo planes and the fp16 plane the fp16 attention reads."""
     from gpu_util import ref_gemm, run_gemm
     g = torch.Generator().manual_seed(10)
     B, T, d = 3, 200, 256
     x = torch.randn(B, T, d, generator=g).to(DEV)
     w = (torch.randn(d, 3 * d, generator=g) / 16).to(DEV)
     b = torch.randn(3 * d, generator=g).to(DEV)
-    out = run_gemm([x], w, b, [0], [0], [d], precision=precision, impl=impl, block_n=d, vt=(2 * d, d))
+    out = run_gemm([x], w, b, [0], [0], [d], precision=precision, impl=impl, block_n=d)
     ref = ref_gemm([x], w, b, [0], [0], [d], precision=precision)
-    assert _relerr(out['f32'][..., :2 * d], ref[..., :2 * d]) < _tol(precision)
-    vt_hi, vt_lo = out['vt']
-    vt = vt_hi.float() + (vt_lo.float() if vt_lo is not None else 0)
-    tol = _tol(precision) if precision == 'bf16x3' else 1e-2  # bf16 mode stores V^T in bf16 only
-    assert _relerr(vt[:, :, :T].transpose(1, 2), ref[..., 2 * d:]) < tol
+    assert _relerr(out['f32'], ref) < _tol(precision)
     if precision == 'bf16x3':
-        assert _relerr(out['hi'][..., :2 * d].float() + out['lo'][..., :2 * d].float(), ref[..., :2 * d]) < 1e-4
+        assert _relerr(out['hi'].float() + out['lo'].float(), ref) < 1e-4
+    out16 = run_gemm([x], w, b, [0], [0], [d], precision=precision, impl=impl, block_n=d, out_fp16=True)
+    h16 = out16['hi'].view(torch.float16).float()
+    assert _relerr(h16, ref) < 3e-3
 
 
 @pytest.mark.parametrize('impl', IMPLS)

@@ -24,48 +24,25 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def test_transpose_with_column_sums():
-    lib = _lib()
-    g = torch.Generator().manual_seed(0)
-    B, T, C = 3, 203, 300
-    x = torch.randn(B, T, 320, generator=g).bfloat16().to(DEV)
-    ld_t = 208
-    dst = torch.zeros(B, C, ld_t, dtype=torch.bfloat16, device=DEV)
-    cs = torch.zeros(C, device=DEV)
-    lib.transpose_bf16(x, B, T, 320, 16, C, dst, C, ld_t, cs, 0)
-    torch.cuda.synchronize()
-    ref = x[:, :, 16:16 + C].transpose(1, 2)
-    assert torch.equal(dst[:, :, :T], ref)
-    assert _rel(cs, x[:, :, 16:16 + C].float().sum((0, 1))) < 1e-5
-
-
 def test_wgrad_conv_and_concat():
-    """dW of Conv1D(k=3,'same') and of the concat projection against x^T g on the CPU."""
+    """dW of Conv1D(k=3,'same') and of the concat projection against x^T g on the CPU (operands read MN-major)."""
     lib = _lib()
-    from transformertts_b200.model.training import TrainEngine
     g = torch.Generator().manual_seed(1)
     B, T, Cin, N = 5, 333, 256, 226
     x = torch.randn(B, T, Cin, generator=g).bfloat16()
-    gy = torch.randn(B, T, N, generator=g).bfloat16()
-    ld_t = 336
-
-    def tr(t, shift=0):
-        C = t.shape[2]
-        out = torch.full((t.shape[0], C, ld_t), float('nan'), dtype=torch.bfloat16, device=DEV)
-        lib.transpose_bf16(t.to(DEV), t.shape[0], T, C, 0, C, out, C, ld_t, None, shift)
-        return out
-
-    xt, gt = tr(x), tr(gy)
-    taps = [tr(x, sh) for sh in (-1, 0, 1)]
+    gy = torch.zeros(B, T, 256).bfloat16()
+    gy[..., :N] = torch.randn(B, T, N, generator=g).bfloat16()
+    x_d, g_d = x.to(DEV), gy.to(DEV)
     dw = torch.zeros(3 * Cin, N, device=DEV)
     a = lib.WgradArgs()
     a.B, a.T, a.Cin, a.N, a.num_segments = B, T, Cin, N, 3
-    for s in range(3):
-        a.xt[s], a.xt_rows[s] = taps[s].data_ptr(), Cin
-    a.gt, a.gt_rows, a.ld_t, a.dw = gt.data_ptr(), N, ld_t, dw.data_ptr()
+    for s_, sh in enumerate((-1, 0, 1)):
+        a.seg_src[s_], a.seg_shift[s_] = 0, sh
+    a.x[0], a.ldx[0] = x_d.data_ptr(), Cin
+    a.g, a.ldg, a.dw = g_d.data_ptr(), 256, dw.data_ptr()
     lib.wgrad(a)
     torch.cuda.synchronize()
-    xd, gd = x.double(), gy.double()
+    xd, gd = x.double(), gy[..., :N].double()
     ref = torch.zeros(3, Cin, N, dtype=torch.float64)
     for tap, sh in enumerate((-1, 0, 1)):
         lo, hi = max(0, -sh), min(T, T - sh)
@@ -73,12 +50,13 @@ def test_wgrad_conv_and_concat():
     assert _rel(dw.view(3, Cin, N), ref) < 1e-4
     # two sources (concat projection), accumulate on top of existing values
     x2 = torch.randn(B, T, Cin, generator=g).bfloat16()
+    x2_d = x2.to(DEV)
     dw2 = torch.ones(2 * Cin, N, device=DEV)
     a2 = lib.WgradArgs()
     a2.B, a2.T, a2.Cin, a2.N, a2.num_segments = B, T, Cin, N, 2
-    x2t = tr(x2)
-    a2.xt[0], a2.xt[1], a2.xt_rows[0], a2.xt_rows[1] = xt.data_ptr(), x2t.data_ptr(), Cin, Cin
-    a2.gt, a2.gt_rows, a2.ld_t, a2.dw = gt.data_ptr(), N, ld_t, dw2.data_ptr()
+    a2.seg_src[0], a2.seg_src[1] = 0, 1
+    a2.x[0], a2.x[1], a2.ldx[0], a2.ldx[1] = x_d.data_ptr(), x2_d.data_ptr(), Cin, Cin
+    a2.g, a2.ldg, a2.dw = g_d.data_ptr(), 256, dw2.data_ptr()
     lib.wgrad(a2)
     torch.cuda.synchronize()
     ref2 = 1 + torch.cat([torch.einsum('btc,btn->cn', xd, gd), torch.einsum('btc,btn->cn', x2.double(), gd)])
@@ -105,9 +83,8 @@ def test_attention_train_path_forward_and_backward(H, dh, T):
                (dh, 0, 0, d), alpha=1.0 / math.sqrt(dh), out_f32=S, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
     P = torch.empty(Z, T, ldp, dtype=torch.bfloat16, device=DEV)
     lib.softmax_fwd(S, B, H, T, T, ldp, lens_d, 0.0, 0, 0, P, P)
-    vT, ld8 = eng._transpose(qkv_d, B, T, 3 * d, 2 * d, d)
     attn = torch.empty(B, T, d, dtype=torch.bfloat16, device=DEV)
-    eng._bgemm(B, H, T, dh, T, P, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), vT, (T, d, B), (ld8, d * ld8), (0, dh, 0, 0),
+    eng._bgemm(B, H, T, dh, T, P, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), qkv_d, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d, 1),
                out_bf16=attn, ld_out=d, out_batch_stride=T * d, out_h_col=dh, out_by_b=1, out_cols=dh)
     torch.cuda.synchronize()
     # reference with autograd (fp64) on the bf16 inputs
@@ -131,15 +108,12 @@ def test_attention_train_path_forward_and_backward(H, dh, T):
                out_f32=dP, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
     dS = torch.empty(Z, T, ldp, dtype=torch.bfloat16, device=DEV)
     lib.softmax_bwd(P, dP, B, H, T, T, ldp, lens_d, 1.0 / math.sqrt(dh), 0.0, 0, 0, dS)
-    qkT, _ = eng._transpose(qkv_d, B, T, 3 * d, 0, 2 * d)
-    dST, _ = eng._transpose(dS, Z, T, ldp, 0, T)
-    PT, _ = eng._transpose(P, Z, T, ldp, 0, T)
-    daT, _ = eng._transpose(dO_m, B, T, d, 0, d)
     dqkv = torch.full((B, T, 3 * d), float('nan'), dtype=torch.bfloat16, device=DEV)
     common = dict(out_bf16=dqkv, ld_out=3 * d, out_batch_stride=T * 3 * d, out_h_col=dh, out_by_b=1, out_cols=dh)
-    eng._bgemm(B, H, T, dh, T, dS, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), qkT, (T, d, B), (ld8, 2 * d * ld8), (0, dh, 0, d * ld8), out_ptr_off=0, **common)
-    eng._bgemm(B, H, T, dh, T, dST, (T, T, Z), (ld8, T * ld8), (0, 0, 1, 0), qkT, (T, d, B), (ld8, 2 * d * ld8), (0, dh, 0, 0), out_ptr_off=d, **common)
-    eng._bgemm(B, H, T, dh, T, PT, (T, T, Z), (ld8, T * ld8), (0, 0, 1, 0), daT, (T, d, B), (ld8, d * ld8), (0, dh, 0, 0), out_ptr_off=2 * d, **common)
+    qd, qs = (d, T, B), (3 * d, 3 * d * T)
+    eng._bgemm(B, H, T, dh, T, dS, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), qkv_d, qd, qs, (dh, 0, 0, d, 1), out_ptr_off=0, **common)
+    eng._bgemm(B, H, T, dh, T, dS, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0, 1), qkv_d, qd, qs, (dh, 0, 0, 0, 1), out_ptr_off=d, **common)
+    eng._bgemm(B, H, T, dh, T, P, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0, 1), dO_m, (d, T, B), (d, d * T), (dh, 0, 0, 0, 1), out_ptr_off=2 * d, **common)
     torch.cuda.synchronize()
     assert torch.isfinite(dqkv.float()).all()
     assert _rel(dqkv.float(), x.grad) < 3e-2
@@ -164,12 +138,17 @@ def test_layernorm_bwd_and_small_ops():
     (y * dz[..., :C].double()).sum().backward()
     du = torch.full((B, T, ld), float('nan'), device=DEV)
     gb = torch.full((B, T, ld), float('nan'), dtype=torch.bfloat16, device=DEV)
-    dg, db = torch.zeros(ld, device=DEV), torch.zeros(ld, device=DEV)
-    lib.layernorm_bwd(dz.to(DEV), u.to(DEV), gamma.to(DEV), B, T, C, ld, 1e-6, lens.to(DEV), True, du, gb, dg, db)
+    dg, db, dbias = torch.zeros(ld, device=DEV), torch.zeros(ld, device=DEV), torch.zeros(ld, device=DEV)
+    lib.layernorm_bwd(dz.to(DEV), u.to(DEV), gamma.to(DEV), B, T, C, ld, 1e-6, lens.to(DEV), True, du, gb, dg, db, dbias=dbias)
     torch.cuda.synchronize()
     assert _rel(du[..., :C], uu.grad) < 1e-4 and torch.count_nonzero(du[..., C:]) == 0
     assert _rel(dg[:C], gg.grad) < 1e-4 and _rel(db[:C], bb.grad) < 1e-4
     assert _rel(gb[..., :C].float(), uu.grad * (u[..., :C] > 0)) < 1e-2
+    assert _rel(dbias[:C], (uu.grad * (u[..., :C] > 0)).sum((0, 1))) < 1e-4
+    cs = torch.zeros(C, device=DEV)
+    lib.colsum_bf16(gb, B * T, C, ld, cs)
+    torch.cuda.synchronize()
+    assert _rel(cs, gb[..., :C].float().sum((0, 1))) < 1e-5
     # MAE loss + gradient (unmasked mean over all elements, int targets)
     pred = torch.randn(3, 20, 1, generator=g)
     tgt = torch.randint(0, 5, (3, 20), generator=g, dtype=torch.int32)

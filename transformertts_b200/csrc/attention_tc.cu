@@ -1,9 +1,9 @@
 // Fused variable-length self-attention on tcgen05 (flash-style, never materialises the (B,H,T,T) tensors):
 //   per CTA one (batch row, head, 128-query tile); loop over 64-key tiles:
 //     S = Q K^T  (tcgen05.mma, fp32 in TMEM)  ->  online softmax in registers (one thread per query row, exp2 domain,
-//     keys >= kv_len masked)  ->  P (bf16 hi/lo) written to 128B-swizzled shared memory  ->  O += P V (tcgen05.mma,
-//     V^T staged by TMA from the transposed V the QKV GEMM epilogue wrote)  ->  O rescaled in TMEM only when a row
-//     maximum moved.
+//     keys >= kv_len masked)  ->  P (bf16 hi/lo or fp16) written to 128B-swizzled shared memory  ->  O += P V
+//     (tcgen05.mma; V is read MN-major straight from the QKV buffer, no transposed copy)  ->  O rescaled in TMEM only
+//     when a row maximum moved.
 // Replaces model/layers.py:123-129,138-147 (split/merge heads) and :176-195 (ScaledDotProductAttention) of the
 // reference, which materialise logits / softmax / dropout tensors of shape (B,H,T,T) in fp32.
 //
@@ -25,7 +25,7 @@ constexpr int ATT_THREADS = 160;  // warps 0-3 softmax/epilogue (TMEM lane quart
 
 struct MhaKParams {
   int B, T, H;
-  int q_col0, k_col0;
+  int q_col0, k_col0, v_col0;
   const int* kv_len;
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
@@ -38,7 +38,7 @@ struct MhaCfg {
   static constexpr int kPlanes = kSplit ? 2 : 1;
   static constexpr int Q_BYTES = ATT_BQ * DH * 2;    // DH/64 panels of [128 x 64]
   static constexpr int K_BYTES = ATT_BKV * DH * 2;   // DH/64 panels of [64 x 64]
-  static constexpr int V_BYTES = DH * ATT_BKV * 2;   // [DH x 64]
+  static constexpr int V_BYTES = DH * ATT_BKV * 2;   // DH/64 boxes of [64 keys x 64 dh] (MN-major B operand)
   static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + kPlanes * Q_BYTES;
@@ -54,8 +54,7 @@ struct MhaCfg {
 template <int DH, bool kSplit, bool kF16>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
-              const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
-              const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, const MhaKParams p) {
+              const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl, const MhaKParams p) {
   using Cfg = MhaCfg<DH, kSplit>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -118,7 +117,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
       uint8_t* sV = smem + Cfg::OFF_V;
       uint8_t* sP = smem + Cfg::OFF_P;
       const uint32_t idesc_s = kF16 ? make_idesc_f16(ATT_BQ, ATT_BKV) : make_idesc_bf16(ATT_BQ, ATT_BKV);
-      const uint32_t idesc_o = kF16 ? make_idesc_f16(ATT_BQ, DH) : make_idesc_bf16(ATT_BQ, DH);
+      const uint32_t idesc_o = (kF16 ? make_idesc_f16(ATT_BQ, DH) : make_idesc_bf16(ATT_BQ, DH)) | (1u << 16);  // B (= V) MN-major
       const uint32_t t_s = tmem_base + Cfg::S_COL;
       const uint32_t t_o = tmem_base + Cfg::O_COL;
 
@@ -136,8 +135,10 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
       };
       auto load_v = [&](int j) {
         mbar_arrive_expect_tx(bar_v, Cfg::kPlanes * Cfg::V_BYTES);
-        tma_load_3d(&tmVh, bar_v, sV, j * ATT_BKV, h * DH, b);
-        if (kSplit) tma_load_3d(&tmVl, bar_v, sV + Cfg::V_BYTES, j * ATT_BKV, h * DH, b);
+        for (int pn = 0; pn < DH / 64; ++pn) {  // same [64 rows x 64 cols] box as K, at the V columns
+          tma_load_3d(&tmKh, bar_v, sV + pn * (ATT_BKV * 128), p.v_col0 + h * DH + pn * 64, j * ATT_BKV, b);
+          if (kSplit) tma_load_3d(&tmKl, bar_v, sV + Cfg::V_BYTES + pn * (ATT_BKV * 128), p.v_col0 + h * DH + pn * 64, j * ATT_BKV, b);
+        }
       };
       load_k(0);
       load_v(0);
@@ -183,20 +184,20 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
 #pragma unroll
         for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
           const uint64_t a = make_smem_desc_sw128(smem_u32(sP)) + 2 * kk;
-          const uint64_t bb = make_smem_desc_sw128(smem_u32(sV)) + 2 * kk;
+          const uint64_t bb = make_smem_desc_mn_sw128(smem_u32(sV), ATT_BKV * 128) + 128 * kk;  // 16 keys = 2048 B
           umma_bf16(t_o, a, bb, idesc_o, (j | kk) != 0);
         }
         if (kSplit) {
 #pragma unroll
           for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
             const uint64_t a = make_smem_desc_sw128(smem_u32(sP + Cfg::P_BYTES)) + 2 * kk;
-            const uint64_t bb = make_smem_desc_sw128(smem_u32(sV)) + 2 * kk;
+            const uint64_t bb = make_smem_desc_mn_sw128(smem_u32(sV), ATT_BKV * 128) + 128 * kk;
             umma_bf16(t_o, a, bb, idesc_o, 1);
           }
 #pragma unroll
           for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
             const uint64_t a = make_smem_desc_sw128(smem_u32(sP)) + 2 * kk;
-            const uint64_t bb = make_smem_desc_sw128(smem_u32(sV + Cfg::V_BYTES)) + 2 * kk;
+            const uint64_t bb = make_smem_desc_mn_sw128(smem_u32(sV + Cfg::V_BYTES), ATT_BKV * 128) + 128 * kk;
             umma_bf16(t_o, a, bb, idesc_o, 1);
           }
         }
@@ -328,9 +329,6 @@ struct MhaSimtPtrs {
   const __nv_bfloat16* qk_hi;
   const __nv_bfloat16* qk_lo;
   int ld_qk;
-  const __nv_bfloat16* vt_hi;
-  const __nv_bfloat16* vt_lo;
-  int ld_vt;
   int dh;
   int f16;           // operands hold IEEE fp16 bit patterns
   float scale;       // 1/sqrt(dh)
@@ -391,9 +389,10 @@ __global__ void mha_simt_kernel(const MhaKParams p, const MhaSimtPtrs q) {
   }
   if (q.weights_only) return;
   for (int c = threadIdx.x; c < q.dh; c += blockDim.x) {
-    const size_t vrow = ((size_t)b * p.H * q.dh + h * q.dh + c) * q.ld_vt;
+    const size_t vcol = (size_t)p.v_col0 + h * q.dh + c;
     float acc = 0.f;
-    for (int tk = 0; tk < p.T; ++tk) acc = fmaf(logit[tk], ld_split(q.vt_hi, q.vt_lo, vrow + tk, q.f16), acc);
+    for (int tk = 0; tk < p.T; ++tk)
+      acc = fmaf(logit[tk], ld_split(q.qk_hi, q.qk_lo, ((size_t)b * p.T + tk) * q.ld_qk + vcol, q.f16), acc);
     acc *= inv;
     __nv_bfloat16 hi, lo;
     split_bf16(acc, hi, lo);
@@ -406,15 +405,12 @@ __global__ void mha_simt_kernel(const MhaKParams p, const MhaSimtPtrs q) {
 template <int DH, bool kSplit, bool kF16>
 static int launch_tc(const ttsb_mha_args* a, const MhaKParams& p, cudaStream_t stream) {
   using Cfg = MhaCfg<DH, kSplit>;
-  CUtensorMap tmQ[2], tmK[2], tmV[2];
+  CUtensorMap tmQ[2], tmK[2];
   for (int hl = 0; hl < 2; ++hl) {
     const void* qk = hl == 0 ? a->qk_hi : (kSplit ? a->qk_lo : a->qk_hi);
-    const void* vt = hl == 0 ? a->vt_hi : (kSplit ? a->vt_lo : a->vt_hi);
     int rc = make_tmap_bf16_3d(&tmQ[hl], qk, (uint64_t)a->ld_qk, a->T, a->B, a->ld_qk, (uint64_t)a->ld_qk * a->T, 64, ATT_BQ);
     if (rc) return rc;
     rc = make_tmap_bf16_3d(&tmK[hl], qk, (uint64_t)a->ld_qk, a->T, a->B, a->ld_qk, (uint64_t)a->ld_qk * a->T, 64, ATT_BKV);
-    if (rc) return rc;
-    rc = make_tmap_bf16_3d(&tmV[hl], vt, (uint64_t)a->T, (uint64_t)a->H * DH, a->B, a->ld_vt, (uint64_t)a->ld_vt * a->H * DH, 64, DH);
     if (rc) return rc;
   }
   static bool attr_set = false;
@@ -423,7 +419,7 @@ static int launch_tc(const ttsb_mha_args* a, const MhaKParams& p, cudaStream_t s
     attr_set = true;
   }
   dim3 grid((a->T + ATT_BQ - 1) / ATT_BQ, a->H, a->B);
-  mha_tc_kernel<DH, kSplit, kF16><<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tmQ[0], tmQ[1], tmK[0], tmK[1], tmV[0], tmV[1], p);
+  mha_tc_kernel<DH, kSplit, kF16><<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tmQ[0], tmQ[1], tmK[0], tmK[1], p);
   count_launch();
   return check_cuda(cudaGetLastError(), "mha_tc_kernel launch");
 }
@@ -435,18 +431,18 @@ using namespace ttsb;
 extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   if (!a) { set_last_error("ttsb_mha_fwd: args is NULL"); return TTSB_ERR_INVALID_ARGUMENT; }
   if (a->B <= 0 || a->T <= 0 || a->H <= 0) { set_last_error("ttsb_mha_fwd: B,T,H must be positive"); return TTSB_ERR_INVALID_ARGUMENT; }
-  if (!a->qk_hi || !a->vt_hi || !a->kv_len || !a->out_hi) { set_last_error("ttsb_mha_fwd: NULL tensor"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (!a->qk_hi || !a->kv_len || !a->out_hi) { set_last_error("ttsb_mha_fwd: NULL tensor"); return TTSB_ERR_INVALID_ARGUMENT; }
   const bool split = a->precision == TTSB_PREC_BF16X3;
   const bool f16 = a->precision == TTSB_PREC_FP16;
-  if (split && (!a->qk_lo || !a->vt_lo || !a->out_lo)) { set_last_error("ttsb_mha_fwd: bf16x3 needs the lo planes"); return TTSB_ERR_INVALID_ARGUMENT; }
-  if (a->ld_qk % 8 || a->ld_vt % 8 || a->ld_out % 8 || a->q_col0 % 8 || a->k_col0 % 8) {
+  if (split && (!a->qk_lo || !a->out_lo)) { set_last_error("ttsb_mha_fwd: bf16x3 needs the lo planes"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->ld_qk % 8 || a->ld_out % 8 || a->q_col0 % 8 || a->k_col0 % 8 || a->v_col0 % 8) {
     set_last_error("ttsb_mha_fwd: leading dimensions / column offsets must be multiples of 8");
     return TTSB_ERR_INVALID_ARGUMENT;
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   MhaKParams p{};
   p.B = a->B; p.T = a->T; p.H = a->H;
-  p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.kv_len = a->kv_len;
+  p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0; p.kv_len = a->kv_len;
   p.out_hi = static_cast<__nv_bfloat16*>(a->out_hi);
   p.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);  // optional second plane of the OUTPUT (consumer may be bf16x3)
   p.ld_out = a->ld_out;
@@ -456,9 +452,6 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   q.qk_hi = static_cast<const __nv_bfloat16*>(a->qk_hi);
   q.qk_lo = split ? static_cast<const __nv_bfloat16*>(a->qk_lo) : nullptr;
   q.ld_qk = a->ld_qk;
-  q.vt_hi = static_cast<const __nv_bfloat16*>(a->vt_hi);
-  q.vt_lo = split ? static_cast<const __nv_bfloat16*>(a->vt_lo) : nullptr;
-  q.ld_vt = a->ld_vt;
   q.dh = a->dh;
   q.scale = 1.f / sqrtf((float)a->dh);
   q.f16 = f16 ? 1 : 0;

@@ -5,9 +5,15 @@
 //                 both operands come from activations (per-(b,h) B operand), e.g. S = Q K^T, O = P V, dP = dO V^T,
 //                 dQ = dS K, dK = dS^T Q, dV = P^T dO of the attention forward/backward (model/layers.py:176-195 and
 //                 its gradient), each operand addressed through a 3-D TMA map with per-head column/row offsets.
-//  mode WGRAD   : dW[seg*Cin + c][n] += sum_b sum_t X^T_seg[b][c][t] * G^T[b][n][t]
+//  mode WGRAD   : dW[seg*Cin + c][n] += sum_b sum_t X_seg[b][t + shift_seg][c] * G[b][t][n]
 //                 weight gradients of Dense / concat-Dense / Conv1D (k taps = k segments), reduction over all B*T
 //                 rows split across CTAs, partial tiles added with fp32 red.global.add (Keras (K,N) layout).
+//
+// Operand majorness.  tcgen05 reads an operand either K-major (the contraction index is contiguous in memory: rows of
+// 128 B hold 64 k) or MN-major (the M/N index is contiguous: rows of 128 B hold 64 m, one row per k).  Supporting both
+// means NO transposed copies are ever made: P^T, dS^T, dO^T, V^T, K^T and the X^T / G^T of the weight gradients are just
+// the same row-major tensors read MN-major.  An MN-major tile is fetched as ceil(rows/64) TMA boxes of [64 k x 64 mn]
+// (8 KiB each, 128B swizzle) and described to the MMA with LBO = 8192 B (next 64-wide MN block), SBO = 1024 B (next 8 k).
 #include <cuda_fp16.h>
 
 #include "../../include/ttsb.h"
@@ -26,11 +32,13 @@ constexpr int BG_B_BYTES = BG_MAX_BN * BG_BK * 2;
 constexpr int BG_STAGE_BYTES = BG_A_BYTES + BG_B_BYTES;
 constexpr int BG_BAR_OFFSET = BG_STAGES * BG_STAGE_BYTES;
 constexpr int BG_SMEM_BYTES = BG_BAR_OFFSET + 256 + 1024;
+constexpr int BG_MN_BOX_BYTES = 64 * 128;  // one [64 k x 64 mn] box
 
 struct BgOperand {
-  int h_col;    // added to coordinate 0 (contiguous dim) per head
-  int h_row;    // added to coordinate 1 per head
-  int z_batch;  // 1: coordinate 2 = z (b*H + h); 0: coordinate 2 = b
+  int h_col;     // added to coordinate 0 (contiguous dim) per head
+  int h_row;     // added to coordinate 1 per head
+  int z_batch;   // 1: coordinate 2 = z (b*H + h); 0: coordinate 2 = b
+  int mn_major;  // 1: coordinate 0 runs over M/N, coordinate 1 over K
 };
 
 struct BgParams {
@@ -49,7 +57,7 @@ struct BgParams {
   const int* row_len;         // optional [B]: rows m >= len[b] are written as zero
   const int* col_len;         // optional [B]: columns n >= len[b] are written as zero
   // wgrad
-  int B, T, Cin, num_seg, splits, b_per_split;
+  int B, T, Cin, num_seg, seg_src[4], seg_shift[4], splits, b_per_split;
   float* dw;                  // fp32 (num_seg*Cin, N) accumulated with atomics
   // common
   int block_n, n_tiles, m_tiles, num_tiles;
@@ -57,7 +65,6 @@ struct BgParams {
 
 __global__ void __launch_bounds__(BG_THREADS, 1)
 bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                 const __grid_constant__ CUtensorMap tmB, const BgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -89,7 +96,10 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t stage_tx = (uint32_t)(BG_A_BYTES + p.block_n * BG_BK * 2);
+  const bool a_mn = p.mode == 1 || p.opA.mn_major;
+  const bool b_mn = p.mode == 1 || p.opB.mn_major;
+  const int b_boxes = (p.block_n + 63) / 64;
+  const uint32_t stage_tx = (uint32_t)(BG_A_BYTES + (b_mn ? b_boxes * BG_MN_BOX_BYTES : p.block_n * BG_BK * 2));
   const int t_chunks = (p.T + BG_BK - 1) / BG_BK;
 
   // number of k-blocks of a tile (uniform across roles)
@@ -113,13 +123,24 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const int b = z / p.H, h = z % p.H;
         const int m0 = m_tile * BG_BM, n0 = n_tile * p.block_n;
         const int kbs = (p.K + BG_BK - 1) / BG_BK;
+        const int za = p.opA.z_batch ? z : b, zb = p.opB.z_batch ? z : b;
         for (int kb = 0; kb < kbs; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* st = smem + stage * BG_STAGE_BYTES;
           mbar_arrive_expect_tx(full_bar + stage, stage_tx);
-          tma_load_3d(&tmA0, full_bar + stage, st, kb * BG_BK + h * p.opA.h_col, m0 + h * p.opA.h_row, p.opA.z_batch ? z : b);
-          tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES, kb * BG_BK + h * p.opB.h_col, n0 + h * p.opB.h_row,
-                      p.opB.z_batch ? z : b);
+          if (a_mn) {
+            for (int i = 0; i < BG_BM / 64; ++i)
+              tma_load_3d(&tmA0, full_bar + stage, st + i * BG_MN_BOX_BYTES, m0 + 64 * i + h * p.opA.h_col, kb * BG_BK + h * p.opA.h_row, za);
+          } else {
+            tma_load_3d(&tmA0, full_bar + stage, st, kb * BG_BK + h * p.opA.h_col, m0 + h * p.opA.h_row, za);
+          }
+          if (b_mn) {
+            for (int i = 0; i < b_boxes; ++i)
+              tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES + i * BG_MN_BOX_BYTES, n0 + 64 * i + h * p.opB.h_col,
+                          kb * BG_BK + h * p.opB.h_row, zb);
+          } else {
+            tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES, kb * BG_BK + h * p.opB.h_col, n0 + h * p.opB.h_row, zb);
+          }
           if (++stage == BG_STAGES) { stage = 0; phase ^= 1; }
         }
       } else {
@@ -128,17 +149,20 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const int n_tile = r % p.n_tiles; r /= p.n_tiles;
         const int m_tile = r % p.m_tiles; r /= p.m_tiles;
         const int seg = r;
-        const CUtensorMap* mA = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
+        const CUtensorMap* mA = p.seg_src[seg] == 0 ? &tmA0 : &tmA1;
         const int c0 = m_tile * BG_BM, n0 = n_tile * p.block_n;
         const int b0 = split * p.b_per_split;
         const int b1 = min(b0 + p.b_per_split, p.B);
+        const int shift = p.seg_shift[seg];
         for (int b = b0; b < b1; ++b) {
           for (int tc = 0; tc < t_chunks; ++tc) {
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* st = smem + stage * BG_STAGE_BYTES;
             mbar_arrive_expect_tx(full_bar + stage, stage_tx);
-            tma_load_3d(mA, full_bar + stage, st, tc * BG_BK, c0, b);
-            tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES, tc * BG_BK, n0, b);
+            for (int i = 0; i < BG_BM / 64; ++i)
+              tma_load_3d(mA, full_bar + stage, st + i * BG_MN_BOX_BYTES, c0 + 64 * i, tc * BG_BK + shift, b);
+            for (int i = 0; i < b_boxes; ++i)
+              tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES + i * BG_MN_BOX_BYTES, n0 + 64 * i, tc * BG_BK, b);
             if (++stage == BG_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -146,7 +170,9 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc_bf16(BG_BM, p.block_n);
+    const uint32_t idesc = make_idesc_bf16(BG_BM, p.block_n) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
+    const uint32_t a_step = a_mn ? (16 * 128) >> 4 : 2;  // descriptor advance per 16 k
+    const uint32_t b_step = b_mn ? (16 * 128) >> 4 : 2;
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -159,10 +185,10 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         mbar_wait(full_bar + stage, phase);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + stage * BG_STAGE_BYTES);
-        const uint64_t a = make_smem_desc_sw128(st);
-        const uint64_t b = make_smem_desc_sw128(st + BG_A_BYTES);
+        const uint64_t a = a_mn ? make_smem_desc_mn_sw128(st, BG_MN_BOX_BYTES) : make_smem_desc_sw128(st);
+        const uint64_t b = b_mn ? make_smem_desc_mn_sw128(st + BG_A_BYTES, BG_MN_BOX_BYTES) : make_smem_desc_sw128(st + BG_A_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < BG_BK / 16; ++kk) umma_bf16(d_tmem, a + 2 * kk, b + 2 * kk, idesc, (kb | kk) != 0);
+        for (int kk = 0; kk < BG_BK / 16; ++kk) umma_bf16(d_tmem, a + a_step * kk, b + b_step * kk, idesc, (kb | kk) != 0);
         umma_commit(empty_bar + stage);
         if (++stage == BG_STAGES) { stage = 0; phase ^= 1; }
       }
@@ -261,14 +287,14 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
 }
 
-static int launch(const CUtensorMap* a, const CUtensorMap& b, const BgParams& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const BgParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     TTSB_CUDA_OK(cudaFuncSetAttribute(bgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMEM_BYTES));
     attr_set = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  bgemm_tc_kernel<<<grid, BG_THREADS, BG_SMEM_BYTES, stream>>>(a[0], a[1], a[2], a[3], b, p);
+  bgemm_tc_kernel<<<grid, BG_THREADS, BG_SMEM_BYTES, stream>>>(a0, a1, b, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "bgemm_tc_kernel launch");
 }
@@ -291,8 +317,8 @@ extern "C" int ttsb_bgemm(const ttsb_bgemm_args* a, void* stream_v) {
   BgParams p{};
   p.mode = 0;
   p.Z = a->B * a->H; p.H = a->H; p.M = a->M; p.N = a->N; p.K = a->K;
-  p.opA = {a->a_h_col, a->a_h_row, a->a_z_batch};
-  p.opB = {a->b_h_col, a->b_h_row, a->b_z_batch};
+  p.opA = {a->a_h_col, a->a_h_row, a->a_z_batch, a->a_mn_major};
+  p.opB = {a->b_h_col, a->b_h_row, a->b_z_batch, a->b_mn_major};
   p.alpha = a->alpha;
   p.out_f32 = a->out_f32;
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
@@ -305,13 +331,12 @@ extern "C" int ttsb_bgemm(const ttsb_bgemm_args* a, void* stream_v) {
   p.T = 1;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_3d(&tmA, a->a, (uint64_t)a->a_dim0, (uint64_t)a->a_dim1, (uint64_t)a->a_dim2, (uint64_t)a->a_stride1,
-                             (uint64_t)a->a_stride2, BG_BK, BG_BM);
+                             (uint64_t)a->a_stride2, BG_BK, a->a_mn_major ? 64 : BG_BM);
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&tmB, a->b, (uint64_t)a->b_dim0, (uint64_t)a->b_dim1, (uint64_t)a->b_dim2, (uint64_t)a->b_stride1,
-                         (uint64_t)a->b_stride2, BG_BK, p.block_n);
+                         (uint64_t)a->b_stride2, BG_BK, a->b_mn_major ? 64 : p.block_n);
   if (rc) return rc;
-  CUtensorMap tmAs[4] = {tmA, tmA, tmA, tmA};
-  return launch(tmAs, tmB, p, stream);
+  return launch(tmA, tmA, tmB, p, stream);
 }
 
 extern "C" int ttsb_wgrad(const ttsb_wgrad_args* a, void* stream_v) {
@@ -320,13 +345,19 @@ extern "C" int ttsb_wgrad(const ttsb_wgrad_args* a, void* stream_v) {
     set_last_error("ttsb_wgrad: bad dimensions");
     return TTSB_ERR_INVALID_ARGUMENT;
   }
-  if (!a->xt[0] || !a->gt || !a->dw || a->ld_t % 8) { set_last_error("ttsb_wgrad: NULL tensor or ld_t not a multiple of 8"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (!a->x[0] || !a->g || !a->dw || a->ldg % 8) { set_last_error("ttsb_wgrad: NULL tensor or ldg not a multiple of 8"); return TTSB_ERR_INVALID_ARGUMENT; }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   BgParams p{};
   p.mode = 1;
   p.B = a->B; p.T = a->T; p.Cin = a->Cin; p.N = a->N; p.num_seg = a->num_segments; p.H = 1;
-  for (int s = 0; s < a->num_segments; ++s)
-    if (!a->xt[s]) { set_last_error("ttsb_wgrad: NULL segment source"); return TTSB_ERR_INVALID_ARGUMENT; }
+  for (int s = 0; s < a->num_segments; ++s) {
+    p.seg_src[s] = a->seg_src[s];
+    p.seg_shift[s] = a->seg_shift[s];
+    if (a->seg_src[s] < 0 || a->seg_src[s] > 1 || !a->x[a->seg_src[s]] || a->ldx[a->seg_src[s]] % 8) {
+      set_last_error("ttsb_wgrad: bad segment source");
+      return TTSB_ERR_INVALID_ARGUMENT;
+    }
+  }
   p.dw = a->dw;
   p.block_n = pick_block_n(a->N);
   p.n_tiles = (a->N + p.block_n - 1) / p.block_n;
@@ -338,15 +369,14 @@ extern "C" int ttsb_wgrad(const ttsb_wgrad_args* a, void* stream_v) {
   p.b_per_split = (a->B + splits - 1) / splits;
   p.splits = (a->B + p.b_per_split - 1) / p.b_per_split;
   p.num_tiles = base_tiles * p.splits;
-  CUtensorMap tmA[4], tmB;
-  for (int i = 0; i < 4; ++i) {
-    const int use = (i < a->num_segments) ? i : 0;
-    int rc = make_tmap_bf16_3d(&tmA[i], a->xt[use], (uint64_t)a->T, (uint64_t)a->Cin, (uint64_t)a->B, (uint64_t)a->ld_t,
-                               (uint64_t)a->ld_t * a->xt_rows[use], BG_BK, BG_BM);
+  CUtensorMap tmA[2], tmB;
+  for (int i = 0; i < 2; ++i) {
+    const int use = a->x[i] ? i : 0;
+    int rc = make_tmap_bf16_3d(&tmA[i], a->x[use], (uint64_t)a->Cin, (uint64_t)a->T, (uint64_t)a->B, (uint64_t)a->ldx[use],
+                               (uint64_t)a->ldx[use] * a->T, BG_BK, 64);
     if (rc) return rc;
   }
-  int rc = make_tmap_bf16_3d(&tmB, a->gt, (uint64_t)a->T, (uint64_t)a->N, (uint64_t)a->B, (uint64_t)a->ld_t,
-                             (uint64_t)a->ld_t * a->gt_rows, BG_BK, p.block_n);
+  int rc = make_tmap_bf16_3d(&tmB, a->g, (uint64_t)a->N, (uint64_t)a->T, (uint64_t)a->B, (uint64_t)a->ldg, (uint64_t)a->ldg * a->T, BG_BK, 64);
   if (rc) return rc;
-  return launch(tmA, tmB, p, stream);
+  return launch(tmA[0], tmA[1], tmB, p, stream);
 }

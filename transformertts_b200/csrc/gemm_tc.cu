@@ -2,7 +2,7 @@
 // persistent warp-specialised tcgen05 kernel -- TMA (3-D maps over (C,T,B), OOB rows = 'same' zero padding) ->
 // 128B-swizzled shared memory -> tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM, double buffered)
 // -> epilogue warps (tcgen05.ld, one thread per output row) fusing bias / ReLU / residual / LayerNorm / row mask and
-// writing fp32 + bf16 hi/lo copies for the next GEMM.
+// writing fp32 + bf16 hi/lo (or fp16) copies for the next GEMM / the attention kernel.
 //
 // Replaces, in the reference (TF2/Keras ops): model/layers.py:134-136,149 (q/k/v + concat projection),
 // :93-94 (FFN), :19-26,36-40 (Conv1D stack + residual LayerNorm), :498-524 (predictor convs), model/models.py:422.
@@ -45,13 +45,10 @@ struct GemmKParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   int ld_out;
-  __nv_bfloat16* vt_hi;
-  __nv_bfloat16* vt_lo;
-  int vt_col0, vt_cols, vt_ld;
   float* out_preln;  // optional fp32 (B,T,ld_out): the pre-LayerNorm value (saved for the backward pass)
   float drop_pre_p, drop_post_p;  // training dropout: on the GEMM output before the residual add / on the LayerNorm output
   uint32_t drop_pre_site, drop_post_site, drop_seed;
-  int h16;  // 1: out_hi / vt_hi receive IEEE fp16 instead of bf16 (single plane; operands of the fp16 attention)
+  int h16;  // 1: out_hi receives IEEE fp16 instead of bf16 (single plane; operands of the fp16 attention)
 };
 
 template <bool kSplit>
@@ -95,25 +92,7 @@ __device__ __forceinline__ void pack_hi_lo(const float (&y)[16], uint32_t (&h)[8
   }
 }
 
-__device__ __forceinline__ void store_chunk(const GemmKParams& p, size_t orow, int b, int t, int col0, const float (&y)[16]) {
-  if (p.vt_hi != nullptr && col0 >= p.vt_col0 && col0 < p.vt_col0 + p.vt_cols) {
-    // transposed store (V^T for the attention kernel): consecutive lanes hold consecutive t -> coalesced per column
-    const size_t base = ((size_t)b * p.vt_cols + (col0 - p.vt_col0)) * (size_t)p.vt_ld + t;
-    if (p.h16) {
-      __half* dst = reinterpret_cast<__half*>(p.vt_hi);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) dst[base + (size_t)j * p.vt_ld] = __float2half_rn(y[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        __nv_bfloat16 hi, lo;
-        split_bf16(y[j], hi, lo);
-        p.vt_hi[base + (size_t)j * p.vt_ld] = hi;
-        if (p.vt_lo) p.vt_lo[base + (size_t)j * p.vt_ld] = lo;
-      }
-    }
-    return;
-  }
+__device__ __forceinline__ void store_chunk(const GemmKParams& p, size_t orow, int col0, const float (&y)[16]) {
   const size_t o = orow * (size_t)p.ld_out + col0;
   if (p.out_f32) {
 #pragma unroll
@@ -199,7 +178,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
 #pragma unroll
         for (int j = 0; j < 16; ++j) y[j] = 0.f;
       }
-      if (row_ok) store_chunk(p, orow, b, t, n0 + c0, y);
+      if (row_ok) store_chunk(p, orow, n0 + c0, y);
     }
     return;
   }
@@ -287,7 +266,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
 #pragma unroll
       for (int j = 0; j < 16; ++j) y[j] = 0.f;
     }
-    if (row_ok) store_chunk(p, orow, b, t, c0, y);
+    if (row_ok) store_chunk(p, orow, c0, y);
   }
 }
 
@@ -510,12 +489,6 @@ __global__ void gemm_simt_kernel(const GemmKParams p, const GemmSimtPtrs q) {
     __nv_bfloat16 hi, lo;
     split_bf16(v, hi, lo);
     if (p.h16) hi = __ushort_as_bfloat16(__half_as_ushort(__float2half_rn(v)));  // same 16-bit slot, fp16 payload
-    if (p.vt_hi && n >= p.vt_col0 && n < p.vt_col0 + p.vt_cols) {
-      const size_t o = ((size_t)b * p.vt_cols + (n - p.vt_col0)) * (size_t)p.vt_ld + t;
-      p.vt_hi[o] = hi;
-      if (p.vt_lo) p.vt_lo[o] = lo;
-      continue;
-    }
     const size_t o = (size_t)row * p.ld_out + n;
     if (p.out_f32) p.out_f32[o] = v;
     if (p.out_hi) p.out_hi[o] = hi;
@@ -551,7 +524,6 @@ static int validate(const ttsb_gemm_args* a, int* k_total_out) {
   }
   if (a->ln_gamma && (n_tiles != 1 || !a->ln_beta)) { set_last_error("ttsb_linear_fwd: LayerNorm epilogue needs N <= block_n and beta"); return TTSB_ERR_INVALID_ARGUMENT; }
   if (a->residual && (a->ld_res % 4)) { set_last_error("ttsb_linear_fwd: ld_res must be a multiple of 4"); return TTSB_ERR_INVALID_ARGUMENT; }
-  if (a->vt_hi && (a->vt_col0 % a->block_n || a->vt_cols % 16)) { set_last_error("ttsb_linear_fwd: vt_col0 must be tile aligned"); return TTSB_ERR_INVALID_ARGUMENT; }
   if (a->precision != TTSB_PREC_BF16 && a->precision != TTSB_PREC_BF16X3) { set_last_error("ttsb_linear_fwd: unknown precision"); return TTSB_ERR_INVALID_ARGUMENT; }
   *k_total_out = kt;
   return 0;
@@ -587,9 +559,6 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
   p.out_hi = static_cast<__nv_bfloat16*>(a->out_hi);
   p.out_lo = split ? static_cast<__nv_bfloat16*>(a->out_lo) : nullptr;
   p.ld_out = a->ld_out;
-  p.vt_hi = static_cast<__nv_bfloat16*>(a->vt_hi);
-  p.vt_lo = split ? static_cast<__nv_bfloat16*>(a->vt_lo) : nullptr;
-  p.vt_col0 = a->vt_col0; p.vt_cols = a->vt_cols; p.vt_ld = a->vt_ld;
   p.h16 = a->out_fp16 ? 1 : 0;
   p.out_preln = a->out_preln;
   p.drop_pre_p = a->drop_pre_p; p.drop_post_p = a->drop_post_p;
@@ -602,7 +571,7 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
     set_last_error("ttsb_linear_fwd: dropout is only implemented in the tcgen05 kernel");
     return TTSB_ERR_UNSUPPORTED;
   }
-  if (p.h16) { p.out_lo = nullptr; p.vt_lo = nullptr; }
+  if (p.h16) p.out_lo = nullptr;
 
   if (a->impl == TTSB_IMPL_SIMT) {
     GemmSimtPtrs q{};

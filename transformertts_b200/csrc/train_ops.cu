@@ -1,7 +1,7 @@
 // Bandwidth-bound kernels of the training step (reference: ForwardTransformer._train_step, model/models.py:464-482,
-// losses utils/losses.py:41-70, Adam utils/training_config_manager.py:102-106): time-transposes feeding the weight-
-// gradient GEMMs (with fused bias-gradient column sums), softmax forward/backward on materialised score rows,
-// LayerNorm backward, ReLU masks, loss + its gradient, length-regulator / embedding / head backward, fused Adam.
+// losses utils/losses.py:41-70, Adam utils/training_config_manager.py:102-106): softmax forward/backward on materialised
+// score rows, LayerNorm backward (with the fused bias / gamma / beta gradients), bias-gradient column sums, ReLU masks,
+// loss + its gradient, length-regulator / embedding / head backward, fused Adam.
 // All are coalesced row kernels; reductions across rows use shared-memory partials + fp32 atomics.
 #include <cuda_fp16.h>
 
@@ -20,34 +20,6 @@ __device__ __forceinline__ float wmax(float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
-}
-
-// ------------------------------------------------------------------------------------------------
-// bf16 (B, T, ld_src)[:, :, col0:col0+C]  ->  (B, C, ld_t) ; optional fp32 column sums (bias gradients)
-// ------------------------------------------------------------------------------------------------
-__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int T, int ld_src, int col0, int C,
-                                      __nv_bfloat16* __restrict__ dst, int dst_rows, int ld_t, float* colsum, int t_shift) {
-  __shared__ __nv_bfloat16 tile[64][66];
-  const int b = blockIdx.z;
-  const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 256 threads: 64 x 4
-  for (int r = ty; r < 64; r += 4) {
-    const int t = t0 + r + t_shift, c = c0 + tx;  // dst[b][c][t'] = src[b][t' + t_shift][c], zero outside [0,T)
-    tile[r][tx] = (t >= 0 && t < T && c < C) ? src[((size_t)b * T + t) * ld_src + col0 + c] : __float2bfloat16(0.f);
-  }
-  __syncthreads();
-  for (int r = ty; r < 64; r += 4) {
-    const int c = c0 + r, t = t0 + tx;
-    if (c < C && t < T) dst[((size_t)b * dst_rows + c) * ld_t + t] = tile[tx][r];
-  }
-  if (colsum != nullptr && ty == 0) {
-    const int c = c0 + tx;
-    if (c < C) {
-      float s = 0.f;
-      for (int r = 0; r < 64; ++r) s += __bfloat162float(tile[r][tx]);
-      atomicAdd(colsum + c, s);
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -126,13 +98,20 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dz, const float* 
                                      int M, int T, int C, int ld, float eps, const int* __restrict__ row_len, int relu_mask,
                                      float pre_drop_p, uint32_t pre_site, float post_drop_p, uint32_t post_site, uint32_t seed,
                                      float* __restrict__ du, __nv_bfloat16* __restrict__ g_out, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  extern __shared__ float part[];  // [2][C] per block
-  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) part[c] = 0.f;
+                                     float* __restrict__ dbeta, float* __restrict__ dbias) {
+  extern __shared__ float part[];  // [3][C] per block: dgamma, dbeta, dbias partials
+  for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) part[c] = 0.f;
   __syncthreads();
   const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
   constexpr int MAXV = 16;  // C <= 512
-  constexpr int RPW = 8;    // rows per warp: fewer global atomics for dgamma/dbeta
+  constexpr int RPW = 16;   // rows per warp; column partials stay in registers across them
+  float acc_g[MAXV], acc_b[MAXV], acc_x[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) acc_g[i] = acc_b[i] = acc_x[i] = 0.f;
+  const uint32_t post_thresh = dropout_thresh(post_drop_p);
+  const float post_scale = post_drop_p > 0.f ? 1.f / (1.f - post_drop_p) : 1.f;
+  const uint32_t pre_thresh = dropout_thresh(pre_drop_p);
+  const float pre_scale = pre_drop_p > 0.f ? 1.f / (1.f - pre_drop_p) : 1.f;
   for (int rr = 0; rr < RPW; ++rr) {
     const int row = (blockIdx.x * warps + (threadIdx.x >> 5)) * RPW + rr;
     if (row >= M) break;
@@ -140,8 +119,6 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dz, const float* 
     const bool live = row_len == nullptr || t < __ldg(row_len + b);
     const size_t base = (size_t)row * ld;
     float uv[MAXV], gz[MAXV];
-    const uint32_t post_thresh = post_drop_p > 0.f ? (uint32_t)(post_drop_p * 4294967296.0) : 0u;
-    const float post_scale = post_drop_p > 0.f ? 1.f / (1.f - post_drop_p) : 1.f;
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
@@ -170,16 +147,12 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dz, const float* 
         const float gg = gz[i] * __ldg(gamma + c);
         sg += gg;
         sgx += gg * xh;
-        if (live) {
-          atomicAdd(part + c, gz[i] * xh);
-          atomicAdd(part + C + c, gz[i]);
-        }
+        acc_g[i] += gz[i] * xh;
+        acc_b[i] += gz[i];
       }
     }
     sg = wsum(sg) / C;
     sgx = wsum(sgx) / C;
-    const uint32_t pre_thresh = pre_drop_p > 0.f ? (uint32_t)(pre_drop_p * 4294967296.0) : 0u;
-    const float pre_scale = pre_drop_p > 0.f ? 1.f / (1.f - pre_drop_p) : 1.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = lane + 32 * i;
@@ -190,20 +163,43 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dz, const float* 
           d = rstd * (gz[i] * __ldg(gamma + c) - sg - xh * sgx);
         }
         if (du) du[base + c] = d;
-        if (g_out) {
-          float gv = d;
-          if (relu_mask && !(uv[i] > 0.f)) gv = 0.f;
-          if (pre_drop_p > 0.f) gv = dropout_keep(seed, pre_site, base + c, pre_thresh) ? gv * pre_scale : 0.f;
-          g_out[base + c] = __float2bfloat16_rn(gv);
-        }
+        float gv = d;
+        if (relu_mask && !(uv[i] > 0.f)) gv = 0.f;
+        if (pre_drop_p > 0.f) gv = dropout_keep(seed, pre_site, base + c, pre_thresh) ? gv * pre_scale : 0.f;
+        if (g_out) g_out[base + c] = __float2bfloat16_rn(gv);
+        if (c < C) acc_x[i] += gv;
       }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) {
+      atomicAdd(part + c, acc_g[i]);
+      atomicAdd(part + C + c, acc_b[i]);
+      atomicAdd(part + 2 * C + c, acc_x[i]);
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    if (part[c] != 0.f) atomicAdd(dgamma + c, part[c]);
-    if (part[C + c] != 0.f) atomicAdd(dbeta + c, part[C + c]);
+    atomicAdd(dgamma + c, part[c]);
+    atomicAdd(dbeta + c, part[C + c]);
+    if (dbias) atomicAdd(dbias + c, part[2 * C + c]);
   }
+}
+
+// column sums of a bf16 matrix (rows, ld)[:, :C] -> fp32 [C] (accumulated): bias gradients
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C, int ld, float* __restrict__ out) {
+  __shared__ float red[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int ry = threadIdx.x >> 6;
+  const int64_t r0 = (int64_t)blockIdx.y * 256;
+  float s = 0.f;
+  if (c < C)
+    for (int64_t r = r0 + ry; r < r0 + 256 && r < rows; r += 4) s += __bfloat162float(x[r * ld + c]);
+  red[ry][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) atomicAdd(out + c, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
 
 // dy (bf16, in place) *= (h > 0)
@@ -218,16 +214,6 @@ __global__ void relu_bwd_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloa
   for (int j = 0; j < 8; ++j)
     if (!(__bfloat162float(hp[j]) > 0.f)) gp[j] = __float2bfloat16(0.f);
   *reinterpret_cast<uint4*>(dy + i) = g;
-}
-
-// fp32 -> bf16 copy with optional row mask / dropout regeneration:  out = x (* keep/(1-p))
-__global__ void cast_bf16_kernel(const float* __restrict__ x, int64_t n, float drop_p, uint32_t seed, uint32_t site,
-                                 __nv_bfloat16* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float v = x[i];
-  if (drop_p > 0.f) v = dropout_keep(seed, site, (uint64_t)i, (uint32_t)(drop_p * 4294967296.0)) ? v / (1.f - drop_p) : 0.f;
-  out[i] = __float2bfloat16_rn(v);
 }
 
 // fp32 (rows, C) -> bf16 (rows, ld_out >= C), zero in the padding columns (K of a GEMM must be a multiple of 64)
@@ -408,14 +394,6 @@ using namespace ttsb;
 #define BF(p) static_cast<__nv_bfloat16*>(p)
 #define CBF(p) static_cast<const __nv_bfloat16*>(p)
 
-extern "C" int ttsb_transpose_bf16(const void* src, int B, int T, int ld_src, int col0, int C, void* dst, int dst_rows, int ld_t,
-                                   float* colsum, int t_shift, void* stream) {
-  if (!src || !dst || B <= 0 || T <= 0 || C <= 0 || ld_t < T || dst_rows < C) return bad("ttsb_transpose_bf16: bad arguments");
-  dim3 grid((T + 63) / 64, (C + 63) / 64, B);
-  transpose_bf16_kernel<<<grid, 256, 0, STREAM(stream)>>>(CBF(src), T, ld_src, col0, C, BF(dst), dst_rows, ld_t, colsum, t_shift);
-  LAUNCH_OK("transpose_bf16_kernel");
-}
-
 extern "C" int ttsb_softmax_fwd(const float* S, int B, int H, int T, int Tk, int ld, const int32_t* kv_len, float drop_p,
                                 uint32_t seed, uint32_t site, void* P_pre, void* P_drop, void* stream) {
   if (!S || !kv_len || !P_pre || !P_drop || B <= 0 || H <= 0 || T <= 0 || Tk <= 0 || ld < Tk) return bad("ttsb_softmax_fwd: bad arguments");
@@ -434,26 +412,28 @@ extern "C" int ttsb_softmax_bwd(const void* P_pre, const float* dP, int B, int H
 
 extern "C" int ttsb_layernorm_bwd(const float* dz, const float* u, const float* gamma, int B, int T, int C, int ld, float eps,
                                   const int32_t* row_len, int relu_mask, float pre_drop_p, uint32_t pre_site, float post_drop_p,
-                                  uint32_t post_site, uint32_t seed, float* du, void* g_bf16, float* dgamma, float* dbeta, void* stream) {
+                                  uint32_t post_site, uint32_t seed, float* du, void* g_bf16, float* dgamma, float* dbeta, float* dbias,
+                                  void* stream) {
   if (!dz || !u || !gamma || !dgamma || !dbeta || B <= 0 || T <= 0 || C <= 0 || C > 512 || ld < C || ld > 512)
     return bad("ttsb_layernorm_bwd: bad arguments (C, ld <= 512)");
   const int rows = B * T;
-  layernorm_bwd_kernel<<<(rows + 63) / 64, 256, 2 * C * sizeof(float), STREAM(stream)>>>(dz, u, gamma, rows, T, C, ld, eps, row_len, relu_mask,
-                                                                                      pre_drop_p, pre_site, post_drop_p, post_site, seed, du,
-                                                                                      BF(g_bf16), dgamma, dbeta);
+  layernorm_bwd_kernel<<<(rows + 127) / 128, 256, 3 * C * sizeof(float), STREAM(stream)>>>(dz, u, gamma, rows, T, C, ld, eps, row_len, relu_mask,
+                                                                                        pre_drop_p, pre_site, post_drop_p, post_site, seed, du,
+                                                                                        BF(g_bf16), dgamma, dbeta, dbias);
   LAUNCH_OK("layernorm_bwd_kernel");
+}
+
+extern "C" int ttsb_colsum_bf16(const void* x, int64_t rows, int C, int ld, float* out, void* stream) {
+  if (!x || !out || rows <= 0 || C <= 0 || ld < C) return bad("ttsb_colsum_bf16: bad arguments");
+  dim3 grid((C + 63) / 64, (unsigned)((rows + 255) / 256));
+  colsum_bf16_kernel<<<grid, 256, 0, STREAM(stream)>>>(CBF(x), rows, C, ld, out);
+  LAUNCH_OK("colsum_bf16_kernel");
 }
 
 extern "C" int ttsb_relu_bwd(void* dy, const void* h, int64_t n, void* stream) {
   if (!dy || !h || n <= 0 || n % 8) return bad("ttsb_relu_bwd: n must be a positive multiple of 8");
   relu_bwd_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, STREAM(stream)>>>(BF(dy), CBF(h), n);
   LAUNCH_OK("relu_bwd_kernel");
-}
-
-extern "C" int ttsb_cast_bf16(const float* x, int64_t n, float drop_p, uint32_t seed, uint32_t site, void* out, void* stream) {
-  if (!x || !out || n <= 0) return bad("ttsb_cast_bf16: bad arguments");
-  cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM(stream)>>>(x, n, drop_p, seed, site, BF(out));
-  LAUNCH_OK("cast_bf16_kernel");
 }
 
 extern "C" int ttsb_cast_bf16_pad(const float* x, int64_t rows, int C, void* out, int ld_out, void* stream) {

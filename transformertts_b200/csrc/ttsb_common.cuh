@@ -135,7 +135,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B, bits [61,64)
   return d;
 }
-// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, dense, no negate.
+// MN-major operand (the M or N index is contiguous: each 128-byte row holds 64 m/n for ONE k): the tile is stored as
+// blocks of [64 k rows x 64 mn] (what a TMA box of 64 x 64 bf16 with the 128B swizzle writes); LBO = byte distance between
+// consecutive 64-wide blocks along M/N, SBO = 1024 B between groups of 8 k rows.  Advancing K by 16 adds 2048 B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major (OR in bit 15 / 16 for an MN-major A / B), dense.
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4)            // c_format = F32
          | (1u << 7)          // a_format = BF16

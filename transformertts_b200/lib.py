@@ -22,8 +22,8 @@ EXPORTS = [
     'ttsb_split_bf16', 'ttsb_embed_ln_pe_fwd', 'ttsb_linear_fwd', 'ttsb_mha_fwd', 'ttsb_statpred_head_fwd',
     'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
     'ttsb_expand_ln_pe_fwd', 'ttsb_mel_lengths', 'ttsb_phoneme_lengths', 'ttsb_stft_mel_log',
-    'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_transpose_bf16', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
-    'ttsb_relu_bwd', 'ttsb_cast_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
+    'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
+    'ttsb_relu_bwd', 'ttsb_colsum_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
     'ttsb_pitch_embed_bwd', 'ttsb_statpred_head_bwd', 'ttsb_adam_tf_step', 'ttsb_embed_ln_pe_train_fwd',
     'ttsb_expand_ln_pe_train_fwd',
 ]
@@ -41,8 +41,7 @@ class GemmArgs(C.Structure):
         ('w_hi', C.c_void_p), ('w_lo', C.c_void_p), ('bias', C.c_void_p), ('relu', C.c_int),
         ('residual', C.c_void_p), ('ld_res', C.c_int), ('ln_gamma', C.c_void_p), ('ln_beta', C.c_void_p),
         ('ln_eps', C.c_float), ('row_len', C.c_void_p), ('out_f32', C.c_void_p), ('out_hi', C.c_void_p),
-        ('out_lo', C.c_void_p), ('ld_out', C.c_int), ('vt_hi', C.c_void_p), ('vt_lo', C.c_void_p),
-        ('vt_col0', C.c_int), ('vt_cols', C.c_int), ('vt_ld', C.c_int), ('out_fp16', C.c_int), ('out_preln', C.c_void_p),
+        ('out_lo', C.c_void_p), ('ld_out', C.c_int), ('out_fp16', C.c_int), ('out_preln', C.c_void_p),
         ('drop_pre_p', C.c_float), ('drop_post_p', C.c_float), ('drop_pre_site', C.c_uint32), ('drop_post_site', C.c_uint32),
         ('drop_seed', C.c_uint32), ('precision', C.c_int), ('impl', C.c_int),
     ]
@@ -52,9 +51,9 @@ class BgemmArgs(C.Structure):
     _fields_ = [
         ('B', C.c_int), ('H', C.c_int), ('M', C.c_int), ('N', C.c_int), ('K', C.c_int),
         ('a', C.c_void_p), ('a_dim0', C.c_longlong), ('a_dim1', C.c_longlong), ('a_dim2', C.c_longlong),
-        ('a_stride1', C.c_longlong), ('a_stride2', C.c_longlong), ('a_h_col', C.c_int), ('a_h_row', C.c_int), ('a_z_batch', C.c_int),
+        ('a_stride1', C.c_longlong), ('a_stride2', C.c_longlong), ('a_h_col', C.c_int), ('a_h_row', C.c_int), ('a_z_batch', C.c_int), ('a_mn_major', C.c_int),
         ('b', C.c_void_p), ('b_dim0', C.c_longlong), ('b_dim1', C.c_longlong), ('b_dim2', C.c_longlong),
-        ('b_stride1', C.c_longlong), ('b_stride2', C.c_longlong), ('b_h_col', C.c_int), ('b_h_row', C.c_int), ('b_z_batch', C.c_int),
+        ('b_stride1', C.c_longlong), ('b_stride2', C.c_longlong), ('b_h_col', C.c_int), ('b_h_row', C.c_int), ('b_z_batch', C.c_int), ('b_mn_major', C.c_int),
         ('alpha', C.c_float), ('out_f32', C.c_void_p), ('out_bf16', C.c_void_p), ('ld_out', C.c_int),
         ('out_batch_stride', C.c_longlong), ('out_h_col', C.c_int), ('out_by_b', C.c_int), ('out_cols', C.c_int),
         ('row_len', C.c_void_p), ('col_len', C.c_void_p),
@@ -64,8 +63,8 @@ class BgemmArgs(C.Structure):
 class WgradArgs(C.Structure):
     _fields_ = [
         ('B', C.c_int), ('T', C.c_int), ('Cin', C.c_int), ('N', C.c_int), ('num_segments', C.c_int),
-        ('xt', C.c_void_p * 4), ('xt_rows', C.c_int * 4),
-        ('gt', C.c_void_p), ('gt_rows', C.c_int), ('ld_t', C.c_int), ('dw', C.c_void_p),
+        ('seg_src', C.c_int * 4), ('seg_shift', C.c_int * 4), ('x', C.c_void_p * 2), ('ldx', C.c_int * 2),
+        ('g', C.c_void_p), ('ldg', C.c_int), ('dw', C.c_void_p),
     ]
 
 
@@ -73,7 +72,7 @@ class MhaArgs(C.Structure):
     _fields_ = [
         ('B', C.c_int), ('T', C.c_int), ('H', C.c_int), ('dh', C.c_int),
         ('qk_hi', C.c_void_p), ('qk_lo', C.c_void_p), ('ld_qk', C.c_int), ('q_col0', C.c_int), ('k_col0', C.c_int),
-        ('vt_hi', C.c_void_p), ('vt_lo', C.c_void_p), ('ld_vt', C.c_int), ('kv_len', C.c_void_p),
+        ('v_col0', C.c_int), ('kv_len', C.c_void_p),
         ('out_hi', C.c_void_p), ('out_lo', C.c_void_p), ('ld_out', C.c_int),
         ('weights_out', C.c_void_p), ('weights_batch_index', C.c_int), ('precision', C.c_int), ('impl', C.c_int),
     ]
@@ -228,11 +227,6 @@ def wgrad(args: WgradArgs):
     _check(load().ttsb_wgrad(C.byref(args), _stream()), 'ttsb_wgrad')
 
 
-def transpose_bf16(src, B, T, ld_src, col0, Cc, dst, dst_rows, ld_t, colsum=None, t_shift=0):
-    _check(load().ttsb_transpose_bf16(ptr(src), B, T, ld_src, col0, Cc, ptr(dst), dst_rows, ld_t, ptr(colsum), int(t_shift), _stream()),
-           'ttsb_transpose_bf16')
-
-
 def softmax_fwd(S, B, H, T, Tk, ld, kv_len, drop_p, seed, site, P_pre, P_drop):
     _check(load().ttsb_softmax_fwd(ptr(S), B, H, T, Tk, ld, ptr(kv_len), C.c_float(drop_p), C.c_uint32(seed), C.c_uint32(site),
                                    ptr(P_pre), ptr(P_drop), _stream()), 'ttsb_softmax_fwd')
@@ -244,20 +238,19 @@ def softmax_bwd(P_pre, dP, B, H, T, Tk, ld, kv_len, scale, drop_p, seed, site, d
 
 
 def layernorm_bwd(dz, u, gamma, B, T, Cc, ld, eps, row_len, relu_mask, du, g_bf16, dgamma, dbeta, pre_drop=(0.0, 0),
-                  post_drop=(0.0, 0), seed=0):
+                  post_drop=(0.0, 0), seed=0, dbias=None):
     _check(load().ttsb_layernorm_bwd(ptr(dz), ptr(u), ptr(gamma), B, T, Cc, ld, C.c_float(eps), ptr(row_len), int(relu_mask),
                                      C.c_float(pre_drop[0]), C.c_uint32(pre_drop[1]), C.c_float(post_drop[0]),
                                      C.c_uint32(post_drop[1]), C.c_uint32(seed), ptr(du), ptr(g_bf16), ptr(dgamma), ptr(dbeta),
-                                     _stream()), 'ttsb_layernorm_bwd')
+                                     ptr(dbias), _stream()), 'ttsb_layernorm_bwd')
+
+
+def colsum_bf16(x, rows, Cc, ld, out):
+    _check(load().ttsb_colsum_bf16(ptr(x), C.c_int64(rows), Cc, ld, ptr(out), _stream()), 'ttsb_colsum_bf16')
 
 
 def relu_bwd(dy, h):
     _check(load().ttsb_relu_bwd(ptr(dy), ptr(h), C.c_int64(dy.numel()), _stream()), 'ttsb_relu_bwd')
-
-
-def cast_bf16(x, out, drop_p=0.0, seed=0, site=0):
-    _check(load().ttsb_cast_bf16(ptr(x), C.c_int64(x.numel()), C.c_float(drop_p), C.c_uint32(seed), C.c_uint32(site), ptr(out),
-                                 _stream()), 'ttsb_cast_bf16')
 
 
 def cast_bf16_pad(x, rows, Cc, out, ld_out):

@@ -312,7 +312,7 @@ class ForwardTransformer:
         return f, hi, lo
 
     def _gemm(self, pl: _PackedLinear, B, T, srcs, seg_src, seg_shift, relu=False, residual=None, ln=None, row_len=None,
-              out_f32=None, out_hi=None, out_lo=None, ld_out=None, vt=None, tag=None, out_fp16=False, out_preln=None,
+              out_f32=None, out_hi=None, out_lo=None, ld_out=None, tag=None, out_fp16=False, out_preln=None,
               dropout=None, dropout_post=None):
         prof = self._prof
         if prof is not None and tag is not None:
@@ -348,11 +348,6 @@ class ForwardTransformer:
         a.out_hi = out_hi.data_ptr() if out_hi is not None else None
         a.out_lo = out_lo.data_ptr() if out_lo is not None else None
         a.ld_out = ld_out if ld_out is not None else pl.n_pad
-        if vt is not None:
-            vt_hi, vt_lo, col0, cols, ld = vt
-            a.vt_hi = vt_hi.data_ptr()
-            a.vt_lo = vt_lo.data_ptr() if vt_lo is not None else None
-            a.vt_col0, a.vt_cols, a.vt_ld = col0, cols, ld
         a.out_fp16 = int(out_fp16)
         a.out_preln = out_preln.data_ptr() if out_preln is not None else None
         if dropout is not None and dropout[0] > 0:
@@ -379,29 +374,22 @@ class ForwardTransformer:
         W = self.weights
         x_f, x_hi, x_lo = x
         dev = self.device
-        # --- q,k,v projections: one GEMM, V written transposed for the attention kernel
+        # --- q,k,v projections: one GEMM into one (B,T,3d) buffer (the attention kernel reads V MN-major from it)
         qkv = P[pre + 'qkv']
-        ld_vt = _round_up(T, 8)
         ap = self.attention_precision
         att_split = ap == 'bf16x3'
         if att_split and not self._split:
             raise lib.TtsbError("attention_precision='bf16x3' needs precision='bf16x3'")
         qk_hi = torch.empty((B, T, qkv.n_pad), dtype=torch.float16 if ap == 'fp16' else torch.bfloat16, device=dev)
         qk_lo = torch.empty_like(qk_hi) if att_split else None
-        vt_hi = torch.empty((B, d, ld_vt), dtype=qk_hi.dtype, device=dev)
-        vt_lo = torch.empty_like(vt_hi) if att_split else None
-        self._gemm(qkv, B, T, [(x_hi, x_lo, d, 0)], [0], [0], out_hi=qk_hi, out_lo=qk_lo, vt=(vt_hi, vt_lo, 2 * d, d, ld_vt),
-                   out_fp16=(ap == 'fp16'))
+        self._gemm(qkv, B, T, [(x_hi, x_lo, d, 0)], [0], [0], out_hi=qk_hi, out_lo=qk_lo, out_fp16=(ap == 'fp16'))
         # --- fused attention
         _, at_hi, at_lo = self._act(B, T, d, f32=False)
         m = lib.MhaArgs()
         m.B, m.T, m.H, m.dh = B, T, H, dh
         m.qk_hi = qk_hi.data_ptr()
         m.qk_lo = qk_lo.data_ptr() if qk_lo is not None else None
-        m.ld_qk, m.q_col0, m.k_col0 = qkv.n_pad, 0, d
-        m.vt_hi = vt_hi.data_ptr()
-        m.vt_lo = vt_lo.data_ptr() if vt_lo is not None else None
-        m.ld_vt = ld_vt
+        m.ld_qk, m.q_col0, m.k_col0, m.v_col0 = qkv.n_pad, 0, d, 2 * d
         m.kv_len = lens.data_ptr()
         m.out_hi = at_hi.data_ptr()
         m.out_lo = at_lo.data_ptr() if at_lo is not None else None

@@ -131,27 +131,18 @@ class TrainEngine:
     def _f32(self, *shape):
         return torch.empty(shape, dtype=torch.float32, device=self.dev)
 
-    def _transpose(self, src, B, T, ld_src, col0, C, colsum=None, t_shift=0):
-        ld_t = _round_up(T, 8)
-        dst = self._bf(B, C, ld_t)
-        lib.transpose_bf16(src, B, T, ld_src, col0, C, dst, C, ld_t, colsum, t_shift)
-        return dst, ld_t
-
-    def _transpose_taps(self, src, B, T, ld_src, C, shifts):
-        """One time-transposed copy per conv tap: xt_s[b][c][t] = src[b][t + s][c]."""
-        return [self._transpose(src, B, T, ld_src, 0, C, t_shift=s)[0] for s in shifts]
-
-    def _wgrad(self, xts: List[torch.Tensor], gt, B, T, Cin, N, ld_t, dw):
-        """xts: one transposed source per segment (conv: one per tap; concat projection: one per input)."""
+    def _wgrad(self, xs, g, ldg, B, T, Cin, N, segs, dw):
+        """xs: [(bf16 (B,T,ld) tensor, ld)] sources; segs: [(source index, time shift)]; g: bf16 (B,T,ldg) output gradient."""
         a = lib.WgradArgs()
         a.B, a.T, a.Cin, a.N = B, T, Cin, N
-        a.num_segments = len(xts)
-        for i, xt in enumerate(xts):
-            a.xt[i] = xt.data_ptr()
-            a.xt_rows[i] = xt.shape[1]
-        a.gt = gt.data_ptr()
-        a.gt_rows = gt.shape[1]
-        a.ld_t = ld_t
+        a.num_segments = len(segs)
+        for s_, (src, shift) in enumerate(segs):
+            a.seg_src[s_], a.seg_shift[s_] = src, shift
+        for i, (x, ld) in enumerate(xs):
+            a.x[i] = x.data_ptr()
+            a.ldx[i] = ld
+        a.g = g.data_ptr()
+        a.ldg = ldg
         a.dw = dw.data_ptr()
         lib.wgrad(a)
 
@@ -163,10 +154,12 @@ class TrainEngine:
         g.a_dim0, g.a_dim1, g.a_dim2 = a_dims
         g.a_stride1, g.a_stride2 = a_strides
         g.a_h_col, g.a_h_row, g.a_z_batch = a_off[:3]
+        g.a_mn_major = a_off[4] if len(a_off) > 4 else 0
         g.b = b.data_ptr() + 2 * b_off[3]
         g.b_dim0, g.b_dim1, g.b_dim2 = b_dims
         g.b_stride1, g.b_stride2 = b_strides
         g.b_h_col, g.b_h_row, g.b_z_batch = b_off[:3]
+        g.b_mn_major = b_off[4] if len(b_off) > 4 else 0
         g.alpha = alpha
         if out_f32 is not None:
             g.out_f32 = out_f32.data_ptr() + 4 * out_ptr_off
@@ -200,10 +193,10 @@ class TrainEngine:
         site_p = self._site()
         lib.softmax_fwd(S, B, H, T, T, ldp, lens, rate, self.seed, site_p, P_pre, P_drop)
         del S
-        vT, ld8 = self._transpose(qkv, B, T, 3 * d, 2 * d, d)
         attn = self._bf(B, T, d)
-        self._bgemm(B, H, T, dh, T, P_drop, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), vT, (T, d, B), (ld8, d * ld8), (0, dh, 0, 0),
-                    out_bf16=attn, ld_out=d, out_batch_stride=T * d, out_h_col=dh, out_by_b=1, out_cols=dh)
+        # O = P V: V is read MN-major straight from the QKV buffer (columns 2d + h*dh), no transposed copy
+        self._bgemm(B, H, T, dh, T, P_drop, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), qkv, (d, T, B), (3 * d, 3 * d * T),
+                    (dh, 0, 0, 2 * d, 1), out_bf16=attn, ld_out=d, out_batch_stride=T * d, out_h_col=dh, out_by_b=1, out_cols=dh)
         y_f, y_bf, u1 = self._f32(B, T, d), self._bf(B, T, d), self._f32(B, T, d)
         site_o = self._site()
         m._gemm(P[pre + 'wo'], B, T, [(x_bf, None, d, 0), (attn, None, d, 0)], [0, 1], [0, 0], residual=x_f,
@@ -249,20 +242,18 @@ class TrainEngine:
         Z = B * H
         # ---- LayerNorm 2 (+ row mask) ; the branch gradient carries the branch dropout mask
         du2, g2 = self._f32(B, T, d), self._bf(B, T, d)
+        last_b = G[pre + ('ffn2.b' if i < st['n_dense'] else f"conv{len(st['filters']) - 1}.b")]
         lib.layernorm_bwd(dz, c['u2'], W[pre + 'ln2.gamma'], B, T, d, d, LN_EPS, lens, False, du2, g2, G[pre + 'ln2.gamma'],
-                          G[pre + 'ln2.beta'], pre_drop=(rate, site_c), seed=self.seed)
+                          G[pre + 'ln2.beta'], pre_drop=(rate, site_c), seed=self.seed, dbias=last_b)
         if i < st['n_dense']:
             F = int(st['ffn'])
             h = c['hs'][0]
-            g2T, ld8 = self._transpose(g2, B, T, d, 0, d, colsum=G[pre + 'ffn2.b'])
-            hT, _ = self._transpose(h, B, T, F, 0, F)
-            self._wgrad([hT], g2T, B, T, F, d, ld8, G[pre + 'ffn2.w'])
+            self._wgrad([(h, F)], g2, d, B, T, F, d, [(0, 0)], G[pre + 'ffn2.w'])
             dh_ = self._bf(B, T, F)
             m._gemm(P[pre + 'ffn2.d'], B, T, [(g2, None, d, 0)], [0], [0], out_hi=dh_, ld_out=F)
             lib.relu_bwd(dh_, h)
-            dhT, _ = self._transpose(dh_, B, T, F, 0, F, colsum=G[pre + 'ffn1.b'])
-            yT, _ = self._transpose(c['y_bf'], B, T, d, 0, d)
-            self._wgrad([yT], dhT, B, T, d, F, ld8, G[pre + 'ffn1.w'])
+            lib.colsum_bf16(dh_, B * T, F, F, G[pre + 'ffn1.b'])
+            self._wgrad([(c['y_bf'], d)], dh_, F, B, T, d, F, [(0, 0)], G[pre + 'ffn1.w'])
             dy = self._f32(B, T, d)
             m._gemm(P[pre + 'ffn1.d'], B, T, [(dh_, None, F, 0)], [0], [0], residual=du2, out_f32=dy, ld_out=d)
         else:
@@ -273,13 +264,11 @@ class TrainEngine:
             inputs = [c['y_bf']] + c['hs']  # input of conv j
             in_dims = [d] + list(st['filters'][:-1])
             g_cur, g_dim = g2, d
-            ld8 = _round_up(T, 8)
             for j in range(n - 1, -1, -1):
                 cin = in_dims[j]
-                gT, _ = self._transpose(g_cur, B, T, g_cur.shape[-1], 0, g_dim, colsum=G[pre + f'conv{j}.b'])
-                xTs = self._transpose_taps(inputs[j], B, T, cin, cin, shifts)
-                self._wgrad(xTs, gT, B, T, cin, g_dim, ld8, G[pre + f'conv{j}.w'])
-                del xTs
+                if j < n - 1:  # (the last conv's bias gradient comes out of the LayerNorm backward kernel)
+                    lib.colsum_bf16(g_cur, B * T, g_dim, g_cur.shape[-1], G[pre + f'conv{j}.b'])
+                self._wgrad([(inputs[j], cin)], g_cur, g_cur.shape[-1], B, T, cin, g_dim, [(0, s_) for s_ in shifts], G[pre + f'conv{j}.w'])
                 kpad = _round_up(g_dim, 64)
                 assert g_cur.shape[-1] == kpad, 'gradient operand must be padded to the packed contraction width'
                 if j > 0:
@@ -293,11 +282,8 @@ class TrainEngine:
         # ---- LayerNorm 1
         du1, g1 = self._f32(B, T, d), self._bf(B, T, d)
         lib.layernorm_bwd(dy, c['u1'], W[pre + 'ln1.gamma'], B, T, d, d, LN_EPS, lens, False, du1, g1, G[pre + 'ln1.gamma'],
-                          G[pre + 'ln1.beta'], pre_drop=(rate, site_o), seed=self.seed)
-        g1T, ld8 = self._transpose(g1, B, T, d, 0, d, colsum=G[pre + 'wo.b'])
-        xT, _ = self._transpose(c['x_bf'], B, T, d, 0, d)
-        aT, _ = self._transpose(c['attn'], B, T, d, 0, d)
-        self._wgrad([xT, aT], g1T, B, T, d, d, ld8, G[pre + 'wo.w'])
+                          G[pre + 'ln1.beta'], pre_drop=(rate, site_o), seed=self.seed, dbias=G[pre + 'wo.b'])
+        self._wgrad([(c['x_bf'], d), (c['attn'], d)], g1, d, B, T, d, d, [(0, 0), (1, 0)], G[pre + 'wo.w'])
         dattn = self._bf(B, T, d)
         m._gemm(P[pre + 'wo.da'], B, T, [(g1, None, d, 0)], [0], [0], out_hi=dattn, ld_out=d)
         dx_acc = self._f32(B, T, d)
@@ -310,26 +296,23 @@ class TrainEngine:
         dS = self._bf(Z, T, ldp)
         lib.softmax_bwd(c['P_pre'], dP, B, H, T, T, ldp, lens, 1.0 / math.sqrt(dh), rate, self.seed, site_p, dS)
         del dP
-        qkT, _ = self._transpose(qkv, B, T, 3 * d, 0, 2 * d)           # rows [0,d) = Q^T, [d,2d) = K^T
-        dST, _ = self._transpose(dS, Z, T, ldp, 0, T)                   # (Z, Tk, ld8)
-        PT, _ = self._transpose(c['P_drop'], Z, T, ldp, 0, T)
-        daT, _ = self._transpose(dattn, B, T, d, 0, d)
         dqkv = self._bf(B, T, 3 * d)
         common = dict(out_bf16=dqkv, ld_out=3 * d, out_batch_stride=T * 3 * d, out_h_col=dh, out_by_b=1, out_cols=dh)
-        # dQ = dS K : A = dS (Z,T,Tk), B = K^T rows d + h*dh
-        self._bgemm(B, H, T, dh, T, dS, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), qkT, (T, d, B), (ld8, 2 * d * ld8), (0, dh, 0, d * ld8),
+        qkv_dims, qkv_str = (d, T, B), (3 * d, 3 * d * T)
+        # dQ = dS K    : A = dS (K-major over keys),     B = K read MN-major (columns d + h*dh of the QKV buffer)
+        self._bgemm(B, H, T, dh, T, dS, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), qkv, qkv_dims, qkv_str, (dh, 0, 0, d, 1),
                     out_ptr_off=0, **common)
-        # dK = dS^T Q : A = dS^T (Z,Tk,T), B = Q^T rows h*dh
-        self._bgemm(B, H, T, dh, T, dST, (T, T, Z), (ld8, T * ld8), (0, 0, 1, 0), qkT, (T, d, B), (ld8, 2 * d * ld8), (0, dh, 0, 0),
+        # dK = dS^T Q  : A = dS read MN-major (= dS^T),  B = Q read MN-major
+        self._bgemm(B, H, T, dh, T, dS, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0, 1), qkv, qkv_dims, qkv_str, (dh, 0, 0, 0, 1),
                     out_ptr_off=d, **common)
-        # dV = P^T dO : A = P_drop^T (Z,Tk,T), B = dO^T rows h*dh
-        self._bgemm(B, H, T, dh, T, PT, (T, T, Z), (ld8, T * ld8), (0, 0, 1, 0), daT, (T, d, B), (ld8, d * ld8), (0, dh, 0, 0),
-                    out_ptr_off=2 * d, **common)
+        # dV = P^T dO  : A = P_drop read MN-major,       B = dO read MN-major
+        self._bgemm(B, H, T, dh, T, c['P_drop'], (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0, 1), dattn, (d, T, B), (d, d * T),
+                    (dh, 0, 0, 0, 1), out_ptr_off=2 * d, **common)
         # ---- q/k/v projections
         bq = self._tmp_zero(3 * d)
-        dqkvT, _ = self._transpose(dqkv, B, T, 3 * d, 0, 3 * d, colsum=bq)
+        lib.colsum_bf16(dqkv, B * T, 3 * d, 3 * d, bq)
         wq = self._tmp_zero(d * 3 * d).view(d, 3 * d)
-        self._wgrad([xT], dqkvT, B, T, d, 3 * d, ld8, wq)
+        self._wgrad([(c['x_bf'], d)], dqkv, 3 * d, B, T, d, 3 * d, [(0, 0)], wq)
         for n_, nm in enumerate(('wq', 'wk', 'wv')):
             G[pre + nm + '.w'].add_(wq[:, n_ * d:(n_ + 1) * d])
             G[pre + nm + '.b'].add_(bq[n_ * d:(n_ + 1) * d])
@@ -370,7 +353,7 @@ class TrainEngine:
         lib.statpred_head_fwd(h_f, int(filt[-1]), W[f'{name}.out.w'].reshape(-1), W[f'{name}.out.b'], relu_head, lens, out)
         return out, dict(us=us, outs=outs, h_f=h_f, x_bf=x_bf, sites=sites, rate=rate, out=out, relu=relu_head)
 
-    def _pred_bwd(self, name, c, gout, lens, B, T, xT_enc, ld8, dx_acc):
+    def _pred_bwd(self, name, c, gout, lens, B, T, dx_acc):
         """Returns the accumulated encoder-output gradient (fp32)."""
         m, P, W, G = self.model, self.P, self.model.weights, self.g
         filt = [int(f) for f in m.config['duration_conv_filters' if name == 'dur_pred' else 'pitch_conv_filters']]
@@ -391,15 +374,12 @@ class TrainEngine:
             dg, db = self._tmp_zero(ld), self._tmp_zero(ld)
             g_bf = self._bf(B, T, ld)
             lib.layernorm_bwd(dz, c['us'][j], gam, B, T, C, ld, LN_EPS, None, True, None, g_bf, dg, db,
-                              post_drop=(c['rate'], c['sites'][j]), seed=self.seed)
+                              post_drop=(c['rate'], c['sites'][j]), seed=self.seed, dbias=G[f'{name}.conv{j}.b'])
             G[f'{name}.ln{j}.gamma'].add_(dg[:C])
             G[f'{name}.ln{j}.beta'].add_(db[:C])
             cin = d_enc if j == 0 else filt[j - 1]
-            gT, _ = self._transpose(g_bf, B, T, ld, 0, C, colsum=G[f'{name}.conv{j}.b'])
             src = c['x_bf'] if j == 0 else c['outs'][j - 1]
-            xTs = self._transpose_taps(src, B, T, src.shape[-1], cin, shifts)
-            self._wgrad(xTs, gT, B, T, cin, C, ld8, G[f'{name}.conv{j}.w'])
-            del xTs
+            self._wgrad([(src, src.shape[-1])], g_bf, ld, B, T, cin, C, [(0, s_) for s_ in shifts], G[f'{name}.conv{j}.w'])
             if j > 0:
                 ldn = c['us'][j - 1].shape[-1]
                 dz = self._f32(B, T, ldn)
@@ -490,9 +470,8 @@ class TrainEngine:
             kpad = _round_up(C, 64)
             g = self._bf(B, Tm, kpad)
             lib.cast_bf16_pad(dmel, B * Tm, C, g, kpad)
-            gT, ld8m = self._transpose(g, B, Tm, kpad, 0, C, colsum=G['out.b'])
-            mT, _ = self._transpose(m_bf, B, Tm, dd, 0, dd)
-            self._wgrad([mT], gT, B, Tm, dd, C, ld8m, G['out.w'])
+            lib.colsum_bf16(g, B * Tm, C, kpad, G['out.b'])
+            self._wgrad([(m_bf, dd)], g, kpad, B, Tm, dd, C, [(0, 0)], G['out.w'])
             dz = self._f32(B, Tm, dd)
             m._gemm(P['out.d'], B, Tm, [(g, None, kpad, 0)], [0], [0], out_f32=dz, ld_out=dd)
             for i in range(len(dec_ctx) - 1, -1, -1):
@@ -503,9 +482,8 @@ class TrainEngine:
             lib.expand_bwd(d_exp, dur_int, dh_pe)
             lib.pitch_embed_bwd(dh_pe, pitch_tgt, pw, W['pitch_embed.b'], G['pitch_embed.w'].view(-1), G['pitch_embed.b'])
             # predictors read the encoder output; their input gradient is accumulated onto dh_pe
-            xT_enc, ld8p = self._transpose(h_bf, B, Tp, d, 0, d)
-            acc = self._pred_bwd('dur_pred', dur_ctx, ddur, enc_len, B, Tp, xT_enc, ld8p, dh_pe)
-            acc = self._pred_bwd('pitch_pred', pit_ctx, dpit, enc_len, B, Tp, xT_enc, ld8p, acc)
+            acc = self._pred_bwd('dur_pred', dur_ctx, ddur, enc_len, B, Tp, dh_pe)
+            acc = self._pred_bwd('pitch_pred', pit_ctx, dpit, enc_len, B, Tp, acc)
             dz = acc
             for i in range(len(enc_ctx) - 1, -1, -1):
                 dz = self._block_bwd('encoder', i, enc_ctx[i], dz, enc_len, B)
