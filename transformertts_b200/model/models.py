@@ -614,15 +614,18 @@ class ForwardTransformer:
             self._engine = TrainEngine(self)
         return self._engine
 
-    def train_step(self, input_sequence, target_sequence, target_durations, target_pitch, grad_sync=None):
-        """reference: model/models.py:464-482.  grad_sync(flat_grad) is the data-parallel hook (NCCL all-reduce)."""
+    def train_step(self, input_sequence, target_sequence, target_durations, target_pitch, data_parallel: bool = False):
+        """reference: model/models.py:464-482.  data_parallel=True: this process holds one shard of the batch; gradients
+        are summed over the default torch.distributed group (bucketed, overlapped with the backward pass) and scaled 1/N."""
         if self.optimizer is None:
             self._compile()
         eng = self._get_engine()
-        out = eng.forward_backward(input_sequence, target_sequence, target_durations, target_pitch, training=True)
-        scale = 1.0
-        if grad_sync is not None:
-            scale = grad_sync(eng.flat_g)
+        sync = None
+        if data_parallel:
+            from ..utils.data_parallel import GradSync
+            sync = GradSync(eng.flat_g)
+        out = eng.forward_backward(input_sequence, target_sequence, target_durations, target_pitch, training=True, sync=sync)
+        scale = sync.finish() if sync is not None else 1.0
         eng.apply_adam(self.optimizer, grad_scale=scale)
         return out
 

@@ -42,12 +42,16 @@ class TrainEngine:
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.dev)
         off = 0
         self.g: Dict[str, torch.Tensor] = {}
+        self.offsets: Dict[str, tuple] = {}
         for n, sz, psz in zip(names, sizes, padded):
+            self.offsets[n] = (off, psz)
             shape = model.weights[n].shape
             self.flat_w[off:off + sz].copy_(model.weights[n].reshape(-1))
             model.weights[n] = self.flat_w[off:off + sz].view(shape)  # parameters become views of the flat buffer
             self.g[n] = self.flat_g[off:off + sz].view(shape)
             off += psz
+        dec = [self.offsets[n] for n in names if n.startswith('decoder.')]
+        self.decoder_range = (dec[0][0], dec[-1][0] + dec[-1][1])  # contiguous slice of the flat buffers
         model._packed = None
         self.P = None
         self.world = 1
@@ -392,7 +396,7 @@ class TrainEngine:
     # ------------------------------------------------------------------------------------------------
     # full step
     # ------------------------------------------------------------------------------------------------
-    def forward_backward(self, phonemes, mel_tgt, dur_tgt, pitch_tgt, training=True):
+    def forward_backward(self, phonemes, mel_tgt, dur_tgt, pitch_tgt, training=True, sync=None):
         m, W, G = self.model, self.model.weights, self.g
         dev = self.dev
         self.use_dropout = training and m.train_dropout
@@ -478,6 +482,8 @@ class TrainEngine:
                 dz = self._block_bwd('decoder', i, dec_ctx[i], dz, dec_len, B)
                 dec_ctx[i] = None
             d_exp = self._prologue_bwd('decoder', dz, expanded, dec_len, B, Tm, site_d)
+            if sync is not None:  # decoder gradients are final: start their all-reduce under the encoder backward
+                sync.bucket_ready(*self.decoder_range)
             dh_pe = self._f32(B, Tp, d)
             lib.expand_bwd(d_exp, dur_int, dh_pe)
             lib.pitch_embed_bwd(dh_pe, pitch_tgt, pw, W['pitch_embed.b'], G['pitch_embed.w'].view(-1), G['pitch_embed.b'])
