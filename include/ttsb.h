@@ -100,7 +100,7 @@ typedef struct ttsb_gemm_args {
   float* out_f32;           /* any of the three may be NULL */
   void* out_hi;
   void* out_lo;
-  int ld_out;               /* row stride of all outputs, >= n_tiles*block_n, multiple of 8 */
+  int ld_out;               /* row stride of all outputs, >= n_tiles*block_n, multiple of 8 (16 with 16-bit outputs) */
   int out_fp16;             /* 1: out_hi receives IEEE fp16 (single plane) instead of bf16 hi/lo */
   float* out_preln;         /* optional fp32 (B,T,ld_out): value before the LayerNorm (saved for the backward pass) */
   /* training dropout (keras semantics, stateless mask from (seed, site, element index)): drop_pre on the GEMM output
@@ -164,7 +164,7 @@ typedef struct ttsb_bgemm_args {
   float alpha;
   float* out_f32;            /* either or both */
   void* out_bf16;
-  int ld_out;                /* row stride (elements), multiple of 8 */
+  int ld_out;                /* row stride (elements), multiple of 16 */
   long long out_batch_stride;/* elements between consecutive z (or b when out_by_b) */
   int out_h_col;             /* column offset per head */
   int out_by_b;              /* 1: output batch index is b (heads side by side in the columns) */

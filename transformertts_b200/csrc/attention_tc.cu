@@ -302,12 +302,8 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
         lo[i] = pack_bf16(l0, l1);
       }
       if (tq < p.T) {
-        st_global_v4(p.out_hi + o + c * 16, hi[0], hi[1], hi[2], hi[3]);
-        st_global_v4(p.out_hi + o + c * 16 + 8, hi[4], hi[5], hi[6], hi[7]);
-        if (p.out_lo) {
-          st_global_v4(p.out_lo + o + c * 16, lo[0], lo[1], lo[2], lo[3]);
-          st_global_v4(p.out_lo + o + c * 16 + 8, lo[4], lo[5], lo[6], lo[7]);
-        }
+        st_global_v8(p.out_hi + o + c * 16, hi);
+        if (p.out_lo) st_global_v8(p.out_lo + o + c * 16, lo);
       }
     }
   }
@@ -435,7 +431,7 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   const bool split = a->precision == TTSB_PREC_BF16X3;
   const bool f16 = a->precision == TTSB_PREC_FP16;
   if (split && (!a->qk_lo || !a->out_lo)) { set_last_error("ttsb_mha_fwd: bf16x3 needs the lo planes"); return TTSB_ERR_INVALID_ARGUMENT; }
-  if (a->ld_qk % 8 || a->ld_out % 8 || a->q_col0 % 8 || a->k_col0 % 8 || a->v_col0 % 8) {
+  if (a->ld_qk % 8 || a->ld_out % 16 || a->q_col0 % 8 || a->k_col0 % 8 || a->v_col0 % 8) {
     set_last_error("ttsb_mha_fwd: leading dimensions / column offsets must be multiples of 8");
     return TTSB_ERR_INVALID_ARGUMENT;
   }

@@ -235,8 +235,8 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               y[j] = (row_keep && n < clen && n < p.N) ? __uint_as_float(r[j]) * p.alpha : 0.f;
             }
             if (p.out_f32) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(p.out_f32 + o + c0 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+              st_global_v8f(p.out_f32 + o + c0, y);
+              st_global_v8f(p.out_f32 + o + c0 + 8, y + 8);
             }
             if (p.out_bf16) {
               uint32_t hh[8];
@@ -245,8 +245,7 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __nv_bfloat162 v = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
                 hh[j] = *reinterpret_cast<const uint32_t*>(&v);
               }
-              st_global_v4(p.out_bf16 + o + c0, hh[0], hh[1], hh[2], hh[3]);
-              st_global_v4(p.out_bf16 + o + c0 + 8, hh[4], hh[5], hh[6], hh[7]);
+              st_global_v8(p.out_bf16 + o + c0, hh);
             }
           }
         }
@@ -312,7 +311,10 @@ extern "C" int ttsb_bgemm(const ttsb_bgemm_args* a, void* stream_v) {
   if (!a) { set_last_error("ttsb_bgemm: args is NULL"); return TTSB_ERR_INVALID_ARGUMENT; }
   if (a->B <= 0 || a->H <= 0 || a->M <= 0 || a->N <= 0 || a->K <= 0) { set_last_error("ttsb_bgemm: non-positive dimension"); return TTSB_ERR_INVALID_ARGUMENT; }
   if (!a->a || !a->b || (!a->out_f32 && !a->out_bf16)) { set_last_error("ttsb_bgemm: NULL tensor"); return TTSB_ERR_INVALID_ARGUMENT; }
-  if (a->ld_out % 8 || a->out_cols % 16 || a->out_cols <= 0) { set_last_error("ttsb_bgemm: ld_out must be a multiple of 8 and out_cols of 16"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->ld_out % 16 || a->out_cols % 16 || a->out_cols <= 0 || a->out_h_col % 16) {
+    set_last_error("ttsb_bgemm: ld_out, out_cols and out_h_col must be multiples of 16 (32-byte stores)");
+    return TTSB_ERR_INVALID_ARGUMENT;
+  }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   BgParams p{};
   p.mode = 0;

@@ -95,9 +95,8 @@ __device__ __forceinline__ void pack_hi_lo(const float (&y)[16], uint32_t (&h)[8
 __device__ __forceinline__ void store_chunk(const GemmKParams& p, size_t orow, int col0, const float (&y)[16]) {
   const size_t o = orow * (size_t)p.ld_out + col0;
   if (p.out_f32) {
-#pragma unroll
-    for (int j = 0; j < 16; j += 4)
-      *reinterpret_cast<float4*>(p.out_f32 + o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+    st_global_v8f(p.out_f32 + o, y);
+    st_global_v8f(p.out_f32 + o + 8, y + 8);
   }
   if (p.out_hi) {
     uint32_t h[8], l[8];
@@ -110,12 +109,8 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, size_t orow, i
     } else {
       pack_hi_lo(y, h, l, p.out_lo != nullptr);
     }
-    st_global_v4(p.out_hi + o, h[0], h[1], h[2], h[3]);
-    st_global_v4(p.out_hi + o + 8, h[4], h[5], h[6], h[7]);
-    if (p.out_lo && !p.h16) {
-      st_global_v4(p.out_lo + o, l[0], l[1], l[2], l[3]);
-      st_global_v4(p.out_lo + o + 8, l[4], l[5], l[6], l[7]);
-    }
+    st_global_v8(p.out_hi + o, h);
+    if (p.out_lo && !p.h16) st_global_v8(p.out_lo + o, l);
   }
 }
 
@@ -166,7 +161,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
       }
       if (p.drop_pre_p > 0.f) apply_dropout16(y, p.drop_pre_p, p.drop_seed, p.drop_pre_site, orow * (uint64_t)p.ld_out + n0 + c0);
       if (p.residual && row_ok) {
-        ldg16(p.residual + orow * (size_t)p.ld_res + n0 + c0, aux);
+        ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + n0 + c0, aux);
+        ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + n0 + c0 + 8, aux + 8);
 #pragma unroll
         for (int j = 0; j < 16; ++j) y[j] += aux[j];
       }
@@ -204,7 +200,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
     }
     if (p.drop_pre_p > 0.f) apply_dropout16(y, p.drop_pre_p, p.drop_seed, p.drop_pre_site, orow * (uint64_t)p.ld_out + c0);
     if (p.residual && row_ok) {
-      ldg16(p.residual + orow * (size_t)p.ld_res + c0, aux);
+      ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + c0, aux);
+      ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + c0 + 8, aux + 8);
 #pragma unroll
       for (int j = 0; j < 16; ++j) y[j] += aux[j];
     }
@@ -219,8 +216,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
     }
     if (p.out_preln && row_ok) {
       float* dst = p.out_preln + orow * (size_t)p.ld_out + c0;
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+      st_global_v8f(dst, y);
+      st_global_v8f(dst + 8, y + 8);
     }
     tmem_st16(taddr + c0, r);
   }
@@ -518,12 +515,13 @@ static int validate(const ttsb_gemm_args* a, int* k_total_out) {
   }
   if (!a->w_hi || (a->precision == TTSB_PREC_BF16X3 && !a->w_lo)) { set_last_error("ttsb_linear_fwd: missing packed weights"); return TTSB_ERR_INVALID_ARGUMENT; }
   const int n_tiles = (a->N + a->block_n - 1) / a->block_n;
-  if (a->ld_out < n_tiles * a->block_n || a->ld_out % 8) {
-    set_last_error("ttsb_linear_fwd: ld_out=%d must be >= %d and a multiple of 8", a->ld_out, n_tiles * a->block_n);
+  if (a->ld_out < n_tiles * a->block_n || a->ld_out % 8 || ((a->out_hi || a->out_lo) && a->ld_out % 16)) {
+    set_last_error("ttsb_linear_fwd: ld_out=%d must be >= %d and a multiple of 8 (16 with 16-bit outputs: 32-byte stores)", a->ld_out,
+                   n_tiles * a->block_n);
     return TTSB_ERR_INVALID_ARGUMENT;
   }
   if (a->ln_gamma && (n_tiles != 1 || !a->ln_beta)) { set_last_error("ttsb_linear_fwd: LayerNorm epilogue needs N <= block_n and beta"); return TTSB_ERR_INVALID_ARGUMENT; }
-  if (a->residual && (a->ld_res % 4)) { set_last_error("ttsb_linear_fwd: ld_res must be a multiple of 4"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->residual && (a->ld_res % 8)) { set_last_error("ttsb_linear_fwd: ld_res must be a multiple of 8 (32-byte loads)"); return TTSB_ERR_INVALID_ARGUMENT; }
   if (a->precision != TTSB_PREC_BF16 && a->precision != TTSB_PREC_BF16X3) { set_last_error("ttsb_linear_fwd: unknown precision"); return TTSB_ERR_INVALID_ARGUMENT; }
   *k_total_out = kt;
   return 0;
