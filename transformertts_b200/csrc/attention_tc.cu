@@ -23,6 +23,13 @@ constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 64;
 constexpr int ATT_THREADS = 160;  // warps 0-3 softmax/epilogue (TMEM lane quarters 0-3), warp 4 TMA + MMA issue
 
+// single MUFU.EX2 (no denormal fix-up code: p < 2^-126 flushes to 0, far below bf16/fp16 resolution of P)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct MhaKParams {
   int B, T, H;
   int q_col0, k_col0, v_col0;
@@ -42,13 +49,14 @@ struct MhaCfg {
   static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + kPlanes * Q_BYTES;
-  static constexpr int OFF_V = OFF_K + kPlanes * K_BYTES;
+  static constexpr int K_STAGE = kPlanes * K_BYTES;  // two K stages: S_{j+1} is issued while softmax_j runs
+  static constexpr int OFF_V = OFF_K + 2 * K_STAGE;
   static constexpr int OFF_P = OFF_V + kPlanes * V_BYTES;
   static constexpr int OFF_BAR = OFF_P + kPlanes * P_BYTES;
   static constexpr int kSmemBytes = OFF_BAR + 128 + 1024;
-  static constexpr int kTmemCols = (ATT_BKV + DH) <= 128 ? 128 : 256;
-  static constexpr int S_COL = 0;
-  static constexpr int O_COL = ATT_BKV;
+  static constexpr int kTmemCols = (2 * ATT_BKV + DH) <= 128 ? 128 : 256;
+  static constexpr int S_COL = 0;             // two S accumulators of ATT_BKV columns
+  static constexpr int O_COL = 2 * ATT_BKV;
 };
 
 template <int DH, bool kSplit, bool kF16>
@@ -60,12 +68,12 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* bar_q = bars + 0;
-  uint64_t* bar_k = bars + 1;
-  uint64_t* bar_v = bars + 2;
-  uint64_t* bar_s = bars + 3;
-  uint64_t* bar_p = bars + 4;
-  uint64_t* bar_pv = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_k = bars + 1;   // [2]
+  uint64_t* bar_v = bars + 3;
+  uint64_t* bar_s = bars + 4;   // [2]
+  uint64_t* bar_p = bars + 6;
+  uint64_t* bar_pv = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,8 +102,10 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1);
     mbar_init(bar_k, 1);
+    mbar_init(bar_k + 1, 1);
     mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
+    mbar_init(bar_s + 1, 1);
     mbar_init(bar_p, 4);
     mbar_init(bar_pv, 1);
     fence_mbar_init();
@@ -127,10 +137,11 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
         if (kSplit) tma_load_3d(&tmQl, bar_q, sQ + Cfg::Q_BYTES + pn * (ATT_BQ * 128), p.q_col0 + h * DH + pn * 64, q0, b);
       }
       auto load_k = [&](int j) {
-        mbar_arrive_expect_tx(bar_k, Cfg::kPlanes * Cfg::K_BYTES);
+        uint8_t* dst = sK + (j & 1) * Cfg::K_STAGE;
+        mbar_arrive_expect_tx(bar_k + (j & 1), Cfg::kPlanes * Cfg::K_BYTES);
         for (int pn = 0; pn < DH / 64; ++pn) {
-          tma_load_3d(&tmKh, bar_k, sK + pn * (ATT_BKV * 128), p.k_col0 + h * DH + pn * 64, j * ATT_BKV, b);
-          if (kSplit) tma_load_3d(&tmKl, bar_k, sK + Cfg::K_BYTES + pn * (ATT_BKV * 128), p.k_col0 + h * DH + pn * 64, j * ATT_BKV, b);
+          tma_load_3d(&tmKh, bar_k + (j & 1), dst + pn * (ATT_BKV * 128), p.k_col0 + h * DH + pn * 64, j * ATT_BKV, b);
+          if (kSplit) tma_load_3d(&tmKl, bar_k + (j & 1), dst + Cfg::K_BYTES + pn * (ATT_BKV * 128), p.k_col0 + h * DH + pn * 64, j * ATT_BKV, b);
         }
       };
       auto load_v = [&](int j) {
@@ -140,43 +151,49 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
           if (kSplit) tma_load_3d(&tmKl, bar_v, sV + Cfg::V_BYTES + pn * (ATT_BKV * 128), p.v_col0 + h * DH + pn * 64, j * ATT_BKV, b);
         }
       };
-      load_k(0);
-      load_v(0);
-      mbar_wait(bar_q, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const uint32_t ph = j & 1;
-        // ---- S = Q K^T
-        mbar_wait(bar_k, ph);
+      // S_j = Q K_j^T into S accumulator j&1, from K stage j&1
+      auto issue_s = [&](int j) {
+        const uint8_t* kst = sK + (j & 1) * Cfg::K_STAGE;
+        const uint32_t ts = t_s + (j & 1) * ATT_BKV;
+        mbar_wait(bar_k + (j & 1), (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) {
           const uint64_t a = make_smem_desc_sw128(smem_u32(sQ + (kk / 4) * (ATT_BQ * 128))) + 2 * (kk % 4);
-          const uint64_t bb = make_smem_desc_sw128(smem_u32(sK + (kk / 4) * (ATT_BKV * 128))) + 2 * (kk % 4);
-          umma_bf16(t_s, a, bb, idesc_s, kk != 0);
+          const uint64_t bb = make_smem_desc_sw128(smem_u32(kst + (kk / 4) * (ATT_BKV * 128))) + 2 * (kk % 4);
+          umma_bf16(ts, a, bb, idesc_s, kk != 0);
         }
         if (kSplit) {
 #pragma unroll
           for (int kk = 0; kk < DH / 16; ++kk) {
             const uint64_t a = make_smem_desc_sw128(smem_u32(sQ + Cfg::Q_BYTES + (kk / 4) * (ATT_BQ * 128))) + 2 * (kk % 4);
-            const uint64_t bb = make_smem_desc_sw128(smem_u32(sK + (kk / 4) * (ATT_BKV * 128))) + 2 * (kk % 4);
-            umma_bf16(t_s, a, bb, idesc_s, 1);
+            const uint64_t bb = make_smem_desc_sw128(smem_u32(kst + (kk / 4) * (ATT_BKV * 128))) + 2 * (kk % 4);
+            umma_bf16(ts, a, bb, idesc_s, 1);
           }
 #pragma unroll
           for (int kk = 0; kk < DH / 16; ++kk) {
             const uint64_t a = make_smem_desc_sw128(smem_u32(sQ + (kk / 4) * (ATT_BQ * 128))) + 2 * (kk % 4);
-            const uint64_t bb = make_smem_desc_sw128(smem_u32(sK + Cfg::K_BYTES + (kk / 4) * (ATT_BKV * 128))) + 2 * (kk % 4);
-            umma_bf16(t_s, a, bb, idesc_s, 1);
+            const uint64_t bb = make_smem_desc_sw128(smem_u32(kst + Cfg::K_BYTES + (kk / 4) * (ATT_BKV * 128))) + 2 * (kk % 4);
+            umma_bf16(ts, a, bb, idesc_s, 1);
           }
         }
-        umma_commit(bar_s);
-        // ---- V_j may be loaded once PV_{j-1} has finished reading the V buffer
-        if (j > 0) {
-          mbar_wait(bar_pv, (j - 1) & 1);
-          load_v(j);
+        umma_commit(bar_s + (j & 1));
+      };
+      load_k(0);
+      load_v(0);
+      if (n_kv > 1) load_k(1);
+      mbar_wait(bar_q, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t ph = j & 1;
+        // ---- software pipeline: S_{j+1} goes to the tensor pipe now, so the softmax warps find it ready when they finish
+        //      tile j (its accumulator was last read for tile j-1, whose bar_p this thread has already seen)
+        if (j + 1 < n_kv) issue_s(j + 1);
+        // ---- K stage j&1 is free once S_j has completed: refill it with K_{j+2}
+        if (j + 2 < n_kv) {
+          mbar_wait(bar_s + (j & 1), (j >> 1) & 1);
+          load_k(j + 2);
         }
-        // ---- K_{j+1} may be loaded once S_j has finished reading the K buffer
-        mbar_wait(bar_s, ph);
-        if (j + 1 < n_kv) load_k(j + 1);
         // ---- O += P V
         mbar_wait(bar_p, ph);
         mbar_wait(bar_v, ph);
@@ -202,6 +219,11 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
           }
         }
         umma_commit(bar_pv);
+        // ---- V_{j+1} may be loaded once PV_j has finished reading the V buffer
+        if (j + 1 < n_kv) {
+          mbar_wait(bar_pv, ph);
+          load_v(j + 1);
+        }
       }
     }
   } else {
@@ -215,28 +237,34 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
     float m = -INFINITY, l = 0.f;
     uint32_t r[16];
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(bar_s, j & 1);
+      mbar_wait(bar_s + (j & 1), (j >> 1) & 1);
       tc_fence_after();
+      const uint32_t t_sj = t_s + (j & 1) * ATT_BKV;
+      // raw scores (un-scaled): the running max is kept in raw units, the softmax scale is folded into one FFMA per
+      // element: p = exp2(s * scale_log2 - m * scale_log2)
       float s[ATT_BKV];
-      float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < ATT_BKV / 16; ++c) {
-        tmem_ld16(t_s + c * 16, r);
+        tmem_ld16(t_sj + c * 16, r);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int key = j * ATT_BKV + c * 16 + i;
-          const float v = key < len ? __uint_as_float(r[i]) * p.scale_log2 : -INFINITY;
-          s[c * 16 + i] = v;
-          mx = fmaxf(mx, v);
-        }
+        for (int i = 0; i < 16; ++i) s[c * 16 + i] = __uint_as_float(r[i]);
       }
+      if ((j + 1) * ATT_BKV > len) {  // only the last key tile can hold padded keys
+#pragma unroll
+        for (int i = 0; i < ATT_BKV; ++i)
+          if (j * ATT_BKV + i >= len) s[i] = -INFINITY;
+      }
+      float mx = s[0];
+#pragma unroll
+      for (int i = 1; i < ATT_BKV; ++i) mx = fmaxf(mx, s[i]);
       const float m_new = fmaxf(m, mx);
-      const float alpha = exp2f(m - m_new);  // first tile: exp2(-inf) = 0
+      const float alpha = fast_exp2((m - m_new) * p.scale_log2);  // first tile: exp2(-inf) = 0
+      const float neg_m = -m_new * p.scale_log2;
       float psum = 0.f;
 #pragma unroll
       for (int i = 0; i < ATT_BKV; ++i) {
-        s[i] = exp2f(s[i] - m_new);
+        s[i] = fast_exp2(fmaf(s[i], p.scale_log2, neg_m));
         psum += s[i];
       }
       l = l * alpha + psum;
