@@ -113,6 +113,12 @@ typedef struct ttsb_gemm_args {
 
 int ttsb_linear_fwd(const ttsb_gemm_args* args, void* stream);
 
+/* Stand-alone LayerNorm (+ row mask) over rows of fp32 x (B,T,ld)[:, :, :d]  (model/layers.py:27,96,207: epsilon 1e-6).
+ * Used when a row is wider than one 256-column accumulator tile (model dimension 384): the GEMM then writes the
+ * pre-norm value and this kernel produces the fp32 + bf16 hi/lo activation triple. */
+int ttsb_layernorm_fwd(const float* x, const float* gamma, const float* beta, int B, int T, int d, int ld, float eps,
+                       const int32_t* row_len, float* out_f32, void* out_hi, void* out_lo, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Fused variable-length self-attention  (model/layers.py:138-147 split/merge heads, :176-195 scaled dot product)
  *   q,k,v: bf16 (B,T,ld_qk) at columns q_col0 + h*dh / k_col0 + h*dh / v_col0 + h*dh of one buffer (the QKV GEMM output)

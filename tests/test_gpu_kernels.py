@@ -275,9 +275,11 @@ def test_gemm_persistent_many_tiles(precision):
 # ----------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('impl', IMPLS)
 @pytest.mark.parametrize('precision', PRECS + ['fp16'])
-@pytest.mark.parametrize('H,d,T', [(2, 256, 200), (2, 128, 333), (2, 256, 64)])
+@pytest.mark.parametrize('H,d,T', [(2, 256, 200), (2, 128, 333), (2, 256, 64), (2, 384, 200)])
 def test_mha_varlen(impl, precision, H, d, T):
     from gpu_util import ref_mha, run_mha
+    if d == 384 and precision == 'bf16x3' and impl == 'tcgen05':
+        pytest.skip('head_dim 192 runs in the single-pass modes (fp16 is the default attention precision)')
     g = torch.Generator().manual_seed(20)
     B = 3
     q = torch.randn(B, T, d, generator=g).to(DEV)

@@ -71,7 +71,7 @@ def test_c1_predict_api_integer_durations():
         assert np.array_equal(o['int_durations'].cpu().numpy()[safe], r['int_durations'].numpy()[safe])
 
 
-@pytest.mark.parametrize('cfg_name', ['LJ256', 'LJ256-dense'])
+@pytest.mark.parametrize('cfg_name', ['LJ256', 'LJ256-dense', 'REF384'])
 def test_lj256_ragged_parity(cfg_name):
     """BASELINE configs[1] model (6+6 layers, d=256) on a small ragged batch the oracle finishes in seconds."""
     torch.set_num_threads(8)

@@ -172,7 +172,7 @@ def test_layernorm_bwd_and_small_ops():
     assert (pd.cpu() - pr).abs().max() < 1e-7
 
 
-@pytest.mark.parametrize('cfg_name,B,Tp,Tm', [('C1', 3, 24, 150), ('LJ256', 2, 32, 260)])
+@pytest.mark.parametrize('cfg_name,B,Tp,Tm', [('C1', 3, 24, 150), ('LJ256', 2, 32, 260), ('REF384', 2, 24, 200)])
 def test_train_step_loss_grads_and_adam(cfg_name, B, Tp, Tm):
     """One deterministic training step (dropout off): loss, every parameter gradient and the Adam update vs the
     oracle (torch autograd on the restated fp32 graph).  The GPU forward/backward is single-pass bf16."""

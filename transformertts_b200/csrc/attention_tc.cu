@@ -54,7 +54,7 @@ struct MhaCfg {
   static constexpr int OFF_P = OFF_V + kPlanes * V_BYTES;
   static constexpr int OFF_BAR = OFF_P + kPlanes * P_BYTES;
   static constexpr int kSmemBytes = OFF_BAR + 128 + 1024;
-  static constexpr int kTmemCols = (2 * ATT_BKV + DH) <= 128 ? 128 : 256;
+  static constexpr int kTmemCols = (2 * ATT_BKV + DH) <= 128 ? 128 : ((2 * ATT_BKV + DH) <= 256 ? 256 : 512);
   static constexpr int S_COL = 0;             // two S accumulators of ATT_BKV columns
   static constexpr int O_COL = 2 * ATT_BKV;
 };
@@ -492,7 +492,8 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   int rc;
   if (a->dh == 128) rc = split ? launch_tc<128, true, false>(a, p, stream) : (f16 ? launch_tc<128, false, true>(a, p, stream) : launch_tc<128, false, false>(a, p, stream));
   else if (a->dh == 64) rc = split ? launch_tc<64, true, false>(a, p, stream) : (f16 ? launch_tc<64, false, true>(a, p, stream) : launch_tc<64, false, false>(a, p, stream));
-  else { set_last_error("ttsb_mha_fwd: head_dim %d not supported by the tcgen05 kernel (64, 128)", a->dh); return TTSB_ERR_UNSUPPORTED; }
+  else if (a->dh == 192 && !split) rc = f16 ? launch_tc<192, false, true>(a, p, stream) : launch_tc<192, false, false>(a, p, stream);
+  else { set_last_error("ttsb_mha_fwd: head_dim %d not supported by the tcgen05 kernel (64, 128; 192 in single-pass modes)", a->dh); return TTSB_ERR_UNSUPPORTED; }
   if (rc) return rc;
   if (a->weights_out) {
     if (a->weights_batch_index < 0 || a->weights_batch_index >= a->B) { set_last_error("ttsb_mha_fwd: weights_batch_index out of range"); return TTSB_ERR_INVALID_ARGUMENT; }

@@ -42,7 +42,7 @@ __device__ __forceinline__ void ln_pe_store(float4 (&v)[ROW_MAX_V4], int nv, int
     if (i < nv && c0 < d) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0));
       const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c0));
-      const float4 pe = __ldg(reinterpret_cast<const float4*>(pe_row + c0));
+      const float4 pe = pe_row ? __ldg(reinterpret_cast<const float4*>(pe_row + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 y;
       y.x = (v[i].x - mean) * rstd * g.x + bt.x + scalar * pe.x;
       y.y = (v[i].y - mean) * rstd * g.y + bt.y + scalar * pe.y;
@@ -107,6 +107,35 @@ __global__ void expand_ln_pe_kernel(const float* __restrict__ x, const int* __re
   const size_t o = (size_t)row * d;
   ln_pe_store(v, nv, d, lane, gamma, beta, eps, pe + (size_t)t * d, __ldg(pos_scalar), out_f32 ? out_f32 + o : nullptr,
               out_hi ? out_hi + o : nullptr, out_lo ? out_lo + o : nullptr, drop_p, seed, site, (uint64_t)o);
+}
+
+// Stand-alone LayerNorm + row mask for model dimensions whose row does not fit one 256-column accumulator tile (d = 384):
+// the GEMM writes the pre-norm value (acc + bias + residual), this kernel normalises it (model/layers.py:211,40,102).
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* gamma, const float* beta, int rows, int T, int d,
+                                     int ld, float eps, const int* __restrict__ row_len, float* out_f32, __nv_bfloat16* out_hi,
+                                     __nv_bfloat16* out_lo) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / T, t = row % T;
+  const int nv = (d + 127) / 128;
+  const size_t o = (size_t)row * ld;
+  if (row_len != nullptr && t >= __ldg(row_len + b)) {
+    for (int c0 = lane * 4; c0 < d; c0 += 128) {
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + o + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (out_hi) *reinterpret_cast<uint2*>(out_hi + o + c0) = make_uint2(0u, 0u);
+      if (out_lo) *reinterpret_cast<uint2*>(out_lo + o + c0) = make_uint2(0u, 0u);
+    }
+    return;
+  }
+  float4 v[ROW_MAX_V4];
+#pragma unroll
+  for (int i = 0; i < ROW_MAX_V4; ++i) {
+    const int c0 = (i * 32 + lane) * 4;
+    v[i] = (i < nv && c0 < d) ? __ldg(reinterpret_cast<const float4*>(x + o + c0)) : make_float4(0, 0, 0, 0);
+  }
+  ln_pe_store(v, nv, d, lane, gamma, beta, eps, nullptr, 0.f, out_f32 ? out_f32 + o : nullptr, out_hi ? out_hi + o : nullptr,
+              out_lo ? out_lo + o : nullptr);
 }
 
 // Expand (model/layers.py:549-565) as a gather: 16-byte vectorised, one warp per output frame.
@@ -356,6 +385,16 @@ extern "C" int ttsb_expand_ln_pe_fwd(const float* x, const int32_t* idx, const f
                                      const float* pos_scalar, int B, int Tp, int Tm, int d, float eps, float* out_f32, void* out_hi,
                                      void* out_lo, void* stream) {
   return ttsb_expand_ln_pe_train_fwd(x, idx, gamma, beta, pe, pos_scalar, B, Tp, Tm, d, eps, 0.f, 0u, 0u, out_f32, out_hi, out_lo, stream);
+}
+
+extern "C" int ttsb_layernorm_fwd(const float* x, const float* gamma, const float* beta, int B, int T, int d, int ld, float eps,
+                                  const int32_t* row_len, float* out_f32, void* out_hi, void* out_lo, void* stream) {
+  if (!x || !gamma || !beta) return bad("ttsb_layernorm_fwd: NULL input");
+  if (B <= 0 || T <= 0 || d <= 0 || d % 4 || d > 128 * ROW_MAX_V4 || ld < d || ld % 4) return bad("ttsb_layernorm_fwd: need d % 4 == 0, d <= 512");
+  const int rows = B * T;
+  layernorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(x, gamma, beta, rows, T, d, ld, eps, row_len, out_f32,
+                                                                  static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo));
+  LAUNCH_OK("layernorm_fwd_kernel");
 }
 
 extern "C" int ttsb_length_regulate_fwd(const float* x, const int32_t* idx, int B, int Tp, int Tm, int d, float* out, void* stream) {

@@ -19,7 +19,7 @@ _lib = None
 
 EXPORTS = [
     'ttsb_last_error', 'ttsb_abi_version', 'ttsb_launch_count', 'ttsb_reset_launch_count', 'ttsb_pack_weight',
-    'ttsb_split_bf16', 'ttsb_embed_ln_pe_fwd', 'ttsb_linear_fwd', 'ttsb_mha_fwd', 'ttsb_statpred_head_fwd',
+    'ttsb_split_bf16', 'ttsb_embed_ln_pe_fwd', 'ttsb_linear_fwd', 'ttsb_layernorm_fwd', 'ttsb_mha_fwd', 'ttsb_statpred_head_fwd',
     'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
     'ttsb_expand_ln_pe_fwd', 'ttsb_mel_lengths', 'ttsb_phoneme_lengths', 'ttsb_stft_mel_log',
     'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
@@ -148,6 +148,12 @@ def split_bf16(x: torch.Tensor, split: bool):
 
 def linear_fwd(args: GemmArgs):
     _check(load().ttsb_linear_fwd(C.byref(args), _stream()), 'ttsb_linear_fwd')
+
+
+def layernorm_fwd(x, gamma, beta, d, eps, row_len, out_f32, out_hi, out_lo):
+    B, T, ld = x.shape
+    _check(load().ttsb_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), B, T, d, ld, C.c_float(eps), ptr(row_len), ptr(out_f32),
+                                     ptr(out_hi), ptr(out_lo), _stream()), 'ttsb_layernorm_fwd')
 
 
 def mha_fwd(args: MhaArgs):

@@ -34,8 +34,7 @@ def _pick_block_n(N: int, need_single_tile: bool) -> int:
     n16 = _round_up(N, 16)
     if n16 <= 256:
         return n16
-    if need_single_tile:
-        raise lib.TtsbError(f'LayerNorm-epilogue GEMM needs N <= 256 (got {N}); model dimension 384 is not supported yet')
+    # wider rows (model dimension 384): several N tiles; a LayerNorm epilogue then runs as a separate row kernel
     for bn in range(256, 15, -16):
         if n16 % bn == 0:
             return bn
@@ -338,6 +337,20 @@ class ForwardTransformer:
         if residual is not None:
             a.residual = residual.data_ptr()
             a.ld_res = residual.shape[-1]
+        unfused_ln = None
+        if ln is not None and pl.n_tiles > 1:
+            # the row does not fit one accumulator tile: GEMM writes the pre-norm value, LayerNorm runs as a row kernel
+            if dropout_post is not None and dropout_post[0] > 0:
+                raise lib.TtsbError('post-LayerNorm dropout needs the fused epilogue (N <= 256)')
+            unfused_ln = (ln, row_len, out_f32, out_hi, out_lo)
+            if out_preln is None:
+                out_preln = torch.empty((B, T, pl.n_pad), dtype=torch.float32, device=self.device)
+            out_f32, out_hi, out_lo, row_len, ln = out_preln, None, None, None, None
+            a.out_f32 = out_f32.data_ptr()
+            a.out_hi = None
+            a.out_lo = None
+            a.row_len = None
+            out_preln = None
         if ln is not None:
             ln = (_pad_vec(ln[0], pl.n_pad), _pad_vec(ln[1], pl.n_pad))
             a.ln_gamma = ln[0].data_ptr()
@@ -358,6 +371,9 @@ class ForwardTransformer:
         a.precision = self._prec
         a.impl = self._impl
         lib.linear_fwd(a)
+        if unfused_ln is not None:
+            (g_, b_), rl, of, oh, ol = unfused_ln
+            lib.layernorm_fwd(out_f32, g_, b_, pl.N, LN_EPS, rl, of, oh, ol if self._split else None)
         if prof is not None and tag is not None:
             e1.record()
             prof.setdefault(tag, []).append((e0, e1, 2.0 * B * T * pl.K * pl.N))
