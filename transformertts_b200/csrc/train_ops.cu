@@ -56,7 +56,7 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ S, int Z, int H, in
   }
 }
 
-// dS = scale * P_pre * (dPp - sum_k P_pre dPp),  dPp = dP * keep/(1-p)
+// dS = scale * P_pre * (dPp - sum_k P_pre dPp),  dPp = dP * keep/(1-p).  The row (<= 1280 keys) stays in registers.
 __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P_pre, const float* __restrict__ dP, int Z, int H, int T, int Tk,
                                    int ld, const int* __restrict__ kv_len, float scale, float drop_p, uint32_t seed, uint32_t site,
                                    __nv_bfloat16* __restrict__ dS) {
@@ -67,24 +67,28 @@ __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P_pre, cons
   const int len = min(max(__ldg(kv_len + b), 0), Tk);
   const size_t base = (size_t)row * ld;
   const bool live = t < len;
-  const uint32_t thresh = drop_p > 0.f ? (uint32_t)(drop_p * 4294967296.0) : 0u;
+  const uint32_t thresh = dropout_thresh(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  constexpr int NV = 40;  // 32 lanes x 40 = 1280 keys
+  float pv[NV], gv[NV];
   float dot = 0.f;
-  if (live)
-    for (int k = lane; k < len; k += 32) {
-      const bool keep = drop_p <= 0.f || dropout_keep(seed, site, base + k, thresh);
-      const float g = keep ? dP[base + k] * keep_scale : 0.f;
-      dot += __bfloat162float(P_pre[base + k]) * g;
-    }
-  dot = wsum(dot);
-  for (int k = lane; k < ld; k += 32) {
-    float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int k = lane + 32 * i;
+    pv[i] = 0.f;
+    gv[i] = 0.f;
     if (live && k < len) {
       const bool keep = drop_p <= 0.f || dropout_keep(seed, site, base + k, thresh);
-      const float g = keep ? dP[base + k] * keep_scale : 0.f;
-      v = scale * __bfloat162float(P_pre[base + k]) * (g - dot);
+      pv[i] = __bfloat162float(P_pre[base + k]);
+      gv[i] = keep ? dP[base + k] * keep_scale : 0.f;
+      dot += pv[i] * gv[i];
     }
-    dS[base + k] = __float2bfloat16_rn(v);
+  }
+  dot = wsum(dot);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int k = lane + 32 * i;
+    if (k < ld) dS[base + k] = __float2bfloat16_rn(scale * pv[i] * (gv[i] - dot));
   }
 }
 
@@ -94,6 +98,7 @@ __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P_pre, cons
 //   outputs: du fp32 (optional), g bf16 = du (* relu mask u>0 if relu_mask) (* dropout mask) for the GEMMs,
 //   dgamma/dbeta accumulated with atomics.  dz_drop_*: dropout applied AFTER the LayerNorm in the forward pass.
 // ------------------------------------------------------------------------------------------------
+template <int MAXV>
 __global__ void layernorm_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ u, const float* __restrict__ gamma,
                                      int M, int T, int C, int ld, float eps, const int* __restrict__ row_len, int relu_mask,
                                      float pre_drop_p, uint32_t pre_site, float post_drop_p, uint32_t post_site, uint32_t seed,
@@ -103,8 +108,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dz, const float* 
   for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) part[c] = 0.f;
   __syncthreads();
   const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-  constexpr int MAXV = 16;  // C <= 512
-  constexpr int RPW = 16;   // rows per warp; column partials stay in registers across them
+  constexpr int RPW = 4;  // rows per warp; column partials stay in registers across them (MAXV = ceil(C/32))
   float acc_g[MAXV], acc_b[MAXV], acc_x[MAXV];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) acc_g[i] = acc_b[i] = acc_x[i] = 0.f;
@@ -188,18 +192,34 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dz, const float* 
   }
 }
 
-// column sums of a bf16 matrix (rows, ld)[:, :C] -> fp32 [C] (accumulated): bias gradients
+// column sums of a bf16 matrix (rows, ld)[:, :C] -> fp32 [C] (accumulated): bias gradients.
+// Block = 8 warps x 128 rows; a warp reads 512 contiguous bytes of a row (32 lanes x 8 bf16), partials meet in smem.
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C, int ld, float* __restrict__ out) {
-  __shared__ float red[4][64];
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int ry = threadIdx.x >> 6;
-  const int64_t r0 = (int64_t)blockIdx.y * 256;
-  float s = 0.f;
-  if (c < C)
-    for (int64_t r = r0 + ry; r < r0 + 256 && r < rows; r += 4) s += __bfloat162float(x[r * ld + c]);
-  red[ry][threadIdx.x & 63] = s;
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * 128;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < C) {
+    for (int64_t r = r0 + w; r < r0 + 128 && r < rows; r += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + r * ld + c0);
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(h[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[w][lane * 8 + j] = acc[j];
   __syncthreads();
-  if (ry == 0 && c < C) atomicAdd(out + c, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += red[k][threadIdx.x];
+    atomicAdd(out + c, sum);
+  }
 }
 
 // dy (bf16, in place) *= (h > 0)
@@ -404,7 +424,8 @@ extern "C" int ttsb_softmax_fwd(const float* S, int B, int H, int T, int Tk, int
 
 extern "C" int ttsb_softmax_bwd(const void* P_pre, const float* dP, int B, int H, int T, int Tk, int ld, const int32_t* kv_len,
                                 float scale, float drop_p, uint32_t seed, uint32_t site, void* dS, void* stream) {
-  if (!P_pre || !dP || !kv_len || !dS || B <= 0 || H <= 0 || T <= 0 || Tk <= 0 || ld < Tk) return bad("ttsb_softmax_bwd: bad arguments");
+  if (!P_pre || !dP || !kv_len || !dS || B <= 0 || H <= 0 || T <= 0 || Tk <= 0 || ld < Tk || ld > 1280)
+    return bad("ttsb_softmax_bwd: bad arguments (rows of up to 1280 keys)");
   const int rows = B * H * T;
   softmax_bwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(CBF(P_pre), dP, B * H, H, T, Tk, ld, kv_len, scale, drop_p, seed, site, BF(dS));
   LAUNCH_OK("softmax_bwd_kernel");
@@ -417,15 +438,22 @@ extern "C" int ttsb_layernorm_bwd(const float* dz, const float* u, const float* 
   if (!dz || !u || !gamma || !dgamma || !dbeta || B <= 0 || T <= 0 || C <= 0 || C > 512 || ld < C || ld > 512)
     return bad("ttsb_layernorm_bwd: bad arguments (C, ld <= 512)");
   const int rows = B * T;
-  layernorm_bwd_kernel<<<(rows + 127) / 128, 256, 3 * C * sizeof(float), STREAM(stream)>>>(dz, u, gamma, rows, T, C, ld, eps, row_len, relu_mask,
-                                                                                        pre_drop_p, pre_site, post_drop_p, post_site, seed, du,
-                                                                                        BF(g_bf16), dgamma, dbeta, dbias);
+  const int blocks = (rows + 31) / 32;
+  const size_t sm = 3 * C * sizeof(float);
+#define TTSB_LNB(NV)                                                                                                              \
+  layernorm_bwd_kernel<NV><<<blocks, 256, sm, STREAM(stream)>>>(dz, u, gamma, rows, T, C, ld, eps, row_len, relu_mask, pre_drop_p, \
+                                                                 pre_site, post_drop_p, post_site, seed, du, BF(g_bf16), dgamma, dbeta, dbias)
+  if (ld <= 128) TTSB_LNB(4);
+  else if (ld <= 256) TTSB_LNB(8);
+  else if (ld <= 384) TTSB_LNB(12);
+  else TTSB_LNB(16);
+#undef TTSB_LNB
   LAUNCH_OK("layernorm_bwd_kernel");
 }
 
 extern "C" int ttsb_colsum_bf16(const void* x, int64_t rows, int C, int ld, float* out, void* stream) {
-  if (!x || !out || rows <= 0 || C <= 0 || ld < C) return bad("ttsb_colsum_bf16: bad arguments");
-  dim3 grid((C + 63) / 64, (unsigned)((rows + 255) / 256));
+  if (!x || !out || rows <= 0 || C <= 0 || ld < C || ld % 8 || (ld < ((C + 7) / 8) * 8)) return bad("ttsb_colsum_bf16: need ld % 8 == 0 and ld >= round_up(C, 8)");
+  dim3 grid((C + 255) / 256, (unsigned)((rows + 127) / 128));
   colsum_bf16_kernel<<<grid, 256, 0, STREAM(stream)>>>(CBF(x), rows, C, ld, out);
   LAUNCH_OK("colsum_bf16_kernel");
 }

@@ -313,13 +313,10 @@ class TrainEngine:
         self._bgemm(B, H, T, dh, T, c['P_drop'], (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0, 1), dattn, (d, T, B), (d, d * T),
                     (dh, 0, 0, 0, 1), out_ptr_off=2 * d, **common)
         # ---- q/k/v projections
-        bq = self._tmp_zero(3 * d)
-        lib.colsum_bf16(dqkv, B * T, 3 * d, 3 * d, bq)
-        wq = self._tmp_zero(d * 3 * d).view(d, 3 * d)
-        self._wgrad([(c['x_bf'], d)], dqkv, 3 * d, B, T, d, 3 * d, [(0, 0)], wq)
-        for n_, nm in enumerate(('wq', 'wk', 'wv')):
-            G[pre + nm + '.w'].add_(wq[:, n_ * d:(n_ + 1) * d])
-            G[pre + nm + '.b'].add_(bq[n_ * d:(n_ + 1) * d])
+        for n_, nm in enumerate(('wq', 'wk', 'wv')):  # the three Dense layers own separate (d,d) kernels: one column slice each
+            gs = dqkv[..., n_ * d:]
+            lib.colsum_bf16(gs, B * T, d, 3 * d, G[pre + nm + '.b'])
+            self._wgrad([(c['x_bf'], d)], gs, 3 * d, B, T, d, d, [(0, 0)], G[pre + nm + '.w'])
         dx = self._f32(B, T, d)
         m._gemm(P[pre + 'qkv.d'], B, T, [(dqkv, None, 3 * d, 0)], [0], [0], residual=dx_acc, out_f32=dx, ld_out=d)
         return dx
