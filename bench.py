@@ -160,6 +160,86 @@ def cpu_reference_line(args, rank, world):
             'note': 'TF2 reference cannot be installed offline (no tensorflow wheel); oracle/ is its CPU restatement'}
 
 
+def hbm_bench(args, rank, world, dev, cfg):
+    """The two HBM-bound rows of the scope table, each timed alone with CUDA events and an L2 flush between iterations:
+    'stft'  : BASELINE configs[3], 256 clips x 220500 samples -> (256, 862, 80) log-mel, algorithmic bytes = audio in + mel out;
+    'expand': the length regulator of C2 (durations -> int -> index map -> gather), algorithmic bytes = x in + expanded out."""
+    import numpy as np
+    import torch.distributed as dist
+    from oracle import audio_oracle as ao
+    from oracle import forward_oracle as fo
+    from transformertts_b200 import lib
+    from transformertts_b200.data.audio import Audio
+    _, peak_hbm, _ = _peaks()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    steps = max(args.steps, 10)
+    times = []
+    if args.mode == 'stft':
+        n_clips, n_samples = 256, 220500
+        audio = Audio(sampling_rate=22050, n_fft=1024, mel_channels=80, hop_length=256, win_length=1024, f_min=0, f_max=8000,
+                      normalizer='MelGAN', device=str(dev))
+        clips = ao.make_clips(4, n_samples, seed=400 + rank)
+        wav = torch.from_numpy(np.tile(clips, (n_clips // 4, 1))).to(dev)
+        wav += 0.01 * torch.randn_like(wav)
+        fn = lambda: audio.mel_spectrogram_device(wav)
+        out = fn()
+        alg_bytes = wav.numel() * 4 + out.numel() * 4
+        units, unit_name, metric = n_clips, 'clips/s', 'stft_mel_clips_per_sec'
+        workload = 'C4: STFT->log-mel, 256 clips x 10 s @ 22.05 kHz, n_fft 1024 hop 256, 80 mels'
+        ref = ao.mel_spectrogram(wav[0].cpu().numpy())
+        err = float(np.abs(out[0].cpu().numpy() - ref).max())
+        t0 = time.perf_counter()
+        for i in range(4):
+            ao.mel_spectrogram(wav[i].cpu().numpy())
+        cpu = {'value': 4 / (time.perf_counter() - t0), 'unit': unit_name, 'cores': 1, 'kind': 'port',
+               'sample': '4 clips, numpy restatement of librosa.stft + mel filterbank (single thread)', 'max_abs_err_gpu_vs_cpu': err}
+    else:
+        tok, dur, pit = fo.make_inputs('full', B, TP, TM, seed=200 + rank)
+        d = cfg['encoder_model_dimension']
+        x = torch.randn(B, TP, d, device=dev)
+        dur_f = dur.to(dev).float()
+        dur_i = torch.empty((B, TP), dtype=torch.int32, device=dev)
+        lens = torch.empty((B,), dtype=torch.int32, device=dev)
+        idx = torch.empty((B, TM), dtype=torch.int32, device=dev)
+        out = torch.empty((B, TM, d), dtype=torch.float32, device=dev)
+
+        def fn():
+            lib.durations_to_int(dur_f, 1.0, None, None, dur_i, lens)
+            lib.expand_indices(dur_i, TM, idx)
+            lib.length_regulate_fwd(x, idx, out)
+            return out
+        fn()
+        alg_bytes = x.numel() * 4 + dur_f.numel() * 4 + out.numel() * 4
+        units, unit_name, metric = B * TM, 'frames/s', 'length_regulator_frames_per_sec'
+        workload = 'C2-LR: length regulator alone, B=64, 128 phonemes -> 1000 frames, d=256 fp32'
+        want = fo.expand(x.cpu(), dur[..., None].float())
+        cpu = {'value': None, 'unit': unit_name, 'cores': 0, 'kind': 'port', 'sample': 'parity only',
+               'bit_exact_vs_oracle': bool(torch.equal(out.cpu(), want))}
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    t = torch.tensor([sum(times) / len(times)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        print(json.dumps({'metric': metric, 'value': units * world / (ms * 1e-3), 'unit': unit_name, 'n_gpus': world, 'steps': steps, 'warmup': 3,
+                          'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                          'config': {'workload': workload, 'l2': '256 MB buffer rewritten between timed iterations (L2 flush)'},
+                          'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': peak_hbm, 'unit': 'GB/s', 'frac': gbs / peak_hbm, 'traffic': None,
+                                       'algorithmic_bytes_per_launch': alg_bytes},
+                          'cpu_baseline': cpu}), flush=True)
+
+
 def train_bench(args, rank, world, dev, cfg, params):
     """BASELINE configs[2]: LJ256 training step (fwd + bwd + Adam, dropout 0.1, bf16 tensor-core products), batch 32 per
     GPU, 128 phonemes -> 1000 frames, gradients all-reduced with NCCL (sum, scaled 1/N inside the Adam kernel)."""
@@ -242,8 +322,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
-                    help="'train': BASELINE configs[2] (fwd+bwd+Adam, bf16, batch 32/GPU, NCCL data parallel)")
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'stft', 'expand'],
+                    help="'train': BASELINE configs[2] (fwd+bwd+Adam, bf16, batch 32/GPU, NCCL data parallel); 'stft': configs[3] "
+                         "(STFT->mel, 256 clips x 10 s); 'expand': the length regulator alone (C2-LR)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -270,6 +351,11 @@ def main():
 
     cfg = fo.CONFIGS[CFG_NAME]
     params = fo.init_params(cfg, seed=7)  # random-init weights of the named architecture
+    if args.mode in ('stft', 'expand'):
+        hbm_bench(args, rank, world, dev, cfg)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.mode == 'train':
         train_bench(args, rank, world, dev, cfg, params)
         if world > 1:
