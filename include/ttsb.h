@@ -54,6 +54,21 @@ void ttsb_reset_launch_count(void);
 /* Keras kernel (K, N) fp32 (Conv1D (k, Cin, Cout) is the same memory with K = k*Cin) -> packed bf16 hi/lo
  * [n_pad, K], rows >= N zero.  w_lo may be NULL. */
 int ttsb_pack_weight(const float* w_kn, int K, int N, int n_pad, void* w_hi, void* w_lo, void* stream);
+/* Batched refresh of packed operands (training: the weights change every step).  One descriptor per destination block:
+ *   dst[r][c] = (r < R && c % cb < cb_valid) ? src[r*sr + (c / cb)*s_outer + (c % cb)*s_inner] : 0,   r < R_pad, c < C_cols
+ * which covers the forward packing (K,N)->[N_pad,K], the data-gradient packings of Dense ((K,N)->[K_pad,N_pad]) and Conv1D
+ * ((k,Cin,Cout)->[Cin_pad, k*Cout_pad]) and zero-padded fp32 vectors (bias, LayerNorm gamma/beta).  The descriptor array
+ * lives in DEVICE memory (built once); one launch refreshes everything. */
+typedef struct ttsb_pack_desc {
+  const float* src;
+  void* dst;
+  int R, R_pad, C_cols;
+  int cb, cb_valid;
+  long long sr, s_outer, s_inner;
+  int dst_ld;
+  int dst_f32; /* 1: destination is fp32, 0: bf16 */
+} ttsb_pack_desc;
+int ttsb_repack_batched(const ttsb_pack_desc* descs_device, int n, void* stream);
 /* fp32 [n] -> bf16 hi (and lo when non-NULL) */
 int ttsb_split_bf16(const float* x, int64_t n, void* x_hi, void* x_lo, void* stream);
 

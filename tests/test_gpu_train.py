@@ -218,7 +218,7 @@ def test_train_step_loss_grads_and_adam(cfg_name, B, Tp, Tm):
     torch.cuda.synchronize()
     m_ref, v_ref, w_ref = torch.zeros_like(w0).cpu(), torch.zeros_like(w0).cpu(), w0.cpu().clone()
     fo.adam_tf_step(w_ref, g0.cpu(), m_ref, v_ref, 1, 1e-4)
-    assert (eng.flat_w.cpu() - w_ref).abs().max() < 1e-7
+    assert (eng.flat_w.cpu() - w_ref).abs().max() < 3e-7
     assert model.step == 1
     # a second full step runs (weights were re-packed) and lowers nothing to NaN
     out2 = model.train_step(tok, mel_tgt, dur, pit)

@@ -319,6 +319,22 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int K, int N, in
   if (lo) lo[i] = l;
 }
 
+// Batched operand preparation for the training step: every packed bf16 weight (forward and data-gradient layouts), padded
+// bias and padded LayerNorm vector is described once (ttsb_pack_desc, device array) and refreshed by ONE launch per step.
+//   dst[r][c] = (r < R && c % cb < cb_valid) ? src[r*sr + (c / cb)*s_outer + (c % cb)*s_inner] : 0
+__global__ void repack_batched_kernel(const ttsb_pack_desc* __restrict__ descs) {
+  const ttsb_pack_desc d = descs[blockIdx.y];
+  const long long total = (long long)d.R_pad * d.C_cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / d.C_cols), c = (int)(i % d.C_cols);
+    const int blk = c / d.cb, ci = c % d.cb;
+    const float v = (r < d.R && ci < d.cb_valid) ? d.src[(long long)r * d.sr + (long long)blk * d.s_outer + (long long)ci * d.s_inner] : 0.f;
+    const long long o = (long long)r * d.dst_ld + c;
+    if (d.dst_f32) static_cast<float*>(d.dst)[o] = v;
+    else static_cast<__nv_bfloat16*>(d.dst)[o] = __float2bfloat16_rn(v);
+  }
+}
+
 static inline int bad(const char* msg) {
   set_last_error("%s", msg);
   return TTSB_ERR_INVALID_ARGUMENT;
@@ -339,6 +355,12 @@ extern "C" int ttsb_pack_weight(const float* w_kn, int K, int N, int n_pad, void
   pack_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM(stream)>>>(w_kn, K, N, n_pad, static_cast<__nv_bfloat16*>(w_hi),
                                                                             static_cast<__nv_bfloat16*>(w_lo));
   LAUNCH_OK("pack_weight_kernel");
+}
+
+extern "C" int ttsb_repack_batched(const ttsb_pack_desc* descs_device, int n, void* stream) {
+  if (!descs_device || n <= 0) return bad("ttsb_repack_batched: bad arguments");
+  repack_batched_kernel<<<dim3(96, n), 256, 0, STREAM(stream)>>>(descs_device);
+  LAUNCH_OK("repack_batched_kernel");
 }
 
 extern "C" int ttsb_split_bf16(const float* x, int64_t n, void* x_hi, void* x_lo, void* stream) {

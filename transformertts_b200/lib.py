@@ -19,6 +19,7 @@ _lib = None
 
 EXPORTS = [
     'ttsb_last_error', 'ttsb_abi_version', 'ttsb_launch_count', 'ttsb_reset_launch_count', 'ttsb_pack_weight',
+    'ttsb_repack_batched',
     'ttsb_split_bf16', 'ttsb_embed_ln_pe_fwd', 'ttsb_linear_fwd', 'ttsb_layernorm_fwd', 'ttsb_mha_fwd', 'ttsb_statpred_head_fwd',
     'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
     'ttsb_expand_ln_pe_fwd', 'ttsb_mel_lengths', 'ttsb_phoneme_lengths', 'ttsb_stft_mel_log',
@@ -44,6 +45,14 @@ class GemmArgs(C.Structure):
         ('out_lo', C.c_void_p), ('ld_out', C.c_int), ('out_fp16', C.c_int), ('out_preln', C.c_void_p),
         ('drop_pre_p', C.c_float), ('drop_post_p', C.c_float), ('drop_pre_site', C.c_uint32), ('drop_post_site', C.c_uint32),
         ('drop_seed', C.c_uint32), ('precision', C.c_int), ('impl', C.c_int),
+    ]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [
+        ('src', C.c_void_p), ('dst', C.c_void_p), ('R', C.c_int), ('R_pad', C.c_int), ('C_cols', C.c_int),
+        ('cb', C.c_int), ('cb_valid', C.c_int), ('sr', C.c_longlong), ('s_outer', C.c_longlong), ('s_inner', C.c_longlong),
+        ('dst_ld', C.c_int), ('dst_f32', C.c_int),
     ]
 
 
@@ -136,6 +145,17 @@ def pack_weight(w_kn: torch.Tensor, n_pad: int, split: bool):
     lo = torch.empty_like(hi) if split else None
     _check(load().ttsb_pack_weight(ptr(w2), K, N, n_pad, ptr(hi), ptr(lo), _stream()), 'ttsb_pack_weight')
     return hi, lo
+
+
+def upload_pack_descs(descs, device) -> torch.Tensor:
+    """ctypes PackDesc list -> device byte tensor (kept alive by the caller)."""
+    arr = (PackDesc * len(descs))(*descs)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device)
+
+
+def repack_batched(descs_dev: torch.Tensor, n: int):
+    _check(load().ttsb_repack_batched(ptr(descs_dev), n, _stream()), 'ttsb_repack_batched')
 
 
 def split_bf16(x: torch.Tensor, split: bool):

@@ -61,6 +61,21 @@ class _PackedLinear:
             self.bias[:N] = bias.float()
 
 
+def _packed_empty(K: int, N: int, seg_k: List[int], device, single_tile: bool = False, block_n: Optional[int] = None, bias: bool = True):
+    """A _PackedLinear whose buffers are allocated but not filled (the training engine refreshes them every step with one
+    batched launch, lib.repack_batched)."""
+    pl = _PackedLinear.__new__(_PackedLinear)
+    assert sum(seg_k) == K, (seg_k, K)
+    pl.N, pl.K, pl.seg_k = N, K, seg_k
+    pl.block_n = block_n or _pick_block_n(N, single_tile)
+    pl.n_tiles = (N + pl.block_n - 1) // pl.block_n
+    pl.n_pad = pl.n_tiles * pl.block_n
+    pl.w_hi = torch.empty((pl.n_pad, K), dtype=torch.bfloat16, device=device)
+    pl.w_lo = None
+    pl.bias = torch.zeros(pl.n_pad, dtype=torch.float32, device=device) if bias else None
+    return pl
+
+
 def _pad_vec(v: torch.Tensor, n: int) -> torch.Tensor:
     if v.numel() == n:
         return v.contiguous()

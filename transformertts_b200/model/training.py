@@ -63,68 +63,115 @@ class TrainEngine:
     # ------------------------------------------------------------------------------------------------
     # packed operands for the step (weights change every step)
     # ------------------------------------------------------------------------------------------------
-    def _pack(self):
+    def _build_packs(self):
+        """Allocate every packed operand of the step once and describe how to refresh it from the flat fp32 parameters
+        (one ttsb_pack_desc per destination block); _pack() then is a single kernel launch per step."""
+        from .models import _packed_empty
         m = self.model
         W = m.weights
-        P = {}
+        P, descs = {}, []
+        dev = self.dev
 
-        def fwd(key, w, b, seg_k, single=False, block_n=None):
-            P[key] = _PackedLinear(w, b, seg_k, False, single_tile=single, block_n=block_n)
+        def desc(src, dst_ptr, R, R_pad, C_cols, cb, cb_valid, sr, s_outer, s_inner, dst_ld, f32=0):
+            d_ = lib.PackDesc()
+            d_.src, d_.dst = src.data_ptr() if torch.is_tensor(src) else src, dst_ptr
+            d_.R, d_.R_pad, d_.C_cols, d_.cb, d_.cb_valid = R, R_pad, C_cols, cb, cb_valid
+            d_.sr, d_.s_outer, d_.s_inner, d_.dst_ld, d_.dst_f32 = sr, s_outer, s_inner, dst_ld, f32
+            descs.append(d_)
 
-        def dgrad_dense(key, w):  # (K,N) -> data gradient operator: out K columns, contraction over N (padded to 64)
-            K, N = w.shape
+        def vec(src, dst, n_valid):  # zero-padded fp32 vector copy
+            desc(src, dst.data_ptr(), 1, 1, dst.numel(), dst.numel(), n_valid, 0, 0, 1, dst.numel(), f32=1)
+
+        def fwd(key, parts, K, seg_k, single=False, block_n=None):
+            """parts: [(w (K,Ni) view, b (Ni))] concatenated along N (q|k|v) -- forward packing [N_pad, K]."""
+            N = sum(w.shape[-1] for w, _ in parts)
+            pl = _packed_empty(K, N, seg_k, dev, single_tile=single, block_n=block_n)
+            row = 0
+            for i, (w, b) in enumerate(parts):
+                Ni = w.shape[-1]
+                last = i == len(parts) - 1
+                desc(w, pl.w_hi.data_ptr() + 2 * row * K, Ni, (pl.n_pad - row) if last else Ni, K, K, K, 1, 0, Ni, K)
+                desc(b, pl.bias.data_ptr() + 4 * row, 1, 1, (pl.n_pad - row) if last else Ni, pl.n_pad, Ni, 0, 0, 1, pl.n_pad, f32=1)
+                row += Ni
+            P[key] = pl
+
+        def dgrad_dense(key, parts, K):
+            """parts: [w (K,Ni)] concatenated along N -- data-gradient packing [K_pad, N_pad] (contraction over N)."""
+            N = sum(w.shape[-1] for w in parts)
             npad = _round_up(N, 64)
-            wt = torch.zeros((npad, K), dtype=torch.float32, device=self.dev)
-            wt[:N] = w.t()
-            P[key] = _PackedLinear(wt, None, [npad], False)
+            pl = _packed_empty(npad, K, [npad], dev, bias=False)
+            col = 0
+            for i, w in enumerate(parts):
+                Ni = w.shape[-1]
+                last = i == len(parts) - 1
+                width = (npad - col) if last else Ni
+                desc(w, pl.w_hi.data_ptr() + 2 * col, K, pl.n_pad, width, width, Ni, Ni, 0, 1, npad)
+                col += Ni
+            P[key] = pl
 
-        def dgrad_conv(key, w):  # (k,Cin,Cout) -> [Cin, k*Cout_pad]
+        def dgrad_conv(key, w):
             k, cin, cout = w.shape
             cpad = _round_up(cout, 64)
-            wt = torch.zeros((k, cpad, cin), dtype=torch.float32, device=self.dev)
-            wt[:, :cout] = w.permute(0, 2, 1)
-            P[key] = _PackedLinear(wt.reshape(k * cpad, cin), None, [cpad] * k, False)
+            pl = _packed_empty(k * cpad, cin, [cpad] * k, dev, bias=False)
+            desc(w, pl.w_hi.data_ptr(), cin, pl.n_pad, k * cpad, cpad, cout, cout, cin * cout, 1, k * cpad)
+            P[key] = pl
 
         for name, st in m._stacks.items():
             d = st['d']
             for i, _ in enumerate(st['heads']):
                 pre = f'{name}.b{i}.'
-                wqkv = torch.cat([W[pre + 'wq.w'], W[pre + 'wk.w'], W[pre + 'wv.w']], dim=1)
-                bqkv = torch.cat([W[pre + 'wq.b'], W[pre + 'wk.b'], W[pre + 'wv.b']])
-                fwd(pre + 'qkv', wqkv, bqkv, [d], block_n=d if d <= 256 else d // 2)
-                dgrad_dense(pre + 'qkv.d', wqkv)
-                fwd(pre + 'wo', W[pre + 'wo.w'], W[pre + 'wo.b'], [d, d], single=True)
-                dgrad_dense(pre + 'wo.dx', W[pre + 'wo.w'][:d])
-                dgrad_dense(pre + 'wo.da', W[pre + 'wo.w'][d:])
+                qkv = [(W[pre + n + '.w'], W[pre + n + '.b']) for n in ('wq', 'wk', 'wv')]
+                fwd(pre + 'qkv', qkv, d, [d], block_n=d if d <= 256 else d // 2)
+                dgrad_dense(pre + 'qkv.d', [w for w, _ in qkv], d)
+                fwd(pre + 'wo', [(W[pre + 'wo.w'], W[pre + 'wo.b'])], 2 * d, [d, d], single=True)
+                dgrad_dense(pre + 'wo.dx', [W[pre + 'wo.w'][:d]], d)
+                dgrad_dense(pre + 'wo.da', [W[pre + 'wo.w'][d:]], d)
                 if i < st['n_dense']:
                     F = int(st['ffn'])
-                    fwd(pre + 'ffn1', W[pre + 'ffn1.w'], W[pre + 'ffn1.b'], [d])
-                    fwd(pre + 'ffn2', W[pre + 'ffn2.w'], W[pre + 'ffn2.b'], [F], single=True)
-                    dgrad_dense(pre + 'ffn1.d', W[pre + 'ffn1.w'])
-                    dgrad_dense(pre + 'ffn2.d', W[pre + 'ffn2.w'])
+                    fwd(pre + 'ffn1', [(W[pre + 'ffn1.w'], W[pre + 'ffn1.b'])], d, [d])
+                    fwd(pre + 'ffn2', [(W[pre + 'ffn2.w'], W[pre + 'ffn2.b'])], F, [F], single=True)
+                    dgrad_dense(pre + 'ffn1.d', [W[pre + 'ffn1.w']], d)
+                    dgrad_dense(pre + 'ffn2.d', [W[pre + 'ffn2.w']], F)
                 else:
                     cin = d
                     n = len(st['filters'])
+                    kk = int(st['kernel'])
                     for j, f in enumerate(st['filters']):
-                        fwd(pre + f'conv{j}', W[pre + f'conv{j}.w'], W[pre + f'conv{j}.b'], [cin] * int(st['kernel']), single=(j == n - 1))
-                        dgrad_conv(pre + f'conv{j}.d', W[pre + f'conv{j}.w'])
+                        w = W[pre + f'conv{j}.w']
+                        fwd(pre + f'conv{j}', [(w.view(kk * cin, f), W[pre + f'conv{j}.b'])], kk * cin, [cin] * kk, single=(j == n - 1))
+                        dgrad_conv(pre + f'conv{j}.d', w)
                         cin = f
         d_enc = m._stacks['encoder']['d']
         for name, filt, k in (('dur_pred', m.config['duration_conv_filters'], m.config['duration_kernel_size']),
                               ('pitch_pred', m.config['pitch_conv_filters'], m.config['pitch_kernel_size'])):
             cin = d_enc
+            kk = int(k)
             for j, f in enumerate(filt):
-                bn = _round_up(int(f), 64)  # 226 -> 256 columns so the next contraction is a multiple of 64
-                fwd(f'{name}.conv{j}', W[f'{name}.conv{j}.w'], W[f'{name}.conv{j}.b'], [cin] * int(k), single=True, block_n=bn)
-                P[f'{name}.ln{j}'] = (_pad_vec(W[f'{name}.ln{j}.gamma'], bn), _pad_vec(W[f'{name}.ln{j}.beta'], bn))
-                dgrad_conv(f'{name}.conv{j}.d', W[f'{name}.conv{j}.w'])
-                cin = int(f)
-        fwd('out', W['out.w'], W['out.b'], [m._stacks['decoder']['d']])
-        dgrad_dense('out.d', W['out.w'])
+                f = int(f)
+                bn = _round_up(f, 64)  # 226 -> 256 columns so the next contraction is a multiple of 64
+                w = W[f'{name}.conv{j}.w']
+                fwd(f'{name}.conv{j}', [(w.view(kk * cin, f), W[f'{name}.conv{j}.b'])], kk * cin, [cin] * kk, single=True, block_n=bn)
+                g_pad = torch.zeros(bn, dtype=torch.float32, device=dev)
+                b_pad = torch.zeros(bn, dtype=torch.float32, device=dev)
+                vec(W[f'{name}.ln{j}.gamma'], g_pad, f)
+                vec(W[f'{name}.ln{j}.beta'], b_pad, f)
+                P[f'{name}.ln{j}'] = (g_pad, b_pad)
+                dgrad_conv(f'{name}.conv{j}.d', w)
+                cin = f
+        dd = m._stacks['decoder']['d']
+        fwd('out', [(W['out.w'], W['out.b'])], dd, [dd])
+        dgrad_dense('out.d', [W['out.w']], dd)
         for name, st in m._stacks.items():
             P[f'{name}.pe'] = m._prepare_pe(name)
         self.P = P
-        return P
+        self._n_descs = len(descs)
+        self._descs_dev = lib.upload_pack_descs(descs, dev)
+
+    def _pack(self):
+        if self.P is None:
+            self._build_packs()
+        lib.repack_batched(self._descs_dev, self._n_descs)
+        return self.P
 
     # ------------------------------------------------------------------------------------------------
     # small helpers
