@@ -112,3 +112,47 @@ def test_lj256_full_size_properties():
     sel = [3, 41]
     ref = fo.forward_transformer_call(p, cfg, tok[sel], dur[sel][..., None], pit[sel][..., None])
     assert (mel[sel].cpu() - ref['mel']).abs().max() < MEL_TOL
+
+
+def test_spectrogram_ops_and_losses_mirror_reference_api():
+    """utils/spectrogram_ops.py and utils/losses.py of the reference, same names, on the CUDA kernels."""
+    from oracle import audio_oracle as ao
+    from transformertts_b200.utils import losses, spectrogram_ops
+    g = torch.Generator().manual_seed(5)
+    mel = torch.randn(4, 60, 80, generator=g)
+    mel[0, 40:] = 0
+    mel[2, 10:] = 0
+    ph = torch.randint(1, 127, (4, 30), generator=g)
+    ph[1, 12:] = 0
+    assert spectrogram_ops.mel_lengths(mel).cpu().tolist() == ao.mel_lengths(mel.numpy()).tolist()
+    assert spectrogram_ops.phoneme_lengths(ph).cpu().tolist() == ao.phoneme_lengths(ph.numpy()).tolist()
+    assert torch.equal(spectrogram_ops.mel_padding_mask(mel), 1.0 - (mel == 0).float())
+    pred = torch.randn(4, 60, 80, generator=g)
+    ref = fo.masked_mean_absolute_error(mel, pred)
+    got = losses.masked_mean_absolute_error(mel, pred)
+    assert abs(got.item() - ref.item()) < 1e-5
+    dur_t = torch.randint(0, 9, (4, 30), generator=g, dtype=torch.int32)
+    dur_p = torch.rand(4, 30, 1, generator=g) * 8
+    tot, vals = losses.weighted_sum_losses((mel, dur_t[..., None], dur_t[..., None]), (pred, dur_p, dur_p),
+                                           [losses.masked_mean_absolute_error] * 3, [1., 1., 3.])
+    rt, _ = fo.weighted_sum_losses((mel, dur_t[..., None], dur_t[..., None]), (pred, dur_p, dur_p))
+    assert abs(float(tot) - float(rt)) < 1e-4
+
+
+def test_save_load_roundtrip_and_factory(tmp_path):
+    """save_model / load_model / factory.tts_custom keep the reference's two-file layout (config.yaml + weights)."""
+    from transformertts_b200.model import factory
+    from transformertts_b200.model.models import ForwardTransformer
+    p = fo.init_params(fo.CONFIGS['C1'], seed=7)
+    m = _model('C1', p)
+    tok, dur, pit = fo.make_inputs('ragged', 2, 16, 60, seed=9)
+    want = m.call(tok, target_durations=dur, target_pitch=pit)['mel']
+    m.save_model(str(tmp_path / 'step_1'))
+    assert (tmp_path / 'step_1' / 'config.yaml').exists() and (tmp_path / 'step_1' / 'model_weights.pt').exists()
+    m2 = ForwardTransformer.load_model(str(tmp_path / 'step_1'))
+    assert torch.equal(m2.call(tok, target_durations=dur, target_pitch=pit)['mel'], want)
+    m3, cfg = factory.tts_custom(str(tmp_path / 'step_1' / 'config.yaml'), str(tmp_path / 'step_1'))
+    assert cfg['encoder_model_dimension'] == 128
+    assert torch.equal(m3.call(tok, target_durations=dur, target_pitch=pit)['mel'], want)
+    with pytest.raises(NotImplementedError):
+        factory.tts_ljspeech()

@@ -16,6 +16,7 @@ import torch
 
 from .. import lib
 from .models import LN_EPS, _PackedLinear, _pad_vec, _round_up
+from .transformer_utils import mask_from_lengths
 
 
 class Adam:
@@ -507,7 +508,7 @@ class TrainEngine:
             lib.mae_loss(dur_out, B, Tp, Tp, 1, dur_tgt, wts[1], losses[1:2], ddur)
             lib.mae_loss(pit_out, B, Tp, Tp, 1, pitch_tgt, wts[2], losses[2:3], dpit)
             out = {'mel': mel, 'duration': dur_out[..., None], 'pitch': pit_out[..., None],
-                   'expanded_mask': None, 'encoder_attention': {}, 'decoder_attention': {},
+                   'expanded_mask': mask_from_lengths(dec_len, Tm), 'encoder_attention': {}, 'decoder_attention': {},
                    'losses': {'mel': losses[0], 'duration': losses[1], 'pitch': losses[2]},
                    'loss': wts[0] * losses[0] + wts[1] * losses[1] + wts[2] * losses[2], 'mel_lengths': dec_len}
             if not training:
