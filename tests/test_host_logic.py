@@ -14,7 +14,8 @@ def test_block_n_selection():
     assert _pick_block_n(226, True) == 240
     assert _pick_block_n(80, False) == 80
     assert _pick_block_n(128, True) == 128
-    assert _pick_block_n(384, True) == 192    # d=384: two N tiles, LayerNorm runs as a separate row kernel
+    assert _pick_block_n(384, True) == 384    # d=384 LayerNorm GEMM: one logical tile, run as a CTA pair of 192 columns each
+    assert _pick_block_n(400, True) == 80     # not pairable: several N tiles + separate LayerNorm row kernel
     assert _pick_block_n(1152, False) == 192
 
 

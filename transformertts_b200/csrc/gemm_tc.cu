@@ -11,6 +11,7 @@
 // latter gives fp32-class products (needed for the 1e-3 mel parity gate) at 3x the tensor-core work.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/ttsb.h"
 #include <cuda_fp16.h>
@@ -51,14 +52,54 @@ struct GemmKParams {
   int h16;  // 1: out_hi receives IEEE fp16 instead of bf16 (single plane; operands of the fp16 attention)
 };
 
-template <bool kSplit>
+// kPair: the LayerNorm GEMMs run as a cluster of two CTAs that split the N (row) dimension of one 128-row tile in halves
+// (twice as many work items -> no wave-quantisation tail, small-M encoder GEMMs fill the chip) and exchange per-row
+// (mean, M2) through distributed shared memory before normalising.
+constexpr int PAIR_MAX_BN = 192;
+template <bool kSplit, bool kPair>
 struct GemmCfg {
   static constexpr int kStages = kSplit ? 2 : 4;
-  static constexpr int kStageBytes = (kSplit ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int kBTile = kPair ? PAIR_MAX_BN * GEMM_BK * 2 : B_TILE_BYTES;
+  static constexpr int kStageBytes = (kSplit ? 2 : 1) * (A_TILE_BYTES + kBTile);
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kRedOffset = kBarOffset + 256;          // LayerNorm pair-exchange scratch: [2 acc][2][2][128] floats
-  static constexpr int kSmemBytes = kRedOffset + 4096 + 1024;  // + alignment slack
+  static constexpr int kRedOffset = kBarOffset + 256;           // [2 acc][2][2][128] floats of intra-CTA exchange
+  static constexpr int kXchgOffset = kRedOffset + 4096;         // pair mode: [2 slots][128] float2 written by the peer CTA
+  static constexpr int kXbarOffset = kXchgOffset + 2048;        // pair mode: 2 mbarriers
+  static constexpr int kSmemBytes = kXbarOffset + 64 + 1024;    // + alignment slack
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_peer(uint32_t saddr, uint32_t peer) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(peer));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins == 0x10000000u) asm volatile("trap;");
+  }
+}
 
 // ----------------------------------------------------------------------------------------------------
 // Epilogue for one 128 x block_n accumulator tile.  8 epilogue warps: warp (quarter, half) owns TMEM lanes
@@ -128,8 +169,18 @@ __device__ __forceinline__ float pair_sum(float part, float* red, int half, int 
   return part + red[(half ^ 1) * GEMM_BM + row];
 }
 
+struct PairCtx {
+  int active;          // 1: this tile's LayerNorm statistics are combined with the peer CTA's half of the row
+  uint32_t peer_slot;  // shared::cluster address of the peer's exchange slot array for this tile parity
+  uint32_t peer_bar;   // shared::cluster address of the peer's exchange mbarrier for this tile parity
+  float2* my_slot;     // where the peer writes its (mean, M2)
+  uint64_t* my_bar;
+  uint32_t parity;
+};
+
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t taddr, int b, int t0, int n0, int row, int half,
-                                              int quarter, float* red /* [2][2][128] for this accumulator stage */) {
+                                              int quarter, float* red /* [2][2][128] for this accumulator stage */,
+                                              const PairCtx& px) {
   const int t = t0 + row;
   const bool row_ok = t < p.T;
   const bool row_keep = row_ok && (p.row_len == nullptr || t < __ldg(p.row_len + b));
@@ -186,7 +237,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
     const int c0 = ch << 4;
     __syncwarp();
     tmem_ld16(taddr + c0, r);
-    if (p.bias) ldg16(p.bias + c0, aux);
+    if (p.bias) ldg16(p.bias + n0 + c0, aux);
     tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]);
@@ -198,10 +249,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
 #pragma unroll
       for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
     }
-    if (p.drop_pre_p > 0.f) apply_dropout16(y, p.drop_pre_p, p.drop_seed, p.drop_pre_site, orow * (uint64_t)p.ld_out + c0);
+    if (p.drop_pre_p > 0.f) apply_dropout16(y, p.drop_pre_p, p.drop_seed, p.drop_pre_site, orow * (uint64_t)p.ld_out + n0 + c0);
     if (p.residual && row_ok) {
-      ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + c0, aux);
-      ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + c0 + 8, aux + 8);
+      ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + n0 + c0, aux);
+      ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + n0 + c0 + 8, aux + 8);
 #pragma unroll
       for (int j = 0; j < 16; ++j) y[j] += aux[j];
     }
@@ -215,14 +266,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
       r[j] = __float_as_uint(y[j]);
     }
     if (p.out_preln && row_ok) {
-      float* dst = p.out_preln + orow * (size_t)p.ld_out + c0;
+      float* dst = p.out_preln + orow * (size_t)p.ld_out + n0 + c0;
       st_global_v8f(dst, y);
       st_global_v8f(dst + 8, y + 8);
     }
     tmem_st16(taddr + c0, r);
   }
   tmem_wait_st();
-  const float mean = pair_sum(sum, red, half, row, quarter) * inv_n;
+  float mean = pair_sum(sum, red, half, row, quarter) * inv_n;  // mean over this CTA's columns
   float ssq = 0.f;
   for (int ch = ch_begin; ch < ch_end; ++ch) {
     const int c0 = ch << 4;
@@ -243,18 +294,33 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
       }
     }
   }
-  const float rstd = rsqrtf(pair_sum(ssq, red + 2 * GEMM_BM, half, row, quarter) * inv_n + p.eps);
+  float m2 = pair_sum(ssq, red + 2 * GEMM_BM, half, row, quarter);
+  float n_total = (float)ncols;
+  if (px.active) {
+    // combine with the peer CTA's half of the row (Chan et al.): exact two-pass statistics with ONE exchange
+    if (half == 0) st_cluster_v2(px.peer_slot + (uint32_t)row * 8u, mean, m2);
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(px.peer_bar);
+    mbar_wait_cluster(px.my_bar, px.parity);
+    const float2 pr = px.my_slot[row];
+    const float delta = mean - pr.x;
+    m2 = m2 + pr.y + delta * delta * (0.5f * (float)ncols);
+    mean = 0.5f * (mean + pr.x);
+    n_total = 2.f * (float)ncols;
+  }
+  const float rstd = rsqrtf(m2 / n_total + p.eps);
   for (int ch = ch_begin; ch < ch_end; ++ch) {
     const int c0 = ch << 4;
     __syncwarp();
     tmem_ld16(taddr + c0, r);
     float bt[16];
-    ldg16(p.gamma + c0, aux);
-    ldg16(p.beta + c0, bt);
+    ldg16(p.gamma + n0 + c0, aux);
+    ldg16(p.beta + n0 + c0, bt);
     tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; ++j) y[j] = (__uint_as_float(r[j]) - mean) * rstd * aux[j] + bt[j];
-    if (p.drop_post_p > 0.f) apply_dropout16(y, p.drop_post_p, p.drop_seed, p.drop_post_site, orow * (uint64_t)p.ld_out + c0);
+    if (p.drop_post_p > 0.f) apply_dropout16(y, p.drop_post_p, p.drop_seed, p.drop_post_site, orow * (uint64_t)p.ld_out + n0 + c0);
     if (partial) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) y[j] = (c0 + j < ncols) ? y[j] : 0.f;
@@ -263,19 +329,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
 #pragma unroll
       for (int j = 0; j < 16; ++j) y[j] = 0.f;
     }
-    if (row_ok) store_chunk(p, orow, c0, y);
+    if (row_ok) store_chunk(p, orow, n0 + c0, y);
   }
 }
 
 // ----------------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------------
-template <bool kSplit>
+template <bool kSplit, bool kPair>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant__ CUtensorMap tmA0l,
                const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
                const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const GemmKParams p) {
-  using Cfg = GemmCfg<kSplit>;
+  using Cfg = GemmCfg<kSplit, kPair>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOffset);
@@ -286,6 +352,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // pair mode: the two CTAs of a cluster work on the same 128-row tile, CTA rank r owns columns [r*block_n, (r+1)*block_n)
+  const int cta_rank = kPair ? (int)cluster_ctarank() : 0;
+  const int work_id = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int work_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + Cfg::kXbarOffset);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA0h);
@@ -297,6 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full + s, 1);
       mbar_init(tmem_empty + s, GEMM_EPI_WARPS);
+      if (kPair) mbar_init(xbar + s, GEMM_EPI_WARPS);  // one arrival per epilogue warp of the PEER CTA
     }
     fence_mbar_init();
   }
@@ -307,6 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (kPair) cluster_sync_all();  // the peer's exchange barriers are initialised before anyone arrives on them
   const uint32_t tmem_base = *tmem_slot;
 
   const uint32_t stage_tx = (kSplit ? 2u : 1u) * (uint32_t)(A_TILE_BYTES + p.block_n * GEMM_BK * 2);
@@ -315,9 +388,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+    for (int tile = work_id; tile < p.num_tiles; tile += work_stride) {
+      const int n_tile = kPair ? cta_rank : tile % p.n_tiles;
+      const int m_tile = kPair ? tile : tile / p.n_tiles;
       const int b = m_tile / p.tiles_per_row;
       const int t0 = (m_tile % p.tiles_per_row) * GEMM_BM;
       const int n0 = n_tile * p.block_n;
@@ -332,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
           tma_load_3d(mh, full_bar + stage, st, kb * GEMM_BK, t0 + p.seg_shift[s], b);
           tma_load_2d(&tmWh, full_bar + stage, st + A_TILE_BYTES, kglob * GEMM_BK, n0);
           if (kSplit) {
-            uint8_t* st2 = st + A_TILE_BYTES + B_TILE_BYTES;
+            uint8_t* st2 = st + A_TILE_BYTES + Cfg::kBTile;
             tma_load_3d(ml, full_bar + stage, st2, kb * GEMM_BK, t0 + p.seg_shift[s], b);
             tma_load_2d(&tmWl, full_bar + stage, st2 + A_TILE_BYTES, kglob * GEMM_BK, n0);
           }
@@ -349,7 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     uint32_t acc_phase = 0;
     int total_kb = 0;
     for (int s = 0; s < p.num_seg; ++s) total_kb += p.seg_kblocks[s];
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = work_id; tile < p.num_tiles; tile += work_stride) {
       mbar_wait(tmem_empty + acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * GEMM_MAX_BN;
@@ -364,8 +437,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
           umma_bf16(d_tmem, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (kb | kk) != 0);
         }
         if (kSplit) {
-          const uint64_t a_lo = make_smem_desc_sw128(st + A_TILE_BYTES + B_TILE_BYTES);
-          const uint64_t b_lo = make_smem_desc_sw128(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+          const uint64_t a_lo = make_smem_desc_sw128(st + A_TILE_BYTES + Cfg::kBTile);
+          const uint64_t b_lo = make_smem_desc_sw128(st + 2 * A_TILE_BYTES + Cfg::kBTile);
 #pragma unroll
           for (int kk = 0; kk < GEMM_BK / 16; ++kk) umma_bf16(d_tmem, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
 #pragma unroll
@@ -384,15 +457,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     float* red_all = reinterpret_cast<float*>(smem + Cfg::kRedOffset);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+    int iter = 0;
+    float2* xslots = reinterpret_cast<float2*>(smem + Cfg::kXchgOffset);
+    for (int tile = work_id; tile < p.num_tiles; tile += work_stride, ++iter) {
+      const int n_tile = kPair ? cta_rank : tile % p.n_tiles;
+      const int m_tile = kPair ? tile : tile / p.n_tiles;
       const int b = m_tile / p.tiles_per_row;
       const int t0 = (m_tile % p.tiles_per_row) * GEMM_BM;
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GEMM_MAX_BN;
-      epilogue_tile(p, taddr, b, t0, n_tile * p.block_n, quarter * 32 + lane, half, quarter, red_all + acc * (4 * GEMM_BM));
+      PairCtx px{};
+      if (kPair) {
+        const int slot = iter & 1;
+        px.active = 1;
+        px.my_slot = xslots + slot * GEMM_BM;
+        px.my_bar = xbar + slot;
+        px.peer_slot = map_to_peer(smem_u32(px.my_slot), (uint32_t)(cta_rank ^ 1));
+        px.peer_bar = map_to_peer(smem_u32(px.my_bar), (uint32_t)(cta_rank ^ 1));
+        px.parity = (uint32_t)((iter >> 1) & 1);
+      }
+      epilogue_tile(p, taddr, b, t0, n_tile * p.block_n, quarter * 32 + lane, half, quarter, red_all + acc * (4 * GEMM_BM), px);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
@@ -402,6 +487,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // keep this CTA's shared memory alive until the peer's last remote write / arrive landed
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -499,7 +585,8 @@ __global__ void gemm_simt_kernel(const GemmKParams p, const GemmSimtPtrs q) {
 static int validate(const ttsb_gemm_args* a, int* k_total_out) {
   if (!a) { set_last_error("ttsb_linear_fwd: args is NULL"); return TTSB_ERR_INVALID_ARGUMENT; }
   if (a->B <= 0 || a->T <= 0 || a->N <= 0) { set_last_error("ttsb_linear_fwd: B,T,N must be positive"); return TTSB_ERR_INVALID_ARGUMENT; }
-  if (a->block_n < 16 || a->block_n > GEMM_MAX_BN || a->block_n % 16) {
+  const bool wide_pair = a->ln_gamma && a->block_n == a->N && a->N % 32 == 0 && a->N / 2 <= PAIR_MAX_BN;  // N up to 384 as a CTA pair
+  if (a->block_n < 16 || (a->block_n > GEMM_MAX_BN && !wide_pair) || a->block_n % 16) {
     set_last_error("ttsb_linear_fwd: block_n=%d must be a multiple of 16 in [16,256]", a->block_n);
     return TTSB_ERR_INVALID_ARGUMENT;
   }
@@ -543,6 +630,15 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
   p.n_tiles = (a->N + a->block_n - 1) / a->block_n;
   p.tiles_per_row = (a->T + GEMM_BM - 1) / GEMM_BM;
   p.num_tiles = a->B * p.tiles_per_row * p.n_tiles;
+  // LayerNorm GEMMs whose row splits into two equal halves run as CTA pairs (see GemmCfg); TTSB_NO_PAIR=1 disables it
+  static const bool no_pair = getenv("TTSB_NO_PAIR") != nullptr;
+  const bool pair = !no_pair && a->impl != TTSB_IMPL_SIMT && a->ln_gamma != nullptr && p.n_tiles == 1 && a->N == a->block_n &&
+                    a->N % 32 == 0 && a->N / 2 <= PAIR_MAX_BN && a->N >= 64;
+  if (pair) {
+    p.block_n = a->N / 2;
+    p.n_tiles = 1;  // per work item; the two column halves belong to the two CTAs of the cluster
+    p.num_tiles = a->B * p.tiles_per_row;
+  }
   p.num_seg = a->num_segments;
   int src_k[2] = {0, 0};
   for (int s = 0; s < a->num_segments; ++s) {
@@ -601,25 +697,59 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
   }
   for (int h = 0; h < 2; ++h) {
     const void* base = h == 0 ? a->w_hi : (split ? a->w_lo : a->w_hi);
-    rc = make_tmap_bf16_2d(&tmW[h], base, k_total, p.n_tiles * p.block_n, (uint64_t)k_total, GEMM_BK, p.block_n);
+    rc = make_tmap_bf16_2d(&tmW[h], base, k_total, pair ? a->N : p.n_tiles * p.block_n, (uint64_t)k_total, GEMM_BK, p.block_n);
     if (rc) return rc;
   }
 
+  if (pair) {
+    // cluster of two CTAs per 128-row tile; grid = 2 x min(tiles, SMs/2)
+    const int pairs = p.num_tiles < num_sms() / 2 ? p.num_tiles : num_sms() / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (split) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true, true>::kSmemBytes));
+        attr_set = true;
+      }
+      cfg.dynamicSmemBytes = GemmCfg<true, true>::kSmemBytes;
+      TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p));
+    } else {
+      static bool attr_set = false;
+      if (!attr_set) {
+        TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false, true>::kSmemBytes));
+        attr_set = true;
+      }
+      cfg.dynamicSmemBytes = GemmCfg<false, true>::kSmemBytes;
+      TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p));
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "gemm_tc_kernel<pair> launch");
+  }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   if (split) {
     static bool attr_set = false;
     if (!attr_set) {
-      TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true>::kSmemBytes));
+      TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true, false>::kSmemBytes));
       attr_set = true;
     }
-    gemm_tc_kernel<true><<<grid, GEMM_THREADS, GemmCfg<true>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p);
+    gemm_tc_kernel<true, false><<<grid, GEMM_THREADS, GemmCfg<true, false>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p);
   } else {
     static bool attr_set = false;
     if (!attr_set) {
-      TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false>::kSmemBytes));
+      TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false, false>::kSmemBytes));
       attr_set = true;
     }
-    gemm_tc_kernel<false><<<grid, GEMM_THREADS, GemmCfg<false>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p);
+    gemm_tc_kernel<false, false><<<grid, GEMM_THREADS, GemmCfg<false, false>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p);
   }
   count_launch();
   return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");

@@ -34,7 +34,9 @@ def _pick_block_n(N: int, need_single_tile: bool) -> int:
     n16 = _round_up(N, 16)
     if n16 <= 256:
         return n16
-    # wider rows (model dimension 384): several N tiles; a LayerNorm epilogue then runs as a separate row kernel
+    if need_single_tile and N <= 384 and N % 32 == 0:
+        return N  # LayerNorm GEMM run as a CTA pair, each CTA owning N/2 <= 192 columns (csrc/gemm_tc.cu, kPair)
+    # wider / odd rows: several N tiles; a LayerNorm epilogue then runs as a separate row kernel
     for bn in range(256, 15, -16):
         if n16 % bn == 0:
             return bn
