@@ -11,6 +11,7 @@
 // fp32 add every such logit equals -1e9 and its softmax weight underflows to exactly 0 whenever the row has at least
 // one valid key, so skipping those keys is exact.  Rows of padded QUERIES are zeroed by the caller's row mask
 // (layers.py:229,262), so they are not computed here (written as zeros).
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "../../include/ttsb.h"
@@ -21,7 +22,11 @@ namespace ttsb {
 
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 64;
-constexpr int ATT_THREADS = 160;  // warps 0-3 softmax/epilogue (TMEM lane quarters 0-3), warp 4 TMA + MMA issue
+// narrow layout: warps 0-3 softmax/epilogue (TMEM lane quarters 0-3), warp 4 TMA + MMA issue               (160 threads)
+// wide layout:   warps 0-7 softmax/epilogue, warp w owns lane quarter w&3 and column half w>>2 of every S/P/O tile,
+//                warp 8 TMA + MMA issue                                                                        (288 threads)
+constexpr int ATT_THREADS_NARROW = 160;
+constexpr int ATT_THREADS_WIDE = 288;
 
 // single MUFU.EX2 (no denormal fix-up code: p < 2^-126 flushes to 0, far below bf16/fp16 resolution of P)
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -38,7 +43,20 @@ struct MhaKParams {
   __nv_bfloat16* out_lo;
   int ld_out;
   float scale_log2;  // log2(e)/sqrt(dh)
+#ifdef TTSB_ATT_TRACE
+  long long* trace;  // debug build only: clock64 stamps of CTA (0,0,0): [2 roles][64 tiles][8 events]
+#endif
 };
+
+#ifdef TTSB_ATT_TRACE
+#define ATT_TRACE(role, j, ev)                                                                         \
+  do {                                                                                                 \
+    if (p.trace && (threadIdx.x & 31) == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64)                 \
+      p.trace[((role) * 64 + (j)) * 8 + (ev)] = clock64();                                             \
+  } while (0)
+#else
+#define ATT_TRACE(role, j, ev) do {} while (0)
+#endif
 
 template <int DH, bool kSplit>
 struct MhaCfg {
@@ -49,18 +67,20 @@ struct MhaCfg {
   static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + kPlanes * Q_BYTES;
-  static constexpr int K_STAGE = kPlanes * K_BYTES;  // two K stages: S_{j+1} is issued while softmax_j runs
-  static constexpr int OFF_V = OFF_K + 2 * K_STAGE;
-  static constexpr int OFF_P = OFF_V + kPlanes * V_BYTES;
+  // three key/value slots: slot j%3 holds K_j until S_j has completed, then V_j until PV_j has completed, then K_{j+3}.
+  // Every load is therefore issued about one key tile ahead of its consumer (no TMA latency on the critical path).
+  static constexpr int K_STAGE = kPlanes * K_BYTES;
+  static constexpr int OFF_P = OFF_K + 3 * K_STAGE;
   static constexpr int OFF_BAR = OFF_P + kPlanes * P_BYTES;
-  static constexpr int kSmemBytes = OFF_BAR + 128 + 1024;
+  static constexpr int OFF_RED = OFF_BAR + 128;      // wide layout: row max [2 tiles][2 halves][128] + row sum [2][128]
+  static constexpr int kSmemBytes = OFF_RED + 3072 + 1024;
   static constexpr int kTmemCols = (2 * ATT_BKV + DH) <= 128 ? 128 : ((2 * ATT_BKV + DH) <= 256 ? 256 : 512);
   static constexpr int S_COL = 0;             // two S accumulators of ATT_BKV columns
   static constexpr int O_COL = 2 * ATT_BKV;
 };
 
-template <int DH, bool kSplit, bool kF16>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int DH, bool kSplit, bool kF16, bool kWide>
+__global__ void __launch_bounds__(kWide ? ATT_THREADS_WIDE : ATT_THREADS_NARROW, (kWide && !kSplit && DH <= 128) ? 2 : 1)
 mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
               const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl, const MhaKParams p) {
   using Cfg = MhaCfg<DH, kSplit>;
@@ -68,15 +88,18 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* bar_q = bars + 0;
-  uint64_t* bar_k = bars + 1;   // [2]
-  uint64_t* bar_v = bars + 3;
+  uint64_t* bar_kv = bars + 1;  // [3] slot full: completes once for K_j (parity 0) and once for V_j (parity 1) per use
   uint64_t* bar_s = bars + 4;   // [2]
   uint64_t* bar_p = bars + 6;
   uint64_t* bar_pv = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
+  constexpr int NH = kWide ? 2 : 1;        // column halves per S/P/O tile
+  constexpr int kMmaWarp = 4 * NH;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+  const int half = kWide ? (warp >> 2) & 1 : 0;
   const int q0 = blockIdx.x * ATT_BQ;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
@@ -85,11 +108,11 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
 
   if (q0 >= len) {
     // whole query tile is padding: defined (zero) output, no tensor work
-    if (warp < 4) {
-      const int t = q0 + warp * 32 + lane;
+    if (warp < kMmaWarp) {
+      const int t = q0 + quarter * 32 + lane;
       if (t < p.T) {
-        const size_t o = ((size_t)b * p.T + t) * p.ld_out + h * DH;
-        for (int c = 0; c < DH; c += 8) {
+        const size_t o = ((size_t)b * p.T + t) * p.ld_out + h * DH + half * (DH / NH);
+        for (int c = 0; c < DH / NH; c += 8) {
           st_global_v4(p.out_hi + o + c, 0, 0, 0, 0);
           if (p.out_lo) st_global_v4(p.out_lo + o + c, 0, 0, 0, 0);
         }
@@ -101,16 +124,16 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1);
-    mbar_init(bar_k, 1);
-    mbar_init(bar_k + 1, 1);
-    mbar_init(bar_v, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_kv + 1, 1);
+    mbar_init(bar_kv + 2, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 1, 1);
-    mbar_init(bar_p, 4);
+    mbar_init(bar_p, 4 * NH);
     mbar_init(bar_pv, 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -119,44 +142,44 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
-    if (lane == 0) {
-      // ===================== TMA + MMA issue thread =====================
+  if (warp == kMmaWarp) {
+    {
+      // ===================== TMA + MMA issue warp: warp-uniform control flow, one elected lane issues =====================
+      const bool leader = elect_one();
       uint8_t* sQ = smem + Cfg::OFF_Q;
-      uint8_t* sK = smem + Cfg::OFF_K;
-      uint8_t* sV = smem + Cfg::OFF_V;
+      uint8_t* sKV = smem + Cfg::OFF_K;
       uint8_t* sP = smem + Cfg::OFF_P;
       const uint32_t idesc_s = kF16 ? make_idesc_f16(ATT_BQ, ATT_BKV) : make_idesc_bf16(ATT_BQ, ATT_BKV);
       const uint32_t idesc_o = (kF16 ? make_idesc_f16(ATT_BQ, DH) : make_idesc_bf16(ATT_BQ, DH)) | (1u << 16);  // B (= V) MN-major
       const uint32_t t_s = tmem_base + Cfg::S_COL;
       const uint32_t t_o = tmem_base + Cfg::O_COL;
 
-      mbar_arrive_expect_tx(bar_q, Cfg::kPlanes * Cfg::Q_BYTES);
-      for (int pn = 0; pn < DH / 64; ++pn) {
-        tma_load_3d(&tmQh, bar_q, sQ + pn * (ATT_BQ * 128), p.q_col0 + h * DH + pn * 64, q0, b);
-        if (kSplit) tma_load_3d(&tmQl, bar_q, sQ + Cfg::Q_BYTES + pn * (ATT_BQ * 128), p.q_col0 + h * DH + pn * 64, q0, b);
-      }
-      auto load_k = [&](int j) {
-        uint8_t* dst = sK + (j & 1) * Cfg::K_STAGE;
-        mbar_arrive_expect_tx(bar_k + (j & 1), Cfg::kPlanes * Cfg::K_BYTES);
+      if (leader) {
+        mbar_arrive_expect_tx(bar_q, Cfg::kPlanes * Cfg::Q_BYTES);
         for (int pn = 0; pn < DH / 64; ++pn) {
-          tma_load_3d(&tmKh, bar_k + (j & 1), dst + pn * (ATT_BKV * 128), p.k_col0 + h * DH + pn * 64, j * ATT_BKV, b);
-          if (kSplit) tma_load_3d(&tmKl, bar_k + (j & 1), dst + Cfg::K_BYTES + pn * (ATT_BKV * 128), p.k_col0 + h * DH + pn * 64, j * ATT_BKV, b);
+          tma_load_3d(&tmQh, bar_q, sQ + pn * (ATT_BQ * 128), p.q_col0 + h * DH + pn * 64, q0, b);
+          if (kSplit) tma_load_3d(&tmQl, bar_q, sQ + Cfg::Q_BYTES + pn * (ATT_BQ * 128), p.q_col0 + h * DH + pn * 64, q0, b);
+        }
+      }
+      // K_j and V_j are the same [64 keys x 64 columns] boxes of the QKV buffer, at the K resp. V columns
+      auto load_kv = [&](int j, int col0) {
+        uint8_t* dst = sKV + (j % 3) * Cfg::K_STAGE;
+        uint64_t* bar = bar_kv + (j % 3);
+        if (leader) {
+          mbar_arrive_expect_tx(bar, Cfg::kPlanes * Cfg::K_BYTES);
+          for (int pn = 0; pn < DH / 64; ++pn) {
+            tma_load_3d(&tmKh, bar, dst + pn * (ATT_BKV * 128), col0 + h * DH + pn * 64, j * ATT_BKV, b);
+            if (kSplit) tma_load_3d(&tmKl, bar, dst + Cfg::K_BYTES + pn * (ATT_BKV * 128), col0 + h * DH + pn * 64, j * ATT_BKV, b);
+          }
         }
       };
-      auto load_v = [&](int j) {
-        mbar_arrive_expect_tx(bar_v, Cfg::kPlanes * Cfg::V_BYTES);
-        for (int pn = 0; pn < DH / 64; ++pn) {  // same [64 rows x 64 cols] box as K, at the V columns
-          tma_load_3d(&tmKh, bar_v, sV + pn * (ATT_BKV * 128), p.v_col0 + h * DH + pn * 64, j * ATT_BKV, b);
-          if (kSplit) tma_load_3d(&tmKl, bar_v, sV + Cfg::V_BYTES + pn * (ATT_BKV * 128), p.v_col0 + h * DH + pn * 64, j * ATT_BKV, b);
-        }
-      };
-      // S_j = Q K_j^T into S accumulator j&1, from K stage j&1
+      // S_j = Q K_j^T into S accumulator j&1
       auto issue_s = [&](int j) {
-        const uint8_t* kst = sK + (j & 1) * Cfg::K_STAGE;
+        const uint8_t* kst = sKV + (j % 3) * Cfg::K_STAGE;
         const uint32_t ts = t_s + (j & 1) * ATT_BKV;
-        mbar_wait(bar_k + (j & 1), (j >> 1) & 1);
+        mbar_wait(bar_kv + (j % 3), 0);
         tc_fence_after();
+        if (leader) {
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) {
           const uint64_t a = make_smem_desc_sw128(smem_u32(sQ + (kk / 4) * (ATT_BQ * 128))) + 2 * (kk % 4);
@@ -178,26 +201,36 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
           }
         }
         umma_commit(bar_s + (j & 1));
+        }
       };
-      load_k(0);
-      load_v(0);
-      if (n_kv > 1) load_k(1);
+      load_kv(0, p.k_col0);
+      if (n_kv > 1) load_kv(1, p.k_col0);
+      if (n_kv > 2) load_kv(2, p.k_col0);
       mbar_wait(bar_q, 0);
       issue_s(0);
+      mbar_wait(bar_s, 0);        // S_0 complete: its K slot takes V_0
+      load_kv(0, p.v_col0);
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t ph = j & 1;
         // ---- software pipeline: S_{j+1} goes to the tensor pipe now, so the softmax warps find it ready when they finish
         //      tile j (its accumulator was last read for tile j-1, whose bar_p this thread has already seen)
+        ATT_TRACE(1, j, 0);
         if (j + 1 < n_kv) issue_s(j + 1);
-        // ---- K stage j&1 is free once S_j has completed: refill it with K_{j+2}
-        if (j + 2 < n_kv) {
-          mbar_wait(bar_s + (j & 1), (j >> 1) & 1);
-          load_k(j + 2);
+        ATT_TRACE(1, j, 1);
+        // ---- slot (j-1)%3 is free once PV_{j-1} has completed: refill it with K_{j+2}
+        if (j >= 1 && j + 2 < n_kv) {
+          mbar_wait(bar_pv, (j - 1) & 1);
+          load_kv(j + 2, p.k_col0);
         }
         // ---- O += P V
+        const uint8_t* sV = sKV + (j % 3) * Cfg::K_STAGE;
+        ATT_TRACE(1, j, 2);
+        mbar_wait(bar_kv + (j % 3), 1);
+        ATT_TRACE(1, j, 3);
         mbar_wait(bar_p, ph);
-        mbar_wait(bar_v, ph);
+        ATT_TRACE(1, j, 4);
         tc_fence_after();
+        if (leader) {
 #pragma unroll
         for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
           const uint64_t a = make_smem_desc_sw128(smem_u32(sP)) + 2 * kk;
@@ -214,67 +247,92 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
 #pragma unroll
           for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
             const uint64_t a = make_smem_desc_sw128(smem_u32(sP)) + 2 * kk;
-            const uint64_t bb = make_smem_desc_mn_sw128(smem_u32(sV + Cfg::V_BYTES), ATT_BKV * 128) + 128 * kk;
+            const uint64_t bb = make_smem_desc_mn_sw128(smem_u32(sV + Cfg::K_BYTES), ATT_BKV * 128) + 128 * kk;
             umma_bf16(t_o, a, bb, idesc_o, 1);
           }
         }
         umma_commit(bar_pv);
-        // ---- V_{j+1} may be loaded once PV_j has finished reading the V buffer
-        if (j + 1 < n_kv) {
-          mbar_wait(bar_pv, ph);
-          load_v(j + 1);
         }
+        ATT_TRACE(1, j, 5);
+        // ---- S_{j+1} (issued above, ahead of PV_j) completes first: its K slot takes V_{j+1}, a whole softmax ahead of PV_{j+1}
+        if (j + 1 < n_kv) {
+          mbar_wait(bar_s + ((j + 1) & 1), ((j + 1) >> 1) & 1);
+          load_kv(j + 1, p.v_col0);
+        }
+        ATT_TRACE(1, j, 6);
       }
     }
   } else {
-    // ===================== softmax / epilogue warps: one thread per query row =====================
-    const int row = warp * 32 + lane;
+    // ===================== softmax / epilogue warps =====================
+    // one thread per (query row, column half): with the wide layout two partner warps (w, w+4) share a row, each
+    // reading its half of S, writing its half of P and owning its half of O; row max / row sum are combined through
+    // shared memory behind a 64-thread named barrier.
+    constexpr int SW = ATT_BKV / NH;   // S / P columns of this thread
+    constexpr int OW = DH / NH;        // O columns of this thread
+    const int row = quarter * 32 + lane;
     const int tq = q0 + row;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_base + Cfg::S_COL;
-    const uint32_t t_o = tmem_base + lane_base + Cfg::O_COL;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + Cfg::S_COL + half * SW;
+    const uint32_t t_o = tmem_base + lane_base + Cfg::O_COL + half * OW;
     uint8_t* sP = smem + Cfg::OFF_P;
+    float* red_max = reinterpret_cast<float*>(smem + Cfg::OFF_RED);          // [2][2][128]
+    float* red_sum = red_max + 2 * 2 * ATT_BQ;                               // [2][128]
     float m = -INFINITY, l = 0.f;
     uint32_t r[16];
     for (int j = 0; j < n_kv; ++j) {
+      if (threadIdx.x == 0) ATT_TRACE(0, j, 0);
       mbar_wait(bar_s + (j & 1), (j >> 1) & 1);
+      if (threadIdx.x == 0) ATT_TRACE(0, j, 1);
       tc_fence_after();
       const uint32_t t_sj = t_s + (j & 1) * ATT_BKV;
       // raw scores (un-scaled): the running max is kept in raw units, the softmax scale is folded into one FFMA per
       // element: p = exp2(s * scale_log2 - m * scale_log2)
-      float s[ATT_BKV];
+      float s[SW];
+      {
+        // all TMEM loads are issued back to back and waited for once
+        uint32_t qq[SW / 16][16];
 #pragma unroll
-      for (int c = 0; c < ATT_BKV / 16; ++c) {
-        tmem_ld16(t_sj + c * 16, r);
+        for (int c = 0; c < SW / 16; ++c) tmem_ld16(t_sj + c * 16, qq[c]);
         tmem_wait_ld();
+        if (threadIdx.x == 0) ATT_TRACE(0, j, 2);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s[c * 16 + i] = __uint_as_float(r[i]);
+        for (int c = 0; c < SW / 16; ++c)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s[c * 16 + i] = __uint_as_float(qq[c][i]);
       }
       if ((j + 1) * ATT_BKV > len) {  // only the last key tile can hold padded keys
 #pragma unroll
-        for (int i = 0; i < ATT_BKV; ++i)
-          if (j * ATT_BKV + i >= len) s[i] = -INFINITY;
+        for (int i = 0; i < SW; ++i)
+          if (j * ATT_BKV + half * SW + i >= len) s[i] = -INFINITY;
       }
       float mx = s[0];
 #pragma unroll
-      for (int i = 1; i < ATT_BKV; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 1; i < SW; ++i) mx = fmaxf(mx, s[i]);
+      if (kWide) {
+        float* rm = red_max + (j & 1) * 2 * ATT_BQ;
+        rm[half * ATT_BQ + row] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        mx = fmaxf(mx, rm[(half ^ 1) * ATT_BQ + row]);
+      }
       const float m_new = fmaxf(m, mx);
       const float alpha = fast_exp2((m - m_new) * p.scale_log2);  // first tile: exp2(-inf) = 0
       const float neg_m = -m_new * p.scale_log2;
       float psum = 0.f;
 #pragma unroll
-      for (int i = 0; i < ATT_BKV; ++i) {
+      for (int i = 0; i < SW; ++i) {
         s[i] = fast_exp2(fmaf(s[i], p.scale_log2, neg_m));
         psum += s[i];
       }
-      l = l * alpha + psum;
+      l = l * alpha + psum;   // wide layout: partial sum over this thread's column half
       m = m_new;
+      if (threadIdx.x == 0) ATT_TRACE(0, j, 3);
       if (j > 0) {
         mbar_wait(bar_pv, (j - 1) & 1);  // O_{j-1} complete, P buffer free
+        if (threadIdx.x == 0) ATT_TRACE(0, j, 4);
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll
-          for (int c = 0; c < DH / 16; ++c) {
+          for (int c = 0; c < OW / 16; ++c) {
             tmem_ld16(t_o + c * 16, r);
             tmem_wait_ld();
 #pragma unroll
@@ -284,20 +342,22 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
           tmem_wait_st();
         }
       }
+      if (threadIdx.x == 0) ATT_TRACE(0, j, 5);
       // P -> shared memory, K-major rows of 128 B with the 128B swizzle (16-byte chunk index ^= row & 7)
 #pragma unroll
-      for (int ch = 0; ch < ATT_BKV / 8; ++ch) {
+      for (int c8 = 0; c8 < SW / 8; ++c8) {
+        const int ch = half * (SW / 8) + c8;
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (kF16) {
-            const __half2 hh = __floats2half2_rn(s[ch * 8 + 2 * i], s[ch * 8 + 2 * i + 1]);
+            const __half2 hh = __floats2half2_rn(s[c8 * 8 + 2 * i], s[c8 * 8 + 2 * i + 1]);
             hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
             lo[i] = 0;
           } else {
             __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(s[ch * 8 + 2 * i], h0, l0);
-            split_bf16(s[ch * 8 + 2 * i + 1], h1, l1);
+            split_bf16(s[c8 * 8 + 2 * i], h0, l0);
+            split_bf16(s[c8 * 8 + 2 * i + 1], h1, l1);
             hi[i] = pack_bf16(h0, h1);
             lo[i] = pack_bf16(l0, l1);
           }
@@ -310,14 +370,20 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
+      if (threadIdx.x == 0) ATT_TRACE(0, j, 6);
     }
     // ---- epilogue: O / l -> bf16 hi/lo at columns [h*DH, (h+1)*DH)
+    if (kWide) {
+      red_sum[half * ATT_BQ + row] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      l += red_sum[(half ^ 1) * ATT_BQ + row];
+    }
     mbar_wait(bar_pv, (n_kv - 1) & 1);
     tc_fence_after();
     const float inv = l > 0.f ? 1.f / l : 0.f;
-    const size_t o = ((size_t)b * p.T + (tq < p.T ? tq : 0)) * p.ld_out + h * DH;
+    const size_t o = ((size_t)b * p.T + (tq < p.T ? tq : 0)) * p.ld_out + h * DH + half * OW;
 #pragma unroll
-    for (int c = 0; c < DH / 16; ++c) {
+    for (int c = 0; c < OW / 16; ++c) {
       tmem_ld16(t_o + c * 16, r);
       tmem_wait_ld();
       uint32_t hi[8], lo[8];
@@ -338,7 +404,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -426,7 +492,7 @@ __global__ void mha_simt_kernel(const MhaKParams p, const MhaSimtPtrs q) {
   }
 }
 
-template <int DH, bool kSplit, bool kF16>
+template <int DH, bool kSplit, bool kF16, bool kWide>
 static int launch_tc(const ttsb_mha_args* a, const MhaKParams& p, cudaStream_t stream) {
   using Cfg = MhaCfg<DH, kSplit>;
   CUtensorMap tmQ[2], tmK[2];
@@ -439,11 +505,11 @@ static int launch_tc(const ttsb_mha_args* a, const MhaKParams& p, cudaStream_t s
   }
   static bool attr_set = false;
   if (!attr_set) {
-    TTSB_CUDA_OK(cudaFuncSetAttribute(mha_tc_kernel<DH, kSplit, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    TTSB_CUDA_OK(cudaFuncSetAttribute(mha_tc_kernel<DH, kSplit, kF16, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   dim3 grid((a->T + ATT_BQ - 1) / ATT_BQ, a->H, a->B);
-  mha_tc_kernel<DH, kSplit, kF16><<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tmQ[0], tmQ[1], tmK[0], tmK[1], p);
+  mha_tc_kernel<DH, kSplit, kF16, kWide><<<grid, kWide ? ATT_THREADS_WIDE : ATT_THREADS_NARROW, Cfg::kSmemBytes, stream>>>(tmQ[0], tmQ[1], tmK[0], tmK[1], p);
   count_launch();
   return check_cuda(cudaGetLastError(), "mha_tc_kernel launch");
 }
@@ -471,6 +537,12 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   p.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);  // optional second plane of the OUTPUT (consumer may be bf16x3)
   p.ld_out = a->ld_out;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)a->dh);
+#ifdef TTSB_ATT_TRACE
+  {
+    const char* e = getenv("TTSB_ATT_TRACE_PTR");  // device pointer (hex) of a 2*64*8 int64 buffer
+    p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
+  }
+#endif
 
   MhaSimtPtrs q{};
   q.qk_hi = static_cast<const __nv_bfloat16*>(a->qk_hi);
@@ -489,10 +561,17 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
     count_launch();
     return check_cuda(cudaGetLastError(), "mha_simt_kernel launch");
   }
+  // wide (8 softmax warps) is the default layout; TTSB_ATT_NARROW=1 selects the 4-warp layout for A/B measurements
+  static const bool narrow = [] { const char* e = getenv("TTSB_ATT_NARROW"); return e && e[0] == '1'; }();
   int rc;
-  if (a->dh == 128) rc = split ? launch_tc<128, true, false>(a, p, stream) : (f16 ? launch_tc<128, false, true>(a, p, stream) : launch_tc<128, false, false>(a, p, stream));
-  else if (a->dh == 64) rc = split ? launch_tc<64, true, false>(a, p, stream) : (f16 ? launch_tc<64, false, true>(a, p, stream) : launch_tc<64, false, false>(a, p, stream));
-  else if (a->dh == 192 && !split) rc = f16 ? launch_tc<192, false, true>(a, p, stream) : launch_tc<192, false, false>(a, p, stream);
+#define TTSB_MHA_DISPATCH(DH_, W_)                                                                                  \
+  (split ? launch_tc<DH_, true, false, W_>(a, p, stream)                                                            \
+         : (f16 ? launch_tc<DH_, false, true, W_>(a, p, stream) : launch_tc<DH_, false, false, W_>(a, p, stream)))
+#define TTSB_MHA_DISPATCH1(DH_, W_) \
+  (f16 ? launch_tc<DH_, false, true, W_>(a, p, stream) : launch_tc<DH_, false, false, W_>(a, p, stream))
+  if (a->dh == 128) rc = narrow ? TTSB_MHA_DISPATCH(128, false) : TTSB_MHA_DISPATCH(128, true);
+  else if (a->dh == 64) rc = narrow ? TTSB_MHA_DISPATCH(64, false) : TTSB_MHA_DISPATCH(64, true);
+  else if (a->dh == 192 && !split) rc = narrow ? TTSB_MHA_DISPATCH1(192, false) : TTSB_MHA_DISPATCH1(192, true);
   else { set_last_error("ttsb_mha_fwd: head_dim %d not supported by the tcgen05 kernel (64, 128; 192 in single-pass modes)", a->dh); return TTSB_ERR_UNSUPPORTED; }
   if (rc) return rc;
   if (a->weights_out) {

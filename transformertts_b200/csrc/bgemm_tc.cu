@@ -111,8 +111,9 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     return nb > 0 ? nb * t_chunks : 0;
   };
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer: warp-uniform control flow, the elected lane issues (see elect_one) ==========
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -127,19 +128,21 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int kb = 0; kb < kbs; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* st = smem + stage * BG_STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar + stage, stage_tx);
-          if (a_mn) {
-            for (int i = 0; i < BG_BM / 64; ++i)
-              tma_load_3d(&tmA0, full_bar + stage, st + i * BG_MN_BOX_BYTES, m0 + 64 * i + h * p.opA.h_col, kb * BG_BK + h * p.opA.h_row, za);
-          } else {
-            tma_load_3d(&tmA0, full_bar + stage, st, kb * BG_BK + h * p.opA.h_col, m0 + h * p.opA.h_row, za);
-          }
-          if (b_mn) {
-            for (int i = 0; i < b_boxes; ++i)
-              tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES + i * BG_MN_BOX_BYTES, n0 + 64 * i + h * p.opB.h_col,
-                          kb * BG_BK + h * p.opB.h_row, zb);
-          } else {
-            tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES, kb * BG_BK + h * p.opB.h_col, n0 + h * p.opB.h_row, zb);
+          if (leader) {
+            mbar_arrive_expect_tx(full_bar + stage, stage_tx);
+            if (a_mn) {
+              for (int i = 0; i < BG_BM / 64; ++i)
+                tma_load_3d(&tmA0, full_bar + stage, st + i * BG_MN_BOX_BYTES, m0 + 64 * i + h * p.opA.h_col, kb * BG_BK + h * p.opA.h_row, za);
+            } else {
+              tma_load_3d(&tmA0, full_bar + stage, st, kb * BG_BK + h * p.opA.h_col, m0 + h * p.opA.h_row, za);
+            }
+            if (b_mn) {
+              for (int i = 0; i < b_boxes; ++i)
+                tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES + i * BG_MN_BOX_BYTES, n0 + 64 * i + h * p.opB.h_col,
+                            kb * BG_BK + h * p.opB.h_row, zb);
+            } else {
+              tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES, kb * BG_BK + h * p.opB.h_col, n0 + h * p.opB.h_row, zb);
+            }
           }
           if (++stage == BG_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -158,18 +161,21 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           for (int tc = 0; tc < t_chunks; ++tc) {
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* st = smem + stage * BG_STAGE_BYTES;
-            mbar_arrive_expect_tx(full_bar + stage, stage_tx);
-            for (int i = 0; i < BG_BM / 64; ++i)
-              tma_load_3d(mA, full_bar + stage, st + i * BG_MN_BOX_BYTES, c0 + 64 * i, tc * BG_BK + shift, b);
-            for (int i = 0; i < b_boxes; ++i)
-              tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES + i * BG_MN_BOX_BYTES, n0 + 64 * i, tc * BG_BK, b);
+            if (leader) {
+              mbar_arrive_expect_tx(full_bar + stage, stage_tx);
+              for (int i = 0; i < BG_BM / 64; ++i)
+                tma_load_3d(mA, full_bar + stage, st + i * BG_MN_BOX_BYTES, c0 + 64 * i, tc * BG_BK + shift, b);
+              for (int i = 0; i < b_boxes; ++i)
+                tma_load_3d(&tmB, full_bar + stage, st + BG_A_BYTES + i * BG_MN_BOX_BYTES, n0 + 64 * i, tc * BG_BK, b);
+            }
             if (++stage == BG_STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer: warp-uniform control flow, the elected lane issues =====================
+    const bool leader = elect_one();
     const uint32_t idesc = make_idesc_bf16(BG_BM, p.block_n) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
     const uint32_t a_step = a_mn ? (16 * 128) >> 4 : 2;  // descriptor advance per 16 k
     const uint32_t b_step = b_mn ? (16 * 128) >> 4 : 2;
@@ -187,12 +193,14 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const uint32_t st = smem_u32(smem + stage * BG_STAGE_BYTES);
         const uint64_t a = a_mn ? make_smem_desc_mn_sw128(st, BG_MN_BOX_BYTES) : make_smem_desc_sw128(st);
         const uint64_t b = b_mn ? make_smem_desc_mn_sw128(st + BG_A_BYTES, BG_MN_BOX_BYTES) : make_smem_desc_sw128(st + BG_A_BYTES);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < BG_BK / 16; ++kk) umma_bf16(d_tmem, a + a_step * kk, b + b_step * kk, idesc, (kb | kk) != 0);
-        umma_commit(empty_bar + stage);
+          for (int kk = 0; kk < BG_BK / 16; ++kk) umma_bf16(d_tmem, a + a_step * kk, b + b_step * kk, idesc, (kb | kk) != 0);
+          umma_commit(empty_bar + stage);
+        }
         if (++stage == BG_STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full + acc);
+      if (leader) umma_commit(tmem_full + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 2) {

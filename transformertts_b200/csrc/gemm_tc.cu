@@ -384,8 +384,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
 
   const uint32_t stage_tx = (kSplit ? 2u : 1u) * (uint32_t)(A_TILE_BYTES + p.block_n * GEMM_BK * 2);
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer: warp-uniform control flow, the elected lane issues (see elect_one) ==========
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = work_id; tile < p.num_tiles; tile += work_stride) {
@@ -401,20 +402,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
         for (int kb = 0; kb < p.seg_kblocks[s]; ++kb, ++kglob) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(full_bar + stage, stage_tx);
-          tma_load_3d(mh, full_bar + stage, st, kb * GEMM_BK, t0 + p.seg_shift[s], b);
-          tma_load_2d(&tmWh, full_bar + stage, st + A_TILE_BYTES, kglob * GEMM_BK, n0);
-          if (kSplit) {
-            uint8_t* st2 = st + A_TILE_BYTES + Cfg::kBTile;
-            tma_load_3d(ml, full_bar + stage, st2, kb * GEMM_BK, t0 + p.seg_shift[s], b);
-            tma_load_2d(&tmWl, full_bar + stage, st2 + A_TILE_BYTES, kglob * GEMM_BK, n0);
+          if (leader) {
+            mbar_arrive_expect_tx(full_bar + stage, stage_tx);
+            tma_load_3d(mh, full_bar + stage, st, kb * GEMM_BK, t0 + p.seg_shift[s], b);
+            tma_load_2d(&tmWh, full_bar + stage, st + A_TILE_BYTES, kglob * GEMM_BK, n0);
+            if (kSplit) {
+              uint8_t* st2 = st + A_TILE_BYTES + Cfg::kBTile;
+              tma_load_3d(ml, full_bar + stage, st2, kb * GEMM_BK, t0 + p.seg_shift[s], b);
+              tma_load_2d(&tmWl, full_bar + stage, st2 + A_TILE_BYTES, kglob * GEMM_BK, n0);
+            }
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer: warp-uniform control flow, the elected lane issues =====================
+    const bool leader = elect_one();
     const uint32_t idesc = make_idesc_bf16(GEMM_BM, p.block_n);
     int stage = 0;
     uint32_t phase = 0;
@@ -432,22 +436,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
         const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint64_t a_hi = make_smem_desc_sw128(st);
         const uint64_t b_hi = make_smem_desc_sw128(st + A_TILE_BYTES);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
-          umma_bf16(d_tmem, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (kb | kk) != 0);
+          for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
+            umma_bf16(d_tmem, a_hi + 2 * kk, b_hi + 2 * kk, idesc, (kb | kk) != 0);
+          }
+          if (kSplit) {
+            const uint64_t a_lo = make_smem_desc_sw128(st + A_TILE_BYTES + Cfg::kBTile);
+            const uint64_t b_lo = make_smem_desc_sw128(st + 2 * A_TILE_BYTES + Cfg::kBTile);
+#pragma unroll
+            for (int kk = 0; kk < GEMM_BK / 16; ++kk) umma_bf16(d_tmem, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
+#pragma unroll
+            for (int kk = 0; kk < GEMM_BK / 16; ++kk) umma_bf16(d_tmem, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1);
+          }
+          umma_commit(empty_bar + stage);  // frees the smem stage once these MMAs have read it
         }
-        if (kSplit) {
-          const uint64_t a_lo = make_smem_desc_sw128(st + A_TILE_BYTES + Cfg::kBTile);
-          const uint64_t b_lo = make_smem_desc_sw128(st + 2 * A_TILE_BYTES + Cfg::kBTile);
-#pragma unroll
-          for (int kk = 0; kk < GEMM_BK / 16; ++kk) umma_bf16(d_tmem, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1);
-#pragma unroll
-          for (int kk = 0; kk < GEMM_BK / 16; ++kk) umma_bf16(d_tmem, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1);
-        }
-        umma_commit(empty_bar + stage);  // frees the smem stage once these MMAs have read it
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full + acc);  // accumulator complete
+      if (leader) umma_commit(tmem_full + acc);  // accumulator complete
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 2) {

@@ -160,6 +160,16 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t
   return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// One lane of a fully converged warp.  The TMA / MMA issuing warps run their role code warp-uniformly and predicate only
+// the issuing instructions on this: every operand then lives in uniform registers.  Entering the role under
+// `if (lane == 0)` instead makes ptxas wrap each UTCHMMA / UTMALDG in an ELECT + R2UR + BRA.U.ANY loop (~12 dependent
+// instructions, ~100 clk per MMA measured with clock64 stamps).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

@@ -3,6 +3,7 @@ fails, a TtsbError is raised."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional
 
@@ -14,7 +15,8 @@ PREC_FP16 = 2
 IMPL_TCGEN05 = 0
 IMPL_SIMT = 1
 
-_LIB_PATH = Path(__file__).resolve().parent / 'libttsb.so'
+# TTSB_LIB selects another build of the same library (e.g. the clock-trace debug build made by tools/att_trace.py)
+_LIB_PATH = Path(os.environ.get('TTSB_LIB') or Path(__file__).resolve().parent / 'libttsb.so')
 _lib = None
 
 EXPORTS = [
