@@ -314,8 +314,13 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
         mx = fmaxf(mx, rm[(half ^ 1) * ATT_BQ + row]);
       }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = fast_exp2((m - m_new) * p.scale_log2);  // first tile: exp2(-inf) = 0
+      // lazy running max: the reference point only moves when the row max grew by more than 2^8 (in exponent units), so
+      // P stays <= 256 (exact range for fp16/bf16, fp32 accumulation) and the O rescale below becomes rare.  l and O
+      // use the same reference, so the final O / l is unchanged.
+      const float m_cand = fmaxf(m, mx);
+      const bool grow = (m_cand - m) * p.scale_log2 > 8.f;        // first tile: m = -inf -> true
+      const float m_new = grow ? m_cand : m;
+      const float alpha = grow ? fast_exp2((m - m_new) * p.scale_log2) : 1.f;  // first tile: exp2(-inf) = 0
       const float neg_m = -m_new * p.scale_log2;
       float psum = 0.f;
 #pragma unroll
