@@ -31,7 +31,7 @@ extern "C" {
 #define TTSB_ERR_CUDA (-2)
 #define TTSB_ERR_UNSUPPORTED (-3)
 
-#define TTSB_ABI_VERSION 1
+#define TTSB_ABI_VERSION 2
 
 /* precision of the tensor-core products */
 #define TTSB_PREC_BF16 0   /* single bf16 pass, fp32 accumulate */
@@ -135,11 +135,20 @@ int ttsb_layernorm_fwd(const float* x, const float* gamma, const float* beta, in
                        const int32_t* row_len, float* out_f32, void* out_hi, void* out_lo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * Fused variable-length self-attention  (model/layers.py:138-147 split/merge heads, :176-195 scaled dot product)
- *   q,k,v: bf16 (B,T,ld_qk) at columns q_col0 + h*dh / k_col0 + h*dh / v_col0 + h*dh of one buffer (the QKV GEMM output)
- *   out: bf16 hi (and lo when out_lo != NULL) (B,T,ld_out), head h at columns h*dh.  Keys t >= kv_len[b] are masked
- *   (the reference adds -1e9).  precision TTSB_PREC_FP16: qk_hi holds IEEE fp16 (written by ttsb_linear_fwd
- *   with out_fp16 = 1), one tensor-core pass.
+ * Fused variable-length attention  (model/layers.py:138-147 split/merge heads, :176-195 scaled dot product)
+ *   self-attention (kv_hi == NULL): q,k,v are columns q_col0 + h*dh / k_col0 + h*dh / v_col0 + h*dh of ONE buffer
+ *     (B,T,ld_qk), the QKV GEMM output; Tk = T.
+ *   cross-attention (kv_hi != NULL; model/layers.py:315-327 CrossAttentionResnorm): q from (B,T,ld_qk) at q_col0,
+ *     k and v from a second buffer (B,Tk,ld_kv) at k_col0 / v_col0 (the K|V GEMM of the encoder output).
+ *   out: bf16 hi (and lo when out_lo != NULL) (B,T,ld_out), head h at columns h*dh.
+ *   Masking follows the reference's additive -1e9 masks: keys t >= kv_len[b] (padding mask, transformer_utils.py:24-32)
+ *   and, with causal = 1, keys t > query index (look-ahead mask, transformer_utils.py:35-37; the Aligner passes
+ *   max(padding, look-ahead), models.py:136-138).
+ *   full_queries = 0: query rows >= kv_len[b] are written as zeros (ForwardTransformer blocks multiply them by the
+ *   mask right after, layers.py:228-230); 1: every query row is computed from the unmasked keys as the reference does
+ *   (Aligner decoder blocks never re-mask their rows).
+ *   precision TTSB_PREC_FP16: the buffers hold IEEE fp16 (written by ttsb_linear_fwd with out_fp16 = 1), one
+ *   tensor-core pass.  Head dims 64, 128 (all precisions), 192, 256 (single-pass precisions).
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct ttsb_mha_args {
   int B, T, H, dh;
@@ -150,11 +159,20 @@ typedef struct ttsb_mha_args {
   void* out_hi;
   void* out_lo;
   int ld_out;
-  /* optional: materialise softmax weights of ONE batch row (reference returns all; its callers read item 0) */
-  float* weights_out; /* (H,T,T) fp32 or NULL */
+  /* optional: materialised softmax weights, reference-exact fp32 (logits + mask * -1e9, softmax).
+   * weights_all = 0: ONE batch row, (H,T,Tk) (the ForwardTransformer's callers read item 0 only);
+   * weights_all = 1: every row, (B,H,T,Tk) (the Aligner's cross-attention is a model output, models.py:150-153) */
+  float* weights_out;
   int weights_batch_index;
   int precision;
   int impl;
+  /* ---- ABI 2 ---- */
+  const void* kv_hi;     /* NULL: self-attention */
+  const void* kv_lo;
+  int ld_kv, Tk;
+  int causal;
+  int full_queries;
+  int weights_all;
 } ttsb_mha_args;
 
 int ttsb_mha_fwd(const ttsb_mha_args* args, void* stream);
@@ -230,6 +248,16 @@ int ttsb_cast_bf16_pad(const float* x, int64_t rows, int C, void* out_bf16, int 
  * *loss_out; grad = weight * sign(pred - target) / numel (zero for rows >= Tt). */
 int ttsb_mae_loss(const float* pred, int B, int Tp, int Tt, int C, const float* target_f32, const int32_t* target_i32,
                   float weight, float* loss_out, float* grad, void* stream);
+/* Aligner losses.
+ * ttsb_scaled_ce_loss: utils/losses.py:4-21 new_scaled_crossentropy -- sparse softmax CE of logits (B,Tp,ld)[:, :Tt, :C] against
+ *   int targets (B,Tt); sample weight (target != 0) + (target == index) * (scaling - 1); Keras SUM_OVER_BATCH_SIZE
+ *   (sum / (B*Tt)); added to *loss_out.
+ * ttsb_diag_loss: utils/metrics.py:47-70 batch_diagonal_mask + models.py:189-205 -- mean over (b,h) of
+ *   sum_{q<q_len, k<k_len} att[b,h,q,k] * |k/k_len - q/q_len|, divided by 10; added to *loss_out. */
+int ttsb_scaled_ce_loss(const float* logits, int B, int Tp, int Tt, int C, int ld, const int32_t* targets, int index,
+                        float scaling, float* loss_out, void* stream);
+int ttsb_diag_loss(const float* att, int B, int H, int Tq, int Tk, const int32_t* q_len, const int32_t* k_len,
+                   float* loss_out, void* stream);
 int ttsb_expand_bwd(const float* dm, const int32_t* dur_int, int B, int Tp, int Tm, int d, float* dx, void* stream);
 int ttsb_embedding_bwd(const float* dx, const int32_t* tokens, int B, int T, int d, int vocab, float* demb, void* stream);
 /* d(pos_encoding_scalar) = sum dropout(g) * PE[t]; (drop_p, seed, site) regenerate the prologue dropout mask */

@@ -151,3 +151,69 @@ def ref_mha(q, k, v, kv_len, H, precision):
     w = torch.softmax(logits, -1)
     out = (w @ sp(v)).permute(0, 2, 1, 3).reshape(B, T, d)
     return out, w
+
+
+def run_mha_general(q, kv_k, kv_v, kv_len, H, *, precision='fp16', impl='tcgen05', causal=False, cross=False, full_queries=True,
+                    weights_all=False):
+    """General form of ttsb_mha_fwd: q fp32 (B,T,d); k,v fp32 (B,Tk,d).  cross=True keeps k|v in a second buffer."""
+    split = precision == 'bf16x3'
+    B, T, d = q.shape
+    Tk = kv_k.shape[1]
+    dh = d // H
+    m = lib.MhaArgs()
+    m.B, m.T, m.H, m.dh = B, T, H, dh
+    if cross:
+        qb_hi, qb_lo = _to16(q.contiguous(), precision, split)
+        kv = torch.cat([kv_k, kv_v], dim=-1).contiguous()
+        kv_hi, kv_lo = _to16(kv, precision, split)
+        m.qk_hi = qb_hi.data_ptr()
+        m.qk_lo = qb_lo.data_ptr() if split else None
+        m.ld_qk, m.q_col0 = d, 0
+        m.kv_hi = kv_hi.data_ptr()
+        m.kv_lo = kv_lo.data_ptr() if split else None
+        m.ld_kv, m.Tk, m.k_col0, m.v_col0 = 2 * d, Tk, 0, d
+    else:
+        assert Tk == T
+        qk = torch.cat([q, kv_k, kv_v], dim=-1).contiguous()
+        qk_hi, qk_lo = _to16(qk, precision, split)
+        m.qk_hi = qk_hi.data_ptr()
+        m.qk_lo = qk_lo.data_ptr() if split else None
+        m.ld_qk, m.q_col0, m.k_col0, m.v_col0 = 3 * d, 0, d, 2 * d
+    m.kv_len = kv_len.data_ptr()
+    out_hi = torch.full((B, T, d), float('nan'), device=DEV, dtype=torch.bfloat16)
+    out_lo = torch.full((B, T, d), float('nan'), device=DEV, dtype=torch.bfloat16)
+    m.out_hi = out_hi.data_ptr()
+    m.out_lo = out_lo.data_ptr()
+    m.ld_out = d
+    m.causal = int(causal)
+    m.full_queries = int(full_queries)
+    wts = None
+    if weights_all:
+        wts = torch.full((B, H, T, Tk), float('nan'), device=DEV)
+        m.weights_out = wts.data_ptr()
+        m.weights_all = 1
+    m.precision = {'bf16x3': lib.PREC_BF16X3, 'bf16': lib.PREC_BF16, 'fp16': lib.PREC_FP16}[precision]
+    m.impl = lib.IMPL_SIMT if impl == 'simt' else lib.IMPL_TCGEN05
+    lib.mha_fwd(m)
+    torch.cuda.synchronize()
+    return out_hi.float() + out_lo.float(), wts
+
+
+def ref_mha_general(q, k, v, kv_len, H, precision, causal=False):
+    """float64 CPU attention; additive -1e9 mask = max(key padding, look-ahead) (models.py:136-138, layers.py:186-187)."""
+    cast = {'bf16x3': lambda t: t.detach().cpu().double(), 'bf16': lambda t: t.detach().cpu().bfloat16().double(),
+            'fp16': lambda t: t.detach().cpu().half().double()}[precision]
+    q, k, v = cast(q), cast(k), cast(v)
+    B, T, d = q.shape
+    Tk = k.shape[1]
+    dh = d // H
+    sp = lambda t: t.reshape(B, t.shape[1], H, dh).permute(0, 2, 1, 3)
+    logits = sp(q) @ sp(k).transpose(-1, -2) / (dh ** 0.5)
+    mask = (torch.arange(Tk)[None, :] >= kv_len.cpu()[:, None]).double()[:, None, None, :].expand(B, 1, T, Tk)
+    if causal:
+        look = (torch.arange(Tk)[None, :] > torch.arange(T)[:, None]).double()[None, None]
+        mask = torch.maximum(mask, look)
+    logits = (logits.float() + (mask * -1e9).float()).double()
+    w = torch.softmax(logits, -1)
+    out = (w @ sp(v)).permute(0, 2, 1, 3).reshape(B, T, d)
+    return out, w

@@ -297,6 +297,33 @@ def test_mha_varlen(impl, precision, H, d, T):
     assert torch.isfinite(out).all()
 
 
+@pytest.mark.parametrize('impl', ['tcgen05', 'simt'])
+@pytest.mark.parametrize('precision,H,d,T,Tk,causal,cross', [
+    ('fp16', 4, 256, 300, 300, True, False),     # Aligner decoder self-attention: look-ahead + padding (models.py:136-138)
+    ('fp16', 1, 256, 200, 200, True, False),     # last decoder block: one head of 256
+    ('fp16', 4, 256, 333, 77, False, True),      # cross-attention onto the encoder output
+    ('fp16', 1, 256, 130, 45, False, True),
+    ('bf16x3', 4, 256, 140, 70, False, True),
+    ('bf16x3', 2, 256, 260, 260, True, False),
+    ('bf16', 4, 256, 129, 129, True, False),
+])
+def test_mha_causal_and_cross(impl, precision, H, d, T, Tk, causal, cross):
+    from gpu_util import ref_mha_general, run_mha_general
+    g = torch.Generator().manual_seed(21)
+    B = 3
+    q = torch.randn(B, T, d, generator=g).to(DEV)
+    k = torch.randn(B, Tk, d, generator=g).to(DEV)
+    v = torch.randn(B, Tk, d, generator=g).to(DEV)
+    lens = torch.tensor([Tk, max(1, Tk // 3), min(Tk, 65)], dtype=torch.int32, device=DEV)
+    out, wts = run_mha_general(q, k, v, lens, H, precision=precision, impl=impl, causal=causal, cross=cross,
+                               full_queries=True, weights_all=True)
+    ref, wref = ref_mha_general(q, k, v, lens, H, precision, causal=causal)
+    tol = {'bf16x3': 5e-5, 'bf16': 8e-3, 'fp16': 1e-3}[precision]
+    assert torch.isfinite(out).all()
+    assert _relerr(out, ref) < tol                      # every query row, padded ones included (full_queries)
+    assert (wts.cpu().double() - wref).abs().max() < (1e-5 if precision == 'bf16x3' else 5e-3)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # STFT -> mel -> log
 # ----------------------------------------------------------------------------------------------------------

@@ -37,6 +37,9 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 struct MhaKParams {
   int B, T, H;
+  int Tk;            // key/value rows (== T for self-attention)
+  int causal;        // keys > query index are masked
+  int full_queries;  // 0: query rows >= kv_len[b] are written as zeros
   int q_col0, k_col0, v_col0;
   const int* kv_len;
   __nv_bfloat16* out_hi;
@@ -104,10 +107,10 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   int len = __ldg(p.kv_len + b);
-  len = len < 0 ? 0 : (len > p.T ? p.T : len);
+  len = len < 0 ? 0 : (len > p.Tk ? p.Tk : len);
 
-  if (q0 >= len) {
-    // whole query tile is padding: defined (zero) output, no tensor work
+  if (len == 0 || (!p.full_queries && q0 >= len)) {
+    // whole query tile is padding (or no key at all): defined (zero) output, no tensor work
     if (warp < kMmaWarp) {
       const int t = q0 + quarter * 32 + lane;
       if (t < p.T) {
@@ -120,7 +123,8 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
     }
     return;
   }
-  const int n_kv = (len + ATT_BKV - 1) / ATT_BKV;
+  int n_kv = (len + ATT_BKV - 1) / ATT_BKV;
+  if (p.causal) n_kv = min(n_kv, (q0 + ATT_BQ + ATT_BKV - 1) / ATT_BKV);  // key tiles beyond the last query row are all masked
 
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1);
@@ -305,6 +309,11 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
         for (int i = 0; i < SW; ++i)
           if (j * ATT_BKV + half * SW + i >= len) s[i] = -INFINITY;
       }
+      if (p.causal && (j + 1) * ATT_BKV - 1 > q0) {  // look-ahead mask: tiles that reach past the first query row of this CTA
+#pragma unroll
+        for (int i = 0; i < SW; ++i)
+          if (j * ATT_BKV + half * SW + i > tq) s[i] = -INFINITY;
+      }
       float mx = s[0];
 #pragma unroll
       for (int i = 1; i < SW; ++i) mx = fmaxf(mx, s[i]);
@@ -424,12 +433,16 @@ struct MhaSimtPtrs {
   const __nv_bfloat16* qk_hi;
   const __nv_bfloat16* qk_lo;
   int ld_qk;
+  const __nv_bfloat16* kv_hi;  // == qk_hi for self-attention
+  const __nv_bfloat16* kv_lo;
+  int ld_kv;
   int dh;
   int f16;           // operands hold IEEE fp16 bit patterns
   float scale;       // 1/sqrt(dh)
-  float* weights;    // (H,T,T) or null
+  float* weights;    // (H,T,Tk), (B,H,T,Tk) with weights_all, or null
   int weights_b;
-  int weights_only;  // 1: only fill weights for batch row weights_b
+  int weights_all;
+  int weights_only;  // 1: only fill weights (for batch row weights_b, or every row with weights_all)
 };
 
 __device__ __forceinline__ float ld_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t i, int f16 = 0) {
@@ -441,26 +454,27 @@ __device__ __forceinline__ float ld_split(const __nv_bfloat16* hi, const __nv_bf
 
 __global__ void mha_simt_kernel(const MhaKParams p, const MhaSimtPtrs q) {
   const int tq = blockIdx.x, h = blockIdx.y;
-  const int b = q.weights_only ? q.weights_b : blockIdx.z;
-  extern __shared__ float sm[];  // T logits + dh query + scratch
+  const int b = (q.weights_only && !q.weights_all) ? q.weights_b : blockIdx.z;
+  extern __shared__ float sm[];  // Tk logits + dh query + scratch
   float* logit = sm;
-  float* qv = sm + p.T;
+  float* qv = sm + p.Tk;
   __shared__ float red[32];
-  const int len = min(max(p.kv_len[b], 0), p.T);
+  const int len = min(max(p.kv_len[b], 0), p.Tk);
   const size_t qrow = ((size_t)b * p.T + tq) * q.ld_qk;
   for (int c = threadIdx.x; c < q.dh; c += blockDim.x) qv[c] = ld_split(q.qk_hi, q.qk_lo, qrow + p.q_col0 + h * q.dh + c, q.f16);
   __syncthreads();
-  for (int tk = threadIdx.x; tk < p.T; tk += blockDim.x) {
-    const size_t krow = ((size_t)b * p.T + tk) * q.ld_qk + p.k_col0 + h * q.dh;
+  for (int tk = threadIdx.x; tk < p.Tk; tk += blockDim.x) {
+    const size_t krow = ((size_t)b * p.Tk + tk) * q.ld_kv + p.k_col0 + h * q.dh;
     float acc = 0.f;
-    for (int c = 0; c < q.dh; ++c) acc = fmaf(qv[c], ld_split(q.qk_hi, q.qk_lo, krow + c, q.f16), acc);
+    for (int c = 0; c < q.dh; ++c) acc = fmaf(qv[c], ld_split(q.kv_hi, q.kv_lo, krow + c, q.f16), acc);
     acc = acc * q.scale;
-    if (tk >= len) acc += -1e9f;  // reference: logits += mask * -1e9
+    // reference: logits += mask * -1e9 with mask = max(padding, look-ahead) in {0,1} (models.py:136-138, layers.py:186-187)
+    if (tk >= len || (p.causal && tk > tq)) acc += -1e9f;
     logit[tk] = acc;
   }
   __syncthreads();
   float mx = -INFINITY;
-  for (int tk = threadIdx.x; tk < p.T; tk += blockDim.x) mx = fmaxf(mx, logit[tk]);
+  for (int tk = threadIdx.x; tk < p.Tk; tk += blockDim.x) mx = fmaxf(mx, logit[tk]);
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
@@ -468,7 +482,7 @@ __global__ void mha_simt_kernel(const MhaKParams p, const MhaSimtPtrs q) {
   for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
   __syncthreads();
   float sum = 0.f;
-  for (int tk = threadIdx.x; tk < p.T; tk += blockDim.x) {
+  for (int tk = threadIdx.x; tk < p.Tk; tk += blockDim.x) {
     const float e = expf(logit[tk] - mx);
     logit[tk] = e;
     sum += e;
@@ -479,15 +493,16 @@ __global__ void mha_simt_kernel(const MhaKParams p, const MhaSimtPtrs q) {
   sum = 0.f;
   for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
   const float inv = 1.f / sum;
-  if (q.weights && b == q.weights_b) {
-    for (int tk = threadIdx.x; tk < p.T; tk += blockDim.x) q.weights[((size_t)h * p.T + tq) * p.T + tk] = logit[tk] * inv;
+  if (q.weights && (q.weights_all || b == q.weights_b)) {
+    float* wrow = q.weights + (((size_t)(q.weights_all ? b : 0) * p.H + h) * p.T + tq) * p.Tk;
+    for (int tk = threadIdx.x; tk < p.Tk; tk += blockDim.x) wrow[tk] = logit[tk] * inv;
   }
   if (q.weights_only) return;
   for (int c = threadIdx.x; c < q.dh; c += blockDim.x) {
     const size_t vcol = (size_t)p.v_col0 + h * q.dh + c;
     float acc = 0.f;
-    for (int tk = 0; tk < p.T; ++tk)
-      acc = fmaf(logit[tk], ld_split(q.qk_hi, q.qk_lo, ((size_t)b * p.T + tk) * q.ld_qk + vcol, q.f16), acc);
+    for (int tk = 0; tk < p.Tk; ++tk)
+      acc = fmaf(logit[tk], ld_split(q.kv_hi, q.kv_lo, ((size_t)b * p.Tk + tk) * q.ld_kv + vcol, q.f16), acc);
     acc *= inv;
     __nv_bfloat16 hi, lo;
     split_bf16(acc, hi, lo);
@@ -501,11 +516,15 @@ template <int DH, bool kSplit, bool kF16, bool kWide>
 static int launch_tc(const ttsb_mha_args* a, const MhaKParams& p, cudaStream_t stream) {
   using Cfg = MhaCfg<DH, kSplit>;
   CUtensorMap tmQ[2], tmK[2];
+  const bool cross = a->kv_hi != nullptr;
+  const int Tk = cross ? a->Tk : a->T;
+  const int ld_kv = cross ? a->ld_kv : a->ld_qk;
   for (int hl = 0; hl < 2; ++hl) {
     const void* qk = hl == 0 ? a->qk_hi : (kSplit ? a->qk_lo : a->qk_hi);
+    const void* kv = cross ? (hl == 0 ? a->kv_hi : (kSplit ? a->kv_lo : a->kv_hi)) : qk;
     int rc = make_tmap_bf16_3d(&tmQ[hl], qk, (uint64_t)a->ld_qk, a->T, a->B, a->ld_qk, (uint64_t)a->ld_qk * a->T, 64, ATT_BQ);
     if (rc) return rc;
-    rc = make_tmap_bf16_3d(&tmK[hl], qk, (uint64_t)a->ld_qk, a->T, a->B, a->ld_qk, (uint64_t)a->ld_qk * a->T, 64, ATT_BKV);
+    rc = make_tmap_bf16_3d(&tmK[hl], kv, (uint64_t)ld_kv, Tk, a->B, ld_kv, (uint64_t)ld_kv * Tk, 64, ATT_BKV);
     if (rc) return rc;
   }
   static bool attr_set = false;
@@ -530,6 +549,13 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   const bool split = a->precision == TTSB_PREC_BF16X3;
   const bool f16 = a->precision == TTSB_PREC_FP16;
   if (split && (!a->qk_lo || !a->out_lo)) { set_last_error("ttsb_mha_fwd: bf16x3 needs the lo planes"); return TTSB_ERR_INVALID_ARGUMENT; }
+  const bool cross = a->kv_hi != nullptr;
+  if (cross && (a->Tk <= 0 || a->ld_kv % 8 || (split && !a->kv_lo))) {
+    set_last_error("ttsb_mha_fwd: cross-attention needs Tk > 0, ld_kv %% 8 == 0 and (bf16x3) the kv lo plane");
+    return TTSB_ERR_INVALID_ARGUMENT;
+  }
+  if (cross && !a->full_queries) { set_last_error("ttsb_mha_fwd: cross-attention computes every query row (set full_queries = 1)"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if (a->causal && cross) { set_last_error("ttsb_mha_fwd: the look-ahead mask applies to self-attention only"); return TTSB_ERR_INVALID_ARGUMENT; }
   if (a->ld_qk % 8 || a->ld_out % 16 || a->q_col0 % 8 || a->k_col0 % 8 || a->v_col0 % 8) {
     set_last_error("ttsb_mha_fwd: leading dimensions / column offsets must be multiples of 8");
     return TTSB_ERR_INVALID_ARGUMENT;
@@ -537,6 +563,9 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   MhaKParams p{};
   p.B = a->B; p.T = a->T; p.H = a->H;
+  p.Tk = cross ? a->Tk : a->T;
+  p.causal = a->causal ? 1 : 0;
+  p.full_queries = a->full_queries ? 1 : 0;
   p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0; p.kv_len = a->kv_len;
   p.out_hi = static_cast<__nv_bfloat16*>(a->out_hi);
   p.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);  // optional second plane of the OUTPUT (consumer may be bf16x3)
@@ -553,12 +582,25 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   q.qk_hi = static_cast<const __nv_bfloat16*>(a->qk_hi);
   q.qk_lo = split ? static_cast<const __nv_bfloat16*>(a->qk_lo) : nullptr;
   q.ld_qk = a->ld_qk;
+  q.kv_hi = cross ? static_cast<const __nv_bfloat16*>(a->kv_hi) : q.qk_hi;
+  q.kv_lo = cross ? (split ? static_cast<const __nv_bfloat16*>(a->kv_lo) : nullptr) : q.qk_lo;
+  q.ld_kv = cross ? a->ld_kv : a->ld_qk;
   q.dh = a->dh;
   q.scale = 1.f / sqrtf((float)a->dh);
   q.f16 = f16 ? 1 : 0;
   q.weights = a->weights_out;
   q.weights_b = a->weights_batch_index;
-  const size_t simt_smem = (size_t)(a->T + a->dh) * sizeof(float);
+  q.weights_all = a->weights_all ? 1 : 0;
+  const size_t simt_smem = (size_t)(p.Tk + a->dh) * sizeof(float);
+  const bool need_simt = a->impl == TTSB_IMPL_SIMT || a->weights_out != nullptr;
+  if (need_simt && simt_smem > 200 * 1024) { set_last_error("ttsb_mha_fwd: Tk too large for the weights / SIMT kernel"); return TTSB_ERR_UNSUPPORTED; }
+  if (need_simt && simt_smem > 48 * 1024) {
+    static size_t simt_attr = 0;
+    if (simt_smem > simt_attr) {
+      TTSB_CUDA_OK(cudaFuncSetAttribute(mha_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt_smem));
+      simt_attr = simt_smem;
+    }
+  }
 
   if (a->impl == TTSB_IMPL_SIMT) {
     q.weights_only = 0;
@@ -577,12 +619,13 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   if (a->dh == 128) rc = narrow ? TTSB_MHA_DISPATCH(128, false) : TTSB_MHA_DISPATCH(128, true);
   else if (a->dh == 64) rc = narrow ? TTSB_MHA_DISPATCH(64, false) : TTSB_MHA_DISPATCH(64, true);
   else if (a->dh == 192 && !split) rc = narrow ? TTSB_MHA_DISPATCH1(192, false) : TTSB_MHA_DISPATCH1(192, true);
-  else { set_last_error("ttsb_mha_fwd: head_dim %d not supported by the tcgen05 kernel (64, 128; 192 in single-pass modes)", a->dh); return TTSB_ERR_UNSUPPORTED; }
+  else if (a->dh == 256 && !split) rc = narrow ? TTSB_MHA_DISPATCH1(256, false) : TTSB_MHA_DISPATCH1(256, true);
+  else { set_last_error("ttsb_mha_fwd: head_dim %d not supported by the tcgen05 kernel (64, 128; 192, 256 in single-pass modes)", a->dh); return TTSB_ERR_UNSUPPORTED; }
   if (rc) return rc;
   if (a->weights_out) {
-    if (a->weights_batch_index < 0 || a->weights_batch_index >= a->B) { set_last_error("ttsb_mha_fwd: weights_batch_index out of range"); return TTSB_ERR_INVALID_ARGUMENT; }
+    if (!a->weights_all && (a->weights_batch_index < 0 || a->weights_batch_index >= a->B)) { set_last_error("ttsb_mha_fwd: weights_batch_index out of range"); return TTSB_ERR_INVALID_ARGUMENT; }
     q.weights_only = 1;
-    mha_simt_kernel<<<dim3(a->T, a->H, 1), 128, simt_smem, stream>>>(p, q);
+    mha_simt_kernel<<<dim3(a->T, a->H, a->weights_all ? a->B : 1), 128, simt_smem, stream>>>(p, q);
     count_launch();
     return check_cuda(cudaGetLastError(), "mha weights kernel launch");
   }

@@ -277,6 +277,64 @@ __global__ void mae_loss_kernel(const float* __restrict__ pred, int64_t B, int64
 }
 
 // ------------------------------------------------------------------------------------------------
+// Aligner losses
+//   scaled_ce: utils/losses.py:4-21 -- sparse softmax cross entropy of logits (B,Tp,C)[:, :Tt] vs int targets (B,Tt),
+//     weight = (target != 0) + (target == index) * (scaling - 1), Keras SUM_OVER_BATCH_SIZE: sum / (B*Tt)
+//   diag_loss: utils/metrics.py:47-70 + models.py:189-205 -- mean over (b,h) of sum_{q,k} att * |k/k_len - q/q_len| / 10
+// ------------------------------------------------------------------------------------------------
+__global__ void scaled_ce_kernel(const float* __restrict__ logits, int64_t B, int64_t Tp, int64_t Tt, int C, int ld,
+                                 const int* __restrict__ tgt, int index, float scaling, float* __restrict__ loss_out) {
+  const int64_t n = B * Tt;
+  float local = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / Tt, t = i % Tt;
+    const float* row = logits + (b * Tp + t) * ld;
+    const int y = tgt[i];
+    float mx = row[0];
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, row[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(row[c] - mx);
+    const float ce = (y >= 0 && y < C) ? (logf(se) + mx - row[y]) : 0.f;
+    const float w = (y != 0 ? 1.f : 0.f) + (y == index ? scaling - 1.f : 0.f);
+    local += ce * w;
+  }
+  local = wsum(local);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    atomicAdd(loss_out, s / (float)n);
+  }
+}
+
+__global__ void diag_loss_kernel(const float* __restrict__ att, int H, int Tq, int Tk, const int* __restrict__ q_len,
+                                 const int* __restrict__ k_len, float scale, float* __restrict__ loss_out) {
+  const int bh = blockIdx.x;
+  const int b = bh / H;
+  const int max_m = min(max(q_len[b], 0), Tq);  // metrics.py:62-64
+  const int max_n = min(max(k_len[b], 0), Tk);
+  const float* a = att + (size_t)bh * Tq * Tk;
+  float local = 0.f;
+  for (int i = threadIdx.x; i < max_m * max_n; i += blockDim.x) {
+    const int q = i / max_n, k = i % max_n;
+    // the reference divides int32 ranges (-> float64), takes |.|, then casts the mask to float32
+    const float m = (float)fabs((double)k / (double)max_n - (double)q / (double)max_m);
+    local += a[(size_t)q * Tk + k] * m;
+  }
+  local = wsum(local);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    atomicAdd(loss_out, s * scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Expand backward: dx[b,i,:] = sum of dm[b, t, :] over the frames t copied from phoneme i (contiguous segment)
 // ------------------------------------------------------------------------------------------------
 __global__ void expand_bwd_kernel(const float* __restrict__ dm, const int* __restrict__ dur, int Tp, int Tm, int d,
@@ -473,6 +531,21 @@ extern "C" int ttsb_mae_loss(const float* pred, int B, int Tp, int Tt, int C, co
     return bad("ttsb_mae_loss: bad arguments (need Tt <= Tp)");
   mae_loss_kernel<<<592, 256, 0, STREAM(stream)>>>(pred, B, Tp, Tt, C, target_f32, target_i32, weight, loss_out, grad);
   LAUNCH_OK("mae_loss_kernel");
+}
+
+extern "C" int ttsb_scaled_ce_loss(const float* logits, int B, int Tp, int Tt, int C, int ld, const int32_t* targets, int index,
+                                   float scaling, float* loss_out, void* stream) {
+  if (!logits || !targets || !loss_out || B <= 0 || Tp <= 0 || Tt <= 0 || Tt > Tp || C <= 0 || ld < C)
+    return bad("ttsb_scaled_ce_loss: bad arguments (need Tt <= Tp, ld >= C)");
+  scaled_ce_kernel<<<148, 256, 0, STREAM(stream)>>>(logits, B, Tp, Tt, C, ld, targets, index, scaling, loss_out);
+  LAUNCH_OK("scaled_ce_kernel");
+}
+
+extern "C" int ttsb_diag_loss(const float* att, int B, int H, int Tq, int Tk, const int32_t* q_len, const int32_t* k_len,
+                              float* loss_out, void* stream) {
+  if (!att || !q_len || !k_len || !loss_out || B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0) return bad("ttsb_diag_loss: bad arguments");
+  diag_loss_kernel<<<B * H, 256, 0, STREAM(stream)>>>(att, H, Tq, Tk, q_len, k_len, 1.f / (10.f * (float)(B * H)), loss_out);
+  LAUNCH_OK("diag_loss_kernel");
 }
 
 extern "C" int ttsb_expand_bwd(const float* dm, const int32_t* dur_int, int B, int Tp, int Tm, int d, float* dx, void* stream) {

@@ -26,7 +26,7 @@ EXPORTS = [
     'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
     'ttsb_expand_ln_pe_fwd', 'ttsb_mel_lengths', 'ttsb_phoneme_lengths', 'ttsb_stft_mel_log',
     'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
-    'ttsb_relu_bwd', 'ttsb_colsum_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
+    'ttsb_relu_bwd', 'ttsb_colsum_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_scaled_ce_loss', 'ttsb_diag_loss', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
     'ttsb_pitch_embed_bwd', 'ttsb_statpred_head_bwd', 'ttsb_adam_tf_step', 'ttsb_embed_ln_pe_train_fwd',
     'ttsb_expand_ln_pe_train_fwd',
 ]
@@ -86,6 +86,8 @@ class MhaArgs(C.Structure):
         ('v_col0', C.c_int), ('kv_len', C.c_void_p),
         ('out_hi', C.c_void_p), ('out_lo', C.c_void_p), ('ld_out', C.c_int),
         ('weights_out', C.c_void_p), ('weights_batch_index', C.c_int), ('precision', C.c_int), ('impl', C.c_int),
+        ('kv_hi', C.c_void_p), ('kv_lo', C.c_void_p), ('ld_kv', C.c_int), ('Tk', C.c_int), ('causal', C.c_int),
+        ('full_queries', C.c_int), ('weights_all', C.c_int),
     ]
 
 
@@ -290,6 +292,17 @@ def mae_loss(pred, B, Tp, Tt, Cc, target, weight, loss_out, grad):
     ti = ptr(target) if target.dtype == torch.int32 else None
     _check(load().ttsb_mae_loss(ptr(pred), B, Tp, Tt, Cc, tf, ti, C.c_float(weight), ptr(loss_out), ptr(grad), _stream()),
            'ttsb_mae_loss')
+
+
+def scaled_ce_loss(logits, Tt, Cc, targets, index, scaling, loss_out):
+    B, Tp, ld = logits.shape
+    _check(load().ttsb_scaled_ce_loss(ptr(logits), B, Tp, Tt, Cc, ld, ptr(targets), int(index), C.c_float(scaling), ptr(loss_out),
+                                      _stream()), 'ttsb_scaled_ce_loss')
+
+
+def diag_loss(att, q_len, k_len, loss_out):
+    B, H, Tq, Tk = att.shape
+    _check(load().ttsb_diag_loss(ptr(att), B, H, Tq, Tk, ptr(q_len), ptr(k_len), ptr(loss_out), _stream()), 'ttsb_diag_loss')
 
 
 def expand_bwd(dm, dur_int, dx):

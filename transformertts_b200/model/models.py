@@ -429,9 +429,11 @@ class ForwardTransformer:
         m.ld_out = d
         wts = None
         if attn_out is not None and self.return_attention_weights:
-            wts = torch.empty((1, H, T, T), dtype=torch.float32, device=dev)
+            all_rows = bool(getattr(self, '_weights_all', False))  # Aligner: attention maps of every row are outputs
+            wts = torch.empty((B if all_rows else 1, H, T, T), dtype=torch.float32, device=dev)
             m.weights_out = wts.data_ptr()
             m.weights_batch_index = 0
+            m.weights_all = int(all_rows)
         m.precision = {'fp16': lib.PREC_FP16, 'bf16': lib.PREC_BF16, 'bf16x3': lib.PREC_BF16X3}[ap]
         m.impl = self._impl
         lib.mha_fwd(m)
