@@ -15,6 +15,7 @@ import torch
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from oracle import audio_oracle as ao  # noqa: E402
+from oracle import aligner_oracle as alo  # noqa: E402
 from oracle import forward_oracle as fo  # noqa: E402
 
 OUT = Path(__file__).resolve().parent
@@ -44,6 +45,16 @@ def main():
     mels = np.stack([ao.mel_spectrogram(c) for c in clips])
     np.savez_compressed(OUT / 'audio_mel.npz', clips_seed=400, n_samples=11008, mel=mels,
                         mel_wavernn=ao.mel_spectrogram(clips[0], normalizer='WaveRNN'))
+    # Aligner: plumbing-size config, ragged batch of 3, teacher-forced forward + losses
+    acfg = alo.ALIGNER_CONFIGS['A-small']
+    ap = alo.init_aligner_params(acfg, seed=7)
+    tokens, amel, stop = alo.make_aligner_inputs(acfg, 3, 24, 61, seed=503)
+    aout = alo.gta_forward(ap, acfg, tokens, amel, stop, r=1, force_decoder_diagonal=True)
+    np.savez_compressed(OUT / 'aligner_small.npz', B=3, Tp=24, Tm=61, seed=503, mel=aout['mel'].numpy(),
+                        stop_prob=aout['stop_prob'].numpy(),
+                        last_attention=aout['decoder_attention']['Decoder_LastBlock_CrossAttention'].numpy(),
+                        loss=float(aout['loss']), mel_loss=float(aout['losses']['mel']),
+                        stop_loss=float(aout['losses']['stop_prob']), diag_loss=float(aout['losses']['diag_loss']))
     print('wrote', [f.name for f in OUT.glob('*.npz')])
 
 

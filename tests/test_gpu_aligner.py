@@ -1,0 +1,124 @@
+"""GPU parity of the Aligner teacher-forced forward + validation losses through the
+reference-facing API (Aligner.call / _val_step), against oracle/aligner_oracle.py and the committed golden vectors."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import aligner_oracle as alo
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / 'golden'
+TOL = 1e-3   # same bar as the text->mel path: fp32 outputs within 1e-3 abs
+ATT_TOL = 2e-3
+
+
+def _model(cfg_name, params, **kw):
+    from transformertts_b200.model.aligner import Aligner
+    cfg = alo.ALIGNER_CONFIGS[cfg_name]
+    m = Aligner.from_config(dict(cfg, **kw), max_r=cfg['max_r'])
+    m.set_weights(params)
+    return m
+
+
+def _cmp_outputs(out, ref, lens_q=None):
+    assert (out['mel'].cpu() - ref['mel']).abs().max() < TOL
+    assert (out['stop_prob'].cpu() - ref['stop_prob']).abs().max() < TOL
+    assert (out['linear'].cpu() - ref['linear']).abs().max() < TOL
+    assert set(out['decoder_attention']) == set(ref['decoder_attention'])
+    assert set(out['encoder_attention']) == set(ref['encoder_attention'])
+    for k, w in ref['decoder_attention'].items():
+        got = out['decoder_attention'][k].cpu()
+        assert got.shape == w.shape
+        assert (got - w).abs().max() < ATT_TOL, k
+    for k, w in ref['encoder_attention'].items():
+        assert (out['encoder_attention'][k].cpu() - w).abs().max() < ATT_TOL, k
+    assert torch.equal(out['mel_mask'].cpu(), ref['mel_mask'])
+    assert torch.equal(out['text_mask'].cpu(), ref['text_mask'])
+
+
+@pytest.mark.parametrize('impl', ['tcgen05', 'simt'])
+def test_aligner_small_golden_and_losses(impl):
+    g = np.load(GOLD / 'aligner_small.npz')
+    cfg = alo.ALIGNER_CONFIGS['A-small']
+    p = alo.init_aligner_params(cfg, seed=7)
+    tokens, mel, stop = alo.make_aligner_inputs(cfg, int(g['B']), int(g['Tp']), int(g['Tm']), seed=int(g['seed']))
+    m = _model('A-small', p, impl=impl)
+    m.set_constants(reduction_factor=1, force_decoder_diagonal=True)
+    out = m._val_step(tokens, mel, stop)
+    assert np.abs(out['mel'].cpu().numpy() - g['mel']).max() < TOL
+    assert np.abs(out['stop_prob'].cpu().numpy() - g['stop_prob']).max() < TOL
+    assert np.abs(out['decoder_attention']['Decoder_LastBlock_CrossAttention'].cpu().numpy() - g['last_attention']).max() < ATT_TOL
+    assert abs(float(out['losses']['mel']) - float(g['mel_loss'])) < 1e-3
+    assert abs(float(out['losses']['stop_prob']) - float(g['stop_loss'])) < 1e-3
+    assert abs(float(out['losses']['diag_loss']) - float(g['diag_loss'])) < 1e-3
+    assert abs(float(out['loss']) - float(g['loss'])) < 2e-3
+
+
+@pytest.mark.parametrize('r', [1, 2])
+def test_aligner_small_all_outputs_vs_oracle(r):
+    torch.set_num_threads(8)
+    cfg = alo.ALIGNER_CONFIGS['A-small']
+    p = alo.init_aligner_params(cfg, seed=7)
+    tokens, mel, _ = alo.make_aligner_inputs(cfg, 3, 30, 150, seed=504)
+    tgt = mel[:, 0::r].contiguous()
+    m = _model('A-small', p)
+    m.set_constants(reduction_factor=r)
+    out = m.call(tokens, tgt, training=False)
+    ref = alo.aligner_call(p, cfg, tokens, tgt, r=r)
+    assert out['mel'].shape == (3, tgt.shape[1] * r, 80)
+    _cmp_outputs(out, ref)
+
+
+def test_aligner_shipped_config_ragged_batch():
+    """aligner_settings as shipped (config/training_config.yaml:58-69): 4 encoder blocks of 4 heads, decoder heads
+    [4,4,4,4,1] -> the last block attends with ONE head of dimension 256."""
+    torch.set_num_threads(16)
+    cfg = alo.ALIGNER_CONFIGS['A5']
+    p = alo.init_aligner_params(cfg, seed=7)
+    tokens, mel, stop = alo.make_aligner_inputs(cfg, 3, 70, 333, seed=500)
+    m = _model('A5', p)
+    m.set_constants(reduction_factor=1, force_decoder_diagonal=True, force_encoder_diagonal=True)
+    out = m._val_step(tokens, mel, stop)
+    ref = alo.gta_forward(p, cfg, tokens, mel, stop, r=1, stop_scaling=8.0, force_decoder_diagonal=True, force_encoder_diagonal=True)
+    _cmp_outputs(out, ref)
+    for k in ('mel', 'stop_prob', 'diag_loss'):
+        assert abs(float(out['losses'][k]) - float(ref['losses'][k])) < 1e-3, k
+    assert out['decoder_attention']['Decoder_LastBlock_CrossAttention'].shape == (3, 1, 332, 70)
+
+
+def test_scaled_ce_kernel_matches_reference_known_answers():
+    """reference tests/test_loss.py:12-24 -- the same known answers, through the CUDA kernel."""
+    from transformertts_b200 import lib
+    dev = torch.device('cuda:0')
+    targets = torch.tensor([[0, 1, 2]], dtype=torch.int32, device=dev)
+    logits = torch.tensor([[[.3, .2, .1], [.3, .2, .1], [.3, .2, .1]]], dtype=torch.float32, device=dev)
+    for scaling, want in ((5.0, 2.3705523014068604), (1.0, 0.7679619193077087)):
+        out = torch.zeros(1, device=dev)
+        lib.scaled_ce_loss(logits, 3, 3, targets, 2, scaling, out)
+        assert abs(float(out) - want) < 1e-6
+
+
+def test_diag_loss_kernel_vs_oracle():
+    from transformertts_b200 import lib
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(3)
+    att = torch.softmax(torch.randn(3, 2, 50, 17, generator=g), -1)
+    q_len = torch.tensor([50, 31, 7], dtype=torch.int32)
+    k_len = torch.tensor([17, 9, 3], dtype=torch.int32)
+    want = (att * alo.batch_diagonal_mask(att, q_len, k_len)).sum((-2, -1)).mean() / 10.0
+    out = torch.zeros(1, device=dev)
+    lib.diag_loss(att.to(dev).contiguous(), q_len.to(dev), k_len.to(dev), out)
+    assert abs(float(out) - float(want)) < 1e-5
+
+
+def test_aligner_unbuilt_paths_fail_loudly():
+    from transformertts_b200 import lib
+    cfg = alo.ALIGNER_CONFIGS['A-small']
+    m = _model('A-small', alo.init_aligner_params(cfg, seed=7))
+    tokens, mel, stop = alo.make_aligner_inputs(cfg, 2, 12, 20, seed=1)
+    with pytest.raises(lib.TtsbError):
+        m._train_step(tokens, mel, stop)
+    with pytest.raises(lib.TtsbError):
+        m.call(tokens, mel, training=True)

@@ -66,6 +66,8 @@ class Aligner(ForwardTransformer):
         self.return_attention_weights = True      # attention maps are model outputs (models.py:150-153, 297)
         self._weights_all = True
         self.debug = debug
+        self.alphabet = kwargs.get('alphabet')
+        self.train_dropout = False
         self.max_r = int(max_r)
         self.r = int(max_r)                        # models.py:46 -- starts at max_r, lowered by the schedule via set_constants
         self.stop_prob_index = 2
@@ -444,5 +446,5 @@ class Aligner(ForwardTransformer):
                 'phoneme_language', 'with_stress', 'decoder_prenet_dropout', 'model_breathing',
                 'encoder_feed_forward_dimension', 'decoder_feed_forward_dimension')
         kw = {k: config[k] for k in keys if k in config}
-        extra = {k: config[k] for k in ('vocab_size', 'precision', 'attention_precision', 'device', 'seed', 'stop_loss_scaling') if k in config}
+        extra = {k: config[k] for k in ('vocab_size', 'precision', 'attention_precision', 'impl', 'device', 'seed', 'stop_loss_scaling') if k in config}
         return cls(max_r=max_r, debug=config.get('debug', False), **kw, **extra)
