@@ -314,6 +314,106 @@ def train_bench(args, rank, world, dev, cfg, params):
         print(json.dumps(line), flush=True)
 
 
+def aligner_flops(cfg, B, Tp, T, r=1):
+    """Algorithmic FLOPs of one teacher-forced Aligner forward (2 per multiply-add; the look-ahead mask halves the
+    decoder self-attention products)."""
+    de, dd, mel = cfg['encoder_model_dimension'], cfg['decoder_model_dimension'], cfg['mel_channels']
+    fe, fd = cfg['encoder_feed_forward_dimension'], cfg['decoder_feed_forward_dimension']
+    enc = len(cfg['encoder_num_heads']) * (2 * de * 3 * de + 2 * 2 * de * de + 4 * de * fe + 4 * Tp * de)
+    dec_layers = len(cfg['decoder_num_heads'])
+    dec = dec_layers * (2 * dd * 3 * dd + 4 * dd * dd + 2 * T * dd + 2 * dd * dd + 4 * dd * dd + 4 * Tp * dd + 4 * dd * fd)
+    kv = dec_layers * 2 * de * 2 * dd
+    pre = 2 * (mel * cfg['decoder_prenet_dimension'] + cfg['decoder_prenet_dimension'] * dd)
+    post = 2 * dd * r * mel + r * 2 * mel * (mel + 3)
+    return float(B) * (Tp * (enc + kv) + T * (dec + pre + post))
+
+
+def aligner_bench(args, rank, world, dev):
+    """BASELINE configs[4] (C5): Aligner teacher-forced step, batch 16, 800 mel frames, r = 1, aligner_settings as shipped.
+    Built so far: forward + validation losses (mel MAE, scaled stop CE, diagonal attention loss); no backward."""
+    import torch.distributed as dist
+    from oracle import aligner_oracle as alo
+    from transformertts_b200 import lib
+    from transformertts_b200.model.aligner import Aligner
+    B, Tp, T = 16, 130, 800
+    cfg = alo.ALIGNER_CONFIGS['A5']
+    params = alo.init_aligner_params(cfg, seed=7)
+    model = Aligner.from_config(dict(cfg, device=str(dev)), max_r=cfg['max_r'])
+    model.set_weights(params)
+    model.set_constants(reduction_factor=1, force_decoder_diagonal=True)
+    tok, mel, stop = alo.make_aligner_inputs(cfg, B, Tp, T + 1, seed=500 + rank, ragged=False)
+    tok_d, mel_d, stop_d = tok.to(dev), mel.to(dev), stop.to(dev)
+
+    def step():
+        return model._val_step(tok_d, mel_d, stop_d)
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = lib.launch_count()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    tok_h, mel_h, stop_h = tok.pin_memory(), mel.pin_memory(), stop.pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o = model._val_step(tok_h.to(dev, non_blocking=True), mel_h.to(dev, non_blocking=True), stop_h.to(dev, non_blocking=True))
+        loss_val = float(o['loss'])
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    peak_tf, _, peak_src = _peaks()
+    flops = aligner_flops(cfg, B, Tp, T)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        nthr = _pick_threads()
+        torch.set_num_threads(nthr)
+        rows = 2
+        with torch.no_grad():
+            alo.gta_forward(params, cfg, tok[:rows], mel[:rows], stop[:rows], r=1, force_decoder_diagonal=True)
+            c0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - c0 < 10.0:
+                alo.gta_forward(params, cfg, tok[:rows], mel[:rows], stop[:rows], r=1, force_decoder_diagonal=True)
+                reps += 1
+            cdt = time.perf_counter() - c0
+        cpu = {'value': reps * rows / B / cdt, 'unit': 'steps/s', 'cores': nthr, 'kind': 'port',
+               'sample': f'{reps} oracle passes over {rows} of the 16 rows in {cdt:.1f} s (torch CPU fp32), scaled to 16-row steps'}
+    if rank == 0:
+        sps = args.steps / (ms * 1e-3)
+        line = {'metric': 'aligner_teacher_forced_steps_per_sec', 'value': sps * world, 'unit': 'steps/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16x3 GEMMs + fp16 attention, fp32 accumulate', 'data': 'synthetic',
+                'config': {'workload': 'C5: Aligner teacher-forced forward + validation losses (mel MAE, scaled stop CE, diagonal loss), '
+                                       '16 rows/GPU, 130 tokens, 800 decoder frames, r=1, aligner_settings as shipped; backward not built',
+                           'model': 'A5', 'global_batch': B * world, 'seq_len': T, 'parallelism': f'independent replicas x{world}',
+                           'l2': 'working set (~0.6 GB of activations + attention maps) exceeds the 126 MB L2'},
+                'frames_per_sec': sps * B * T * world,
+                'e2e': {'value': args.steps / float(dt.item()) * world, 'unit': 'steps/s',
+                        'h2d_bytes_per_step': int(tok.numel() * 4 + mel.numel() * 4 + stop.numel() * 4), 'd2h_bytes_per_step': 4},
+                'gpu_launches': int(launches), 'clocks': clocks, 'loss': loss_val,
+                'roofline': {'bound': 'tensor', 'achieved': flops / (ms / args.steps * 1e-3) / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                             'frac': flops / (ms / args.steps * 1e-3) / 1e12 / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                             'kernel': 'whole step (algorithmic forward FLOPs); 63 small launches per step, launch-bound at this size'},
+                'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -322,7 +422,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'stft', 'expand'],
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'stft', 'expand', 'aligner'],
                     help="'train': BASELINE configs[2] (fwd+bwd+Adam, bf16, batch 32/GPU, NCCL data parallel); 'stft': configs[3] "
                          "(STFT->mel, 256 clips x 10 s); 'expand': the length regulator alone (C2-LR)")
     args = ap.parse_args()
@@ -353,6 +453,11 @@ def main():
     params = fo.init_params(cfg, seed=7)  # random-init weights of the named architecture
     if args.mode in ('stft', 'expand'):
         hbm_bench(args, rank, world, dev, cfg)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    if args.mode == 'aligner':
+        aligner_bench(args, rank, world, dev)
         if world > 1:
             dist.destroy_process_group()
         return

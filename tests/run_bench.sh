@@ -6,6 +6,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.jso
 python bench.py --mode train --steps 10 --warmup 3 > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err
 python bench.py --mode stft > gpurun_out/bench_stft.json 2> gpurun_out/bench_stft.err
 python bench.py --mode expand > gpurun_out/bench_expand.json 2> gpurun_out/bench_expand.err
+python bench.py --mode aligner > gpurun_out/bench_aligner.json 2> gpurun_out/bench_aligner.err
 ncu --metrics gpu__time_duration.sum --clock-control none -s 240 -c 200 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1300 -c 1200 --csv --log-file gpurun_out/launches_train.csv \

@@ -44,3 +44,29 @@ def test_scheduling_and_losses_mirror_reference():
     assert piecewise_linear_schedule(50, sched) == pytest.approx(7.5e-5)
     assert piecewise_linear_schedule(1000, sched) == pytest.approx(1e-5)
     assert reduction_schedule(90000, [[0, 10], [80000, 5], [100000, 2]]) == 5
+
+
+def test_aligner_host_mirror_parameters_and_persistence(tmp_path):
+    """Constructor / parameter dictionary / save-load of the Aligner mirror (no kernels involved: device='cpu')."""
+    import torch
+    from oracle import aligner_oracle as alo
+    from transformertts_b200 import lib
+    from transformertts_b200.model.aligner import Aligner
+    cfg = alo.ALIGNER_CONFIGS['A5']
+    m = Aligner.from_config(dict(cfg, device='cpu'), max_r=cfg['max_r'])
+    want = alo.init_aligner_params(cfg, seed=7)
+    shapes = m._param_shapes()
+    assert set(shapes) == set(want)
+    assert all(tuple(want[k].shape) == tuple(shapes[k]) for k in want)
+    m.set_weights(want)
+    m.save_model(tmp_path / 'aligner')
+    m2 = Aligner.load_model(tmp_path / 'aligner', device='cpu')
+    assert m2.max_r == cfg['max_r'] and m2.r == cfg['max_r']
+    assert all(torch.equal(m2.weights[k].cpu(), want[k]) for k in want)
+    m2.set_constants(reduction_factor=2, force_decoder_diagonal=True)
+    assert m2.r == 2 and m2.force_decoder_diagonal and not m2.force_encoder_diagonal
+    import pytest
+    with pytest.raises(lib.TtsbError):
+        m2._train_step(None, None, None)
+    with pytest.raises(lib.TtsbError):
+        m2.predict(None)

@@ -230,17 +230,33 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
     return;
   }
 
-  // ---- LayerNorm epilogue (single N tile): pass 1 builds v = acc + bias (+relu) (+residual) and parks it in TMEM
+  // ---- LayerNorm epilogue (single N tile), two passes over TMEM:
+  //   pass 1 builds v = acc + bias (+relu) (+dropout) (+residual), parks it back in TMEM and accumulates SHIFTED sums
+  //          s = sum(v - K), q = sum((v - K)^2) with K = the thread's first value (no cancellation: this is Welford's
+  //          statistic for the thread's column range, (mean_h, M2_h) = (K + s/n_h, q - s^2/n_h));
+  //   the two warps of a lane quarter (column halves) and, in pair mode, the two CTAs of the cluster combine their
+  //   (mean, M2, n) with Chan's parallel formula; pass 2 normalises.  TMEM loads and the residual row are fetched one
+  //   chunk ahead of their use.
   const float inv_n = 1.f / (float)ncols;
-  float sum = 0.f;
-  for (int ch = ch_begin; ch < ch_end; ++ch) {
+  uint32_t r2[16];
+  float res[16], res2[16];
+  const bool has_res = p.residual != nullptr && row_ok;
+  const float* res_row = has_res ? p.residual + orow * (size_t)p.ld_res + n0 : nullptr;
+  auto fetch = [&](int ch, uint32_t (&rr)[16], float (&rs)[16]) {
     const int c0 = ch << 4;
-    __syncwarp();
-    tmem_ld16(taddr + c0, r);
+    tmem_ld16(taddr + c0, rr);
+    if (has_res) {
+      ld_global_nc_v8f(res_row + c0, rs);
+      ld_global_nc_v8f(res_row + c0 + 8, rs + 8);
+    }
+  };
+  float s_sh = 0.f, q_sh = 0.f, shiftK = 0.f;
+  bool have_k = false;
+  auto pass1_chunk = [&](int ch, uint32_t (&rr)[16], float (&rs)[16]) {
+    const int c0 = ch << 4;
     if (p.bias) ldg16(p.bias + n0 + c0, aux);
-    tmem_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]);
+    for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(rr[j]);
     if (p.bias) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) y[j] += aux[j];
@@ -250,51 +266,78 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
       for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
     }
     if (p.drop_pre_p > 0.f) apply_dropout16(y, p.drop_pre_p, p.drop_seed, p.drop_pre_site, orow * (uint64_t)p.ld_out + n0 + c0);
-    if (p.residual && row_ok) {
-      ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + n0 + c0, aux);
-      ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + n0 + c0 + 8, aux + 8);
+    if (has_res) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) y[j] += aux[j];
+      for (int j = 0; j < 16; ++j) y[j] += rs[j];
     }
     if (partial) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) y[j] = (c0 + j < ncols) ? y[j] : 0.f;
     }
+    if (!have_k) { shiftK = y[0]; have_k = true; }   // column c0 of the first chunk is always a logical column when n_h > 0
+    if (partial) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      sum += y[j];
-      r[j] = __float_as_uint(y[j]);
+      for (int j = 0; j < 16; ++j) {
+        const float dv = (c0 + j < ncols) ? y[j] - shiftK : 0.f;
+        s_sh += dv;
+        q_sh = fmaf(dv, dv, q_sh);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float dv = y[j] - shiftK;
+        s_sh += dv;
+        q_sh = fmaf(dv, dv, q_sh);
+      }
     }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(y[j]);
     if (p.out_preln && row_ok) {
       float* dst = p.out_preln + orow * (size_t)p.ld_out + n0 + c0;
       st_global_v8f(dst, y);
       st_global_v8f(dst + 8, y + 8);
     }
-    tmem_st16(taddr + c0, r);
-  }
-  tmem_wait_st();
-  float mean = pair_sum(sum, red, half, row, quarter) * inv_n;  // mean over this CTA's columns
-  float ssq = 0.f;
-  for (int ch = ch_begin; ch < ch_end; ++ch) {
-    const int c0 = ch << 4;
-    __syncwarp();
-    tmem_ld16(taddr + c0, r);
-    tmem_wait_ld();
-    if (partial) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float dlt = (c0 + j < ncols) ? (__uint_as_float(r[j]) - mean) : 0.f;
-        ssq += dlt * dlt;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float dlt = __uint_as_float(r[j]) - mean;
-        ssq += dlt * dlt;
-      }
+    tmem_st16(taddr + c0, rr);
+  };
+  __syncwarp();
+  if (ch_begin < ch_end) fetch(ch_begin, r, res);
+  for (int ch = ch_begin; ch < ch_end; ch += 2) {
+    tmem_wait_ld_tied(r);
+    if (ch + 1 < ch_end) fetch(ch + 1, r2, res2);
+    pass1_chunk(ch, r, res);
+    if (ch + 1 < ch_end) {
+      tmem_wait_ld_tied(r2);
+      if (ch + 2 < ch_end) fetch(ch + 2, r, res);
+      pass1_chunk(ch + 1, r2, res2);
     }
   }
-  float m2 = pair_sum(ssq, red + 2 * GEMM_BM, half, row, quarter);
+  tmem_wait_st();
+  // (mean, M2, n) of this thread's column range, then of the CTA's columns (half 0 is always operand 'a': both warps of
+  // the pair evaluate the same expression and get bit-identical statistics)
+  const int n_mine = max(0, min(ncols, ch_end << 4) - (ch_begin << 4));
+  const float nf = (float)n_mine;
+  float mean_h = 0.f, m2_h = 0.f;
+  if (n_mine > 0) {
+    mean_h = shiftK + s_sh / nf;
+    m2_h = fmaxf(q_sh - s_sh * s_sh / nf, 0.f);
+  }
+  float* red_m2 = red + 2 * GEMM_BM;
+  red[half * GEMM_BM + row] = mean_h;
+  red_m2[half * GEMM_BM + row] = m2_h;
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+  const float mean_o = red[(half ^ 1) * GEMM_BM + row], m2_o = red_m2[(half ^ 1) * GEMM_BM + row];
+  const float n_a = half == 0 ? nf : (float)(ncols - n_mine), n_b = (float)ncols - n_a;
+  const float mean_a = half == 0 ? mean_h : mean_o, mean_b = half == 0 ? mean_o : mean_h;
+  const float m2_a = half == 0 ? m2_h : m2_o, m2_b = half == 0 ? m2_o : m2_h;
+  float mean, m2;
+  if (n_b > 0.f && n_a > 0.f) {
+    const float delta = mean_b - mean_a;
+    mean = mean_a + delta * (n_b * inv_n);
+    m2 = m2_a + m2_b + delta * delta * (n_a * n_b * inv_n);
+  } else {
+    mean = n_a > 0.f ? mean_a : mean_b;
+    m2 = n_a > 0.f ? m2_a : m2_b;
+  }
   float n_total = (float)ncols;
   if (px.active) {
     // combine with the peer CTA's half of the row (Chan et al.): exact two-pass statistics with ONE exchange
@@ -310,16 +353,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
     n_total = 2.f * (float)ncols;
   }
   const float rstd = rsqrtf(m2 / n_total + p.eps);
-  for (int ch = ch_begin; ch < ch_end; ++ch) {
+  auto pass2_chunk = [&](int ch, uint32_t (&rr)[16]) {
     const int c0 = ch << 4;
-    __syncwarp();
-    tmem_ld16(taddr + c0, r);
     float bt[16];
     ldg16(p.gamma + n0 + c0, aux);
     ldg16(p.beta + n0 + c0, bt);
-    tmem_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) y[j] = (__uint_as_float(r[j]) - mean) * rstd * aux[j] + bt[j];
+    for (int j = 0; j < 16; ++j) y[j] = (__uint_as_float(rr[j]) - mean) * rstd * aux[j] + bt[j];
     if (p.drop_post_p > 0.f) apply_dropout16(y, p.drop_post_p, p.drop_seed, p.drop_post_site, orow * (uint64_t)p.ld_out + n0 + c0);
     if (partial) {
 #pragma unroll
@@ -330,6 +370,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
       for (int j = 0; j < 16; ++j) y[j] = 0.f;
     }
     if (row_ok) store_chunk(p, orow, n0 + c0, y);
+  };
+  __syncwarp();
+  if (ch_begin < ch_end) tmem_ld16(taddr + (ch_begin << 4), r);
+  for (int ch = ch_begin; ch < ch_end; ch += 2) {
+    tmem_wait_ld_tied(r);
+    if (ch + 1 < ch_end) tmem_ld16(taddr + ((ch + 1) << 4), r2);
+    pass2_chunk(ch, r);
+    if (ch + 1 < ch_end) {
+      tmem_wait_ld_tied(r2);
+      if (ch + 2 < ch_end) tmem_ld16(taddr + ((ch + 2) << 4), r);
+      pass2_chunk(ch + 1, r2);
+    }
   }
 }
 

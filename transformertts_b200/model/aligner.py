@@ -447,4 +447,4 @@ class Aligner(ForwardTransformer):
                 'encoder_feed_forward_dimension', 'decoder_feed_forward_dimension')
         kw = {k: config[k] for k in keys if k in config}
         extra = {k: config[k] for k in ('vocab_size', 'precision', 'attention_precision', 'impl', 'device', 'seed', 'stop_loss_scaling') if k in config}
-        return cls(max_r=max_r, debug=config.get('debug', False), **kw, **extra)
+        return cls(max_r=int(config.get('max_r', max_r)), debug=config.get('debug', False), **kw, **extra)

@@ -7,6 +7,7 @@ from typing import Tuple
 import torch
 import yaml
 
+from .aligner import Aligner
 from .models import ForwardTransformer
 
 
@@ -27,6 +28,26 @@ def tts_custom(config_path: str, weights_path: str) -> Tuple[ForwardTransformer,
     with open(config_path, 'rb') as f:
         config = _flatten(yaml.safe_load(f))
     model = ForwardTransformer.from_config(config)
+    model.build_model_weights()
+    wp = Path(weights_path)
+    if wp.is_dir():
+        wp = wp / 'model_weights.pt'
+    model.set_weights(torch.load(wp, map_location='cpu'))
+    return model, config
+
+
+def aligner_custom(config_path: str, weights_path: str) -> Tuple[Aligner, dict]:
+    """reference: model/factory.py:32-39.  weights_path: ``model_weights.pt`` with the flat parameter dictionary
+    documented in transformertts_b200/model/aligner.py (or the directory holding it)."""
+    with open(config_path, 'rb') as f:
+        raw = yaml.safe_load(f)
+    config = {}
+    if 'aligner_settings' in raw:
+        for key in ('paths', 'naming', 'training_data_settings', 'audio_settings', 'text_settings', 'aligner_settings'):
+            config.update(raw.get(key, {}))
+    else:
+        config = dict(raw)
+    model = Aligner.from_config(config, max_r=int(config.get('max_r', 10)))
     model.build_model_weights()
     wp = Path(weights_path)
     if wp.is_dir():

@@ -621,11 +621,13 @@ class ForwardTransformer:
         torch.save({k: v.cpu() for k, v in self.weights.items()}, path / 'model_weights.pt')
 
     @classmethod
-    def load_model(cls, path):
+    def load_model(cls, path, **overrides):
+        """reference: model/models.py:621-638.  ``overrides`` (e.g. device=..., precision=...) update the stored config."""
         import yaml
         path = Path(path)
         with open(path / 'config.yaml', 'r') as f:
             config = yaml.safe_load(f)
+        config.update(overrides)
         model = cls.from_config(config)
         model.set_weights(torch.load(path / 'model_weights.pt', map_location='cpu'))
         return model
