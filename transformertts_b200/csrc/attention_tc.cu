@@ -512,6 +512,89 @@ __global__ void mha_simt_kernel(const MhaKParams p, const MhaSimtPtrs q) {
   }
 }
 
+// ----------------------------------------------------------------------------------------------------
+// Attention weights as a model output (reference-exact fp32: logits + mask * -1e9, softmax; layers.py:176-195).
+// Block = 32 queries of one (batch row, head); key tiles of 32 rows are staged through shared memory as fp32
+// (hi + lo recombined), lane = key, each warp owns 4 queries.  Three light passes over the (L2-resident) output row:
+// logits + running max, exp + sum, scale.  Row stride DH + 4 floats keeps the 128-bit shared loads conflict-free.
+// ----------------------------------------------------------------------------------------------------
+constexpr int AW_Q = 32;   // queries per block
+constexpr int AW_K = 32;   // keys per staged tile
+
+__global__ void __launch_bounds__(256) mha_weights_kernel(const MhaKParams p, const MhaSimtPtrs q) {
+  extern __shared__ float aw_sm[];
+  const int dh = q.dh;
+  const int kst = dh + 4;
+  float* Qs = aw_sm;                 // [AW_Q][dh]
+  float* Ks = aw_sm + AW_Q * dh;     // [AW_K][dh + 4]
+  const int q0 = blockIdx.x * AW_Q, h = blockIdx.y;
+  const int b = q.weights_all ? blockIdx.z : q.weights_b;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int len = min(max(p.kv_len[b], 0), p.Tk);
+  for (int i = threadIdx.x; i < AW_Q * dh; i += blockDim.x) {
+    const int r = i / dh, c = i - r * dh;
+    const int tq = q0 + r;
+    Qs[i] = tq < p.T ? ld_split(q.qk_hi, q.qk_lo, ((size_t)b * p.T + tq) * q.ld_qk + p.q_col0 + h * dh + c, q.f16) : 0.f;
+  }
+  float* wbase = q.weights + ((size_t)(q.weights_all ? b : 0) * p.H + h) * (size_t)p.T * p.Tk;
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  const int n_tiles = (p.Tk + AW_K - 1) / AW_K;
+  for (int kt = 0; kt < n_tiles; ++kt) {
+    __syncthreads();  // Qs ready (first tile) / previous tile consumed
+    for (int i = threadIdx.x; i < AW_K * dh; i += blockDim.x) {
+      const int r = i / dh, c = i - r * dh;
+      const int tk = kt * AW_K + r;
+      Ks[r * kst + c] = tk < p.Tk ? ld_split(q.kv_hi, q.kv_lo, ((size_t)b * p.Tk + tk) * q.ld_kv + p.k_col0 + h * dh + c, q.f16) : 0.f;
+    }
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* krow = reinterpret_cast<const float4*>(Ks + lane * kst);
+#pragma unroll 2
+    for (int c4 = 0; c4 < dh / 4; ++c4) {
+      const float4 kv = krow[c4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 qv = reinterpret_cast<const float4*>(Qs + (warp * 4 + i) * dh)[c4];
+        acc[i] = fmaf(qv.x, kv.x, acc[i]);
+        acc[i] = fmaf(qv.y, kv.y, acc[i]);
+        acc[i] = fmaf(qv.z, kv.z, acc[i]);
+        acc[i] = fmaf(qv.w, kv.w, acc[i]);
+      }
+    }
+    const int tk = kt * AW_K + lane;
+    if (tk < p.Tk) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tq = q0 + warp * 4 + i;
+        if (tq < p.T) {
+          float l = acc[i] * q.scale;
+          if (tk >= len || (p.causal && tk > tq)) l += -1e9f;  // mask = max(padding, look-ahead) in {0,1}, times -1e9
+          wbase[(size_t)tq * p.Tk + tk] = l;
+          mx[i] = fmaxf(mx[i], l);
+        }
+      }
+    }
+  }
+  // every lane re-reads only what it wrote itself: no fence needed
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int tq = q0 + warp * 4 + i;
+    if (tq >= p.T) continue;   // warp-uniform
+    float m = mx[i];
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float* wrow = wbase + (size_t)tq * p.Tk;
+    float sum = 0.f;
+    for (int tk = lane; tk < p.Tk; tk += 32) {
+      const float e = expf(wrow[tk] - m);
+      wrow[tk] = e;
+      sum += e;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    for (int tk = lane; tk < p.Tk; tk += 32) wrow[tk] *= inv;
+  }
+}
+
 template <int DH, bool kSplit, bool kF16, bool kWide>
 static int launch_tc(const ttsb_mha_args* a, const MhaKParams& p, cudaStream_t stream) {
   using Cfg = MhaCfg<DH, kSplit>;
@@ -592,7 +675,7 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   q.weights_b = a->weights_batch_index;
   q.weights_all = a->weights_all ? 1 : 0;
   const size_t simt_smem = (size_t)(p.Tk + a->dh) * sizeof(float);
-  const bool need_simt = a->impl == TTSB_IMPL_SIMT || a->weights_out != nullptr;
+  const bool need_simt = a->impl == TTSB_IMPL_SIMT;  // the weights-only pass has its own tiled kernel (any Tk)
   if (need_simt && simt_smem > 200 * 1024) { set_last_error("ttsb_mha_fwd: Tk too large for the weights / SIMT kernel"); return TTSB_ERR_UNSUPPORTED; }
   if (need_simt && simt_smem > 48 * 1024) {
     static size_t simt_attr = 0;
@@ -625,7 +708,14 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   if (a->weights_out) {
     if (!a->weights_all && (a->weights_batch_index < 0 || a->weights_batch_index >= a->B)) { set_last_error("ttsb_mha_fwd: weights_batch_index out of range"); return TTSB_ERR_INVALID_ARGUMENT; }
     q.weights_only = 1;
-    mha_simt_kernel<<<dim3(a->T, a->H, a->weights_all ? a->B : 1), 128, simt_smem, stream>>>(p, q);
+    if (a->dh % 4) { set_last_error("ttsb_mha_fwd: the weights kernel needs head_dim %% 4 == 0"); return TTSB_ERR_UNSUPPORTED; }
+    const size_t aw_smem = (size_t)(AW_Q * a->dh + AW_K * (a->dh + 4)) * sizeof(float);
+    static size_t aw_attr = 48 * 1024;
+    if (aw_smem > aw_attr) {
+      TTSB_CUDA_OK(cudaFuncSetAttribute(mha_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aw_smem));
+      aw_attr = aw_smem;
+    }
+    mha_weights_kernel<<<dim3((a->T + AW_Q - 1) / AW_Q, a->H, a->weights_all ? a->B : 1), 256, aw_smem, stream>>>(p, q);
     count_launch();
     return check_cuda(cudaGetLastError(), "mha weights kernel launch");
   }

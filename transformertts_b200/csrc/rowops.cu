@@ -263,11 +263,13 @@ __global__ void pitch_embed_add_kernel(const float* __restrict__ x, const float*
 
 // utils/spectrogram_ops.py:8-13, literally: a frame counts iff (#channels != pad) != C*pad
 __global__ void mel_lengths_kernel(const float* __restrict__ mel, int T, int C, float pad, int* __restrict__ out) {
+  // grid (B, ceil(T / 64)): every block counts 64 frames (8 warps x 8 frames) and adds its count to out[b] (zeroed by the host)
   const int b = blockIdx.x;
   const float sum_tot = (float)C * pad;
   int local = 0;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int t = wid; t < T; t += nw) {
+  const int t_end = min(T, (int)(blockIdx.y + 1) * 64);
+  for (int t = blockIdx.y * 64 + wid; t < t_end; t += nw) {
     int cnt = 0;
     for (int c = lane; c < C; c += 32) cnt += (mel[((size_t)b * T + t) * C + c] != pad) ? 1 : 0;
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -279,7 +281,7 @@ __global__ void mel_lengths_kernel(const float* __restrict__ mel, int T, int C, 
   if (threadIdx.x == 0) {
     int s = 0;
     for (int w = 0; w < nw; ++w) s += red[w];
-    out[b] = s;
+    if (s) atomicAdd(out + b, s);
   }
 }
 
@@ -461,7 +463,8 @@ extern "C" int ttsb_pitch_embed_add_fwd(const float* x, const float* pitch, cons
 
 extern "C" int ttsb_mel_lengths(const float* mel, int B, int T, int C, float padding_value, int32_t* out, void* stream) {
   if (!mel || !out || B <= 0 || T <= 0 || C <= 0) return bad("ttsb_mel_lengths: bad arguments");
-  mel_lengths_kernel<<<B, 256, 0, STREAM(stream)>>>(mel, T, C, padding_value, out);
+  TTSB_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(int32_t) * (size_t)B, STREAM(stream)));
+  mel_lengths_kernel<<<dim3(B, (T + 63) / 64), 256, 0, STREAM(stream)>>>(mel, T, C, padding_value, out);
   LAUNCH_OK("mel_lengths_kernel");
 }
 

@@ -311,26 +311,31 @@ __global__ void scaled_ce_kernel(const float* __restrict__ logits, int64_t B, in
 
 __global__ void diag_loss_kernel(const float* __restrict__ att, int H, int Tq, int Tk, const int* __restrict__ q_len,
                                  const int* __restrict__ k_len, float scale, float* __restrict__ loss_out) {
+  // grid (B*H, ceil(Tq / 32)): one warp per query row, lanes across the keys
   const int bh = blockIdx.x;
   const int b = bh / H;
   const int max_m = min(max(q_len[b], 0), Tq);  // metrics.py:62-64
   const int max_n = min(max(k_len[b], 0), Tk);
   const float* a = att + (size_t)bh * Tq * Tk;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float local = 0.f;
-  for (int i = threadIdx.x; i < max_m * max_n; i += blockDim.x) {
-    const int q = i / max_n, k = i % max_n;
-    // the reference divides int32 ranges (-> float64), takes |.|, then casts the mask to float32
-    const float m = (float)fabs((double)k / (double)max_n - (double)q / (double)max_m);
-    local += a[(size_t)q * Tk + k] * m;
+  const int q_end = min(max_m, (int)(blockIdx.y + 1) * 32);
+  for (int q = blockIdx.y * 32 + wid; q < q_end; q += nw) {
+    const double jq = (double)q / (double)max_m;
+    for (int k = lane; k < max_n; k += 32) {
+      // the reference divides int32 ranges (-> float64), takes |.|, then casts the mask to float32
+      const float m = (float)fabs((double)k / (double)max_n - jq);
+      local += a[(size_t)q * Tk + k] * m;
+    }
   }
   local = wsum(local);
   __shared__ float red[32];
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  if (lane == 0) red[wid] = local;
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-    atomicAdd(loss_out, s * scale);
+    for (int w = 0; w < nw; ++w) s += red[w];
+    if (s != 0.f) atomicAdd(loss_out, s * scale);
   }
 }
 
@@ -544,7 +549,7 @@ extern "C" int ttsb_scaled_ce_loss(const float* logits, int B, int Tp, int Tt, i
 extern "C" int ttsb_diag_loss(const float* att, int B, int H, int Tq, int Tk, const int32_t* q_len, const int32_t* k_len,
                               float* loss_out, void* stream) {
   if (!att || !q_len || !k_len || !loss_out || B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0) return bad("ttsb_diag_loss: bad arguments");
-  diag_loss_kernel<<<B * H, 256, 0, STREAM(stream)>>>(att, H, Tq, Tk, q_len, k_len, 1.f / (10.f * (float)(B * H)), loss_out);
+  diag_loss_kernel<<<dim3(B * H, (Tq + 31) / 32), 256, 0, STREAM(stream)>>>(att, H, Tq, Tk, q_len, k_len, 1.f / (10.f * (float)(B * H)), loss_out);
   LAUNCH_OK("diag_loss_kernel");
 }
 
