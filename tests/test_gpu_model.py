@@ -107,7 +107,9 @@ def test_lj256_full_size_properties():
     # batch-permutation equivariance (rows independent)
     perm = torch.randperm(64, generator=torch.Generator().manual_seed(0))
     out_p = m.call(tok[perm], target_durations=dur[perm], target_pitch=pit[perm])
-    assert (out_p['mel'] - mel[perm.to(mel.device)]).abs().max() < 1e-5
+    # rows are independent; a row that lands in the pair-mode tail of a LayerNorm GEMM (csrc/gemm_tc.cu, hybrid schedule)
+    # has its row statistics combined in a different (mathematically equivalent) order, so equality is to rounding noise
+    assert (out_p['mel'] - mel[perm.to(mel.device)]).abs().max() < 2e-4
     # oracle parity on two rows
     sel = [3, 41]
     ref = fo.forward_transformer_call(p, cfg, tok[sel], dur[sel][..., None], pit[sel][..., None])

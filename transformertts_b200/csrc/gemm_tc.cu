@@ -32,6 +32,7 @@ constexpr int TMEM_COLS = 512;
 
 struct GemmKParams {
   int B, T, N, block_n, n_tiles, tiles_per_row, num_tiles;
+  int tile_begin;  // this launch covers work items [tile_begin, num_tiles)
   int num_seg;
   int seg_src[4], seg_shift[4], seg_kblocks[4];
   const float* bias;
@@ -441,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = work_id; tile < p.num_tiles; tile += work_stride) {
+    for (int tile = p.tile_begin + work_id; tile < p.num_tiles; tile += work_stride) {
       const int n_tile = kPair ? cta_rank : tile % p.n_tiles;
       const int m_tile = kPair ? tile : tile / p.n_tiles;
       const int b = m_tile / p.tiles_per_row;
@@ -478,7 +479,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     uint32_t acc_phase = 0;
     int total_kb = 0;
     for (int s = 0; s < p.num_seg; ++s) total_kb += p.seg_kblocks[s];
-    for (int tile = work_id; tile < p.num_tiles; tile += work_stride) {
+    for (int tile = p.tile_begin + work_id; tile < p.num_tiles; tile += work_stride) {
       mbar_wait(tmem_empty + acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * GEMM_MAX_BN;
@@ -517,7 +518,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     uint32_t acc_phase = 0;
     int iter = 0;
     float2* xslots = reinterpret_cast<float2*>(smem + Cfg::kXchgOffset);
-    for (int tile = work_id; tile < p.num_tiles; tile += work_stride, ++iter) {
+    for (int tile = p.tile_begin + work_id; tile < p.num_tiles; tile += work_stride, ++iter) {
       const int n_tile = kPair ? cta_rank : tile % p.n_tiles;
       const int m_tile = kPair ? tile : tile / p.n_tiles;
       const int b = m_tile / p.tiles_per_row;
@@ -688,15 +689,27 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
   p.n_tiles = (a->N + a->block_n - 1) / a->block_n;
   p.tiles_per_row = (a->T + GEMM_BM - 1) / GEMM_BM;
   p.num_tiles = a->B * p.tiles_per_row * p.n_tiles;
-  // LayerNorm GEMMs whose row splits into two equal halves run as CTA pairs (see GemmCfg); TTSB_NO_PAIR=1 disables it
+  // LayerNorm GEMMs whose row splits into two equal halves can run as CTA pairs (see GemmCfg): a pair finishes a 128-row
+  // tile in ~0.57 of the single-CTA time, so work is handed out at half-tile granularity.  The schedule with the fewest
+  // (weighted) rounds wins: all single-CTA tiles, all pairs, or full waves of single-CTA tiles followed by a pair-mode
+  // tail (two launches).  TTSB_NO_PAIR=1 forces single-CTA tiles where the row fits one accumulator.
   static const bool no_pair = getenv("TTSB_NO_PAIR") != nullptr;
-  const bool pair = !no_pair && a->impl != TTSB_IMPL_SIMT && a->ln_gamma != nullptr && p.n_tiles == 1 && a->N == a->block_n &&
-                    a->N % 32 == 0 && a->N / 2 <= PAIR_MAX_BN && a->N >= 64;
-  if (pair) {
-    p.block_n = a->N / 2;
-    p.n_tiles = 1;  // per work item; the two column halves belong to the two CTAs of the cluster
-    p.num_tiles = a->B * p.tiles_per_row;
+  const bool pair_ok = a->impl != TTSB_IMPL_SIMT && a->ln_gamma != nullptr && p.n_tiles == 1 && a->N == a->block_n &&
+                       a->N % 32 == 0 && a->N / 2 <= PAIR_MAX_BN && a->N >= 64;
+  const bool single_ok = a->block_n <= GEMM_MAX_BN;
+  bool pair = false;
+  int hybrid_full = 0;  // > 0: tiles [0, hybrid_full) single-CTA, the rest as pairs
+  if (pair_ok && !(no_pair && single_ok)) {
+    const int t = a->B * p.tiles_per_row, sms = num_sms(), clusters = sms / 2;
+    const float kPairCost = 0.57f;
+    const float c_single = single_ok ? (float)((t + sms - 1) / sms) : 1e30f;
+    const float c_pair = kPairCost * (float)((t + clusters - 1) / clusters);
+    const int full = (t / sms) * sms, rem = t - full;
+    const float c_hyb = (single_ok && full > 0 && rem > 0) ? (float)(full / sms) + kPairCost * (float)((rem + clusters - 1) / clusters) : 1e30f;
+    if (c_hyb < c_single && c_hyb < c_pair) { pair = true; hybrid_full = full; }
+    else pair = c_pair < c_single;
   }
+  const int num_m_tiles = a->B * p.tiles_per_row;
   p.num_seg = a->num_segments;
   int src_k[2] = {0, 0};
   for (int s = 0; s < a->num_segments; ++s) {
@@ -742,7 +755,7 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
   }
 
   // tensor maps: activations as (C, T, B) boxes of (64, 128, 1); weights as (K_total, N_pad) boxes of (64, block_n)
-  CUtensorMap tmA[2][2], tmW[2];
+  CUtensorMap tmA[2][2];
   for (int i = 0; i < 2; ++i) {
     const int use = a->a_hi[i] ? i : 0;  // unused slots alias source 0 so the kernel params stay valid
     const int kext = src_k[use] > 0 ? src_k[use] : GEMM_BK;
@@ -753,62 +766,79 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
       if (rc) return rc;
     }
   }
-  for (int h = 0; h < 2; ++h) {
-    const void* base = h == 0 ? a->w_hi : (split ? a->w_lo : a->w_hi);
-    rc = make_tmap_bf16_2d(&tmW[h], base, k_total, pair ? a->N : p.n_tiles * p.block_n, (uint64_t)k_total, GEMM_BK, p.block_n);
-    if (rc) return rc;
-  }
-
-  if (pair) {
-    // cluster of two CTAs per 128-row tile; grid = 2 x min(tiles, SMs/2)
-    const int pairs = p.num_tiles < num_sms() / 2 ? p.num_tiles : num_sms() / 2;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+  auto launch = [&](bool as_pair, int tile_begin, int tile_end) -> int {
+    GemmKParams q = p;
+    if (as_pair) {
+      q.block_n = a->N / 2;
+      q.n_tiles = 1;  // per work item; the two column halves belong to the two CTAs of the cluster
+    }
+    q.tile_begin = tile_begin;
+    q.num_tiles = tile_end;
+    const int work = tile_end - tile_begin;
+    CUtensorMap tmW[2];
+    for (int h = 0; h < 2; ++h) {
+      const void* base = h == 0 ? a->w_hi : (split ? a->w_lo : a->w_hi);
+      int rc2 = make_tmap_bf16_2d(&tmW[h], base, k_total, as_pair ? a->N : q.n_tiles * q.block_n, (uint64_t)k_total, GEMM_BK, q.block_n);
+      if (rc2) return rc2;
+    }
+    if (as_pair) {
+      // cluster of two CTAs per 128-row tile; grid = 2 x min(tiles, SMs/2)
+      const int pairs = work < num_sms() / 2 ? work : num_sms() / 2;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * pairs);
+      cfg.blockDim = dim3(GEMM_THREADS);
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (split) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true, true>::kSmemBytes));
+          attr_set = true;
+        }
+        cfg.dynamicSmemBytes = GemmCfg<true, true>::kSmemBytes;
+        TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], q));
+      } else {
+        static bool attr_set = false;
+        if (!attr_set) {
+          TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false, true>::kSmemBytes));
+          attr_set = true;
+        }
+        cfg.dynamicSmemBytes = GemmCfg<false, true>::kSmemBytes;
+        TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], q));
+      }
+      count_launch();
+      return check_cuda(cudaGetLastError(), "gemm_tc_kernel<pair> launch");
+    }
+    const int grid = work < num_sms() ? work : num_sms();
     if (split) {
       static bool attr_set = false;
       if (!attr_set) {
-        TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true, true>::kSmemBytes));
+        TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true, false>::kSmemBytes));
         attr_set = true;
       }
-      cfg.dynamicSmemBytes = GemmCfg<true, true>::kSmemBytes;
-      TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p));
+      gemm_tc_kernel<true, false><<<grid, GEMM_THREADS, GemmCfg<true, false>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], q);
     } else {
       static bool attr_set = false;
       if (!attr_set) {
-        TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false, true>::kSmemBytes));
+        TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false, false>::kSmemBytes));
         attr_set = true;
       }
-      cfg.dynamicSmemBytes = GemmCfg<false, true>::kSmemBytes;
-      TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p));
+      gemm_tc_kernel<false, false><<<grid, GEMM_THREADS, GemmCfg<false, false>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], q);
     }
     count_launch();
-    return check_cuda(cudaGetLastError(), "gemm_tc_kernel<pair> launch");
+    return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
+  };
+  if (pair && hybrid_full > 0) {
+    rc = launch(false, 0, hybrid_full);
+    if (rc) return rc;
+    return launch(true, hybrid_full, num_m_tiles);
   }
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  if (split) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true, false>::kSmemBytes));
-      attr_set = true;
-    }
-    gemm_tc_kernel<true, false><<<grid, GEMM_THREADS, GemmCfg<true, false>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p);
-  } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false, false>::kSmemBytes));
-      attr_set = true;
-    }
-    gemm_tc_kernel<false, false><<<grid, GEMM_THREADS, GemmCfg<false, false>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], p);
-  }
-  count_launch();
-  return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
+  if (pair) return launch(true, 0, num_m_tiles);
+  return launch(false, 0, p.num_tiles);
 }
