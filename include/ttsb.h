@@ -230,10 +230,12 @@ int ttsb_wgrad(const ttsb_wgrad_args* args, void* stream);
 
 /* Row softmax of materialised, pre-scaled scores S fp32 (B*H, T, ld) with key masking (model/layers.py:186-192) and
  * attention dropout: P_pre = softmax, P_drop = dropout(P_pre) (pass the same pointer twice when drop_p == 0). */
+/* flags: bit 0 = look-ahead mask (keys > query index masked, transformer_utils.py:35-37); bit 1 = every query row is live
+ * (Aligner blocks); without it query rows >= kv_len[b] are written as zeros (they are masked downstream). */
 int ttsb_softmax_fwd(const float* S, int B, int H, int T, int Tk, int ld, const int32_t* kv_len, float drop_p,
-                     uint32_t seed, uint32_t site, void* P_pre, void* P_drop, void* stream);
+                     uint32_t seed, uint32_t site, int flags, void* P_pre, void* P_drop, void* stream);
 int ttsb_softmax_bwd(const void* P_pre, const float* dP, int B, int H, int T, int Tk, int ld, const int32_t* kv_len,
-                     float scale, float drop_p, uint32_t seed, uint32_t site, void* dS, void* stream);
+                     float scale, float drop_p, uint32_t seed, uint32_t site, int flags, void* dS, void* stream);
 /* LayerNorm backward from the saved pre-norm values u (keras LayerNormalization, model/layers.py:27,96,207,295,508). */
 int ttsb_layernorm_bwd(const float* dz, const float* u, const float* gamma, int B, int T, int C, int ld, float eps,
                        const int32_t* row_len, int relu_mask, float pre_drop_p, uint32_t pre_site, float post_drop_p,
@@ -255,7 +257,12 @@ int ttsb_mae_loss(const float* pred, int B, int Tp, int Tt, int C, const float* 
  * ttsb_diag_loss: utils/metrics.py:47-70 batch_diagonal_mask + models.py:189-205 -- mean over (b,h) of
  *   sum_{q<q_len, k<k_len} att[b,h,q,k] * |k/k_len - q/q_len|, divided by 10; added to *loss_out. */
 int ttsb_scaled_ce_loss(const float* logits, int B, int Tp, int Tt, int C, int ld, const int32_t* targets, int index,
-                        float scaling, float* loss_out, void* stream);
+                        float scaling, float* loss_out, float grad_weight, float* grad /* optional (B,Tp,ld_grad) */, int ld_grad,
+                        void* stream);
+/* training form of ttsb_diag_loss on the post-dropout probabilities P (bf16, (B*H,Tq,ld)): *loss_out += loss_scale * loss,
+ * dP (fp32, same layout, optional) += grad_scale * d loss / d P */
+int ttsb_diag_loss_train(const void* P_bf16, int B, int H, int Tq, int Tk, int ld, const int32_t* q_len, const int32_t* k_len,
+                         float loss_scale, float* loss_out, float grad_scale, float* dP, void* stream);
 int ttsb_diag_loss(const float* att, int B, int H, int Tq, int Tk, const int32_t* q_len, const int32_t* k_len,
                    float* loss_out, void* stream);
 int ttsb_expand_bwd(const float* dm, const int32_t* dur_int, int B, int Tp, int Tm, int d, float* dx, void* stream);

@@ -265,3 +265,15 @@ def make_aligner_inputs(cfg: dict, B: int, Tp: int, Tm: int, seed: int = 500, ra
         stop[b, :tm - 1] = 1
         stop[b, tm - 1] = 2
     return tokens, mel, stop
+
+
+def loss_and_grads(p: Dict[str, Tensor], cfg: dict, inp: Tensor, tar: Tensor, stop_prob: Tensor, r: int = 1,
+                   stop_scaling: float = 8.0, force_encoder_diagonal: bool = False, force_decoder_diagonal: bool = False):
+    """Forward (dropout off) + backward with torch autograd on the restated graph: the oracle of the hand-written
+    Aligner backward pass (models.py:212-216).  Returns (outputs, {name: grad})."""
+    q = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    out = gta_forward(q, cfg, inp, tar, stop_prob, r=r, stop_scaling=stop_scaling, force_encoder_diagonal=force_encoder_diagonal,
+                      force_decoder_diagonal=force_decoder_diagonal, training=False)
+    out['loss'].backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in q.items()}
+    return out, grads

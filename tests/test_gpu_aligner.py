@@ -119,6 +119,83 @@ def test_aligner_unbuilt_paths_fail_loudly():
     m = _model('A-small', alo.init_aligner_params(cfg, seed=7))
     tokens, mel, stop = alo.make_aligner_inputs(cfg, 2, 12, 20, seed=1)
     with pytest.raises(lib.TtsbError):
-        m._train_step(tokens, mel, stop)
+        m.predict(tokens)
     with pytest.raises(lib.TtsbError):
-        m.call(tokens, mel, training=True)
+        m.call(tokens, mel, training=True)   # training goes through _train_step (dropout + backward)
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize('cfg_name,B,Tp,Tm,r,diag', [('A-small', 3, 20, 97, 1, True), ('A-small', 2, 16, 81, 2, False),
+                                                     ('A5', 2, 40, 161, 1, True)])
+def test_aligner_train_step_loss_grads_and_adam(cfg_name, B, Tp, Tm, r, diag):
+    """One deterministic Aligner training step (dropout off): losses, every parameter gradient and the Adam update vs
+    torch autograd on the restated fp32 graph.  The GPU forward/backward is single-pass bf16 (as the ForwardTransformer's
+    training step), hence the same tolerances as tests/test_gpu_train.py."""
+    import math
+    torch.set_num_threads(8)
+    from oracle import forward_oracle as fo
+    from transformertts_b200.model.training import Adam
+    cfg = alo.ALIGNER_CONFIGS[cfg_name]
+    p = alo.init_aligner_params(cfg, seed=7)
+    tokens, mel, stop = alo.make_aligner_inputs(cfg, B, Tp, Tm, seed=510)
+    ref_out, ref_g = alo.loss_and_grads(p, cfg, tokens, mel, stop, r=r, stop_scaling=8.0, force_decoder_diagonal=diag,
+                                        force_encoder_diagonal=diag)
+    m = _model(cfg_name, p, train_dropout=False)
+    m._compile(8.0, Adam(1e-4))
+    m.set_constants(reduction_factor=r, force_decoder_diagonal=diag, force_encoder_diagonal=diag)
+    eng = m._get_engine()
+    out = eng.forward_backward(tokens, mel, stop, training=True)
+    torch.cuda.synchronize()
+    for k in ('mel', 'stop_prob', 'diag_loss'):
+        assert abs(out['losses'][k].item() - float(ref_out['losses'][k])) < 2e-2 * abs(float(ref_out['losses'][k])) + 1e-4, k
+    assert abs(out['loss'].item() - float(ref_out['loss'])) < 2e-2 * abs(float(ref_out['loss']))
+    worst = []
+    gscale = max(float(g.norm()) for g in ref_g.values())
+    unused_fp = cfg['mel_channels'] * r
+    for name, gref in ref_g.items():
+        got = eng.g[name].detach().double().cpu()
+        if name.startswith('final_proj'):
+            # only the first r*mel output columns take part (models.py:146): the rest has exactly zero gradient
+            assert float(got[..., unused_fp:].abs().max() if got[..., unused_fp:].numel() else 0.0) == 0.0
+        if float(gref.norm()) < 1e-6 * gscale:
+            assert float(got.norm()) < 2e-3 * gscale, name   # analytically zero (key biases)
+            continue
+        if gref.dim() == 0:
+            assert abs(float(got) - float(gref)) < 0.5 * abs(float(gref)) + 5e-3 * gscale, name
+            continue
+        cos = float((got * gref.double()).sum() / (got.norm() * gref.double().norm()))
+        worst.append((_rel(got, gref), cos, name))
+    worst.sort(reverse=True)
+    print('worst gradient relative errors:', worst[:8])
+    assert worst[0][0] < 0.3 and min(w[1] for w in worst) > 0.95, worst[:8]
+    w0, g0 = eng.flat_w.clone(), eng.flat_g.clone()
+    eng.apply_adam(m.optimizer)
+    torch.cuda.synchronize()
+    m_ref, v_ref, w_ref = torch.zeros_like(w0).cpu(), torch.zeros_like(w0).cpu(), w0.cpu().clone()
+    fo.adam_tf_step(w_ref, g0.cpu(), m_ref, v_ref, 1, 1e-4)
+    assert (eng.flat_w.cpu() - w_ref).abs().max() < 3e-7
+    assert m.step == 1
+    out2 = m.train_step(tokens, mel, stop)
+    assert math.isfinite(out2['loss'].item())
+    # the high-precision validation path still works after training (weights re-packed from the flat buffer)
+    out3 = m._val_step(tokens, mel, stop)
+    assert math.isfinite(float(out3['loss']))
+
+
+def test_aligner_training_with_dropout_runs_and_differs():
+    cfg = alo.ALIGNER_CONFIGS['A-small']
+    p = alo.init_aligner_params(cfg, seed=7)
+    tokens, mel, stop = alo.make_aligner_inputs(cfg, 3, 18, 64, seed=511)
+    m = _model('A-small', p, train_dropout=True)
+    m.set_constants(reduction_factor=1, force_decoder_diagonal=True)
+    eng = m._get_engine()
+    a = eng.forward_backward(tokens, mel, stop, training=True)['loss'].item()
+    b = eng.forward_backward(tokens, mel, stop, training=True)['loss'].item()
+    e = eng.forward_backward(tokens, mel, stop, training=False)['loss'].item()
+    assert abs(a - b) < 1e-5 * abs(a)          # same step counter -> same dropout masks
+    assert abs(a - e) > 1e-4                    # dropout really was active
+    assert torch.isfinite(eng.flat_g).all()

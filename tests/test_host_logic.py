@@ -67,6 +67,4 @@ def test_aligner_host_mirror_parameters_and_persistence(tmp_path):
     assert m2.r == 2 and m2.force_decoder_diagonal and not m2.force_encoder_diagonal
     import pytest
     with pytest.raises(lib.TtsbError):
-        m2._train_step(None, None, None)
-    with pytest.raises(lib.TtsbError):
         m2.predict(None)

@@ -26,15 +26,18 @@ __device__ __forceinline__ float wmax(float v) {
 // softmax over materialised score rows (training attention):  S fp32 (Z, T, ld) already scaled by 1/sqrt(dh)
 // ------------------------------------------------------------------------------------------------
 __global__ void softmax_fwd_kernel(const float* __restrict__ S, int Z, int H, int T, int Tk, int ld, const int* __restrict__ kv_len,
-                                   float drop_p, uint32_t seed, uint32_t site, __nv_bfloat16* __restrict__ P_pre,
+                                   float drop_p, uint32_t seed, uint32_t site, int flags, __nv_bfloat16* __restrict__ P_pre,
                                    __nv_bfloat16* __restrict__ P_drop) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= Z * T) return;
   const int lane = threadIdx.x & 31;
   const int z = row / T, t = row % T, b = z / H;
-  const int len = min(max(__ldg(kv_len + b), 0), Tk);
+  int len = min(max(__ldg(kv_len + b), 0), Tk);
   const size_t base = (size_t)row * ld;
-  const bool live = t < len;  // padded query rows are masked downstream: write zeros
+  // flags bit 1 (full queries): every query row is live (Aligner blocks); otherwise padded query rows are masked
+  // downstream and written as zeros.  bit 0 (look-ahead mask): keys > t are masked.
+  const bool live = (flags & 2) ? len > 0 : t < len;
+  if (flags & 1) len = min(len, t + 1);
   float mx = -INFINITY;
   if (live)
     for (int k = lane; k < len; k += 32) mx = fmaxf(mx, S[base + k]);
@@ -60,14 +63,15 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ S, int Z, int H, in
 // hits L2); keeping the row in registers instead was measured 2-4x slower (occupancy).
 __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P_pre, const float* __restrict__ dP, int Z, int H, int T, int Tk,
                                    int ld, const int* __restrict__ kv_len, float scale, float drop_p, uint32_t seed, uint32_t site,
-                                   __nv_bfloat16* __restrict__ dS) {
+                                   int flags, __nv_bfloat16* __restrict__ dS) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= Z * T) return;
   const int lane = threadIdx.x & 31;
   const int z = row / T, t = row % T, b = z / H;
-  const int len = min(max(__ldg(kv_len + b), 0), Tk);
+  int len = min(max(__ldg(kv_len + b), 0), Tk);
   const size_t base = (size_t)row * ld;
-  const bool live = t < len;
+  const bool live = (flags & 2) ? len > 0 : t < len;
+  if (flags & 1) len = min(len, t + 1);
   const uint32_t thresh = dropout_thresh(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float dot = 0.f;
@@ -283,13 +287,20 @@ __global__ void mae_loss_kernel(const float* __restrict__ pred, int64_t B, int64
 //   diag_loss: utils/metrics.py:47-70 + models.py:189-205 -- mean over (b,h) of sum_{q,k} att * |k/k_len - q/q_len| / 10
 // ------------------------------------------------------------------------------------------------
 __global__ void scaled_ce_kernel(const float* __restrict__ logits, int64_t B, int64_t Tp, int64_t Tt, int C, int ld,
-                                 const int* __restrict__ tgt, int index, float scaling, float* __restrict__ loss_out) {
+                                 const int* __restrict__ tgt, int index, float scaling, float* __restrict__ loss_out,
+                                 float grad_weight, float* __restrict__ grad, int ld_grad) {
   const int64_t n = B * Tt;
   float local = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / Tt, t = i % Tt;
+  // rows of the prediction beyond the target length (t >= Tt) carry no loss: zero gradient
+  const int64_t total = grad ? B * Tp : n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = grad ? i / Tp : i / Tt, t = grad ? i % Tp : i % Tt;
+    if (t >= Tt) {
+      for (int c = 0; c < C; ++c) grad[(b * Tp + t) * ld_grad + c] = 0.f;
+      continue;
+    }
     const float* row = logits + (b * Tp + t) * ld;
-    const int y = tgt[i];
+    const int y = tgt[b * Tt + t];
     float mx = row[0];
     for (int c = 1; c < C; ++c) mx = fmaxf(mx, row[c]);
     float se = 0.f;
@@ -297,6 +308,10 @@ __global__ void scaled_ce_kernel(const float* __restrict__ logits, int64_t B, in
     const float ce = (y >= 0 && y < C) ? (logf(se) + mx - row[y]) : 0.f;
     const float w = (y != 0 ? 1.f : 0.f) + (y == index ? scaling - 1.f : 0.f);
     local += ce * w;
+    if (grad) {
+      const float gs = grad_weight * w / (float)n;
+      for (int c = 0; c < C; ++c) grad[(b * Tp + t) * ld_grad + c] = gs * (expf(row[c] - mx) / se - (c == y ? 1.f : 0.f));
+    }
   }
   local = wsum(local);
   __shared__ float red[32];
@@ -336,6 +351,40 @@ __global__ void diag_loss_kernel(const float* __restrict__ att, int H, int Tq, i
     float s = 0.f;
     for (int w = 0; w < nw; ++w) s += red[w];
     if (s != 0.f) atomicAdd(loss_out, s * scale);
+  }
+}
+
+// training form of the diagonal loss: the maps are the post-dropout probabilities P (bf16, (B*H, Tq, ld)); the loss is
+// added to *loss_out (scaled by loss_scale / (10*B*H)) and its gradient grad_scale / (10*B*H) * mask is added to dP (fp32,
+// same layout), the gradient of the P.V product, before the softmax backward.
+__global__ void diag_loss_train_kernel(const __nv_bfloat16* __restrict__ P, int H, int Tq, int Tk, int ld, const int* __restrict__ q_len,
+                                       const int* __restrict__ k_len, float loss_scale, float* __restrict__ loss_out, float grad_scale,
+                                       float* __restrict__ dP) {
+  const int bh = blockIdx.x;
+  const int b = bh / H;
+  const int max_m = min(max(q_len[b], 0), Tq);
+  const int max_n = min(max(k_len[b], 0), Tk);
+  const size_t base = (size_t)bh * Tq * ld;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float local = 0.f;
+  const int q_end = min(max_m, (int)(blockIdx.y + 1) * 32);
+  for (int q = blockIdx.y * 32 + wid; q < q_end; q += nw) {
+    const double jq = (double)q / (double)max_m;
+    for (int k = lane; k < max_n; k += 32) {
+      const float m = (float)fabs((double)k / (double)max_n - jq);
+      const size_t i = base + (size_t)q * ld + k;
+      local += __bfloat162float(P[i]) * m;
+      if (dP) dP[i] += grad_scale * m;
+    }
+  }
+  local = wsum(local);
+  __shared__ float red[32];
+  if (lane == 0) red[wid] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    if (s != 0.f) atomicAdd(loss_out, s * loss_scale);
   }
 }
 
@@ -475,18 +524,18 @@ using namespace ttsb;
 #define CBF(p) static_cast<const __nv_bfloat16*>(p)
 
 extern "C" int ttsb_softmax_fwd(const float* S, int B, int H, int T, int Tk, int ld, const int32_t* kv_len, float drop_p,
-                                uint32_t seed, uint32_t site, void* P_pre, void* P_drop, void* stream) {
+                                uint32_t seed, uint32_t site, int flags, void* P_pre, void* P_drop, void* stream) {
   if (!S || !kv_len || !P_pre || !P_drop || B <= 0 || H <= 0 || T <= 0 || Tk <= 0 || ld < Tk) return bad("ttsb_softmax_fwd: bad arguments");
   const int rows = B * H * T;
-  softmax_fwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(S, B * H, H, T, Tk, ld, kv_len, drop_p, seed, site, BF(P_pre), BF(P_drop));
+  softmax_fwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(S, B * H, H, T, Tk, ld, kv_len, drop_p, seed, site, flags, BF(P_pre), BF(P_drop));
   LAUNCH_OK("softmax_fwd_kernel");
 }
 
 extern "C" int ttsb_softmax_bwd(const void* P_pre, const float* dP, int B, int H, int T, int Tk, int ld, const int32_t* kv_len,
-                                float scale, float drop_p, uint32_t seed, uint32_t site, void* dS, void* stream) {
+                                float scale, float drop_p, uint32_t seed, uint32_t site, int flags, void* dS, void* stream) {
   if (!P_pre || !dP || !kv_len || !dS || B <= 0 || H <= 0 || T <= 0 || Tk <= 0 || ld < Tk) return bad("ttsb_softmax_bwd: bad arguments");
   const int rows = B * H * T;
-  softmax_bwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(CBF(P_pre), dP, B * H, H, T, Tk, ld, kv_len, scale, drop_p, seed, site, BF(dS));
+  softmax_bwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(CBF(P_pre), dP, B * H, H, T, Tk, ld, kv_len, scale, drop_p, seed, site, flags, BF(dS));
   LAUNCH_OK("softmax_bwd_kernel");
 }
 
@@ -539,10 +588,10 @@ extern "C" int ttsb_mae_loss(const float* pred, int B, int Tp, int Tt, int C, co
 }
 
 extern "C" int ttsb_scaled_ce_loss(const float* logits, int B, int Tp, int Tt, int C, int ld, const int32_t* targets, int index,
-                                   float scaling, float* loss_out, void* stream) {
-  if (!logits || !targets || !loss_out || B <= 0 || Tp <= 0 || Tt <= 0 || Tt > Tp || C <= 0 || ld < C)
+                                   float scaling, float* loss_out, float grad_weight, float* grad, int ld_grad, void* stream) {
+  if (!logits || !targets || !loss_out || B <= 0 || Tp <= 0 || Tt <= 0 || Tt > Tp || C <= 0 || ld < C || (grad && ld_grad < C))
     return bad("ttsb_scaled_ce_loss: bad arguments (need Tt <= Tp, ld >= C)");
-  scaled_ce_kernel<<<148, 256, 0, STREAM(stream)>>>(logits, B, Tp, Tt, C, ld, targets, index, scaling, loss_out);
+  scaled_ce_kernel<<<148, 256, 0, STREAM(stream)>>>(logits, B, Tp, Tt, C, ld, targets, index, scaling, loss_out, grad_weight, grad, ld_grad);
   LAUNCH_OK("scaled_ce_kernel");
 }
 
@@ -551,6 +600,15 @@ extern "C" int ttsb_diag_loss(const float* att, int B, int H, int Tq, int Tk, co
   if (!att || !q_len || !k_len || !loss_out || B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0) return bad("ttsb_diag_loss: bad arguments");
   diag_loss_kernel<<<dim3(B * H, (Tq + 31) / 32), 256, 0, STREAM(stream)>>>(att, H, Tq, Tk, q_len, k_len, 1.f / (10.f * (float)(B * H)), loss_out);
   LAUNCH_OK("diag_loss_kernel");
+}
+
+extern "C" int ttsb_diag_loss_train(const void* P_bf16, int B, int H, int Tq, int Tk, int ld, const int32_t* q_len,
+                                    const int32_t* k_len, float loss_scale, float* loss_out, float grad_scale, float* dP, void* stream) {
+  if (!P_bf16 || !q_len || !k_len || !loss_out || B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || ld < Tk) return bad("ttsb_diag_loss_train: bad arguments");
+  const float inv = 1.f / (10.f * (float)(B * H));
+  diag_loss_train_kernel<<<dim3(B * H, (Tq + 31) / 32), 256, 0, STREAM(stream)>>>(CBF(P_bf16), H, Tq, Tk, ld, q_len, k_len, loss_scale * inv,
+                                                                                  loss_out, grad_scale * inv, dP);
+  LAUNCH_OK("diag_loss_train_kernel");
 }
 
 extern "C" int ttsb_expand_bwd(const float* dm, const int32_t* dur_int, int B, int Tp, int Tm, int d, float* dx, void* stream) {

@@ -26,7 +26,7 @@ EXPORTS = [
     'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
     'ttsb_expand_ln_pe_fwd', 'ttsb_mel_lengths', 'ttsb_phoneme_lengths', 'ttsb_stft_mel_log',
     'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
-    'ttsb_relu_bwd', 'ttsb_colsum_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_scaled_ce_loss', 'ttsb_diag_loss', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
+    'ttsb_relu_bwd', 'ttsb_colsum_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_scaled_ce_loss', 'ttsb_diag_loss', 'ttsb_diag_loss_train', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
     'ttsb_pitch_embed_bwd', 'ttsb_statpred_head_bwd', 'ttsb_adam_tf_step', 'ttsb_embed_ln_pe_train_fwd',
     'ttsb_expand_ln_pe_train_fwd',
 ]
@@ -257,14 +257,17 @@ def wgrad(args: WgradArgs):
     _check(load().ttsb_wgrad(C.byref(args), _stream()), 'ttsb_wgrad')
 
 
-def softmax_fwd(S, B, H, T, Tk, ld, kv_len, drop_p, seed, site, P_pre, P_drop):
+SOFTMAX_CAUSAL, SOFTMAX_FULL_QUERIES = 1, 2
+
+
+def softmax_fwd(S, B, H, T, Tk, ld, kv_len, drop_p, seed, site, P_pre, P_drop, flags=0):
     _check(load().ttsb_softmax_fwd(ptr(S), B, H, T, Tk, ld, ptr(kv_len), C.c_float(drop_p), C.c_uint32(seed), C.c_uint32(site),
-                                   ptr(P_pre), ptr(P_drop), _stream()), 'ttsb_softmax_fwd')
+                                   int(flags), ptr(P_pre), ptr(P_drop), _stream()), 'ttsb_softmax_fwd')
 
 
-def softmax_bwd(P_pre, dP, B, H, T, Tk, ld, kv_len, scale, drop_p, seed, site, dS):
+def softmax_bwd(P_pre, dP, B, H, T, Tk, ld, kv_len, scale, drop_p, seed, site, dS, flags=0):
     _check(load().ttsb_softmax_bwd(ptr(P_pre), ptr(dP), B, H, T, Tk, ld, ptr(kv_len), C.c_float(scale), C.c_float(drop_p),
-                                   C.c_uint32(seed), C.c_uint32(site), ptr(dS), _stream()), 'ttsb_softmax_bwd')
+                                   C.c_uint32(seed), C.c_uint32(site), int(flags), ptr(dS), _stream()), 'ttsb_softmax_bwd')
 
 
 def layernorm_bwd(dz, u, gamma, B, T, Cc, ld, eps, row_len, relu_mask, du, g_bf16, dgamma, dbeta, pre_drop=(0.0, 0),
@@ -294,10 +297,16 @@ def mae_loss(pred, B, Tp, Tt, Cc, target, weight, loss_out, grad):
            'ttsb_mae_loss')
 
 
-def scaled_ce_loss(logits, Tt, Cc, targets, index, scaling, loss_out):
+def scaled_ce_loss(logits, Tt, Cc, targets, index, scaling, loss_out, grad_weight=1.0, grad=None):
     B, Tp, ld = logits.shape
     _check(load().ttsb_scaled_ce_loss(ptr(logits), B, Tp, Tt, Cc, ld, ptr(targets), int(index), C.c_float(scaling), ptr(loss_out),
-                                      _stream()), 'ttsb_scaled_ce_loss')
+                                      C.c_float(grad_weight), ptr(grad), grad.shape[-1] if grad is not None else 0, _stream()),
+           'ttsb_scaled_ce_loss')
+
+
+def diag_loss_train(P_bf16, B, H, Tq, Tk, ld, q_len, k_len, loss_scale, loss_out, grad_scale, dP):
+    _check(load().ttsb_diag_loss_train(ptr(P_bf16), B, H, Tq, Tk, ld, ptr(q_len), ptr(k_len), C.c_float(loss_scale), ptr(loss_out),
+                                       C.c_float(grad_scale), ptr(dP), _stream()), 'ttsb_diag_loss_train')
 
 
 def diag_loss(att, q_len, k_len, loss_out):

@@ -3,8 +3,8 @@ that produces the attention maps durations are extracted from (SURVEY.md section
 
 Built here: the teacher-forced forward (``call`` / ``_forward`` / ``_forward_encoder`` / ``_forward_decoder``) and the
 validation step with its losses (``_val_step`` = ``_gta_forward(training=False)``, models.py:168-220), every layer
-through libttsb.so.  Not built in this round: the backward pass / ``_train_step`` and the autoregressive ``predict``
-(both raise TtsbError) -- they are listed as open in DESIGN.md.
+through libttsb.so; ``_train_step`` (teacher-forced forward with dropout in single-pass bf16, hand-written backward,
+Keras-form Adam) lives in aligner_training.py.  Not built: the autoregressive ``predict`` (raises TtsbError).
 
 Parameter names (flat dict, Keras layouts):
   embedding; encoder.* exactly as ForwardTransformer dense blocks (models.py docstring);
@@ -67,7 +67,7 @@ class Aligner(ForwardTransformer):
         self._weights_all = True
         self.debug = debug
         self.alphabet = kwargs.get('alphabet')
-        self.train_dropout = False
+        self.train_dropout = bool(kwargs.get('train_dropout', True))  # False: deterministic training step (parity tests)
         self.max_r = int(max_r)
         self.r = int(max_r)                        # models.py:46 -- starts at max_r, lowered by the schedule via set_constants
         self.stop_prob_index = 2
@@ -200,6 +200,8 @@ class Aligner(ForwardTransformer):
 
     def _decoder_pe(self, r: int) -> torch.Tensor:
         """pos_encoding[:, :T*r:r] (layers.py:409) as a dense table so row t of the table is position t*r."""
+        if not hasattr(self, '_pe_r'):
+            self._pe_r = {}
         if r not in self._pe_r:
             st = self._stacks['decoder']
             self._pe_r[r] = positional_encoding(st['max_pos'], st['d'])[0][::r].to(self.device).contiguous()
@@ -405,9 +407,26 @@ class Aligner(ForwardTransformer):
 
     val_step = _val_step
 
-    def _train_step(self, inp, tar, stop_prob):
-        raise lib.TtsbError('Aligner._train_step (backward + Adam) is not built yet (DESIGN.md, open rows); '
-                            'the teacher-forced forward and _val_step are')
+    def _get_engine(self):
+        if self._engine is None:
+            from .aligner_training import AlignerTrainEngine
+            self._engine = AlignerTrainEngine(self)
+        return self._engine
+
+    def _train_step(self, inp, tar, stop_prob, data_parallel: bool = False):
+        """models.py:212-216: teacher-forced forward (dropout on, single-pass bf16), hand-written backward, Adam.
+        The returned dictionary has the losses and outputs; attention maps are not materialised in fp32 on this path."""
+        if self.optimizer is None:
+            self._compile(self.stop_scaling)
+        eng = self._get_engine()
+        sync = None
+        if data_parallel:
+            from ..utils.data_parallel import GradSync
+            sync = GradSync(eng.flat_g)
+        out = eng.forward_backward(inp, tar, stop_prob, training=True, sync=sync)
+        scale = sync.finish() if sync is not None else 1.0
+        eng.apply_adam(self.optimizer, grad_scale=scale)
+        return out
 
     train_step = _train_step
 
@@ -416,9 +435,10 @@ class Aligner(ForwardTransformer):
 
     def _compile(self, stop_scaling=8.0, optimizer=None):
         """models.py:222-227."""
+        from .training import Adam
         self.loss_weights = [1., 1.]
         self.stop_scaling = float(stop_scaling)
-        self.optimizer = optimizer
+        self.optimizer = optimizer if optimizer is not None else Adam(1.0e-4)
 
     def _set_r(self, r):
         self.r = int(r)
@@ -435,7 +455,7 @@ class Aligner(ForwardTransformer):
 
     @property
     def step(self) -> int:
-        return self._step
+        return int(self.optimizer.iterations) if self.optimizer is not None else 0
 
     @classmethod
     def from_config(cls, config: dict, max_r: int = 10):
@@ -446,5 +466,5 @@ class Aligner(ForwardTransformer):
                 'phoneme_language', 'with_stress', 'decoder_prenet_dropout', 'model_breathing',
                 'encoder_feed_forward_dimension', 'decoder_feed_forward_dimension')
         kw = {k: config[k] for k in keys if k in config}
-        extra = {k: config[k] for k in ('vocab_size', 'precision', 'attention_precision', 'impl', 'device', 'seed', 'stop_loss_scaling') if k in config}
+        extra = {k: config[k] for k in ('vocab_size', 'precision', 'attention_precision', 'impl', 'device', 'seed', 'stop_loss_scaling', 'train_dropout') if k in config}
         return cls(max_r=int(config.get('max_r', max_r)), debug=config.get('debug', False), **kw, **extra)

@@ -345,6 +345,9 @@ class TrainEngine:
         dP = self._f32(Z, T, ldp)
         self._bgemm(B, H, T, T, dh, dattn, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
                     out_f32=dP, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
+        diag = getattr(self, '_enc_diag', None)  # Aligner: diagonal loss on the encoder maps adds its gradient to dP
+        if diag is not None and name == 'encoder':
+            lib.diag_loss_train(c['P_drop'], B, H, T, T, ldp, diag[1], diag[1], 0.0, self._scratch1, diag[0], dP)
         dS = self._bf(Z, T, ldp)
         lib.softmax_bwd(c['P_pre'], dP, B, H, T, T, ldp, lens, 1.0 / math.sqrt(dh), rate, self.seed, site_p, dS)
         del dP
