@@ -377,6 +377,29 @@ def aligner_bench(args, rank, world, dev):
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    # ---- the training step (models.py:212-216): forward with dropout 0.1 in single-pass bf16 + backward + Adam
+    from transformertts_b200.model.training import Adam
+    tmodel = Aligner.from_config(dict(cfg, device=str(dev), train_dropout=True), max_r=cfg['max_r'])
+    tmodel.set_weights(params)
+    tmodel._compile(cfg['stop_loss_scaling'], Adam(1e-4))
+    tmodel.set_constants(reduction_factor=1, force_decoder_diagonal=True)
+    tmodel._get_engine().rank = rank
+    for _ in range(max(args.warmup, 3)):
+        to = tmodel.train_step(tok_d, mel_d, stop_d)
+    torch.cuda.synchronize()
+    lib.reset_launch_count()
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record()
+    for _ in range(args.steps):
+        to = tmodel.train_step(tok_d, mel_d, stop_d)
+    t1e.record()
+    torch.cuda.synchronize()
+    train_launches = lib.launch_count()
+    tt = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    train_ms = float(tt.item()) / args.steps
+    train_loss = float(to['loss'])
     peak_tf, _, peak_src = _peaks()
     flops = aligner_flops(cfg, B, Tp, T)
     cpu = None
@@ -400,16 +423,19 @@ def aligner_bench(args, rank, world, dev):
                 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16x3 GEMMs + fp16 attention, fp32 accumulate', 'data': 'synthetic',
                 'config': {'workload': 'C5: Aligner teacher-forced forward + validation losses (mel MAE, scaled stop CE, diagonal loss), '
-                                       '16 rows/GPU, 130 tokens, 800 decoder frames, r=1, aligner_settings as shipped; backward not built',
+                                       '16 rows/GPU, 130 tokens, 800 decoder frames, r=1, aligner_settings as shipped; train_step = the full training step',
                            'model': 'A5', 'global_batch': B * world, 'seq_len': T, 'parallelism': f'independent replicas x{world}',
                            'l2': 'working set (~0.6 GB of activations + attention maps) exceeds the 126 MB L2'},
                 'frames_per_sec': sps * B * T * world,
                 'e2e': {'value': args.steps / float(dt.item()) * world, 'unit': 'steps/s',
                         'h2d_bytes_per_step': int(tok.numel() * 4 + mel.numel() * 4 + stop.numel() * 4), 'd2h_bytes_per_step': 4},
                 'gpu_launches': int(launches), 'clocks': clocks, 'loss': loss_val,
+                'train_step': {'value': 1e3 / train_ms * world, 'unit': 'steps/s', 'ms_per_step': train_ms, 'loss': train_loss,
+                               'gpu_launches_per_step': int(train_launches) // args.steps,
+                               'what': 'fwd (dropout 0.1, single-pass bf16) + bwd + Adam, same batch, no gradient all-reduce in this mode'},
                 'roofline': {'bound': 'tensor', 'achieved': flops / (ms / args.steps * 1e-3) / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s',
                              'frac': flops / (ms / args.steps * 1e-3) / 1e12 / peak_tf, 'traffic': None, 'peak_source': peak_src,
-                             'kernel': 'whole step (algorithmic forward FLOPs); 63 small launches per step, launch-bound at this size'},
+                             'kernel': 'whole forward step (algorithmic FLOPs); ~90 small launches per step, latency-bound at this size'},
                 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
 
