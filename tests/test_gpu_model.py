@@ -158,3 +158,74 @@ def test_save_load_roundtrip_and_factory(tmp_path):
     assert torch.equal(m3.call(tok, target_durations=dur, target_pitch=pit)['mel'], want)
     with pytest.raises(NotImplementedError):
         factory.tts_ljspeech()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# edge cases: smallest inputs, rows that expand to nothing, long sequences, duration clamps
+# ----------------------------------------------------------------------------------------------------------
+def test_edge_single_token_and_single_frame():
+    cfg = fo.CONFIGS['C1']
+    p = fo.init_params(cfg, seed=7)
+    m = _model('C1', p)
+    tok = torch.tensor([[5]], dtype=torch.int32)
+    dur = torch.tensor([[1]], dtype=torch.int32)
+    pit = torch.tensor([[0.3]])
+    out = m.call(tok, target_durations=dur, target_pitch=pit)
+    ref = fo.forward_transformer_call(p, cfg, tok, dur[..., None].float(), pit[..., None])
+    assert out['mel'].shape == (1, 1, 80)
+    assert (out['mel'].cpu() - ref['mel']).abs().max() < MEL_TOL
+    assert (out['duration'].cpu() - ref['duration']).abs().max() < 1e-3
+
+
+def test_edge_rows_that_expand_to_zero_frames():
+    """One row of the batch has all-zero durations: its decoder rows are all padding (mel = output bias everywhere,
+    models.py:541-543); a batch where every row is empty returns a (B, 0, 80) mel."""
+    cfg = fo.CONFIGS['C1']
+    p = fo.init_params(cfg, seed=7)
+    m = _model('C1', p)
+    tok, dur, pit = fo.make_inputs('ragged', 3, 20, 60, seed=77)
+    dur = dur.clone()
+    dur[1] = 0
+    out = m.call(tok, target_durations=dur, target_pitch=pit)
+    ref = fo.forward_transformer_call(p, cfg, tok, dur[..., None].float(), pit[..., None])
+    assert out['mel'].shape == ref['mel'].shape
+    assert (out['mel'].cpu() - ref['mel']).abs().max() < MEL_TOL
+    assert int(out['mel_lengths'][1]) == 0
+    assert (out['mel'][1].cpu() - p['out.b']).abs().max() < 1e-6
+    out0 = m.call(tok, target_durations=torch.zeros_like(dur), target_pitch=pit)
+    assert out0['mel'].shape == (3, 0, 80)
+
+
+def test_edge_long_sequences_up_to_the_position_table():
+    """encoder_max_position_encoding = 2000 tokens (C1) and a 3000-frame decoder row: many key tiles, ragged tail tiles."""
+    torch.set_num_threads(16)
+    cfg = fo.CONFIGS['C1']
+    p = fo.init_params(cfg, seed=7)
+    m = _model('C1', p)
+    g = torch.Generator().manual_seed(5)
+    Tp = 2000
+    tok = torch.randint(1, 127, (1, Tp), generator=g, dtype=torch.int32)
+    dur = torch.zeros((1, Tp), dtype=torch.int32)
+    dur[0, :1500] = 2                      # 3000 frames; the last 500 tokens expand to nothing
+    pit = torch.randn(1, Tp, generator=g)
+    out = m.call(tok, target_durations=dur, target_pitch=pit)
+    ref = fo.forward_transformer_call(p, cfg, tok, dur[..., None].float(), pit[..., None])
+    assert out['mel'].shape == (1, 3000, 80)
+    assert (out['mel'].cpu() - ref['mel']).abs().max() < MEL_TOL
+
+
+def test_edge_predict_speed_regulator_and_duration_clamps():
+    """predict(): durations * (1/speed) -> min(max_mask) -> max(min_mask) -> round half to even (models.py:532-539,566)."""
+    cfg = fo.CONFIGS['C1']
+    p = fo.init_params(cfg, seed=7)
+    m = _model('C1', p)
+    tok, _, _ = fo.make_inputs('ragged', 2, 24, 100, seed=78)
+    for speed in (0.5, 1.0, 1.7):
+        out = m.predict(tok, encode=False, speed_regulator=speed)
+        ref = fo.predict(p, cfg, tok, speed_regulator=speed)
+        fl = ref['duration'][..., 0].numpy() * np.float32(1.0 / speed)
+        safe = np.abs(fl - np.floor(fl) - 0.5) > 2e-3          # away from a rounding boundary
+        got, want = out['int_durations'].cpu().numpy(), ref['int_durations'].numpy()
+        assert np.array_equal(got[safe], want[safe])
+        if np.array_equal(got, want):
+            assert (out['mel'].cpu() - ref['mel']).abs().max() < MEL_TOL

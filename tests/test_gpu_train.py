@@ -280,3 +280,38 @@ def test_train_tts_driver_runs_and_saves(tmp_path):
     from transformertts_b200.model.models import ForwardTransformer
     m = ForwardTransformer.load_model(str(tmp_path / 'step_3'))
     assert m.config['encoder_model_dimension'] == 256
+
+
+def test_prefetch_loader_feeds_training_steps(tmp_path):
+    """Row f-3 end to end: per-utterance .npy files -> bucketed, padded, pinned batches -> side-stream H2D -> train_step."""
+    from transformertts_b200.data import datasets as ds
+    from transformertts_b200.model.models import ForwardTransformer
+    from transformertts_b200.model.training import Adam
+    rng = np.random.default_rng(1)
+    for d in ('mels', 'durations', 'pitch_char'):
+        (tmp_path / d).mkdir()
+    lines = []
+    for i in range(24):
+        n_tok = int(rng.integers(8, 24))
+        dur = rng.integers(1, 6, n_tok).astype(np.int32)
+        np.save(tmp_path / 'mels' / f'u{i}.npy', rng.normal(-5, 2, (int(dur.sum()), 80)).astype(np.float32))
+        np.save(tmp_path / 'durations' / f'u{i}.npy', dur)
+        np.save(tmp_path / 'pitch_char' / f'u{i}.npy', rng.normal(0, 1, n_tok).astype(np.float32))
+        lines.append(f'u{i}|' + ''.join(chr(97 + int(c)) for c in rng.integers(0, 26, n_tok)) + '\n')
+    (tmp_path / 'train.txt').write_text(''.join(lines))
+    reader = ds.DataReader(tmp_path / 'train.txt', training=True, is_processed=True)
+    data = ds.TTSDataset(reader, ds.TTSPreprocessor(80, lambda t: [1 + (ord(c) % 100) for c in t]), tmp_path / 'mels',
+                         tmp_path / 'durations', tmp_path / 'pitch_char')
+    loader = ds.PrefetchLoader(data.get_dataset(bucket_batch_sizes=[4, 4], bucket_boundaries=[60], drop_remainder=True), prefetch=2,
+                               device=DEV)
+    model = ForwardTransformer(**fo.CONFIGS['C1'])
+    model._compile(Adam(1e-4))
+    try:
+        for _ in range(3):
+            b = loader.next()
+            assert b['mel'].is_cuda and b['tokens'].dtype == torch.int32
+            out = model.train_step(b['tokens'], b['mel'], b['durations'], b['pitch'])
+            assert math.isfinite(out['loss'].item())
+    finally:
+        loader.close()
+    assert model.step == 3
