@@ -77,7 +77,7 @@ def ncu_table(rep, labels):
 def main():
     tag = sys.argv[1]
     md = [f'# {tag} -- bench lines, launch lists and ncu captures (B200, `bash tests/run_bench.sh`)\n']
-    for f in ('bench_ours.json', 'bench_ref.json', 'bench_train.json'):
+    for f in ('bench_ours.json', 'bench_ref.json', 'bench_train.json', 'bench_stft.json', 'bench_expand.json', 'bench_aligner.json'):
         p = OUT / f
         if p.exists():
             md.append(f'## {f}\n```json\n{p.read_text().strip().splitlines()[-1]}\n```\n')
@@ -86,12 +86,16 @@ def main():
         step = one_step(load_launches(OUT / 'launches.csv'))
         md.append(table(step) + '\n')
         dec = [(n, v) for n, v in step if 'gemm_tc' in n or 'mha_tc' in n]
-        if len(dec) >= 44:
-            names = ['QKV GEMM (K=256,N=768)', 'attention', 'concat-proj GEMM (K=512,N=256,+LN)', 'conv1 GEMM (K=768,N=1024,relu)',
-                     'conv2 GEMM (K=3072,N=256,+LN)']
-            md.append('One decoder block (M = 64 x 1000 rows), launch order:\n\n| launch | us |\n|---|---|')
-            for n, (_, v) in zip(names, dec[34:39]):
-                md.append(f'| {n} | {v:.1f} |')
+        # one decoder block = the launches from the second-to-last attention kernel up to the last one; a LayerNorm GEMM
+        # with a pair-mode tail is two launches (gemm_tc_kernel<1,0> then <1,1>)
+        att = [i for i, (n, _) in enumerate(dec) if 'mha_tc' in n]
+        if len(att) >= 3:
+            blk = dec[att[-2] - 1:att[-1] - 1]
+            md.append('One decoder block (M = 64 x 1000 rows), launch order (QKV GEMM, attention, concat-projection + LN '
+                      '[single-CTA waves, pair-mode tail], conv1 + ReLU, conv2 + LN [single-CTA waves, pair-mode tail]):\n\n| launch | us |\n|---|---|')
+            for n, v in blk:
+                md.append(f'| `{n[:40]}` | {v:.1f} |')
+            md.append(f'| block total | {sum(v for _, v in blk):.1f} |')
             md.append('')
     if (OUT / 'launches_train.csv').exists():
         md.append('## training step (C3, bf16, B=32, dropout 0.1) -- launch list\n')
