@@ -34,6 +34,16 @@ B, TP, TM = 64, 128, 1000
 METRIC, UNIT = 'mel_frames_per_sec_fwd', 'frames/s'
 
 
+def _traffic(key):
+    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture (profiles/traffic.json,
+    written by profiles/summarize.py); None when no capture is committed."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'traffic.json')) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
 def _peaks():
     f = ROOT / 'MEASURED_PEAKS.json'
     if f.exists():
@@ -540,7 +550,8 @@ def main():
     conv_share = sum(dur_ms) / 3 / (ms / args.steps) if dur_ms else None
     roofline = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel (decoder Conv1D k=3 GEMMs: 256->1024 and 1024->256, M=64000)',
                 'achieved': gemm_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': gemm_tf / peak_tf if gemm_tf else None,
-                'traffic': None, 'peak_source': peak_src, 'launches_timed': len(dur_ms),
+                'traffic': _traffic('conv_gemm_mean_bytes_per_launch'), 'traffic_source': _traffic('source'),
+                'peak_source': peak_src, 'launches_timed': len(dur_ms),
                 'avg_launch_ms': sum(dur_ms) / len(dur_ms) if dur_ms else None,
                 'algorithmic_gflop_per_launch': sum(flops) / len(flops) / 1e9 if flops else None,
                 'share_of_step': conv_share}

@@ -210,6 +210,19 @@ typedef struct ttsb_bgemm_args {
   int out_cols;              /* writable columns per row of one problem (multiple of 16); columns >= N are written 0 */
   const int32_t* row_len;    /* optional [B]: rows m >= row_len[b] are written as zeros */
   const int32_t* col_len;    /* optional [B]: columns n >= col_len[b] are written as zeros */
+  /* ---- ABI 2: fused softmax backward.  With sm_P != NULL the product is dP = dO V^T of an attention backward and the
+   * epilogue writes dS = sm_scale * P_pre * (dropout(dP) - D) (bf16, out_bf16) instead of dP, with the masking rules and
+   * dropout hash of ttsb_softmax_bwd: sm_P = P_pre bf16 in the OUTPUT layout (requires out_by_b = 0, out_h_col = 0,
+   * out_batch_stride = M * ld_out), sm_D fp32 [B*H*M] = rowsum(P_drop * dP) = dO . O per (row, head)
+   * (ttsb_rowdot_heads), sm_len = key lengths [B], sm_flags as ttsb_softmax_bwd. */
+  const void* sm_P;
+  const float* sm_D;
+  float sm_scale, sm_drop_p;
+  uint32_t sm_seed, sm_site;
+  int sm_flags;
+  const int32_t* sm_len;
+  const void* sm_Pdrop;      /* optional: the saved post-dropout probabilities (same layout); the dropout decision is then
+                              * read back from it (kept <=> P_drop != 0 where P_pre != 0) instead of re-hashed */
 } ttsb_bgemm_args;
 
 int ttsb_bgemm(const ttsb_bgemm_args* args, void* stream);
@@ -227,6 +240,10 @@ typedef struct ttsb_wgrad_args {
 } ttsb_wgrad_args;
 
 int ttsb_wgrad(const ttsb_wgrad_args* args, void* stream);
+
+/* out[(b*H + h)*T + t] = sum_c x[b,t,h*dh+c] * y[b,t,h*dh+c]  (bf16 (B,T,ld) inputs, fp32 out): the row statistic
+ * D = dO . O of the attention backward (equals rowsum(P_drop * dP), so dP never has to be materialised). */
+int ttsb_rowdot_heads(const void* x_bf16, const void* y_bf16, int B, int T, int H, int dh, int ld, float* out, void* stream);
 
 /* Row softmax of materialised, pre-scaled scores S fp32 (B*H, T, ld) with key masking (model/layers.py:186-192) and
  * attention dropout: P_pre = softmax, P_drop = dropout(P_pre) (pass the same pointer twice when drop_p == 0). */

@@ -100,7 +100,20 @@ def main():
     if (OUT / 'launches_train.csv').exists():
         md.append('## training step (C3, bf16, B=32, dropout 0.1) -- launch list\n')
         md.append(table(one_step(load_launches(OUT / 'launches_train.csv'))) + '\n')
-    for rep, title, labels in (('prof_gemm.ncu-rep', 'gemm_tc_kernel<split=true>, decoder block 0', ['QKV', 'concat-proj + LN', 'conv1 + relu', 'conv2 + LN']),
+    # DRAM traffic of the roofline kernels (decoder conv GEMMs) for bench.py's roofline.traffic: bytes per logical GEMM
+    if (OUT / 'prof_gemm.ncu-rep').exists():
+        rows = ncu_raw(OUT / 'prof_gemm.ncu-rep', ['dram__bytes_read.sum', 'dram__bytes_write.sum'])
+
+        def to_bytes(cell):
+            v, u = float(cell[0]), cell[1].lower()
+            return v * {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}.get(u, 1)
+
+        if len(rows) >= 6:
+            tot = [to_bytes(r['dram__bytes_read.sum']) + to_bytes(r['dram__bytes_write.sum']) for r in rows[:6]]
+            traffic = {'source': f'profiles/{tag}_summary.md (ncu --set full, decoder block 0)', 'conv1_bytes': tot[3],
+                       'conv2_bytes': tot[4] + tot[5], 'conv_gemm_mean_bytes_per_launch': (tot[3] + tot[4] + tot[5]) / 2}
+            (ROOT / 'profiles' / 'traffic.json').write_text(json.dumps(traffic, indent=1))
+    for rep, title, labels in (('prof_gemm.ncu-rep', 'gemm_tc_kernel<split=true>, decoder block 0', ['QKV', 'concat-proj + LN (single-CTA waves)', 'concat-proj + LN (pair tail)', 'conv1 + relu', 'conv2 + LN (single-CTA waves)', 'conv2 + LN (pair tail)']),
                                ('prof_mha.ncu-rep', 'mha_tc_kernel<128, fp16>', ['decoder layer', 'decoder layer']),
                                ('prof_bgemm.ncu-rep', 'bgemm_tc_kernel (training: S, PV of the first blocks)', [])):
         if (OUT / rep).exists():

@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 240 -c 200 --csv --
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1300 -c 1200 --csv --log-file gpurun_out/launches_train.csv \
     python bench.py --mode train --steps 1 --warmup 3 > gpurun_out/ncu_launches_train.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 28 -c 4 -o gpurun_out/prof_gemm -f \
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 28 -c 6 -o gpurun_out/prof_gemm -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:mha_tc_kernel -s 8 -c 2 -o gpurun_out/prof_mha -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_mha.log 2>&1

@@ -117,6 +117,36 @@ def test_attention_train_path_forward_and_backward(H, dh, T):
     torch.cuda.synchronize()
     assert torch.isfinite(dqkv.float()).all()
     assert _rel(dqkv.float(), x.grad) < 3e-2
+    # the fused form: dS straight from the dP product's epilogue with D = dO . O (no fp32 dP round trip) -- without and
+    # with attention dropout (same hash => same masks as the stand-alone kernels)
+    for rate in (0.0, 0.25):
+        Pp = torch.empty(Z, T, ldp, dtype=torch.bfloat16, device=DEV)
+        Pd = torch.empty(Z, T, ldp, dtype=torch.bfloat16, device=DEV) if rate > 0 else Pp
+        lib.softmax_fwd(S, B, H, T, T, ldp, lens_d, rate, 77, 5, Pp, Pd)
+        O2 = torch.empty(B, T, d, dtype=torch.bfloat16, device=DEV)
+        eng._bgemm(B, H, T, dh, T, Pd, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), qkv_d, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d, 1),
+                   out_bf16=O2, ld_out=d, out_batch_stride=T * d, out_h_col=dh, out_by_b=1, out_cols=dh)
+        eng._bgemm(B, H, T, T, dh, dO_m, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv_d, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
+                   out_f32=dP, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
+        dS_ref = torch.empty(Z, T, ldp, dtype=torch.bfloat16, device=DEV)
+        lib.softmax_bwd(Pp, dP, B, H, T, T, ldp, lens_d, 1.0 / math.sqrt(dh), rate, 77, 5, dS_ref)
+        D = torch.empty(Z * T, device=DEV)
+        lib.rowdot_heads(dO_m, O2, H, dh, D)
+        dS_f = torch.full((Z, T, ldp), float('nan'), dtype=torch.bfloat16, device=DEV)
+        eng._bgemm(B, H, T, T, dh, dO_m, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv_d, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
+                   out_bf16=dS_f, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp,
+                   softmax_bwd=(Pp, D, 1.0 / math.sqrt(dh), rate, 77, 5, 0, lens_d))
+        torch.cuda.synchronize()
+        assert torch.isfinite(dS_f.float()).all()
+        # D comes from the bf16-rounded O instead of the fp32 dP: equal up to bf16 rounding of O
+        assert _rel(dS_f.float(), dS_ref.float()) < 2e-2, rate
+        if rate > 0:  # dropout decision read back from the saved P_drop instead of the hash: identical result
+            dS_g = torch.full((Z, T, ldp), float('nan'), dtype=torch.bfloat16, device=DEV)
+            eng._bgemm(B, H, T, T, dh, dO_m, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv_d, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
+                       out_bf16=dS_g, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp,
+                       softmax_bwd=(Pp, D, 1.0 / math.sqrt(dh), rate, 77, 5, 0, lens_d, Pd))
+            torch.cuda.synchronize()
+            assert torch.equal(dS_g, dS_f)
 
 
 def test_layernorm_bwd_and_small_ops():

@@ -56,6 +56,14 @@ struct BgParams {
   int out_cols;               // writable columns of one problem's row (multiple of 16)
   const int* row_len;         // optional [B]: rows m >= len[b] are written as zero
   const int* col_len;         // optional [B]: columns n >= len[b] are written as zero
+  // fused softmax backward (see ttsb_bgemm_args): dS = sm_scale * P_pre * (dropout(acc) - D)
+  const __nv_bfloat16* sm_P;
+  const __nv_bfloat16* sm_Pdrop;  // optional: saved post-dropout probabilities (dropout decision = P_drop != 0)
+  const float* sm_D;
+  float sm_scale, sm_drop_p;
+  uint32_t sm_seed, sm_site;
+  int sm_flags;
+  const int* sm_len;
   // wgrad
   int B, T, Cin, num_seg, seg_src[4], seg_shift[4], splits, b_per_split;
   float* dw;                  // fp32 (num_seg*Cin, N) accumulated with atomics
@@ -230,6 +238,80 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const bool row_keep = row_ok && (p.row_len == nullptr || m < __ldg(p.row_len + b));
         const int clen = p.col_len ? __ldg(p.col_len + b) : p.N;
         const size_t o = (size_t)(p.out_by_b ? b : z) * (size_t)p.out_z_stride + (size_t)(row_ok ? m : 0) * p.ld_out + h * p.out_h_col + n0;
+        if (p.sm_P != nullptr) {
+          // ---- softmax backward fused into the dP product (see ttsb_bgemm_args): this thread owns query row m of
+          //      problem z.  The P_pre row segments of all its chunks are requested before the first TMEM load.
+          int len = min(max(__ldg(p.sm_len + b), 0), p.N);
+          const bool live = row_ok && ((p.sm_flags & 2) ? len > 0 : m < len);
+          if (p.sm_flags & 1) len = min(len, m + 1);
+          const float dsum = live ? __ldg(p.sm_D + (size_t)z * p.M + m) : 0.f;
+          const uint32_t thresh = dropout_thresh(p.sm_drop_p);
+          const float ks = p.sm_drop_p > 0.f ? 1.f / (1.f - p.sm_drop_p) : 1.f;
+          // chunks of this thread in groups of four: the P_pre (and P_drop) row segments of a group are requested before
+          // its first TMEM load.  The dropout decision is read back from the saved P_drop (kept <=> P_drop != 0 wherever
+          // P_pre != 0) when sm_Pdrop is given; otherwise it is regenerated from the hash.
+          constexpr int GRP = 4;
+          for (int g0 = ch_begin; g0 < ch_end; g0 += GRP) {
+            uint4 pv[GRP][2], pd[GRP][2];
+#pragma unroll
+            for (int i = 0; i < GRP; ++i) {
+              const int c0 = (g0 + i) << 4;
+              const bool need = g0 + i < ch_end && live && n0 + c0 < len;
+              if (need) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.sm_P + o + c0);
+                pv[i][0] = __ldg(src);
+                pv[i][1] = __ldg(src + 1);
+              } else {
+                pv[i][0] = make_uint4(0, 0, 0, 0);
+                pv[i][1] = make_uint4(0, 0, 0, 0);
+              }
+              if (need && p.sm_Pdrop != nullptr) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.sm_Pdrop + o + c0);
+                pd[i][0] = __ldg(src);
+                pd[i][1] = __ldg(src + 1);
+              } else {
+                pd[i][0] = make_uint4(0, 0, 0, 0);
+                pd[i][1] = make_uint4(0, 0, 0, 0);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < GRP; ++i) {
+              const int ch = g0 + i;
+              if (ch < ch_end) {   // warp-uniform
+                const int c0 = ch << 4;
+                __syncwarp();
+                tmem_ld16(taddr + c0, r);
+                tmem_wait_ld();
+                if (row_ok && n0 + c0 < p.out_cols) {
+                  const size_t e0 = o + c0;  // element index in the (Z, M, ld_out) layout shared by P_pre, P_drop, dP and dS
+                  uint32_t hh[8];
+                  if (live && n0 + c0 < len) {
+                    const __nv_bfloat16* pp = reinterpret_cast<const __nv_bfloat16*>(pv[i]);
+                    const uint16_t* dd = reinterpret_cast<const uint16_t*>(pd[i]);
+                    float y[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const int k = n0 + c0 + j;
+                      bool keep = true;
+                      if (p.sm_drop_p > 0.f) keep = p.sm_Pdrop != nullptr ? (dd[j] & 0x7fffu) != 0 : dropout_keep(p.sm_seed, p.sm_site, e0 + j, thresh);
+                      const float g = keep ? __uint_as_float(r[j]) * ks : 0.f;
+                      y[j] = k < len ? p.sm_scale * __bfloat162float(pp[j]) * (g - dsum) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const __nv_bfloat162 v = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                      hh[j] = *reinterpret_cast<const uint32_t*>(&v);
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) hh[j] = 0u;
+                  }
+                  st_global_v8(p.out_bf16 + e0, hh);
+                }
+              }
+            }
+          }
+        } else
         for (int ch = ch_begin; ch < ch_end; ++ch) {
           const int c0 = ch << 4;
           __syncwarp();
@@ -334,6 +416,18 @@ extern "C" int ttsb_bgemm(const ttsb_bgemm_args* a, void* stream_v) {
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
   p.ld_out = a->ld_out; p.out_z_stride = a->out_batch_stride; p.out_h_col = a->out_h_col; p.out_by_b = a->out_by_b; p.out_cols = a->out_cols;
   p.row_len = a->row_len; p.col_len = a->col_len;
+  if (a->sm_P) {
+    if (!a->sm_D || !a->sm_len || !a->out_bf16 || a->out_by_b || a->out_h_col || a->out_batch_stride != (long long)a->M * a->ld_out ||
+        a->sm_drop_p < 0.f || a->sm_drop_p >= 1.f) {
+      set_last_error("ttsb_bgemm: the fused softmax backward needs sm_D, sm_len, out_bf16 and the (Z, M, ld_out) output layout");
+      return TTSB_ERR_INVALID_ARGUMENT;
+    }
+    p.sm_P = static_cast<const __nv_bfloat16*>(a->sm_P);
+    p.sm_Pdrop = (a->sm_drop_p > 0.f && a->sm_Pdrop) ? static_cast<const __nv_bfloat16*>(a->sm_Pdrop) : nullptr;
+    p.sm_D = a->sm_D; p.sm_scale = a->sm_scale; p.sm_drop_p = a->sm_drop_p; p.sm_seed = a->sm_seed; p.sm_site = a->sm_site;
+    p.sm_flags = a->sm_flags; p.sm_len = a->sm_len;
+    p.out_f32 = nullptr;
+  }
   p.block_n = pick_block_n(a->N);
   p.n_tiles = (a->N + p.block_n - 1) / p.block_n;
   p.m_tiles = (a->M + BG_BM - 1) / BG_BM;

@@ -389,6 +389,29 @@ __global__ void diag_loss_train_kernel(const __nv_bfloat16* __restrict__ P, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// D[(b*H + h)*T + t] = sum_c x[b,t,h*dh+c] * y[b,t,h*dh+c]   (one warp per (b,t) row, heads in sequence)
+// ------------------------------------------------------------------------------------------------
+__global__ void rowdot_heads_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y, int rows, int T, int H,
+                                    int dh, int ld, float* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / T, t = row % T;
+  const __nv_bfloat162* xr = reinterpret_cast<const __nv_bfloat162*>(x + (size_t)row * ld);
+  const __nv_bfloat162* yr = reinterpret_cast<const __nv_bfloat162*>(y + (size_t)row * ld);
+  for (int h = 0; h < H; ++h) {
+    float acc = 0.f;
+    for (int c = lane; c < dh / 2; c += 32) {
+      const float2 a = __bfloat1622float2(xr[h * (dh / 2) + c]);
+      const float2 v = __bfloat1622float2(yr[h * (dh / 2) + c]);
+      acc = fmaf(a.x, v.x, fmaf(a.y, v.y, acc));
+    }
+    acc = wsum(acc);
+    if (lane == 0) out[((size_t)b * H + h) * T + t] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Expand backward: dx[b,i,:] = sum of dm[b, t, :] over the frames t copied from phoneme i (contiguous segment)
 // ------------------------------------------------------------------------------------------------
 __global__ void expand_bwd_kernel(const float* __restrict__ dm, const int* __restrict__ dur, int Tp, int Tm, int d,
@@ -609,6 +632,13 @@ extern "C" int ttsb_diag_loss_train(const void* P_bf16, int B, int H, int Tq, in
   diag_loss_train_kernel<<<dim3(B * H, (Tq + 31) / 32), 256, 0, STREAM(stream)>>>(CBF(P_bf16), H, Tq, Tk, ld, q_len, k_len, loss_scale * inv,
                                                                                   loss_out, grad_scale * inv, dP);
   LAUNCH_OK("diag_loss_train_kernel");
+}
+
+extern "C" int ttsb_rowdot_heads(const void* x, const void* y, int B, int T, int H, int dh, int ld, float* out, void* stream) {
+  if (!x || !y || !out || B <= 0 || T <= 0 || H <= 0 || dh <= 0 || dh % 2 || ld < H * dh || ld % 2) return bad("ttsb_rowdot_heads: bad arguments");
+  const int rows = B * T;
+  rowdot_heads_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(CBF(x), CBF(y), rows, T, H, dh, ld, out);
+  LAUNCH_OK("rowdot_heads_kernel");
 }
 
 extern "C" int ttsb_expand_bwd(const float* dm, const int32_t* dur_int, int B, int Tp, int Tm, int d, float* dx, void* stream) {

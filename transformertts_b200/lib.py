@@ -25,7 +25,7 @@ EXPORTS = [
     'ttsb_split_bf16', 'ttsb_embed_ln_pe_fwd', 'ttsb_linear_fwd', 'ttsb_layernorm_fwd', 'ttsb_mha_fwd', 'ttsb_statpred_head_fwd',
     'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
     'ttsb_expand_ln_pe_fwd', 'ttsb_mel_lengths', 'ttsb_phoneme_lengths', 'ttsb_stft_mel_log',
-    'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
+    'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_rowdot_heads', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
     'ttsb_relu_bwd', 'ttsb_colsum_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_scaled_ce_loss', 'ttsb_diag_loss', 'ttsb_diag_loss_train', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
     'ttsb_pitch_embed_bwd', 'ttsb_statpred_head_bwd', 'ttsb_adam_tf_step', 'ttsb_embed_ln_pe_train_fwd',
     'ttsb_expand_ln_pe_train_fwd',
@@ -68,6 +68,8 @@ class BgemmArgs(C.Structure):
         ('alpha', C.c_float), ('out_f32', C.c_void_p), ('out_bf16', C.c_void_p), ('ld_out', C.c_int),
         ('out_batch_stride', C.c_longlong), ('out_h_col', C.c_int), ('out_by_b', C.c_int), ('out_cols', C.c_int),
         ('row_len', C.c_void_p), ('col_len', C.c_void_p),
+        ('sm_P', C.c_void_p), ('sm_D', C.c_void_p), ('sm_scale', C.c_float), ('sm_drop_p', C.c_float),
+        ('sm_seed', C.c_uint32), ('sm_site', C.c_uint32), ('sm_flags', C.c_int), ('sm_len', C.c_void_p), ('sm_Pdrop', C.c_void_p),
     ]
 
 
@@ -251,6 +253,11 @@ def stft_mel_log(wav, mel_basis, normalizer, out):
 # ------------------------------------------------------------------------------------------------------------
 def bgemm(args: BgemmArgs):
     _check(load().ttsb_bgemm(C.byref(args), _stream()), 'ttsb_bgemm')
+
+
+def rowdot_heads(x, y, H, dh, out):
+    B, T, ld = x.shape
+    _check(load().ttsb_rowdot_heads(ptr(x), ptr(y), B, T, H, dh, ld, ptr(out), _stream()), 'ttsb_rowdot_heads')
 
 
 def wgrad(args: WgradArgs):

@@ -159,7 +159,7 @@ class AlignerTrainEngine(TrainEngine):
         out = self._bf(B, T, d)
         self._bgemm(B, H, T, dh, Tk, P_drop, (Tk, T, Z), (ldp, T * ldp), (0, 0, 1, 0), kb, (d, Tk, B), (k_ld, k_ld * Tk),
                     (dh, 0, 0, v_col, 1), out_bf16=out, ld_out=d, out_batch_stride=T * d, out_h_col=dh, out_by_b=1, out_cols=dh)
-        return out, dict(P_pre=P_pre, P_drop=P_drop, ldp=ldp, site=site, flags=flags)
+        return out, dict(P_pre=P_pre, P_drop=P_drop, ldp=ldp, site=site, flags=flags, out=out)
 
     def _attn_bwd(self, c, B, H, dh, T, Tk, dout, qb, q_ld, q_col, kb, k_ld, k_col, v_col, lens, dq_buf, dq_ld, dq_col, dkv_buf,
                   dkv_ld, dk_col, dv_col, diag=None):
@@ -168,15 +168,21 @@ class AlignerTrainEngine(TrainEngine):
         d = H * dh
         ldp = c['ldp']
         Z = B * H
-        dP = self._f32(Z, T, ldp)
-        self._bgemm(B, H, T, Tk, dh, dout, (d, T, B), (d, d * T), (dh, 0, 0, 0), kb, (d, Tk, B), (k_ld, k_ld * Tk), (dh, 0, 0, v_col),
-                    out_f32=dP, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
-        if diag is not None:
-            lib.diag_loss_train(c['P_drop'], B, H, T, Tk, ldp, diag[1], diag[2], 0.0, self._scratch1, diag[0], dP)
         dS = self._bf(Z, T, ldp)
-        lib.softmax_bwd(c['P_pre'], dP, B, H, T, Tk, ldp, lens, 1.0 / math.sqrt(dh), self.drop_rate, self.seed, c['site'], dS,
-                        flags=c['flags'])
-        del dP
+        scale = 1.0 / math.sqrt(dh)
+        if diag is not None:
+            dP = self._f32(Z, T, ldp)
+            self._bgemm(B, H, T, Tk, dh, dout, (d, T, B), (d, d * T), (dh, 0, 0, 0), kb, (d, Tk, B), (k_ld, k_ld * Tk), (dh, 0, 0, v_col),
+                        out_f32=dP, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
+            lib.diag_loss_train(c['P_drop'], B, H, T, Tk, ldp, diag[1], diag[2], 0.0, self._scratch1, diag[0], dP)
+            lib.softmax_bwd(c['P_pre'], dP, B, H, T, Tk, ldp, lens, scale, self.drop_rate, self.seed, c['site'], dS, flags=c['flags'])
+            del dP
+        else:  # dS out of the dP product's epilogue (D = dO . O), see TrainEngine._block_bwd
+            D = self._f32(Z * T)
+            lib.rowdot_heads(dout, c['out'], H, dh, D)
+            self._bgemm(B, H, T, Tk, dh, dout, (d, T, B), (d, d * T), (dh, 0, 0, 0), kb, (d, Tk, B), (k_ld, k_ld * Tk), (dh, 0, 0, v_col),
+                        out_bf16=dS, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp,
+                        softmax_bwd=(c['P_pre'], D, scale, self.drop_rate, self.seed, c['site'], c['flags'], lens, c['P_drop']))
         # dQ = dS K : A = dS (K-major over keys), B = K read MN-major
         self._bgemm(B, H, T, dh, Tk, dS, (Tk, T, Z), (ldp, T * ldp), (0, 0, 1, 0), kb, (d, Tk, B), (k_ld, k_ld * Tk),
                     (dh, 0, 0, k_col, 1), out_bf16=dq_buf, ld_out=dq_ld, out_batch_stride=T * dq_ld, out_h_col=dh, out_by_b=1,

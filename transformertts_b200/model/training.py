@@ -199,7 +199,8 @@ class TrainEngine:
         lib.wgrad(a)
 
     def _bgemm(self, B, H, M, N, K, a, a_dims, a_strides, a_off, b, b_dims, b_strides, b_off, alpha=1.0, out_f32=None, out_bf16=None,
-               ld_out=0, out_batch_stride=0, out_h_col=0, out_by_b=0, out_cols=0, out_ptr_off=0, row_len=None, col_len=None):
+               ld_out=0, out_batch_stride=0, out_h_col=0, out_by_b=0, out_cols=0, out_ptr_off=0, row_len=None, col_len=None,
+               softmax_bwd=None):
         g = lib.BgemmArgs()
         g.B, g.H, g.M, g.N, g.K = B, H, M, N, K
         g.a = a.data_ptr() + 2 * a_off[3]
@@ -220,6 +221,12 @@ class TrainEngine:
         g.ld_out, g.out_batch_stride, g.out_h_col, g.out_by_b, g.out_cols = ld_out, out_batch_stride, out_h_col, out_by_b, out_cols
         g.row_len = row_len.data_ptr() if row_len is not None else None
         g.col_len = col_len.data_ptr() if col_len is not None else None
+        if softmax_bwd is not None:  # (P_pre, D, scale, drop_p, seed, site, flags, key lengths): epilogue writes dS, not dP
+            P_pre, D, scale, drop_p, seed, site, flags, lens = softmax_bwd[:8]
+            g.sm_P, g.sm_D, g.sm_len = P_pre.data_ptr(), D.data_ptr(), lens.data_ptr()
+            if len(softmax_bwd) > 8 and softmax_bwd[8] is not None and drop_p > 0:
+                g.sm_Pdrop = softmax_bwd[8].data_ptr()
+            g.sm_scale, g.sm_drop_p, g.sm_seed, g.sm_site, g.sm_flags = scale, drop_p, seed, site, flags
         lib.bgemm(g)
 
     # ------------------------------------------------------------------------------------------------
@@ -342,15 +349,23 @@ class TrainEngine:
         m._gemm(P[pre + 'wo.dx'], B, T, [(g1, None, d, 0)], [0], [0], residual=du1, out_f32=dx_acc, ld_out=d)
         # ---- attention backward on the materialised probabilities
         qkv, ldp = c['qkv'], c['ldp']
-        dP = self._f32(Z, T, ldp)
-        self._bgemm(B, H, T, T, dh, dattn, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
-                    out_f32=dP, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
+        dS = self._bf(Z, T, ldp)
         diag = getattr(self, '_enc_diag', None)  # Aligner: diagonal loss on the encoder maps adds its gradient to dP
         if diag is not None and name == 'encoder':
+            dP = self._f32(Z, T, ldp)
+            self._bgemm(B, H, T, T, dh, dattn, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
+                        out_f32=dP, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
             lib.diag_loss_train(c['P_drop'], B, H, T, T, ldp, diag[1], diag[1], 0.0, self._scratch1, diag[0], dP)
-        dS = self._bf(Z, T, ldp)
-        lib.softmax_bwd(c['P_pre'], dP, B, H, T, T, ldp, lens, 1.0 / math.sqrt(dh), rate, self.seed, site_p, dS)
-        del dP
+            lib.softmax_bwd(c['P_pre'], dP, B, H, T, T, ldp, lens, 1.0 / math.sqrt(dh), rate, self.seed, site_p, dS)
+            del dP
+        else:
+            # dS straight out of the dP = dO V^T product: rowsum(P_drop * dP) = dO . O per (row, head), so the fp32 dP
+            # matrix (Z*T*T*4 bytes) is never written or re-read
+            D = self._f32(Z * T)
+            lib.rowdot_heads(dattn, c['attn'], H, dh, D)
+            self._bgemm(B, H, T, T, dh, dattn, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
+                        out_bf16=dS, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp,
+                        softmax_bwd=(c['P_pre'], D, 1.0 / math.sqrt(dh), rate, self.seed, site_p, 0, lens, c['P_drop']))
         dqkv = self._bf(B, T, 3 * d)
         common = dict(out_bf16=dqkv, ld_out=3 * d, out_batch_stride=T * 3 * d, out_h_col=dh, out_by_b=1, out_cols=dh)
         qkv_dims, qkv_str = (d, T, B), (3 * d, 3 * d * T)
