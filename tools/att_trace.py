@@ -22,7 +22,7 @@ def build():
     tmp.mkdir(parents=True, exist_ok=True)
     for src in b.SOURCES:
         obj = tmp / (src + '.o')
-        cmd = [b._nvcc(), *b.NVCC_FLAGS, '-DTTSB_ATT_TRACE', '-I', str(b.INCLUDE), '-c', str(b.CSRC / src), '-o', str(obj)]
+        cmd = [b._nvcc(), *b.NVCC_FLAGS, '-DTTSB_ATT_TRACE', '-DTTSB_GEMM_TRACE', '-I', str(b.INCLUDE), '-c', str(b.CSRC / src), '-o', str(obj)]
         subprocess.run(cmd, check=True)
         objs.append(str(obj))
     subprocess.run([b._nvcc(), '-shared', '-o', str(LIB), *objs, '-gencode', 'arch=compute_100a,code=sm_100a',

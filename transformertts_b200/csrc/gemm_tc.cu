@@ -51,7 +51,20 @@ struct GemmKParams {
   float drop_pre_p, drop_post_p;  // training dropout: on the GEMM output before the residual add / on the LayerNorm output
   uint32_t drop_pre_site, drop_post_site, drop_seed;
   int h16;  // 1: out_hi receives IEEE fp16 instead of bf16 (single plane; operands of the fp16 attention)
+#ifdef TTSB_GEMM_TRACE
+  long long* trace;  // debug build only: clock64 stamps of CTA 0: [3 roles][64 tiles][4 events]
+#endif
 };
+
+#ifdef TTSB_GEMM_TRACE
+#define GEMM_TRACE(role, it, ev)                                                              \
+  do {                                                                                        \
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it) < 64)                   \
+      p.trace[((role) * 64 + (it)) * 4 + (ev)] = clock64();                                   \
+  } while (0)
+#else
+#define GEMM_TRACE(role, it, ev) do {} while (0)
+#endif
 
 // kPair: the LayerNorm GEMMs run as a cluster of two CTAs that split the N (row) dimension of one 128-row tile in halves
 // (twice as many work items -> no wave-quantisation tail, small-M encoder GEMMs fill the chip) and exchange per-row
@@ -479,12 +492,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     uint32_t acc_phase = 0;
     int total_kb = 0;
     for (int s = 0; s < p.num_seg; ++s) total_kb += p.seg_kblocks[s];
-    for (int tile = p.tile_begin + work_id; tile < p.num_tiles; tile += work_stride) {
+    int trace_it = 0;
+    for (int tile = p.tile_begin + work_id; tile < p.num_tiles; tile += work_stride, ++trace_it) {
+      GEMM_TRACE(1, trace_it, 0);
       mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+      GEMM_TRACE(1, trace_it, 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * GEMM_MAX_BN;
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(full_bar + stage, phase);
+        if (kb == 0) GEMM_TRACE(1, trace_it, 2);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint64_t a_hi = make_smem_desc_sw128(st);
@@ -507,6 +524,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
       if (leader) umma_commit(tmem_full + acc);  // accumulator complete
+      GEMM_TRACE(1, trace_it, 3);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 2) {
@@ -523,7 +541,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
       const int m_tile = kPair ? tile : tile / p.n_tiles;
       const int b = m_tile / p.tiles_per_row;
       const int t0 = (m_tile % p.tiles_per_row) * GEMM_BM;
+      if (warp == 2) GEMM_TRACE(0, iter, 0);
       mbar_wait(tmem_full + acc, acc_phase);
+      if (warp == 2) GEMM_TRACE(0, iter, 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GEMM_MAX_BN;
       PairCtx px{};
@@ -537,6 +557,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
         px.parity = (uint32_t)((iter >> 1) & 1);
       }
       epilogue_tile(p, taddr, b, t0, n_tile * p.block_n, quarter * 32 + lane, half, quarter, red_all + acc * (4 * GEMM_BM), px);
+      if (warp == 2) GEMM_TRACE(0, iter, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
@@ -737,6 +758,12 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
     return TTSB_ERR_UNSUPPORTED;
   }
   if (p.h16) p.out_lo = nullptr;
+#ifdef TTSB_GEMM_TRACE
+  {
+    const char* e = getenv("TTSB_GEMM_TRACE_PTR");  // device pointer (hex) of a 3*64*4 int64 buffer
+    p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
+  }
+#endif
 
   if (a->impl == TTSB_IMPL_SIMT) {
     GemmSimtPtrs q{};
