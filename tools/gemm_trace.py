@@ -75,5 +75,13 @@ def main():
         print(f'  tile {i:2d}: ' + ' '.join(f'{v:7d}' for v in m) + '   | ' + ' '.join(f'{v:7d}' for v in e))
 
 
+    print('epilogue warp 2, last tile, per group of 4 chunks: [group start, TMEM loads landed, chunks stored] (relative to group 0 start)')
+    b2 = int(t[2, 0, 0])
+    for gidx in range(4):
+        if int(t[2, gidx, 0]) == 0:
+            break
+        print('   group', gidx, [int(t[2, gidx, k]) - b2 for k in range(3)])
+
+
 if __name__ == '__main__':
     main()

@@ -51,6 +51,7 @@ struct GemmKParams {
   float drop_pre_p, drop_post_p;  // training dropout: on the GEMM output before the residual add / on the LayerNorm output
   uint32_t drop_pre_site, drop_post_site, drop_seed;
   int h16;  // 1: out_hi receives IEEE fp16 instead of bf16 (single plane; operands of the fp16 attention)
+  int staged;  // 1: 16-bit outputs go through shared memory and TMA tile stores (plain epilogue, block_n % 64 == 0)
 #ifdef TTSB_GEMM_TRACE
   long long* trace;  // debug build only: clock64 stamps of CTA 0: [3 roles][64 tiles][4 events]
 #endif
@@ -79,7 +80,11 @@ struct GemmCfg {
   static constexpr int kRedOffset = kBarOffset + 256;           // [2 acc][2][2][128] floats of intra-CTA exchange
   static constexpr int kXchgOffset = kRedOffset + 4096;         // pair mode: [2 slots][128] float2 written by the peer CTA
   static constexpr int kXbarOffset = kXchgOffset + 2048;        // pair mode: 2 mbarriers
-  static constexpr int kSmemBytes = kXbarOffset + 64 + 1024;    // + alignment slack
+  // plain (non-LayerNorm) epilogue: two planes x four lane quarters of [32 rows x 64 cols] 16-bit staging boxes (4 KB each,
+  // 128B-swizzled) for TMA tile stores; they overlay the LayerNorm exchange area, which that kernel does not use
+  static constexpr int kStageOutOffset = (kRedOffset + 1023) / 1024 * 1024;
+  static constexpr int kStageOutBytes = 2 * 4 * 4096;
+  static constexpr int kSmemBytes = (kStageOutOffset + kStageOutBytes > kXbarOffset + 64 ? kStageOutOffset + kStageOutBytes : kXbarOffset + 64) + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -192,9 +197,10 @@ struct PairCtx {
   uint32_t parity;
 };
 
+template <bool kLN>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t taddr, int b, int t0, int n0, int row, int half,
                                               int quarter, float* red /* [2][2][128] for this accumulator stage */,
-                                              const PairCtx& px) {
+                                              const PairCtx& px, uint8_t* stage_out, const CUtensorMap* tmOh, const CUtensorMap* tmOl) {
   const int t = t0 + row;
   const bool row_ok = t < p.T;
   const bool row_keep = row_ok && (p.row_len == nullptr || t < __ldg(p.row_len + b));
@@ -207,42 +213,134 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
   uint32_t r[16];
   float y[16], aux[16];
 
-  if (p.gamma == nullptr) {
-    for (int ch = ch_begin; ch < ch_end; ++ch) {
-      const int c0 = ch << 4;
+  if constexpr (!kLN) {
+    if (p.staged) {
+      // 16-bit outputs as TMA tile stores.  A thread owns one output ROW, so direct stores are 32-byte pieces of 32
+      // different rows per warp instruction; the clock64 trace (tools/gemm_trace.py) shows ~1000 clk per 16-column chunk
+      // in that form (request-rate bound: 10 kclk per 128x256 fp16 tile, more than the 6.7 kclk of MMAs at K = 256).
+      // Here the two warps of a lane quarter fill a [32 rows x 64 cols] 128B-swizzled box per plane and one lane hands
+      // it to the TMA unit (full 128-byte lines, asynchronous, rows >= T and columns >= N clipped by the tensor map).
+      uint8_t* box_hi = stage_out + quarter * 4096;
+      uint8_t* box_lo = stage_out + 4 * 4096 + quarter * 4096;
+      const bool issuer = half == 0 && (threadIdx.x & 31) == 0;
+      const int lrow = row & 31;
+      const bool two = p.out_lo != nullptr && !p.h16;
+      uint32_t qa[16], qb[16];
+      for (int s0 = 0; s0 < nch; s0 += 4) {   // 64-column slab: this warp handles chunks s0 + 2*half, +1
+        const int ca = s0 + 2 * half, cb = ca + 1;
+        __syncwarp();
+        tmem_ld16(taddr + (ca << 4), qa);
+        tmem_ld16(taddr + (cb << 4), qb);
+        if (issuer) tma_store_wait_read();   // the previous slab's boxes have been read out
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c0 = (u ? cb : ca) << 4;
+          if (p.bias) ldg16(p.bias + n0 + c0, aux);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(u ? qb[j] : qa[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] += aux[j];
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+          }
+          if (p.drop_pre_p > 0.f) apply_dropout16(y, p.drop_pre_p, p.drop_seed, p.drop_pre_site, orow * (uint64_t)p.ld_out + n0 + c0);
+          if (partial) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = (c0 + j < ncols) ? y[j] : 0.f;
+          }
+          if (!row_keep) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = 0.f;
+          }
+          uint32_t h[8], l[8];
+          if (p.h16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __half2 hh = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+              h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+          } else {
+            pack_hi_lo(y, h, l, two);
+          }
+          // 16-byte chunk ids of this 16-column chunk inside the 128-byte box row: 2*(2*half+u), +1; swizzle ^= row & 7
+          const int k0 = 2 * (2 * half + u);
+          const uint32_t o0 = lrow * 128 + (((k0) ^ (lrow & 7)) << 4), o1 = lrow * 128 + (((k0 + 1) ^ (lrow & 7)) << 4);
+          *reinterpret_cast<uint4*>(box_hi + o0) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(box_hi + o1) = make_uint4(h[4], h[5], h[6], h[7]);
+          if (two) {
+            *reinterpret_cast<uint4*>(box_lo + o0) = make_uint4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<uint4*>(box_lo + o1) = make_uint4(l[4], l[5], l[6], l[7]);
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        if (issuer) {
+          tma_store_3d(tmOh, box_hi, n0 + (s0 << 4), t0 + quarter * 32, b);
+          if (two) tma_store_3d(tmOl, box_lo, n0 + (s0 << 4), t0 + quarter * 32, b);
+          tma_store_commit();
+        }
+      }
+      return;
+    }
+    // direct stores (fp32 outputs, residual adds, odd tile widths): two TMEM loads in flight per wait
+    constexpr int IN_FLIGHT = 2;
+    uint32_t q[IN_FLIGHT][16];
+    for (int g0 = ch_begin; g0 < ch_end; g0 += IN_FLIGHT) {
       __syncwarp();
-      tmem_ld16(taddr + c0, r);
-      if (p.bias) ldg16(p.bias + n0 + c0, aux);
+#ifdef TTSB_GEMM_TRACE
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 64) p.trace[(2 * 64 + (g0 - ch_begin) / IN_FLIGHT) * 4 + 0] = clock64();
+#endif
+#pragma unroll
+      for (int i = 0; i < IN_FLIGHT; ++i)
+        if (g0 + i < ch_end) tmem_ld16(taddr + ((g0 + i) << 4), q[i]);
       tmem_wait_ld();
+#ifdef TTSB_GEMM_TRACE
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 64) p.trace[(2 * 64 + (g0 - ch_begin) / IN_FLIGHT) * 4 + 1] = clock64();
+#endif
 #pragma unroll
-      for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]);
-      if (p.bias) {
+      for (int i = 0; i < IN_FLIGHT; ++i) {
+        if (g0 + i < ch_end) {   // warp-uniform
+          const int c0 = (g0 + i) << 4;
+          if (p.bias) ldg16(p.bias + n0 + c0, aux);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) y[j] += aux[j];
+          for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(q[i][j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] += aux[j];
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+          }
+          if (p.drop_pre_p > 0.f) apply_dropout16(y, p.drop_pre_p, p.drop_seed, p.drop_pre_site, orow * (uint64_t)p.ld_out + n0 + c0);
+          if (p.residual && row_ok) {
+            ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + n0 + c0, aux);
+            ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + n0 + c0 + 8, aux + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] += aux[j];
+          }
+          if (partial) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = (c0 + j < ncols) ? y[j] : 0.f;
+          }
+          if (!row_keep) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = 0.f;
+          }
+          if (row_ok) store_chunk(p, orow, n0 + c0, y);
+        }
       }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
-      }
-      if (p.drop_pre_p > 0.f) apply_dropout16(y, p.drop_pre_p, p.drop_seed, p.drop_pre_site, orow * (uint64_t)p.ld_out + n0 + c0);
-      if (p.residual && row_ok) {
-        ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + n0 + c0, aux);
-        ld_global_nc_v8f(p.residual + orow * (size_t)p.ld_res + n0 + c0 + 8, aux + 8);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) y[j] += aux[j];
-      }
-      if (partial) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) y[j] = (c0 + j < ncols) ? y[j] : 0.f;
-      }
-      if (!row_keep) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) y[j] = 0.f;
-      }
-      if (row_ok) store_chunk(p, orow, n0 + c0, y);
+#ifdef TTSB_GEMM_TRACE
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 64) p.trace[(2 * 64 + (g0 - ch_begin) / IN_FLIGHT) * 4 + 2] = clock64();
+#endif
     }
     return;
-  }
+  } else {
 
   // ---- LayerNorm epilogue (single N tile), two passes over TMEM:
   //   pass 1 builds v = acc + bias (+relu) (+dropout) (+residual), parks it back in TMEM and accumulates SHIFTED sums
@@ -397,16 +495,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
       pass2_chunk(ch + 1, r2);
     }
   }
+  }  // kLN
 }
 
 // ----------------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------------
-template <bool kSplit, bool kPair>
+template <bool kSplit, bool kPair, bool kLN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant__ CUtensorMap tmA0l,
                const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
-               const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const GemmKParams p) {
+               const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+               const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl, const GemmKParams p) {
   using Cfg = GemmCfg<kSplit, kPair>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -556,13 +656,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
         px.peer_bar = map_to_peer(smem_u32(px.my_bar), (uint32_t)(cta_rank ^ 1));
         px.parity = (uint32_t)((iter >> 1) & 1);
       }
-      epilogue_tile(p, taddr, b, t0, n_tile * p.block_n, quarter * 32 + lane, half, quarter, red_all + acc * (4 * GEMM_BM), px);
+      epilogue_tile<kLN>(p, taddr, b, t0, n_tile * p.block_n, quarter * 32 + lane, half, quarter, red_all + acc * (4 * GEMM_BM), px,
+                         smem + Cfg::kStageOutOffset, &tmOh, &tmOl);
       if (warp == 2) GEMM_TRACE(0, iter, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (!kLN && p.staged && half == 0 && lane == 0) tma_store_wait_all();  // staged boxes fully written out before exit
   }
 
   tc_fence_before();
@@ -808,6 +910,23 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
       int rc2 = make_tmap_bf16_2d(&tmW[h], base, k_total, as_pair ? a->N : q.n_tiles * q.block_n, (uint64_t)k_total, GEMM_BK, q.block_n);
       if (rc2) return rc2;
     }
+    // plain epilogue with 16-bit outputs only: tile stores through shared memory (TTSB_NO_STAGED_STORE=1 keeps direct stores)
+    static const bool no_staged = getenv("TTSB_NO_STAGED_STORE") != nullptr;
+    CUtensorMap tmO[2] = {tmW[0], tmW[1]};  // placeholders when the staged path is off
+    q.staged = 0;
+    if (!no_staged && !as_pair && q.gamma == nullptr && q.out_hi != nullptr && q.out_f32 == nullptr && q.out_preln == nullptr &&
+        q.residual == nullptr && q.block_n % 64 == 0 && q.ld_out % 8 == 0) {
+      const int width = q.n_tiles * q.block_n;
+      int rc3 = make_tmap_bf16_3d(&tmO[0], q.out_hi, (uint64_t)width, (uint64_t)a->T, (uint64_t)a->B, (uint64_t)q.ld_out,
+                                  (uint64_t)q.ld_out * a->T, 64, 32);
+      if (rc3) return rc3;
+      if (q.out_lo) {
+        rc3 = make_tmap_bf16_3d(&tmO[1], q.out_lo, (uint64_t)width, (uint64_t)a->T, (uint64_t)a->B, (uint64_t)q.ld_out,
+                                (uint64_t)q.ld_out * a->T, 64, 32);
+        if (rc3) return rc3;
+      }
+      q.staged = 1;
+    }
     if (as_pair) {
       // cluster of two CTAs per 128-row tile; grid = 2 x min(tiles, SMs/2)
       const int pairs = work < num_sms() / 2 ? work : num_sms() / 2;
@@ -825,39 +944,40 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
       if (split) {
         static bool attr_set = false;
         if (!attr_set) {
-          TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true, true>::kSmemBytes));
+          TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true, true>::kSmemBytes));
           attr_set = true;
         }
         cfg.dynamicSmemBytes = GemmCfg<true, true>::kSmemBytes;
-        TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], q));
+        TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, true, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], tmO[0], tmO[1], q));
       } else {
         static bool attr_set = false;
         if (!attr_set) {
-          TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false, true>::kSmemBytes));
+          TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false, true>::kSmemBytes));
           attr_set = true;
         }
         cfg.dynamicSmemBytes = GemmCfg<false, true>::kSmemBytes;
-        TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], q));
+        TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, true, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], tmO[0], tmO[1], q));
       }
       count_launch();
       return check_cuda(cudaGetLastError(), "gemm_tc_kernel<pair> launch");
     }
     const int grid = work < num_sms() ? work : num_sms();
-    if (split) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true, false>::kSmemBytes));
-        attr_set = true;
-      }
-      gemm_tc_kernel<true, false><<<grid, GEMM_THREADS, GemmCfg<true, false>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], q);
-    } else {
-      static bool attr_set = false;
-      if (!attr_set) {
-        TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false, false>::kSmemBytes));
-        attr_set = true;
-      }
-      gemm_tc_kernel<false, false><<<grid, GEMM_THREADS, GemmCfg<false, false>::kSmemBytes, stream>>>(tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], q);
-    }
+    const bool ln = q.gamma != nullptr;
+#define TTSB_GEMM_LAUNCH(SPLIT, LN)                                                                                                  \
+  do {                                                                                                                               \
+    static bool attr_set = false;                                                                                                    \
+    if (!attr_set) {                                                                                                                 \
+      TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<SPLIT, false, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
+                                        GemmCfg<SPLIT, false>::kSmemBytes));                                                         \
+      attr_set = true;                                                                                                               \
+    }                                                                                                                                \
+    gemm_tc_kernel<SPLIT, false, LN><<<grid, GEMM_THREADS, GemmCfg<SPLIT, false>::kSmemBytes, stream>>>(                               \
+        tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], tmO[0], tmO[1], q);                                                              \
+  } while (0)
+    // separate instantiations for the LayerNorm and the plain epilogue: each gets its own register allocation
+    if (split) { if (ln) TTSB_GEMM_LAUNCH(true, true); else TTSB_GEMM_LAUNCH(true, false); }
+    else { if (ln) TTSB_GEMM_LAUNCH(false, true); else TTSB_GEMM_LAUNCH(false, false); }
+#undef TTSB_GEMM_LAUNCH
     count_launch();
     return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
   };
