@@ -200,7 +200,8 @@ struct PairCtx {
 template <bool kLN>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t taddr, int b, int t0, int n0, int row, int half,
                                               int quarter, float* red /* [2][2][128] for this accumulator stage */,
-                                              const PairCtx& px, uint8_t* stage_out, const CUtensorMap* tmOh, const CUtensorMap* tmOl) {
+                                              const PairCtx& px, uint8_t* stage_out, const CUtensorMap* tmOh, const CUtensorMap* tmOl,
+                                              uint32_t& slab_ctr) {
   const int t = t0 + row;
   const bool row_ok = t < p.T;
   const bool row_keep = row_ok && (p.row_len == nullptr || t < __ldg(p.row_len + b));
@@ -220,8 +221,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
       // in that form (request-rate bound: 10 kclk per 128x256 fp16 tile, more than the 6.7 kclk of MMAs at K = 256).
       // Here the two warps of a lane quarter fill a [32 rows x 64 cols] 128B-swizzled box per plane and one lane hands
       // it to the TMA unit (full 128-byte lines, asynchronous, rows >= T and columns >= N clipped by the tensor map).
-      uint8_t* box_hi = stage_out + quarter * 4096;
-      uint8_t* box_lo = stage_out + 4 * 4096 + quarter * 4096;
+      uint8_t* box_a = stage_out + quarter * 4096;
+      uint8_t* box_b = stage_out + 4 * 4096 + quarter * 4096;
       const bool issuer = half == 0 && (threadIdx.x & 31) == 0;
       const int lrow = row & 31;
       const bool two = p.out_lo != nullptr && !p.h16;
@@ -231,7 +232,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
         __syncwarp();
         tmem_ld16(taddr + (ca << 4), qa);
         tmem_ld16(taddr + (cb << 4), qb);
-        if (issuer) tma_store_wait_read();   // the previous slab's boxes have been read out
+        // two planes: box_a = hi, box_b = lo, reused every slab; one plane: the two boxes alternate, so only the store
+        // issued two slabs ago has to have been read out
+        uint8_t* box_hi = two ? box_a : ((slab_ctr & 1u) ? box_b : box_a);
+        uint8_t* box_lo = box_b;
+        ++slab_ctr;
+        if (issuer) {
+          if (two) tma_store_wait_read(); else tma_store_wait_read_but_one();
+        }
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
         tmem_wait_ld();
 #pragma unroll
@@ -636,6 +644,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     uint32_t acc_phase = 0;
     int iter = 0;
     float2* xslots = reinterpret_cast<float2*>(smem + Cfg::kXchgOffset);
+    uint32_t slab_ctr = 0;  // staged epilogue: slabs stored so far (selects the staging box of single-plane outputs)
     for (int tile = p.tile_begin + work_id; tile < p.num_tiles; tile += work_stride, ++iter) {
       const int n_tile = kPair ? cta_rank : tile % p.n_tiles;
       const int m_tile = kPair ? tile : tile / p.n_tiles;
@@ -657,7 +666,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
         px.parity = (uint32_t)((iter >> 1) & 1);
       }
       epilogue_tile<kLN>(p, taddr, b, t0, n_tile * p.block_n, quarter * 32 + lane, half, quarter, red_all + acc * (4 * GEMM_BM), px,
-                         smem + Cfg::kStageOutOffset, &tmOh, &tmOl);
+                         smem + Cfg::kStageOutOffset, &tmOh, &tmOl, slab_ctr);
       if (warp == 2) GEMM_TRACE(0, iter, 2);
       tc_fence_before();
       __syncwarp();
