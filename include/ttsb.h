@@ -267,6 +267,18 @@ int ttsb_cast_bf16_pad(const float* x, int64_t rows, int C, void* out_bf16, int 
  * *loss_out; grad = weight * sign(pred - target) / numel (zero for rows >= Tt). */
 int ttsb_mae_loss(const float* pred, int B, int Tp, int Tt, int C, const float* target_f32, const int32_t* target_i32,
                   float weight, float* loss_out, float* grad, void* stream);
+/* Duration extraction from the Aligner's attention maps (utils/alignments.py:103-143; the producer of the durations the
+ * ForwardTransformer trains on).  Lengths are the reference's "mel_lengths(mels) - 1" / "phoneme_lengths(phonemes) - 1".
+ * ttsb_attention_scores: utils/metrics.py:5-44 -> scores (B,H,3) = jumpiness, peakiness, 3 / diagonality.
+ * ttsb_durations_from_attention: reference matrix = att[b, best head, 1:mel_len, 1:phon_len] (or the score-weighted sum of
+ *   the heads), shortest monotonic path through (max - attention) (utils/alignments.py:58-91: scipy Dijkstra; here the
+ *   equivalent anti-diagonal dynamic programme in float64), durations int32 (B,Tk) (zero beyond phon_len - 1).
+ *   scratch: B*Tq*Tk bytes. */
+int ttsb_attention_scores(const float* att, int B, int H, int Tq, int Tk, const int32_t* mel_len, const int32_t* phon_len, int r,
+                          float* scores, void* stream);
+int ttsb_durations_from_attention(const float* att, int B, int H, int Tq, int Tk, const int32_t* mel_len, const int32_t* phon_len,
+                                  const float* scores, int weighted, uint8_t* scratch, int32_t* durations, void* stream);
+
 /* Aligner losses.
  * ttsb_scaled_ce_loss: utils/losses.py:4-21 new_scaled_crossentropy -- sparse softmax CE of logits (B,Tp,ld)[:, :Tt, :C] against
  *   int targets (B,Tt); sample weight (target != 0) + (target == index) * (scaling - 1); Keras SUM_OVER_BATCH_SIZE

@@ -6,9 +6,9 @@ product package; only tests/, __graft_entry__.smoke() and bench.py's CPU legs us
 PARITY UNPINNED for the model arithmetic (TensorFlow/Keras is not installable here).  What IS pinned against the
 reference's own known answers:
   * the stop-token cross entropy -- tests/test_loss.py:12-24 of the reference (2.3705523014068604 with scaling 5,
-    0.7679619193077087 with scaling 1 / masked_crossentropy) -- see tests/test_oracle.py
+    0.7679619193077087 with scaling 1 / masked_crossentropy) -- see tests/test_aligner_oracle.py
   * the look-ahead mask against ``torch.triu`` and the block structure against an independent
-    ``torch.nn.functional.scaled_dot_product_attention`` implementation -- tests/test_oracle.py
+    ``torch.nn.functional.scaled_dot_product_attention`` implementation -- tests/test_aligner_oracle.py
 
 Every function cites the reference lines it restates.  Keras layouts are kept (Dense kernel (in, out)).
 """

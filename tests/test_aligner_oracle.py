@@ -130,3 +130,18 @@ def test_golden_aligner_vectors():
     assert np.abs(out['stop_prob'].numpy() - g['stop_prob']).max() < 1e-4
     assert np.abs(out['decoder_attention']['Decoder_LastBlock_CrossAttention'].numpy() - g['last_attention']).max() < 1e-5
     assert abs(float(out['loss']) - float(g['loss'])) < 1e-5
+
+
+def test_duration_path_search_dp_equals_scipy_dijkstra():
+    """The reference finds the monotonic path with scipy's Dijkstra on an explicit graph (utils/alignments.py:21-91); the CUDA
+    kernel runs the equivalent dynamic programme.  Both restated in oracle/alignment_oracle.py and compared here."""
+    from oracle import alignment_oracle as ao
+    rng = np.random.default_rng(0)
+    for _ in range(25):
+        M = int(rng.integers(5, 50))
+        N = int(rng.integers(3, min(M, 20) + 1))
+        logits = rng.normal(0, 1, (M, N)) - 0.3 * N * np.abs(np.arange(M)[:, None] / M - np.arange(N)[None, :] / N)
+        a = np.exp(logits)
+        a = (a / a.sum(1, keepdims=True)).astype(np.float32)
+        d_ref = ao.extract_durations_with_dijkstra(a)
+        assert d_ref.sum() == M and np.array_equal(d_ref, ao.durations_by_dynamic_programming(a))

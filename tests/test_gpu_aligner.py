@@ -199,3 +199,38 @@ def test_aligner_training_with_dropout_runs_and_differs():
     assert abs(a - b) < 1e-5 * abs(a)          # same step counter -> same dropout masks
     assert abs(a - e) > 1e-4                    # dropout really was active
     assert torch.isfinite(eng.flat_g).all()
+
+
+def test_durations_from_aligner_attention_match_reference_dijkstra():
+    """Aligner forward -> last-block cross-attention -> durations, GPU kernels vs the reference's own procedure
+    (oracle/alignment_oracle.py: numpy scores + scipy.sparse.csgraph.dijkstra exactly as utils/alignments.py calls it)."""
+    from oracle import alignment_oracle as ao
+    from transformertts_b200.utils.alignments import get_durations_from_alignment
+    cfg = alo.ALIGNER_CONFIGS['A-small']
+    p = alo.init_aligner_params(cfg, seed=7)
+    tokens, mel, stop = alo.make_aligner_inputs(cfg, 4, 28, 120, seed=520)
+    m = _model('A-small', p)
+    m.set_constants(reduction_factor=1)
+    out = m.call(tokens, mel[:, :-1].contiguous(), training=False)   # teacher-forced input as in extract_durations.py
+    # the last block of A-small has one head: also exercise a 4-head map with a clear diagonal
+    g = torch.Generator().manual_seed(9)
+    B, H, Tq, Tk = 4, 4, mel.shape[1] - 1, tokens.shape[1]
+    lens_q = (mel.abs().sum(-1) != 0).sum(-1) - 1
+    lens_k = (tokens != 0).sum(-1) - 1
+    logits = torch.randn(B, H, Tq, Tk, generator=g)
+    for b in range(B):
+        qi = torch.arange(Tq)[:, None] / max(int(lens_q[b]), 1)
+        ki = torch.arange(Tk)[None, :] / max(int(lens_k[b]), 1)
+        for h in range(H):
+            logits[b, h] -= (2.0 + 3.0 * h) * Tk * 0.2 * (qi - ki).abs()   # head 3 is the sharpest diagonal
+        logits[b, :, :, int(lens_k[b]) + 1:] = -1e9
+    synth = torch.softmax(logits, -1)
+    for att in (out['decoder_attention']['Decoder_LastBlock_CrossAttention'].cpu(), synth):
+        for weighted in (False, True):
+            d_ref, jump_r, peak_r, diag_r = ao.get_durations_from_alignment(att.numpy(), mel.numpy(), tokens.numpy(), weighted=weighted)
+            d_gpu, _, jump, peak, diag = get_durations_from_alignment(att, mel, tokens, weighted=weighted)
+            assert np.allclose(jump.cpu().numpy(), jump_r, atol=1e-6)
+            assert np.allclose(peak.cpu().numpy(), peak_r, rtol=1e-5, atol=1e-7)
+            assert np.allclose(diag.cpu().numpy(), diag_r, rtol=1e-4)
+            for a, b_ in zip(d_gpu, d_ref):
+                assert a.dtype == np.int32 and np.array_equal(a, b_)      # integer durations: bit-exact

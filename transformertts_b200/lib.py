@@ -26,7 +26,7 @@ EXPORTS = [
     'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
     'ttsb_expand_ln_pe_fwd', 'ttsb_mel_lengths', 'ttsb_phoneme_lengths', 'ttsb_stft_mel_log',
     'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_rowdot_heads', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
-    'ttsb_relu_bwd', 'ttsb_colsum_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_scaled_ce_loss', 'ttsb_diag_loss', 'ttsb_diag_loss_train', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
+    'ttsb_relu_bwd', 'ttsb_colsum_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_scaled_ce_loss', 'ttsb_diag_loss', 'ttsb_diag_loss_train', 'ttsb_attention_scores', 'ttsb_durations_from_attention', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
     'ttsb_pitch_embed_bwd', 'ttsb_statpred_head_bwd', 'ttsb_adam_tf_step', 'ttsb_embed_ln_pe_train_fwd',
     'ttsb_expand_ln_pe_train_fwd',
 ]
@@ -314,6 +314,18 @@ def scaled_ce_loss(logits, Tt, Cc, targets, index, scaling, loss_out, grad_weigh
 def diag_loss_train(P_bf16, B, H, Tq, Tk, ld, q_len, k_len, loss_scale, loss_out, grad_scale, dP):
     _check(load().ttsb_diag_loss_train(ptr(P_bf16), B, H, Tq, Tk, ld, ptr(q_len), ptr(k_len), C.c_float(loss_scale), ptr(loss_out),
                                        C.c_float(grad_scale), ptr(dP), _stream()), 'ttsb_diag_loss_train')
+
+
+def attention_scores(att, mel_len, phon_len, r, scores):
+    B, H, Tq, Tk = att.shape
+    _check(load().ttsb_attention_scores(ptr(att), B, H, Tq, Tk, ptr(mel_len), ptr(phon_len), int(r), ptr(scores), _stream()),
+           'ttsb_attention_scores')
+
+
+def durations_from_attention(att, mel_len, phon_len, scores, weighted, scratch, durations):
+    B, H, Tq, Tk = att.shape
+    _check(load().ttsb_durations_from_attention(ptr(att), B, H, Tq, Tk, ptr(mel_len), ptr(phon_len), ptr(scores), int(bool(weighted)),
+                                                ptr(scratch), ptr(durations), _stream()), 'ttsb_durations_from_attention')
 
 
 def diag_loss(att, q_len, k_len, loss_out):
