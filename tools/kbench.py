@@ -1,7 +1,6 @@
 """Kernel micro-benchmarks through the C ABI (CUDA events on the current stream, after warm-up).
 
     python tools/kbench.py mha  [--B 64 --T 1000 --H 2 --dh 128 --precision fp16]
-    python tools/kbench.py stft [--clips 256]
 
 Prints one JSON line per case.  Used for A/B measurements of a single kernel (e.g. TTSB_ATT_NARROW=1); the
 numbers the judge reads come from bench.py, not from here.
