@@ -14,7 +14,6 @@ Every function cites the reference lines it restates.  Keras layouts are kept (D
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, Optional
 
 import torch

@@ -17,12 +17,12 @@ Parameter names (flat dict, Keras layouts):
 """
 from __future__ import annotations
 
-from typing import Dict, List
+from typing import Dict
 
 import torch
 
 from .. import lib
-from .models import LN_EPS, ForwardTransformer, _PackedLinear, _pad_vec, _round_up
+from .models import LN_EPS, ForwardTransformer, _PackedLinear, _round_up
 from .transformer_utils import mask_from_lengths, positional_encoding
 
 ALIGNER_VOCAB = 129  # 126 symbols + pad + start + end (reference: data/text/tokenizer.py:17-26 with add_start_end=True)

@@ -13,7 +13,6 @@ Differences to the ForwardTransformer blocks that matter for the backward pass:
 from __future__ import annotations
 
 import math
-from typing import Dict
 
 import torch
 

@@ -10,12 +10,12 @@ fp32 buffers so that Adam is one launch and data-parallel all-reduce works on co
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional
+from typing import Dict
 
 import torch
 
 from .. import lib
-from .models import LN_EPS, _PackedLinear, _pad_vec, _round_up
+from .models import LN_EPS, _pad_vec, _round_up
 from .transformer_utils import mask_from_lengths
 
 
