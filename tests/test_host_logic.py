@@ -68,3 +68,12 @@ def test_aligner_host_mirror_parameters_and_persistence(tmp_path):
     import pytest
     with pytest.raises(lib.TtsbError):
         m2.predict(None)
+
+
+def test_duration_to_alignment_matrix():
+    import numpy as np
+    from transformertts_b200.utils.alignments import duration_to_alignment_matrix
+    m = duration_to_alignment_matrix([2, 0, 3, 1])
+    assert m.shape == (4, 6)
+    assert np.array_equal(m, np.array([[1, 1, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0], [0, 0, 1, 1, 1, 0], [0, 0, 0, 0, 0, 1]], dtype=float))
+    assert np.array_equal(m.sum(1), [2, 0, 3, 1]) and np.array_equal(m.sum(0), np.ones(6))

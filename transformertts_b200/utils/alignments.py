@@ -13,6 +13,17 @@ from .. import lib
 from .spectrogram_ops import mel_lengths, phoneme_lengths
 
 
+def duration_to_alignment_matrix(durations) -> np.ndarray:
+    """utils/alignments.py:94-100: (phonemes, frames) 0/1 matrix with durations[i] ones in row i, one after the other."""
+    durations = np.asarray(durations).astype(int)
+    starts = np.cumsum(np.append([0], durations[:-1]))
+    tot = int(np.sum(durations))
+    out = np.zeros((len(durations), tot))
+    for i, (s, d) in enumerate(zip(starts, durations)):
+        out[i, s:s + d] = 1.0
+    return out
+
+
 def attention_score(att: torch.Tensor, mel_len: torch.Tensor, phon_len: torch.Tensor, r: int = 1):
     """utils/metrics.py:5-24 -> (loc_score, peak_score, 3 / diag_score), each (N, heads) float32 on the GPU."""
     att = att.to(dtype=torch.float32).contiguous()
