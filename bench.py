@@ -134,8 +134,46 @@ def _inputs(seed):
     return fo.make_inputs('full', B, TP, TM, seed=seed)
 
 
+def _tf_reference_available() -> bool:
+    """prefer the real TF2 reference when it can be imported on this box (it cannot in this image: there is
+    no tensorflow wheel); tests/golden/make_golden_tf.py is the script that uses it when it exists."""
+    try:
+        import importlib.util
+        return importlib.util.find_spec('tensorflow') is not None and (ROOT / 'baseline' / '_ref').exists()
+    except Exception:
+        return False
+
+
+def _config_dict(world):
+    return {'workload': WORKLOAD, 'model': CFG_NAME, 'global_batch': B * world, 'seq_len': TM}
+
+
+def cpu_forward_rate(budget_s, min_passes=1, max_passes=8):
+    """The CPU path on the WHOLE 64-row batch of the workload (same rows, same shapes as the GPU step): one untimed pass
+    (builds the positional-encoding cache), then whole-batch passes until `budget_s` is used.  Returns (frames/s, passes,
+    seconds, cores, last output)."""
+    from oracle import forward_oracle as fo
+    cores = _pick_threads()
+    cfg = fo.CONFIGS[CFG_NAME]
+    p = fo.init_params(cfg, seed=7)
+    tok, dur, pit = _inputs(200)
+    cache = {}
+    with torch.no_grad():
+        fo.forward_transformer_call(p, cfg, tok[:1], dur[:1, :, None], pit[:1, :, None], _cache=cache)
+        t0 = time.perf_counter()
+        n = 0
+        ref = None
+        while n < min_passes or (time.perf_counter() - t0 < budget_s and n < max_passes):
+            ref = fo.forward_transformer_call(p, cfg, tok, dur[:, :, None], pit[:, :, None], _cache=cache)
+            n += 1
+        dt = time.perf_counter() - t0
+    return B * TM * n / dt, n, dt, cores, ref
+
+
 def cpu_reference_line(args, rank, world):
-    """--impl reference: the CPU path (oracle restatement of the TF2 graph) on the host cores, bounded sample."""
+    """--impl reference: the CPU path (oracle restatement of the TF2 graph) on the host cores.  Every step is the whole
+    64-row batch of the GPU arm's step (same config); when K+W whole steps do not fit the time budget the number of steps
+    actually run is reduced (and stated), never the step."""
     from oracle import forward_oracle as fo
     if rank != 0:
         return None
@@ -145,28 +183,33 @@ def cpu_reference_line(args, rank, world):
     tok, dur, pit = _inputs(200)
     cache = {}
 
-    def run(rows):
+    def run():
         with torch.no_grad():
-            return fo.forward_transformer_call(p, cfg, tok[:rows], dur[:rows, :, None], pit[:rows, :, None], _cache=cache)
+            return fo.forward_transformer_call(p, cfg, tok, dur[:, :, None], pit[:, :, None], _cache=cache)
 
+    with torch.no_grad():
+        fo.forward_transformer_call(p, cfg, tok[:1], dur[:1, :, None], pit[:1, :, None], _cache=cache)
     t0 = time.perf_counter()
-    run(1)
+    run()                                   # first whole step: also the estimate for the budget
     t1 = time.perf_counter() - t0
-    budget = 60.0
-    rows = int(max(1, min(B, budget / max(t1, 1e-3) / (args.steps + args.warmup))))
-    for _ in range(args.warmup):
-        run(rows)
+    budget = 240.0
+    warm = max(0, min(args.warmup - 1, int(0.15 * budget / t1)))
+    steps = max(1, min(args.steps, int((budget - (1 + warm) * t1) / t1)))
+    for _ in range(warm):
+        run()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        run(rows)
+    for _ in range(steps):
+        run()
     dt = time.perf_counter() - t0
-    val = rows * TM * args.steps / dt
-    sample = f'{rows} of {B} rows per step ({rows * TM} frames), torch-CPU fp32 oracle, {cores} threads'
-    return {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD},
+    val = B * TM * steps / dt
+    sample = (f'{steps} whole steps of {B} rows x {TM} frames (asked for {args.steps}; a whole step takes {t1:.1f} s on this host), '
+              f'torch-CPU fp32 oracle, {cores} threads')
+    return {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+            'warmup': warm + 1, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': _config_dict(1),
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'tf_reference_available': _tf_reference_available(),
             'note': 'TF2 reference cannot be installed offline (no tensorflow wheel); oracle/ is its CPU restatement'}
 
 
@@ -250,15 +293,19 @@ def hbm_bench(args, rank, world, dev, cfg):
                           'cpu_baseline': cpu}), flush=True)
 
 
-def train_bench(args, rank, world, dev, cfg, params):
+def train_bench(args, rank, world, dev, cfg, params, steps=None):
     """BASELINE configs[2]: LJ256 training step (fwd + bwd + Adam, dropout 0.1, bf16 tensor-core products), batch 32 per
-    GPU, 128 phonemes -> 1000 frames, gradients all-reduced with NCCL (sum, scaled 1/N inside the Adam kernel)."""
+    GPU, 128 phonemes -> 1000 frames, gradients all-reduced with NCCL (sum, scaled 1/N inside the Adam kernel).
+    Returns the record (rank 0) or None; the caller prints it (alone for --mode train, as the `train` key of the default
+    line otherwise)."""
     import torch.distributed as dist
     from oracle import forward_oracle as fo
     from transformertts_b200 import lib
     from transformertts_b200.model.models import ForwardTransformer
     from transformertts_b200.model.training import Adam
     Bt = 32
+    steps = steps or args.steps
+    warm = max(args.warmup, 3)
     model = ForwardTransformer(**cfg, device=str(dev), train_dropout=True)
     model.set_weights(params)
     model._compile(Adam(1e-4))
@@ -268,60 +315,94 @@ def train_bench(args, rank, world, dev, cfg, params):
     mel = fo.make_mel_targets(dur, cfg['mel_channels'], seed=400 + rank)
     tok_d, dur_d, pit_d, mel_d = tok.to(dev), dur.to(dev), pit.to(dev), mel.to(dev)
 
-    def step():
-        return model.train_step(tok_d, mel_d, dur_d, pit_d, data_parallel=world > 1)
+    def timed(dp):
+        """K device-resident steps, CUDA events, max over ranks -> ms per step."""
+        for _ in range(warm):
+            model.train_step(tok_d, mel_d, dur_d, pit_d, data_parallel=dp)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        lib.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            model.train_step(tok_d, mel_d, dur_d, pit_d, data_parallel=dp)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        n_launch = lib.launch_count()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, n_launch
 
-    for _ in range(max(args.warmup, 3)):
-        out = step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     sampler = ClockSampler(dev.index or 0) if rank == 0 else None
-    lib.reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
+    ms_step, launches = timed(world > 1)
+    clocks = sampler.stop() if sampler else None
+    # the same step WITHOUT the gradient all-reduce: the difference is the communication time the overlap did not hide
+    ms_local = timed(False)[0] if world > 1 else ms_step
+    # end to end through train_step() with HOST batches: the next batch's pinned H2D copies run on a side stream under the
+    # current step, the loss comes back to pinned host memory every step (read one step late, so no per-step host sync)
+    host = [t_.pin_memory() for t_ in (tok, mel, dur, pit)]
+    h2d_bytes = int(sum(t_.numel() * t_.element_size() for t_ in host))
+    side = torch.cuda.Stream(device=dev)
+    loss_h = [torch.zeros(1).pin_memory() for _ in range(2)]
+
+    def stage():
+        with torch.cuda.stream(side):
+            b = [t_.to(dev, non_blocking=True) for t_ in host]
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return b, ev
+
+    def e2e_loop(n):
+        nxt = stage()
+        last = None
+        for i in range(n):
+            (tk, ml, du, pi), ev = nxt
+            torch.cuda.current_stream().wait_event(ev)
+            for t_ in (tk, ml, du, pi):
+                t_.record_stream(torch.cuda.current_stream())
+            if i + 1 < n:
+                nxt = stage()
+            o = model.train_step(tk, ml, du, pi, data_parallel=world > 1)
+            loss_h[i & 1].copy_(o['loss'].reshape(1), non_blocking=True)
+            last = i & 1
+        torch.cuda.synchronize()
+        return float(loss_h[last])
+
+    e2e_loop(warm)
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
-    launches = lib.launch_count()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    clocks = sampler.stop() if sampler else None
-    # end to end: host batch (pinned) -> device every step, loss read back every step (as train_tts.py:151-158 does)
-    tok_h, dur_h, pit_h, mel_h = tok.pin_memory(), dur.pin_memory(), pit.pin_memory(), mel.pin_memory()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        o = model.train_step(tok_h.to(dev, non_blocking=True), mel_h.to(dev, non_blocking=True), dur_h.to(dev, non_blocking=True),
-                             pit_h.to(dev, non_blocking=True), data_parallel=world > 1)
-        loss_val = float(o['loss'])
-    torch.cuda.synchronize()
+    loss_val = e2e_loop(steps)
+    if world > 1:
+        dist.barrier()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     peak_tf, _, peak_src = _peaks()
     flops = 3.0 * fo.forward_flops(cfg, [TP] * Bt, [TM] * Bt)
-    if rank == 0:
-        sps = args.steps / (ms * 1e-3)
-        line = {'metric': 'train_steps_per_sec', 'value': sps, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps,
-                'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-                'config': {'workload': 'C3: LJ256 training step (fwd+bwd+Adam, dropout 0.1, MAE losses [1,1,3]), 32 rows/GPU, 128 phonemes -> 1000 frames',
-                           'model': CFG_NAME, 'global_batch': Bt * world, 'seq_len': TM, 'parallelism': f'dp{world} (NCCL all-reduce of the flat fp32 gradient in 2 buckets, decoder bucket overlapped with the encoder backward)',
-                           'l2': 'per-step working set exceeds the 126 MB L2'},
-                'frames_per_sec': sps * Bt * TM * world,
-                'e2e': {'value': args.steps / float(dt.item()), 'unit': 'steps/s', 'h2d_bytes_per_step': int(tok.numel() * 4 + dur.numel() * 4 + pit.numel() * 4 + mel.numel() * 4),
-                        'd2h_bytes_per_step': 4},
-                'gpu_launches': int(launches), 'clocks': clocks, 'loss': loss_val,
-                'roofline': {'bound': 'tensor', 'achieved': flops * world / (ms / args.steps * 1e-3) / 1e12 / world, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                             'frac': flops / (ms / args.steps * 1e-3) / 1e12 / peak_tf, 'traffic': None, 'peak_source': peak_src,
-                             'kernel': 'whole step (3x forward algorithmic FLOPs per GPU)'},
-                'cpu_baseline': None}
-        print(json.dumps(line), flush=True)
+    if rank != 0:
+        return None
+    sps = 1e3 / ms_step
+    return {'metric': 'train_steps_per_sec', 'value': sps, 'unit': 'steps/s', 'n_gpus': world, 'steps': steps,
+            'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'C3: LJ256 training step (fwd+bwd+Adam, dropout 0.1, MAE losses [1,1,3]), 32 rows/GPU, 128 phonemes -> 1000 frames',
+                       'model': CFG_NAME, 'global_batch': Bt * world, 'seq_len': TM,
+                       'parallelism': f'dp{world} (NCCL all-reduce of the flat fp32 gradient in 2 buckets, decoder bucket overlapped with the encoder backward)',
+                       'l2': 'per-step working set exceeds the 126 MB L2'},
+            'frames_per_sec': sps * Bt * TM * world,
+            'ms_per_step_without_allreduce': ms_local, 'nccl_exposed_ms': max(0.0, ms_step - ms_local) if world > 1 else 0.0,
+            'allreduce_bytes_per_step': int(eng.flat_g.numel() * 4) if world > 1 else 0,
+            'e2e': {'value': steps / float(dt.item()), 'unit': 'steps/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
+            'gpu_launches': int(launches), 'clocks': clocks, 'loss': loss_val,
+            'roofline': {'bound': 'tensor', 'achieved': flops / (ms_step * 1e-3) / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                         'frac': flops / (ms_step * 1e-3) / 1e12 / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                         'kernel': 'whole step (3x forward algorithmic FLOPs per GPU)'},
+            'cpu_baseline': None}
 
 
 def aligner_flops(cfg, B, Tp, T, r=1):
@@ -458,6 +539,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='default mode: skip the C3 training-step record')
     ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'stft', 'expand', 'aligner'],
                     help="'train': BASELINE configs[2] (fwd+bwd+Adam, bf16, batch 32/GPU, NCCL data parallel); 'stft': configs[3] "
                          "(STFT->mel, 256 clips x 10 s); 'expand': the length regulator alone (C2-LR)")
@@ -498,7 +580,9 @@ def main():
             dist.destroy_process_group()
         return
     if args.mode == 'train':
-        train_bench(args, rank, world, dev, cfg, params)
+        rec = train_bench(args, rank, world, dev, cfg, params)
+        if rec is not None:
+            print(json.dumps(rec), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -613,36 +697,34 @@ def main():
                 'mel_max_abs_diff_vs_bf16x3': float((o2['mel'] - out['mel']).abs().max())}
         del m2
 
-    # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 ----------------
+    # ---------------- CPU baseline (oracle port): whole 64-row steps, same method as --impl reference ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = _pick_threads()
-        rows = 2
-        cache = {}
-        with torch.no_grad():
-            fo.forward_transformer_call(params, cfg, tok[:1], dur[:1, :, None], pit[:1, :, None], _cache=cache)
-            t0 = time.perf_counter()
-            reps = 0
-            while time.perf_counter() - t0 < 15.0 and reps < 8:
-                ref = fo.forward_transformer_call(params, cfg, tok[:rows], dur[:rows, :, None], pit[:rows, :, None], _cache=cache)
-                reps += 1
-            dtc = time.perf_counter() - t0
-        cpu = {'value': rows * TM * reps / dtc, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-               'sample': f'{reps} x {rows} rows ({rows * TM} frames) of the same batch, torch-CPU fp32 oracle',
-               'mel_max_abs_err_gpu_vs_cpu': float((out['mel'][:rows].cpu() - ref['mel']).abs().max())}
+        rate, n_pass, secs, cores, ref = cpu_forward_rate(budget_s=20.0, min_passes=1, max_passes=3)
+        cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': f'{n_pass} whole steps of {B} rows x {TM} frames in {secs:.1f} s, torch-CPU fp32 oracle (same as --impl reference)',
+               'mel_max_abs_err_gpu_vs_cpu': float((out['mel'].cpu() - ref['mel']).abs().max())}
+
+    # ---------------- BASELINE configs[2]: the training step (fwd+bwd+Adam, NCCL data parallel when N > 1) ----------------
+    train_rec = None
+    if not args.no_train:
+        del model
+        torch.cuda.empty_cache()
+        train_rec = train_bench(args, rank, world, dev, cfg, params)
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16x3 (3-pass bf16 tensor-core products, fp32 accumulate)' if args.precision == 'bf16x3' else 'bf16',
                 'data': 'synthetic',
-                'config': {'workload': WORKLOAD, 'model': CFG_NAME, 'global_batch': B * world, 'seq_len': TM,
+                'config': {**_config_dict(world),
                            'parallelism': f'batch-sharded replicas x{world}, no collective (inference)',
                            'l2': 'no explicit flush: per-step working set (~1.5 GB of activations) exceeds the 126 MB L2'},
                 'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
                 'model_tflops': model_tf, 'algorithmic_gflop_per_step_per_gpu': step_flops / 1e9,
-                'cpu_baseline': cpu, 'fast_mode': fast}
+                'cpu_baseline': cpu, 'fast_mode': fast, 'train': train_rec,
+                'tf_reference_available': _tf_reference_available()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

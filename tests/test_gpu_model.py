@@ -34,6 +34,7 @@ def test_c1_golden_forced_durations(impl):
 
 
 def test_c1_golden_ragged_batch_and_padding_quirks():
+    """c1_forward.npz is written by the reference's own code (tests/golden/make_golden_ref.py)."""
     g = np.load(GOLD / 'c1_forward.npz')
     p = fo.init_params(fo.CONFIGS['C1'], seed=7)
     m = _model('C1', p)
@@ -47,6 +48,7 @@ def test_c1_golden_ragged_batch_and_padding_quirks():
     assert np.abs(mel[b, lens[b]:] - p['out.b'].numpy()).max() < 1e-6
     want_mask = (np.arange(mel.shape[1])[None] >= lens[:, None]).astype(np.float32)
     assert np.array_equal(out['expanded_mask'].cpu().numpy()[:, 0, 0], want_mask)
+    assert np.array_equal(out['expanded_mask'].cpu().numpy(), g['expanded_mask3'])
 
 
 def test_c1_predict_api_integer_durations():
@@ -229,3 +231,17 @@ def test_edge_predict_speed_regulator_and_duration_clamps():
         assert np.array_equal(got[safe], want[safe])
         if np.array_equal(got, want):
             assert (out['mel'].cpu() - ref['mel']).abs().max() < MEL_TOL
+
+
+def test_lj256_against_reference_code_golden():
+    """tests/golden/ref_lj256.npz: outputs of the UNMODIFIED reference ForwardTransformer (run on tests/tf_shim by
+    tests/golden/make_golden_ref.py) -- the CUDA path against numbers the reference's own code produced."""
+    g = np.load(GOLD / 'ref_lj256.npz')
+    p = fo.init_params(fo.CONFIGS['LJ256'], seed=7)
+    m = _model('LJ256', p)
+    out = m.call(torch.from_numpy(g['tokens']), target_durations=torch.from_numpy(g['durations']),
+                 target_pitch=torch.from_numpy(g['pitch']))
+    assert np.array_equal(out['int_durations'].cpu().numpy(), g['durations'])
+    assert np.abs(out['mel'].cpu().numpy() - g['mel']).max() < MEL_TOL
+    assert np.abs(out['duration'].cpu().numpy() - g['duration_pred']).max() < 1e-3
+    assert np.abs(out['pitch'].cpu().numpy() - g['pitch_pred']).max() < 1e-3

@@ -169,7 +169,8 @@ extern "C" int ttsb_attention_scores(const float* att, int B, int H, int Tq, int
     return bad("ttsb_attention_scores: bad arguments");
   const size_t sm = (size_t)Tq * sizeof(int);
   if (sm > 48 * 1024) {
-    static size_t attr = 48 * 1024;
+    static PerDevice<size_t> attr_pd;
+    size_t& attr = attr_pd.get();
     if (sm > attr) {
       TTSB_CUDA_OK(cudaFuncSetAttribute(attention_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       attr = sm;
@@ -188,7 +189,8 @@ extern "C" int ttsb_durations_from_attention(const float* att, int B, int H, int
   const size_t sm = 3 * (size_t)Tk * sizeof(double) + (size_t)H * sizeof(float) + 16;
   if (sm > 160 * 1024) return bad("ttsb_durations_from_attention: Tk too large");
   if (sm > 48 * 1024) {
-    static size_t attr = 48 * 1024;
+    static PerDevice<size_t> attr_pd;
+    size_t& attr = attr_pd.get();
     if (sm > attr) {
       TTSB_CUDA_OK(cudaFuncSetAttribute(durations_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       attr = sm;

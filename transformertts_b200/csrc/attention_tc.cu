@@ -610,10 +610,10 @@ static int launch_tc(const ttsb_mha_args* a, const MhaKParams& p, cudaStream_t s
     rc = make_tmap_bf16_3d(&tmK[hl], kv, (uint64_t)ld_kv, Tk, a->B, ld_kv, (uint64_t)ld_kv * Tk, 64, ATT_BKV);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice<bool> attr_set;
+  if (!attr_set.get()) {
     TTSB_CUDA_OK(cudaFuncSetAttribute(mha_tc_kernel<DH, kSplit, kF16, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.get() = true;
   }
   dim3 grid((a->T + ATT_BQ - 1) / ATT_BQ, a->H, a->B);
   mha_tc_kernel<DH, kSplit, kF16, kWide><<<grid, kWide ? ATT_THREADS_WIDE : ATT_THREADS_NARROW, Cfg::kSmemBytes, stream>>>(tmQ[0], tmQ[1], tmK[0], tmK[1], p);
@@ -678,7 +678,8 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
   const bool need_simt = a->impl == TTSB_IMPL_SIMT;  // the weights-only pass has its own tiled kernel (any Tk)
   if (need_simt && simt_smem > 200 * 1024) { set_last_error("ttsb_mha_fwd: Tk too large for the weights / SIMT kernel"); return TTSB_ERR_UNSUPPORTED; }
   if (need_simt && simt_smem > 48 * 1024) {
-    static size_t simt_attr = 0;
+    static PerDevice<size_t> simt_attr_pd;
+    size_t& simt_attr = simt_attr_pd.get();
     if (simt_smem > simt_attr) {
       TTSB_CUDA_OK(cudaFuncSetAttribute(mha_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt_smem));
       simt_attr = simt_smem;
@@ -710,8 +711,9 @@ extern "C" int ttsb_mha_fwd(const ttsb_mha_args* a, void* stream_v) {
     q.weights_only = 1;
     if (a->dh % 4) { set_last_error("ttsb_mha_fwd: the weights kernel needs head_dim %% 4 == 0"); return TTSB_ERR_UNSUPPORTED; }
     const size_t aw_smem = (size_t)(AW_Q * a->dh + AW_K * (a->dh + 4)) * sizeof(float);
-    static size_t aw_attr = 48 * 1024;
-    if (aw_smem > aw_attr) {
+    static PerDevice<size_t> aw_attr_pd;
+    size_t& aw_attr = aw_attr_pd.get();
+    if (aw_smem > 48 * 1024 && aw_smem > aw_attr) {
       TTSB_CUDA_OK(cudaFuncSetAttribute(mha_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aw_smem));
       aw_attr = aw_smem;
     }

@@ -377,10 +377,10 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 }
 
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const BgParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice<bool> attr_set;
+  if (!attr_set.get()) {
     TTSB_CUDA_OK(cudaFuncSetAttribute(bgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMEM_BYTES));
-    attr_set = true;
+    attr_set.get() = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   bgemm_tc_kernel<<<grid, BG_THREADS, BG_SMEM_BYTES, stream>>>(a0, a1, b, p);

@@ -951,18 +951,18 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       if (split) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDevice<bool> attr_set;
+        if (!attr_set.get()) {
           TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<true, true>::kSmemBytes));
-          attr_set = true;
+          attr_set.get() = true;
         }
         cfg.dynamicSmemBytes = GemmCfg<true, true>::kSmemBytes;
         TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, true, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], tmO[0], tmO[1], q));
       } else {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDevice<bool> attr_set;
+        if (!attr_set.get()) {
           TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<false, true>::kSmemBytes));
-          attr_set = true;
+          attr_set.get() = true;
         }
         cfg.dynamicSmemBytes = GemmCfg<false, true>::kSmemBytes;
         TTSB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, true, true>, tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], tmO[0], tmO[1], q));
@@ -974,11 +974,11 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
     const bool ln = q.gamma != nullptr;
 #define TTSB_GEMM_LAUNCH(SPLIT, LN)                                                                                                  \
   do {                                                                                                                               \
-    static bool attr_set = false;                                                                                                    \
-    if (!attr_set) {                                                                                                                 \
+    static PerDevice<bool> attr_set;                                                                                                    \
+    if (!attr_set.get()) {                                                                                                                 \
       TTSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<SPLIT, false, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
                                         GemmCfg<SPLIT, false>::kSmemBytes));                                                         \
-      attr_set = true;                                                                                                               \
+      attr_set.get() = true;                                                                                                               \
     }                                                                                                                                \
     gemm_tc_kernel<SPLIT, false, LN><<<grid, GEMM_THREADS, GemmCfg<SPLIT, false>::kSmemBytes, stream>>>(                               \
         tmA[0][0], tmA[0][1], tmA[1][0], tmA[1][1], tmW[0], tmW[1], tmO[0], tmO[1], q);                                                              \

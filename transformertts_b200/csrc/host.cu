@@ -27,12 +27,17 @@ int check_cuda(cudaError_t e, const char* what) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
 int num_sms() {
-  static int n = 0;
+  static PerDevice<int> sms;
+  int& n = sms.get();
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, current_device()) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
 }

@@ -194,7 +194,8 @@ stft_mel_kernel(const float* __restrict__ wav, int n_samples, int n_frames, int 
 }
 
 static int init_tables() {
-  static bool done = false;
+  static PerDevice<bool> done_pd;  // __constant__ tables and function attributes are per device
+  bool& done = done_pd.get();
   if (done) return 0;
   static float tr[NFFT], ti[NFFT], win[NFFT];
   for (int i = 0; i < NFFT; ++i) {

@@ -10,6 +10,15 @@ void set_last_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 void count_launch();
 int num_sms();
+int current_device();
+
+// State that CUDA keeps PER DEVICE (cudaFuncSetAttribute, __constant__ uploads, the SM count) must be initialised once per
+// device, not once per process: a process that touches a second GPU would otherwise run there with default limits / zero tables.
+template <typename T>
+struct PerDevice {
+  T v[64] = {};
+  T& get() { return v[current_device() & 63]; }
+};
 
 // bf16 tensor (dim0 contiguous, dim1 rows, dim2 batches); strides in ELEMENTS; 128-byte swizzle; OOB reads give zeros.
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1,

@@ -85,6 +85,10 @@ class Audio:
         return self._basis
 
     def mel_spectrogram_device(self, wav: torch.Tensor) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            return self._mel_spectrogram_device(wav)
+
+    def _mel_spectrogram_device(self, wav: torch.Tensor) -> torch.Tensor:
         """wav fp32 CUDA (n_clips, n_samples) -> fp32 CUDA (n_clips, 1 + n_samples//hop, n_mels)."""
         n_clips, n_samples = wav.shape
         out = torch.empty((n_clips, 1 + n_samples // self.hop_length, self.mel_channels), dtype=torch.float32, device=wav.device)

@@ -138,9 +138,9 @@ def bucket_index(length: int, boundaries: Sequence[int]) -> int:
     return i
 
 
-def _pad_stack(items: List[np.ndarray], dtype, pin: bool) -> torch.Tensor:
+def _pad_stack(items: List[np.ndarray], dtype, pin: bool, lead: Optional[int] = None) -> torch.Tensor:
     arrs = [np.asarray(a) for a in items]
-    lead = max(a.shape[0] for a in arrs)
+    lead = max([a.shape[0] for a in arrs] + [lead or 0])
     shape = (len(arrs), lead) + tuple(arrs[0].shape[1:])
     out = torch.zeros(shape, dtype=torch.from_numpy(np.zeros(0, dtype=dtype)).dtype)
     if pin and torch.cuda.is_available():
@@ -169,6 +169,14 @@ class Dataset:
         self.shuffle, self.drop_remainder = shuffle, drop_remainder
         self.pin_memory = pin_memory
         self.rank, self.world_size = int(rank), int(world_size)
+        if self.world_size > 1:
+            # data parallel: every emitted (global) batch is split into equal row slices, so that all ranks walk the same
+            # stream of batches, see shards of the same padded shape and the mean of the shard losses IS the loss of the
+            # global batch (the reference loss is a mean over the padded batch tensor, utils/losses.py:41-49)
+            bad = [b for b in self.batch_sizes if b % self.world_size]
+            if bad:
+                raise ValueError(f'data-parallel batching needs bucket batch sizes divisible by world_size={self.world_size}; got {bad} '
+                                 f'(round them with datasets.round_batch_sizes)')
         self._endless: Optional[Iterator] = None
 
     def _datagen(self, shuffle: bool):
@@ -179,12 +187,14 @@ class Dataset:
         return (self.preprocessor(s) for s in samples)
 
     def _emit(self, rows: list) -> dict:
+        # padded lengths come from the GLOBAL batch, so every rank's shard has the same shape
+        leads = [None if dt is None else max(np.asarray(r[k]).shape[0] for r in rows) for k, dt in enumerate(self.dtypes)]
         if self.world_size > 1:  # data parallel: rank r takes rows r, r + W, ... of every global batch
             rows = rows[self.rank::self.world_size]
         batch = {}
         for k, (name, dt) in enumerate(zip(self.fields, self.dtypes)):
             col = [r[k] for r in rows]
-            batch[name] = col if dt is None else _pad_stack(col, dt, self.pin_memory)
+            batch[name] = col if dt is None else _pad_stack(col, dt, self.pin_memory, leads[k])
         return batch
 
     def _one_pass(self) -> Iterator[dict]:
@@ -197,7 +207,10 @@ class Dataset:
                 yield self._emit(rows)
         if not self.drop_remainder:
             for rows in buckets:
-                if rows and len(rows[self.rank::self.world_size]) > 0:
+                # data parallel: the tail is cut to a multiple of world_size (identical on every rank), never skipped by
+                # some ranks only
+                rows = rows[:len(rows) - len(rows) % self.world_size]
+                if rows:
                     yield self._emit(rows)
 
     def all_batches(self) -> Iterator[dict]:
@@ -215,6 +228,12 @@ class Dataset:
                         raise RuntimeError('the dataset yields no batch (every bucket is smaller than its batch size)')
             self._endless = forever()
         return next(self._endless)
+
+
+def round_batch_sizes(batch_sizes: Sequence[int], world_size: int) -> List[int]:
+    """Bucket batch sizes of the single-process config (training_config.yaml:22-23) rounded DOWN to multiples of the
+    data-parallel world size (at least one row per rank)."""
+    return [max(world_size, b - b % world_size) for b in batch_sizes]
 
 
 class _FileDataset:
@@ -324,7 +343,13 @@ class PrefetchLoader:
         if batch is None:
             raise RuntimeError('prefetch thread failed') from self._error
         if event is not None:
-            torch.cuda.current_stream(self.device).wait_event(event)
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(event)
+            # the tensors were allocated on the side stream: tell the caching allocator that the consumer's stream uses them,
+            # or their blocks could be handed to the next prefetch copy while training kernels still read them
+            for v in batch.values():
+                if torch.is_tensor(v) and v.is_cuda:
+                    v.record_stream(cur)
         return batch
 
     __next__ = next

@@ -120,15 +120,27 @@ def _check(rc: int, what: str):
         raise TtsbError(f'{what} failed ({rc}): {load().ttsb_last_error().decode()}')
 
 
+_last_dev = -1  # device index of the last tensor handed to ptr(): checked against the current device by _stream()
+
+
 def ptr(t: Optional[torch.Tensor]):
+    global _last_dev
     if t is None:
         return None
     if not t.is_cuda:
         raise TtsbError('libttsb expects CUDA tensors')
+    _last_dev = t.device.index
     return C.c_void_p(t.data_ptr())
 
 
 def _stream():
+    """Current stream of the current device.  Kernels launch on the CURRENT device, so the tensors must live there: the
+    model classes enter `torch.cuda.device(model.device)` around every public call; raw users of this module get an error
+    instead of a launch on device 0 against device-1 pointers."""
+    cur = torch.cuda.current_device()
+    if _last_dev >= 0 and _last_dev != cur:
+        raise TtsbError(f'tensor lives on cuda:{_last_dev} but the current device is cuda:{cur}; '
+                        f'wrap the call in torch.cuda.device({_last_dev})')
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

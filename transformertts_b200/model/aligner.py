@@ -22,7 +22,7 @@ from typing import Dict
 import torch
 
 from .. import lib
-from .models import LN_EPS, ForwardTransformer, _PackedLinear, _round_up
+from .models import LN_EPS, ForwardTransformer, _on_device, _PackedLinear, _round_up
 from .transformer_utils import mask_from_lengths, positional_encoding
 
 ALIGNER_VOCAB = 129  # 126 symbols + pad + start + end (reference: data/text/tokenizer.py:17-26 with add_start_end=True)
@@ -353,6 +353,7 @@ class Aligner(ForwardTransformer):
                 'decoder_attention': attn, 'decoder_output': x[0], 'linear': linear,
                 'mel_mask': mask_from_lengths(dec_len, T), 'mel_lengths': dec_len}
 
+    @_on_device
     def call(self, inputs, targets, training=False):
         """models.py:294-298."""
         enc, padding_mask, enc_attn, enc_len = self._call_encoder(inputs, training)
@@ -366,13 +367,16 @@ class Aligner(ForwardTransformer):
     def _forward(self, inp, output):
         return self.call(inp, output, training=False)
 
+    @_on_device
     def _forward_encoder(self, inputs):
         enc, mask, attn, _ = self._call_encoder(inputs, training=False)
         return enc, mask, attn
 
+    @_on_device
     def _forward_decoder(self, encoder_output, targets, encoder_padding_mask):
         return self._call_decoder(encoder_output, targets, encoder_padding_mask, training=False)
 
+    @_on_device
     def _gta_forward(self, inp, tar, stop_prob, training=False):
         """models.py:168-210 (forward + losses).  Returns (model_out, None): there is no tape here."""
         tar = torch.as_tensor(tar).to(device=self.device, dtype=torch.float32)
@@ -413,6 +417,7 @@ class Aligner(ForwardTransformer):
             self._engine = AlignerTrainEngine(self)
         return self._engine
 
+    @_on_device
     def _train_step(self, inp, tar, stop_prob, data_parallel: bool = False):
         """models.py:212-216: teacher-forced forward (dropout on, single-pass bf16), hand-written backward, Adam.
         The returned dictionary has the losses and outputs; attention maps are not materialised in fp32 on this path."""

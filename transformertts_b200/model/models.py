@@ -22,6 +22,17 @@ import torch
 from .. import lib
 from .transformer_utils import mask_from_lengths, positional_encoding
 
+def _on_device(fn):
+    """Run a public method with the model's device as the current CUDA device (libttsb launches on the current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
+
+
 LN_EPS = 1e-6  # reference: model/layers.py:27,96,207,295,508
 DEFAULT_VOCAB = 127  # 126 phoneme/punctuation symbols + pad id 0 (reference: data/text/tokenizer.py:17-20)
 
@@ -250,6 +261,7 @@ class ForwardTransformer:
     def trainable_variables(self) -> List[torch.Tensor]:
         return [self.weights[k] for k in self._param_shapes()]
 
+    @_on_device
     def build_model_weights(self) -> None:
         """Reference builds Keras variables with a dummy call (model/models.py:597-598); here they exist already."""
         self._prepare()
@@ -488,6 +500,7 @@ class ForwardTransformer:
     # ------------------------------------------------------------------------------------------------
     # reference API
     # ------------------------------------------------------------------------------------------------
+    @_on_device
     def call(self, x, target_durations=None, target_pitch=None, training=False, durations_scalar=1.,
              max_durations_mask=None, min_durations_mask=None):
         """reference: model/models.py:518-550.  x int (B,Tp) with trailing pad id 0; targets (B,Tp,1) or (B,Tp)."""
@@ -651,6 +664,7 @@ class ForwardTransformer:
             self._engine = TrainEngine(self)
         return self._engine
 
+    @_on_device
     def train_step(self, input_sequence, target_sequence, target_durations, target_pitch, data_parallel: bool = False):
         """reference: model/models.py:464-482.  data_parallel=True: this process holds one shard of the batch; gradients
         are summed over the default torch.distributed group (bucketed, overlapped with the backward pass) and scaled 1/N."""
@@ -666,6 +680,7 @@ class ForwardTransformer:
         eng.apply_adam(self.optimizer, grad_scale=scale)
         return out
 
+    @_on_device
     def val_step(self, input_sequence, target_sequence, target_durations, target_pitch):
         """reference: model/models.py:492-507."""
         return self._get_engine().forward_backward(input_sequence, target_sequence, target_durations, target_pitch, training=False)
