@@ -47,6 +47,9 @@ int ttsb_abi_version(void);
 /* number of kernels this library has launched since load / since the last reset (bench.py "gpu_launches") */
 int64_t ttsb_launch_count(void);
 void ttsb_reset_launch_count(void);
+/* a host that replays a captured CUDA graph of N library launches adds N per replay, so the counter keeps meaning
+ * "kernels of this library that ran" */
+void ttsb_add_launch_count(int64_t n);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Weight / activation preparation
@@ -331,7 +334,8 @@ int ttsb_pitch_embed_add_fwd(const float* x, const float* pitch, const float* w,
  * Length regulator  (model/models.py:532-540, model/layers.py:549-565)
  * ------------------------------------------------------------------------------------------------------- */
 /* durations (B,Tp) fp32 * scalar -> min(max_mask) -> max(min_mask) -> round-half-even -> int32.
- * max_mask / min_mask may be NULL.  Also writes per-row totals to out_len[B]. */
+ * max_mask / min_mask may be NULL.  Also writes per-row totals to out_len[B]; a row that holds a negative duration gets
+ * out_len = -1 (the reference's ragged-tensor construction raises on it; the host checks this one array). */
 int ttsb_durations_to_int(const float* dur, float scalar, const float* max_mask, const float* min_mask, int B, int Tp,
                           int32_t* out_int, int32_t* out_len, void* stream);
 /* int durations (B,Tp) -> frame->phoneme index map (B,Tm) (-1 at padded frames); row totals must be <= Tm */

@@ -245,3 +245,34 @@ def test_lj256_against_reference_code_golden():
     assert np.abs(out['mel'].cpu().numpy() - g['mel']).max() < MEL_TOL
     assert np.abs(out['duration'].cpu().numpy() - g['duration_pred']).max() < 1e-3
     assert np.abs(out['pitch'].cpu().numpy() - g['pitch_pred']).max() < 1e-3
+
+
+def test_cuda_graph_replay_equals_eager():
+    """cuda_graphs=True: the two halves of call() are captured per shape and replayed; results must equal the eager path bit
+    for bit, stay valid after later calls (outputs are copied out of the static buffers), follow new input VALUES on replay,
+    and a new output length must get its own decoder graph."""
+    from transformertts_b200 import lib
+    cfg = fo.CONFIGS['C1']
+    p = fo.init_params(cfg, seed=7)
+    eager = _model('C1', p)
+    graphed = _model('C1', p, cuda_graphs=True)
+    outs = []
+    for seed, Tm in ((11, 180), (12, 180), (13, 210), (11, 180)):
+        tok, dur, pit = fo.make_inputs('ragged', 3, 32, Tm, seed=seed)
+        a = eager.call(tok, target_durations=dur, target_pitch=pit)
+        n0 = lib.launch_count()
+        b = graphed.call(tok, target_durations=dur, target_pitch=pit)
+        assert lib.launch_count() - n0 > 20          # replays are counted as the launches they contain
+        for k in ('mel', 'duration', 'pitch', 'int_durations', 'mel_lengths', 'expanded_mask'):
+            assert torch.equal(a[k], b[k]), (seed, k)
+        outs.append((a['mel'].clone(), b['mel']))
+    for want, got in outs:                            # earlier results were not overwritten by later replays
+        assert torch.equal(want, got)
+    assert len(graphed._enc_graphs) == 1 and len(next(iter(graphed._enc_graphs.values()))['dec']) == 2
+    # predicted durations (no targets) through predict(), graph path == eager path
+    tok, _, _ = fo.make_inputs('ragged', 2, 32, 100, seed=14)
+    a = eager.predict(tok, encode=False, speed_regulator=0.9)
+    b = graphed.predict(tok, encode=False, speed_regulator=0.9)
+    assert torch.equal(a['mel'], b['mel']) and torch.equal(a['int_durations'], b['int_durations'])
+    with pytest.raises(ValueError):
+        graphed.call(tok, target_durations=-torch.ones(2, 32), target_pitch=torch.zeros(2, 32))

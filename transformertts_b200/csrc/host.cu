@@ -109,3 +109,4 @@ extern "C" const char* ttsb_last_error(void) { return ttsb::g_err; }
 extern "C" int ttsb_abi_version(void) { return TTSB_ABI_VERSION; }
 extern "C" int64_t ttsb_launch_count(void) { return ttsb::g_launches.load(); }
 extern "C" void ttsb_reset_launch_count(void) { ttsb::g_launches.store(0); }
+extern "C" void ttsb_add_launch_count(int64_t n) { ttsb::g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -155,7 +155,7 @@ __global__ void length_regulate_kernel(const float* __restrict__ x, const int* _
 __global__ void durations_to_int_kernel(const float* __restrict__ dur, float scalar, const float* max_mask,
                                         const float* min_mask, int Tp, int* __restrict__ out_int, int* __restrict__ out_len) {
   const int b = blockIdx.x;
-  int local = 0;
+  int local = 0, neg = 0;
   for (int i = threadIdx.x; i < Tp; i += blockDim.x) {
     const size_t o = (size_t)b * Tp + i;
     float v = __fmul_rn(dur[o], scalar);
@@ -164,15 +164,21 @@ __global__ void durations_to_int_kernel(const float* __restrict__ dur, float sca
     const int n = __float2int_rn(v);  // round-half-to-even, as tf.math.round (model/layers.py:551)
     out_int[o] = n;
     local += n;
+    neg |= n < 0;
   }
-  __shared__ int red[32];
-  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __shared__ int red[32], red_neg[32];
+  for (int o = 16; o; o >>= 1) {
+    local += __shfl_xor_sync(0xffffffffu, local, o);
+    neg |= __shfl_xor_sync(0xffffffffu, neg, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = local; red_neg[threadIdx.x >> 5] = neg; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int s = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-    out_len[b] = s;
+    int s = 0, any_neg = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s += red[w]; any_neg |= red_neg[w]; }
+    // a negative duration has no meaning for the length regulator (the reference's RaggedTensor construction raises):
+    // flagged through the row length so that the host needs no second device->host read
+    out_len[b] = any_neg ? -1 : s;
   }
 }
 

@@ -20,7 +20,7 @@ _LIB_PATH = Path(os.environ.get('TTSB_LIB') or Path(__file__).resolve().parent /
 _lib = None
 
 EXPORTS = [
-    'ttsb_last_error', 'ttsb_abi_version', 'ttsb_launch_count', 'ttsb_reset_launch_count', 'ttsb_pack_weight',
+    'ttsb_last_error', 'ttsb_abi_version', 'ttsb_launch_count', 'ttsb_reset_launch_count', 'ttsb_add_launch_count', 'ttsb_pack_weight',
     'ttsb_repack_batched',
     'ttsb_split_bf16', 'ttsb_embed_ln_pe_fwd', 'ttsb_linear_fwd', 'ttsb_layernorm_fwd', 'ttsb_mha_fwd', 'ttsb_statpred_head_fwd',
     'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
@@ -108,6 +108,8 @@ def load() -> C.CDLL:
     lib.ttsb_last_error.restype = C.c_char_p
     lib.ttsb_launch_count.restype = C.c_int64
     lib.ttsb_reset_launch_count.restype = None
+    lib.ttsb_add_launch_count.restype = None
+    lib.ttsb_add_launch_count.argtypes = [C.c_int64]
     for name in EXPORTS:
         if not hasattr(lib, name):
             raise TtsbError(f'libttsb.so does not export {name}')
@@ -150,6 +152,10 @@ def launch_count() -> int:
 
 def reset_launch_count():
     load().ttsb_reset_launch_count()
+
+
+def add_launch_count(n: int):
+    load().ttsb_add_launch_count(int(n))
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -143,6 +143,12 @@ class ForwardTransformer:
         # of the tensor work of bf16x3; 'bf16' / 'bf16x3' remain selectable
         self.attention_precision = kwargs.get('attention_precision', 'fp16' if self.precision == 'bf16x3' else 'bf16')
         self.return_attention_weights = bool(kwargs.get('return_attention_weights', False))
+        # inference: capture the two halves of call() as CUDA graphs per input shape and replay them (see call())
+        self.cuda_graphs = bool(kwargs.get('cuda_graphs', False))
+        self.max_cached_graphs = int(kwargs.get('max_cached_graphs', 8))
+        self._enc_graphs = {}
+        self._graph_pool = None
+        self._len_host = None
         self.debug = debug
         self._stacks = {}
         for name in ('encoder', 'decoder'):
@@ -253,6 +259,7 @@ class ForwardTransformer:
             else:
                 self.weights[name] = t.to(self.device).contiguous()
         self._packed = None
+        self._enc_graphs = {}  # captured graphs hold the old packed operands
 
     def get_weights(self) -> Dict[str, torch.Tensor]:
         return {k: v.detach().clone() for k, v in self.weights.items()}
@@ -288,6 +295,7 @@ class ForwardTransformer:
         W = self.weights
         sp = self._split
         P = {'precision': self.precision}
+        self._enc_graphs = {}  # captured graphs read the previous packed operands
         for name, st in self._stacks.items():
             d = st['d']
             P[f'{name}.pe'] = self._prepare_pe(name)
@@ -318,6 +326,7 @@ class ForwardTransformer:
                 P[f'{name}.ln{j}'] = (_pad_vec(W[f'{name}.ln{j}.gamma'], pl.n_pad), _pad_vec(W[f'{name}.ln{j}.beta'], pl.n_pad))
                 cin = int(f)
         P['out'] = _PackedLinear(W['out.w'], W['out.b'], [self._stacks['decoder']['d']], sp)
+        P['pitch_embed.w'] = W['pitch_embed.w'].reshape(-1).contiguous()
         self._packed = P
         return P
 
@@ -500,72 +509,176 @@ class ForwardTransformer:
     # ------------------------------------------------------------------------------------------------
     # reference API
     # ------------------------------------------------------------------------------------------------
-    @_on_device
-    def call(self, x, target_durations=None, target_pitch=None, training=False, durations_scalar=1.,
-             max_durations_mask=None, min_durations_mask=None):
-        """reference: model/models.py:518-550.  x int (B,Tp) with trailing pad id 0; targets (B,Tp,1) or (B,Tp)."""
-        if training:
-            raise lib.TtsbError('training=True goes through train_step (dropout + backward); call() is inference-only')
-        P = self._prepare()
+    # ---- the two halves of call(): everything up to the integer durations, and the length regulator + decoder.  The
+    # output length Tm = max_b sum_i durations[b,i] is data dependent (as in the reference), so the host reads the row
+    # totals once between the two (one device->host copy + sync per call; it also carries the negative-duration flag).
+    def _stage_encoder(self, P, x, tgt_dur, tgt_pitch, scalar: float, mx, mn):
         W = self.weights
         dev = self.device
-        x = torch.as_tensor(x).to(device=dev, dtype=torch.int32).contiguous()
-        if x.dim() != 2:
-            raise ValueError('input tokens must have shape (batch, length)')
         B, Tp = x.shape
         d = self._stacks['encoder']['d']
-        # encoder padding -> per-row valid lengths (count of non-zero ids; batches are padded at the end)
         enc_len = torch.empty((B,), dtype=torch.int32, device=dev)
         lib.phoneme_lengths(x, 0, enc_len)
         h = self._act(B, Tp, d)
         lib.embed_ln_pe_fwd(x, W['embedding'], W['encoder.ln.gamma'], W['encoder.ln.beta'], P['encoder.pe'],
                             W['encoder.pos_scalar'].reshape(1), LN_EPS, h[0], h[1], h[2])
-        enc_attn, dec_attn = {}, {}
+        enc_attn = {}
         for i in range(len(self._stacks['encoder']['heads'])):
             h = self._block(P, 'encoder', i, h, enc_len, B, Tp, enc_attn, self._attn_key('encoder', i))
         durations = self._stat_predictor(P, 'dur_pred', h, enc_len, B, Tp, relu_head=True)
         pitch = self._stat_predictor(P, 'pitch_pred', h, enc_len, B, Tp, relu_head=False)
-        if target_pitch is not None:
-            src_pitch = torch.as_tensor(target_pitch).to(device=dev, dtype=torch.float32).reshape(B, Tp).contiguous()
-        else:
-            src_pitch = pitch
+        src_pitch = tgt_pitch if tgt_pitch is not None else pitch
         h_pe = torch.empty((B, Tp, d), dtype=torch.float32, device=dev)
-        lib.pitch_embed_add_fwd(h[0], src_pitch, W['pitch_embed.w'].reshape(-1).contiguous(), W['pitch_embed.b'], h_pe)
-        if target_durations is not None:
-            use_dur = torch.as_tensor(target_durations).to(device=dev, dtype=torch.float32).reshape(B, Tp).contiguous()
-            scalar = 1.0
-        else:
-            use_dur = durations
-            scalar = float(durations_scalar)
-        mx = torch.as_tensor(max_durations_mask).to(device=dev, dtype=torch.float32).contiguous() if max_durations_mask is not None else None
-        mn = torch.as_tensor(min_durations_mask).to(device=dev, dtype=torch.float32).contiguous() if min_durations_mask is not None else None
+        lib.pitch_embed_add_fwd(h[0], src_pitch, P['pitch_embed.w'], W['pitch_embed.b'], h_pe)
+        use_dur = tgt_dur if tgt_dur is not None else durations
         dur_int = torch.empty((B, Tp), dtype=torch.int32, device=dev)
         dec_len = torch.empty((B,), dtype=torch.int32, device=dev)
         lib.durations_to_int(use_dur, scalar, mx, mn, dur_int, dec_len)
-        Tm = int(dec_len.max().item())  # output shape is data dependent (as in the reference): one host sync
-        if int(dur_int.min().item()) < 0:
-            raise ValueError('negative duration')
+        return {'h_pe': h_pe, 'durations': durations, 'pitch': pitch, 'dur_int': dur_int, 'dec_len': dec_len,
+                'encoder_attention': enc_attn}
+
+    def _stage_decoder(self, P, st, B: int, Tm: int):
+        W = self.weights
+        dev = self.device
         dd = self._stacks['decoder']['d']
+        dec_attn = {}
+        idx = torch.empty((B, Tm), dtype=torch.int32, device=dev)
+        lib.expand_indices(st['dur_int'], Tm, idx)
+        m = self._act(B, Tm, dd)
+        lib.expand_ln_pe_fwd(st['h_pe'], idx, W['decoder.ln.gamma'], W['decoder.ln.beta'], P['decoder.pe'],
+                             W['decoder.pos_scalar'].reshape(1), LN_EPS, m[0], m[1], m[2])
+        for i in range(len(self._stacks['decoder']['heads'])):
+            m = self._block(P, 'decoder', i, m, st['dec_len'], B, Tm, dec_attn, self._attn_key('decoder', i))
+        mel = torch.empty((B, Tm, self.mel_channels), dtype=torch.float32, device=dev)
+        self._gemm(P['out'], B, Tm, [(m[1], m[2], dd, 0)], [0], [0], out_f32=mel, ld_out=self.mel_channels)
+        return mel, dec_attn
+
+    def _read_lengths(self, dec_len: torch.Tensor) -> int:
+        """Row totals -> host (pinned, one sync): returns Tm; raises on a negative duration (flagged as length -1)."""
+        B = dec_len.shape[0]
+        if self._len_host is None or self._len_host.numel() < B:
+            self._len_host = torch.empty((max(B, 64),), dtype=torch.int32).pin_memory()
+        hb = self._len_host[:B]
+        hb.copy_(dec_len, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if int(hb.min()) < 0:
+            raise ValueError('negative duration')
+        return int(hb.max())
+
+    @_on_device
+    def call(self, x, target_durations=None, target_pitch=None, training=False, durations_scalar=1.,
+             max_durations_mask=None, min_durations_mask=None):
+        """reference: model/models.py:518-550.  x int (B,Tp) with trailing pad id 0; targets (B,Tp,1) or (B,Tp).
+
+        With ``cuda_graphs=True`` (constructor keyword) the two halves are captured once per input shape as CUDA graphs
+        and replayed: ~85 dependent launches become two graph launches (the step is otherwise partly host-launch bound)."""
+        if training:
+            raise lib.TtsbError('training=True goes through train_step (dropout + backward); call() is inference-only')
+        P = self._prepare()
+        dev = self.device
+        x = torch.as_tensor(x)
+        if x.dim() != 2:
+            raise ValueError('input tokens must have shape (batch, length)')
+        B, Tp = x.shape
+
+        def prep(t, dtype):
+            return None if t is None else torch.as_tensor(t).reshape(B, Tp)
+
+        tgt_dur, tgt_pitch = prep(target_durations, torch.float32), prep(target_pitch, torch.float32)
+        mx, mn = prep(max_durations_mask, torch.float32), prep(min_durations_mask, torch.float32)
+        scalar = 1.0 if tgt_dur is not None else float(durations_scalar)
+        use_graphs = self.cuda_graphs and not self.return_attention_weights and self._prof is None and self.impl != 'simt'
+        if use_graphs:
+            return self._call_graphed(P, x, tgt_dur, tgt_pitch, scalar, mx, mn)
+
+        def dev_t(t, dtype):
+            return None if t is None else t.to(device=dev, dtype=dtype).contiguous()
+
+        st = self._stage_encoder(P, dev_t(x, torch.int32), dev_t(tgt_dur, torch.float32), dev_t(tgt_pitch, torch.float32), scalar,
+                                 dev_t(mx, torch.float32), dev_t(mn, torch.float32))
+        Tm = self._read_lengths(st['dec_len'])
         if Tm == 0:
-            mel = torch.zeros((B, 0, self.mel_channels), dtype=torch.float32, device=dev)
+            mel, dec_attn = torch.zeros((B, 0, self.mel_channels), dtype=torch.float32, device=dev), {}
         else:
-            idx = torch.empty((B, Tm), dtype=torch.int32, device=dev)
-            lib.expand_indices(dur_int, Tm, idx)
-            m = self._act(B, Tm, dd)
-            lib.expand_ln_pe_fwd(h_pe, idx, W['decoder.ln.gamma'], W['decoder.ln.beta'], P['decoder.pe'],
-                                 W['decoder.pos_scalar'].reshape(1), LN_EPS, m[0], m[1], m[2])
-            for i in range(len(self._stacks['decoder']['heads'])):
-                m = self._block(P, 'decoder', i, m, dec_len, B, Tm, dec_attn, self._attn_key('decoder', i))
-            mel = torch.empty((B, Tm, self.mel_channels), dtype=torch.float32, device=dev)
-            self._gemm(P['out'], B, Tm, [(m[1], m[2], dd, 0)], [0], [0], out_f32=mel, ld_out=self.mel_channels)
-        return {'mel': mel,
-                'duration': durations[..., None],
-                'pitch': pitch[..., None],
+            mel, dec_attn = self._stage_decoder(P, st, B, Tm)
+        return self._outputs(st, mel, dec_attn, Tm)
+
+    def _outputs(self, st, mel, dec_attn, Tm, clone: bool = False):
+        c = (lambda t: t.clone()) if clone else (lambda t: t)
+        dec_len = c(st['dec_len'])
+        return {'mel': c(mel),
+                'duration': c(st['durations'])[..., None],
+                'pitch': c(st['pitch'])[..., None],
                 'expanded_mask': mask_from_lengths(dec_len, Tm),
-                'encoder_attention': enc_attn,
+                'encoder_attention': st['encoder_attention'],
                 'decoder_attention': dec_attn,
-                'int_durations': dur_int,
+                'int_durations': c(st['dur_int']),
                 'mel_lengths': dec_len}
+
+    # ---- CUDA-graph replay of the two halves (static input / output buffers live in one private memory pool)
+    def _capture(self, fn):
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()                       # eager warm-up on the capture shapes (one-time function attributes, allocator warm-up)
+        torch.cuda.current_stream().wait_stream(side)
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        g = torch.cuda.CUDAGraph()
+        n0 = lib.launch_count()
+        with torch.cuda.graph(g, pool=self._graph_pool):
+            out = fn()
+        g.ttsb_launches = lib.launch_count() - n0   # kernels of the library inside this graph (added per replay)
+        return g, out
+
+    @staticmethod
+    def _replay(g):
+        g.replay()
+        lib.add_launch_count(g.ttsb_launches)
+
+    def _call_graphed(self, P, x, tgt_dur, tgt_pitch, scalar, mx, mn):
+        dev = self.device
+        B, Tp = x.shape
+        key = (B, Tp, tgt_dur is not None, tgt_pitch is not None, mx is not None, mn is not None, scalar, self.precision,
+               self.attention_precision, id(P))
+        ent = self._enc_graphs.get(key)
+        if ent is None:
+            if len(self._enc_graphs) >= self.max_cached_graphs:
+                self._enc_graphs.pop(next(iter(self._enc_graphs)))
+            f32 = lambda t: None if t is None else torch.empty((B, Tp), dtype=torch.float32, device=dev)  # noqa: E731
+            ins = {'x': torch.empty((B, Tp), dtype=torch.int32, device=dev), 'dur': f32(tgt_dur), 'pitch': f32(tgt_pitch),
+                   'mx': f32(mx), 'mn': f32(mn)}
+            self._fill(ins, x, tgt_dur, tgt_pitch, mx, mn)
+            g, st = self._capture(lambda: self._stage_encoder(P, ins['x'], ins['dur'], ins['pitch'], scalar, ins['mx'], ins['mn']))
+            ent = {'ins': ins, 'graph': g, 'st': st, 'dec': {}}
+            self._enc_graphs[key] = ent
+        else:
+            self._enc_graphs[key] = self._enc_graphs.pop(key)   # most recently used last
+            self._fill(ent['ins'], x, tgt_dur, tgt_pitch, mx, mn)
+        self._replay(ent['graph'])
+        st = ent['st']
+        Tm = self._read_lengths(st['dec_len'])
+        if Tm == 0:
+            return self._outputs(st, torch.zeros((B, 0, self.mel_channels), dtype=torch.float32, device=dev), {}, 0, clone=True)
+        dec = ent['dec'].get(Tm)
+        if dec is None:
+            if len(ent['dec']) >= self.max_cached_graphs:
+                ent['dec'].pop(next(iter(ent['dec'])))
+            g, (mel, dec_attn) = self._capture(lambda: self._stage_decoder(P, st, B, Tm))
+            dec = {'graph': g, 'mel': mel}
+            ent['dec'][Tm] = dec
+        else:
+            ent['dec'][Tm] = ent['dec'].pop(Tm)
+        self._replay(dec['graph'])
+        # outputs are copied out of the graph's static buffers (20 MB of mel at C2: ~6 us), so a result stays valid
+        # across later calls exactly as in eager mode
+        return self._outputs(st, dec['mel'], {}, Tm, clone=True)
+
+    @staticmethod
+    def _fill(ins, x, tgt_dur, tgt_pitch, mx, mn):
+        for dst, src in ((ins['x'], x), (ins['dur'], tgt_dur), (ins['pitch'], tgt_pitch), (ins['mx'], mx), (ins['mn'], mn)):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
 
     __call__ = call
 
