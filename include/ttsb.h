@@ -31,7 +31,7 @@ extern "C" {
 #define TTSB_ERR_CUDA (-2)
 #define TTSB_ERR_UNSUPPORTED (-3)
 
-#define TTSB_ABI_VERSION 2
+#define TTSB_ABI_VERSION 3
 
 /* precision of the tensor-core products */
 #define TTSB_PREC_BF16 0   /* single bf16 pass, fp32 accumulate */
@@ -127,6 +127,11 @@ typedef struct ttsb_gemm_args {
   uint32_t drop_pre_site, drop_post_site, drop_seed;
   int precision;            /* TTSB_PREC_* */
   int impl;                 /* TTSB_IMPL_* */
+  /* residual given as a bf16 hi/lo pair instead of fp32 (residual == NULL): value = hi + lo, row stride ld_res.  In
+   * bf16x3 inference the activation pair IS the residual stream (16 mantissa bits), so the LayerNorm GEMMs neither write
+   * nor re-read an fp32 copy of every activation (LayerNorm epilogue only). */
+  const void* residual_hi;
+  const void* residual_lo;
 } ttsb_gemm_args;
 
 int ttsb_linear_fwd(const ttsb_gemm_args* args, void* stream);

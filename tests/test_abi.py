@@ -28,7 +28,7 @@ def test_header_symbols_are_all_exported(cdll):
 
 
 def test_abi_version_and_error_text(cdll):
-    assert cdll.ttsb_abi_version() == 2
+    assert cdll.ttsb_abi_version() == 3
     rc = cdll.ttsb_linear_fwd(None, None)
     assert rc == -1
     assert b'NULL' in cdll.ttsb_last_error()

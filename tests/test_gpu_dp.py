@@ -1,0 +1,33 @@
+"""Data-parallel training on NCCL (BASELINE.json configs[2]; the reference has no distributed code): a step on two 16-row
+shards with the gradient all-reduce must be the step of one process on the 32-row batch.  Needs 2 GPUs
+(`gpurun --gpus 2 -- python -m pytest tests/test_gpu_dp.py -m gpu`); skipped on a 1-GPU box."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_dp_step_equals_single_process_step(tmp_path):
+    out = tmp_path / 'dp.pt'
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29541', str(ROOT / 'tests' / 'dp_worker.py'), str(out)],
+                       capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = torch.load(out)
+    assert d['same_across_ranks']
+    assert abs(d['loss_dp'] - d['loss_single']) < 1e-5 * abs(d['loss_single'])
+    g1, g2 = d['g_single'].double(), d['g_dp'].double()
+    gscale = float(g1.abs().max())
+    # same arithmetic on the same rows; only the order of the fp32 sums differs (atomics, two partial sums + all-reduce)
+    assert float((g1 - g2).abs().max()) < 2e-5 * gscale
+    assert float((g1 - g2).norm() / g1.norm()) < 1e-5
+    # weights after Adam: identical wherever the gradient is above rounding noise (Adam's first step is lr * g / |g|)
+    live = g1.abs() > 1e-3 * gscale
+    assert float(((d['w_single'] - d['w_dp']).abs() * live).max()) < 1e-6
+    assert float((d['w_single'] - d['w_dp']).abs().max()) <= 2.1e-4

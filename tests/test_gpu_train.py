@@ -295,21 +295,110 @@ def test_dropout_training_step_is_consistent():
     assert abs(fd1 / g1 - 1) < 0.1
 
 
-def test_train_tts_driver_runs_and_saves(tmp_path):
-    """train_tts.py (loop contract of the reference's script) on synthetic batches: loss is finite, a checkpoint in the
-    reference's two-file layout is written and loads back."""
+def _run_train_tts(args, cwd, nproc=1, timeout=900):
     import subprocess
     import sys
+    cmd = [sys.executable]
+    if nproc > 1:
+        cmd += ['-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={nproc}', '--master-addr', '127.0.0.1',
+                '--master-port', '29531']
+    r = subprocess.run(cmd + [str(cwd / 'train_tts.py')] + args, capture_output=True, text=True, timeout=timeout, cwd=str(cwd))
+    assert r.returncode == 0, r.stderr[-3000:]
+    return r.stdout
+
+
+def _losses(stdout):
+    import re
+    return {int(m.group(1)): float(m.group(2)) for m in re.finditer(r'step (\d+)  loss ([0-9.]+)', stdout)}
+
+
+def test_train_tts_driver_saves_and_resumes(tmp_path):
+    """train_tts.py (loop contract of the reference's script) on synthetic batches: a checkpoint directory in the reference's
+    layout (config.yaml + model_weights.hdf5, plus optimizer.pt) is written and loads back; a run that is stopped and
+    restarted continues with the SAME loss curve as an uninterrupted run (weights, Adam moments, step counter, learning-rate
+    schedule position, dropout seeds and the batch stream are all restored) -- reference train_tts.py:119-129."""
     from pathlib import Path
     root = Path(__file__).resolve().parent.parent
-    r = subprocess.run([sys.executable, str(root / 'train_tts.py'), '--config', str(root / 'config' / 'training_config.yaml'),
-                        '--synthetic', '--max_steps', '3', '--batch_size', '2', '--weights_dir', str(tmp_path)],
-                       capture_output=True, text=True, timeout=600, cwd=str(root))
-    assert r.returncode == 0, r.stderr[-2000:]
-    assert 'step 1  loss' in r.stdout and 'Done.' in r.stdout
+    base = ['--config', str(root / 'config' / 'training_config.yaml'), '--synthetic', '--batch_size', '2', '--checkpoint_frequency', '1']
+    full = _losses(_run_train_tts(base + ['--max_steps', '12', '--weights_dir', str(tmp_path / 'a')], root))
+    assert set(full) >= {1, 10} and all(math.isfinite(v) for v in full.values())
+    out1 = _run_train_tts(base + ['--max_steps', '5', '--weights_dir', str(tmp_path / 'b')], root)
+    assert 'starting training from scratch' in out1
+    out2 = _run_train_tts(base + ['--max_steps', '12', '--weights_dir', str(tmp_path / 'b')], root)
+    assert 'resuming training from step 5' in out2 and 'Done.' in out2
+    resumed = _losses(out2)
+    # weight-gradient sums use fp32 atomics (order varies run to run): equal to rounding noise, not bit-identical
+    assert abs(resumed[10] - full[10]) < 2e-3 * abs(full[10]), (resumed, full)
     from transformertts_b200.model.models import ForwardTransformer
-    m = ForwardTransformer.load_model(str(tmp_path / 'step_3'))
-    assert m.config['encoder_model_dimension'] == 256
+    from transformertts_b200.utils import hdf5_lite
+    m = ForwardTransformer.load_model(str(tmp_path / 'b' / 'step_12'))
+    assert m.config['encoder_model_dimension'] == 256 and m.step == 12 and m.optimizer.m is not None
+    tree = hdf5_lite.read_hdf5(tmp_path / 'b' / 'step_12' / 'model_weights.hdf5')      # the Keras-format weight file
+    assert [n.decode() for n in tree.attrs['layer_names']][:2] == ['Embedding', 'Encoder']
+    (tmp_path / 'b' / 'step_12' / 'model_weights.pt').unlink()                          # load from the HDF5 file alone
+    m2 = ForwardTransformer.load_model(str(tmp_path / 'b' / 'step_12'))
+    for k, v in m.weights.items():
+        assert torch.equal(v, m2.weights[k]), k
+
+
+def _write_training_data(cm, n_train=40, n_valid=8, seed=1):
+    """The on-disk layout of the reference's create_training_data.py / extract_durations.py, filled with random utterances."""
+    from transformertts_b200.data.text import ALL_PHONEMES
+    rng = np.random.default_rng(seed)
+    for d in (cm.data_dir, cm.mel_dir, cm.duration_dir, cm.pitch_per_char):
+        d.mkdir(parents=True, exist_ok=True)
+    letters = [c for c in ALL_PHONEMES if c.isalpha()][:30] + [' ']
+    for meta, n, tag in ((cm.train_metadata_path, n_train, 't'), (cm.valid_metadata_path, n_valid, 'v')):
+        lines = []
+        for i in range(n):
+            n_tok = int(rng.integers(8, 30))
+            dur = rng.integers(1, 7, n_tok).astype(np.int32)
+            name = f'{tag}{i:03d}'
+            np.save(cm.mel_dir / f'{name}.npy', np.clip(rng.normal(-5, 2, (int(dur.sum()), 80)), -11.5, 2).astype(np.float32))
+            np.save(cm.duration_dir / f'{name}.npy', dur)
+            np.save(cm.pitch_per_char / f'{name}.npy', rng.normal(0, 1, n_tok).astype(np.float32))
+            lines.append(f'{name}|' + ''.join(rng.choice(letters, n_tok)) + ('?' if i % 7 == 0 else '') * 0 + '\n')
+        meta.write_text(''.join(lines), encoding='utf-8')
+
+
+def _data_config(tmp_path):
+    import yaml
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    raw = yaml.safe_load((root / 'config' / 'training_config.yaml').read_text())
+    raw.setdefault('paths', {}).update(log_directory=str(tmp_path / 'logs'), train_data_directory=str(tmp_path / 'data'))
+    raw['training_data_settings'].update(bucket_boundaries=[60, 100], bucket_batch_sizes=[8, 6, 4], val_bucket_batch_size=[4, 4, 2])
+    raw['tts_settings'].update(validation_frequency=3, weights_save_frequency=1000, max_steps=4)
+    cfg_path = tmp_path / 'cfg.yaml'
+    cfg_path.write_text(yaml.safe_dump(raw))
+    return cfg_path
+
+
+def test_train_tts_from_disk_dataset(tmp_path):
+    """SURVEY 8(f) row 3 wired in: train_tts.py reads per-utterance .npy files + metadata through data/datasets.py (bucketing,
+    pinned batches, side-stream prefetch), trains and validates."""
+    from pathlib import Path
+    from transformertts_b200.utils.training_config_manager import TrainingConfigManager
+    root = Path(__file__).resolve().parent.parent
+    cfg_path = _data_config(tmp_path)
+    _write_training_data(TrainingConfigManager(str(cfg_path)))
+    out = _run_train_tts(['--config', str(cfg_path), '--max_steps', '4'], root)
+    losses = _losses(out)
+    assert 1 in losses and math.isfinite(losses[1]) and 'validation loss at step 3' in out and 'Done.' in out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (run with gpurun --gpus 2)')
+def test_train_tts_from_disk_dataset_data_parallel(tmp_path):
+    """The same under torchrun with 2 ranks: each rank takes its row slice of every global batch, NCCL all-reduce of the
+    gradient buckets, identical weights on both ranks afterwards (checked through the printed loss being finite and the run
+    completing; weight equality across ranks is asserted in tests/test_gpu_dp.py)."""
+    from pathlib import Path
+    from transformertts_b200.utils.training_config_manager import TrainingConfigManager
+    root = Path(__file__).resolve().parent.parent
+    cfg_path = _data_config(tmp_path)
+    _write_training_data(TrainingConfigManager(str(cfg_path)))
+    out = _run_train_tts(['--config', str(cfg_path), '--max_steps', '4'], root, nproc=2)
+    assert 'validation loss at step 3' in out and 'Done.' in out
 
 
 def test_prefetch_loader_feeds_training_steps(tmp_path):

@@ -246,3 +246,58 @@ def test_tokenizer_and_metadata_readers(tmp_path):
     want_text, want_up = ref_mr.post_processed_reader(str(meta))
     got_text, got_up = ds.post_processed_reader(meta)
     assert got_text == want_text and got_up == want_up and len(got_up) == 20
+
+
+def test_keras_weight_order_follows_the_reference_constructors():
+    """model_weights.hdf5 is matched BY ORDER (transformertts_b200/model/hdf5_weights.py): the order must be the one in
+    which the reference's constructors assign layers and variables (Keras: own variables first, then tracked sub-layers in
+    assignment order) -- walked here on the reference classes themselves through the shim's Layer tracking."""
+    from transformertts_b200.model import hdf5_weights as hw
+    from transformertts_b200.model.models import ForwardTransformer
+    for cfg_name in ('C1', 'LJ256'):
+        cfg = fo.CONFIGS[cfg_name]
+        p = fo.init_params(cfg, seed=7)
+        tok, dur, pit = fo.make_inputs('ragged', 2, 16, 60, seed=5)
+        ref = ref_shim.reference_forward_transformer(cfg, p, (tok, dur[..., None].float(), pit[..., None]))
+        ident = {id(v): k for k, v in ref_shim.ft_named_parameters(ref, cfg).items()}
+        ours = ForwardTransformer(**cfg, device='cpu')
+        want = [(lname, [flat for _, flat in ws]) for lname, ws in hw.keras_layer_order(ours)]
+        got = []
+        for layer in ref.layers:
+            got.append((layer.name, [ident[id(v)] for v in layer.variables if id(v) in ident]))
+        assert [g[1] for g in got] == [w[1] for w in want]
+        # the explicitly named layers keep their names; the two unnamed Dense layers get counter-based names in TF
+        assert [g[0] for g in got if g[0][0].isupper() or '_pred' in g[0] or g[0] == 'expand'] == \
+            ['Embedding', 'Encoder', 'dur_pred', 'expand', 'pitch_pred', 'Decoder']
+
+
+def test_tokenizer_mirror_equals_reference_tokenizer():
+    from data.text.symbols import all_phonemes
+    from data.text.tokenizer import Tokenizer as RefTok
+    from transformertts_b200.data.text import ALL_PHONEMES, Tokenizer
+    assert ALL_PHONEMES == all_phonemes
+    rng = np.random.default_rng(0)
+    for se, br in ((False, False), (True, False), (False, True), (True, True)):
+        a, b = Tokenizer(add_start_end=se, model_breathing=br), RefTok(add_start_end=se, model_breathing=br)
+        assert a.vocab_size == b.vocab_size
+        for _ in range(20):
+            s = ''.join(rng.choice(all_phonemes, size=int(rng.integers(1, 40))))
+            assert a(s) == b(s)
+            assert a.decode(a(s)) == b.decode(b(s))
+    alpha = 'abc xyz'
+    assert Tokenizer(alphabet=alpha)('a cab') == RefTok(alphabet=alpha)('a cab')
+
+
+def test_keras_weight_order_of_the_aligner():
+    from transformertts_b200.model import hdf5_weights as hw
+    from transformertts_b200.model.aligner import Aligner
+    cfg = alo.ALIGNER_CONFIGS['A-small']
+    p = alo.init_aligner_params(cfg, seed=7)
+    tok, mel, _ = alo.make_aligner_inputs(cfg, 2, 12, 21, seed=3)
+    ref = ref_shim.reference_aligner(cfg, p, (tok, mel[:, :-1]))
+    ident = {id(v): k for k, v in ref_shim.aligner_named_parameters(ref, cfg).items()}
+    ours = Aligner.from_config(dict(cfg, device='cpu'), max_r=cfg['max_r'])
+    want = [[flat for _, flat in ws] for _, ws in hw.keras_layer_order(ours)]
+    got = [[ident.get(id(v)) for v in layer.variables] for layer in ref.layers]
+    assert got == want          # includes DecoderPrenet's non-trainable rate variable (None) in last position
+    assert [layer.name for layer in ref.layers] == ['Embedding', 'Encoder', 'DecoderPrenet', 'Decoder', 'FinalProj', 'Postnet']

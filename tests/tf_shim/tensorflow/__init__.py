@@ -330,13 +330,22 @@ class Layer:
                         yield f'{k}.{j}', e
 
     def named_variables(self, prefix=''):
-        out = []
-        for k, v in self._children():
-            if isinstance(v, Variable):
-                out.append((prefix + k, v))
-            else:
-                out.extend(v.named_variables(prefix + k + '.'))
+        """Keras order (Layer.weights): the layer's OWN variables first, then its tracked sub-layers in the order they
+        were assigned as attributes (lists flattened in place)."""
+        return self._gather(prefix, True) + self._gather(prefix, False)
+
+    def _gather(self, prefix, trainable):
+        """Layer.weights = trainable_weights + non_trainable_weights, each: own variables, then the children's."""
+        kids = list(self._children())
+        out = [(prefix + k, v) for k, v in kids if isinstance(v, Variable) and v.requires_grad == trainable]
+        for k, v in kids:
+            if not isinstance(v, Variable):
+                out.extend(v._gather(prefix + k + '.', trainable))
         return out
+
+    @property
+    def layers(self):
+        return [v for _, v in self._children() if isinstance(v, Layer)]
 
     @property
     def variables(self):

@@ -39,6 +39,8 @@ struct GemmKParams {
   int relu;
   const float* residual;
   int ld_res;
+  const __nv_bfloat16* res_hi;  // LayerNorm epilogue: residual = hi + lo (bf16 pair) when `residual` is NULL
+  const __nv_bfloat16* res_lo;
   const float* gamma;
   const float* beta;
   float eps;
@@ -360,14 +362,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
   const float inv_n = 1.f / (float)ncols;
   uint32_t r2[16];
   float res[16], res2[16];
-  const bool has_res = p.residual != nullptr && row_ok;
-  const float* res_row = has_res ? p.residual + orow * (size_t)p.ld_res + n0 : nullptr;
+  const bool pair_res = p.residual == nullptr && p.res_hi != nullptr;
+  const bool has_res = (p.residual != nullptr || pair_res) && row_ok;
+  const float* res_row = (has_res && !pair_res) ? p.residual + orow * (size_t)p.ld_res + n0 : nullptr;
+  const __nv_bfloat16* res_row_hi = (has_res && pair_res) ? p.res_hi + orow * (size_t)p.ld_res + n0 : nullptr;
+  const __nv_bfloat16* res_row_lo = (has_res && pair_res) ? p.res_lo + orow * (size_t)p.ld_res + n0 : nullptr;
   auto fetch = [&](int ch, uint32_t (&rr)[16], float (&rs)[16]) {
     const int c0 = ch << 4;
     tmem_ld16(taddr + c0, rr);
     if (has_res) {
-      ld_global_nc_v8f(res_row + c0, rs);
-      ld_global_nc_v8f(res_row + c0 + 8, rs + 8);
+      if (pair_res) {
+        // 16 columns = 32 bytes of hi + 32 bytes of lo; x = hi + lo (bf16 -> fp32 is a 16-bit shift)
+        uint32_t h[8], l[8];
+        ld_global_nc_v8(res_row_hi + c0, h);
+        ld_global_nc_v8(res_row_lo + c0, l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          rs[2 * j] = __uint_as_float(h[j] << 16) + __uint_as_float(l[j] << 16);
+          rs[2 * j + 1] = __uint_as_float(h[j] & 0xffff0000u) + __uint_as_float(l[j] & 0xffff0000u);
+        }
+      } else {
+        ld_global_nc_v8f(res_row + c0, rs);
+        ld_global_nc_v8f(res_row + c0 + 8, rs + 8);
+      }
     }
   };
   float s_sh = 0.f, q_sh = 0.f, shiftK = 0.f;
@@ -799,7 +816,10 @@ static int validate(const ttsb_gemm_args* a, int* k_total_out) {
     return TTSB_ERR_INVALID_ARGUMENT;
   }
   if (a->ln_gamma && (n_tiles != 1 || !a->ln_beta)) { set_last_error("ttsb_linear_fwd: LayerNorm epilogue needs N <= block_n and beta"); return TTSB_ERR_INVALID_ARGUMENT; }
-  if (a->residual && (a->ld_res % 8)) { set_last_error("ttsb_linear_fwd: ld_res must be a multiple of 8 (32-byte loads)"); return TTSB_ERR_INVALID_ARGUMENT; }
+  if ((a->residual && (a->ld_res % 8)) || (!a->residual && a->residual_hi && (a->ld_res % 16))) {
+    set_last_error("ttsb_linear_fwd: ld_res must be a multiple of 8 (fp32) / 16 (bf16 pair): 32-byte loads");
+    return TTSB_ERR_INVALID_ARGUMENT;
+  }
   if (a->precision != TTSB_PREC_BF16 && a->precision != TTSB_PREC_BF16X3) { set_last_error("ttsb_linear_fwd: unknown precision"); return TTSB_ERR_INVALID_ARGUMENT; }
   *k_total_out = kt;
   return 0;
@@ -851,6 +871,14 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
     if (a->seg_k[s] > src_k[a->seg_src[s]]) src_k[a->seg_src[s]] = a->seg_k[s];
   }
   p.bias = a->bias; p.relu = a->relu; p.residual = a->residual; p.ld_res = a->ld_res;
+  p.res_hi = static_cast<const __nv_bfloat16*>(a->residual_hi);
+  p.res_lo = static_cast<const __nv_bfloat16*>(a->residual_lo);
+  if (!a->residual && (a->residual_hi || a->residual_lo)) {
+    if (!a->residual_hi || !a->residual_lo || !a->ln_gamma || a->impl == TTSB_IMPL_SIMT) {
+      set_last_error("ttsb_linear_fwd: a bf16 hi/lo residual needs both planes and the tcgen05 LayerNorm epilogue");
+      return TTSB_ERR_INVALID_ARGUMENT;
+    }
+  }
   p.gamma = a->ln_gamma; p.beta = a->ln_beta; p.eps = a->ln_eps; p.row_len = a->row_len;
   p.out_f32 = a->out_f32;
   p.out_hi = static_cast<__nv_bfloat16*>(a->out_hi);

@@ -47,6 +47,7 @@ class GemmArgs(C.Structure):
         ('out_lo', C.c_void_p), ('ld_out', C.c_int), ('out_fp16', C.c_int), ('out_preln', C.c_void_p),
         ('drop_pre_p', C.c_float), ('drop_post_p', C.c_float), ('drop_pre_site', C.c_uint32), ('drop_post_site', C.c_uint32),
         ('drop_seed', C.c_uint32), ('precision', C.c_int), ('impl', C.c_int),
+        ('residual_hi', C.c_void_p), ('residual_lo', C.c_void_p),
     ]
 
 
@@ -139,11 +140,17 @@ def _stream():
     """Current stream of the current device.  Kernels launch on the CURRENT device, so the tensors must live there: the
     model classes enter `torch.cuda.device(model.device)` around every public call; raw users of this module get an error
     instead of a launch on device 0 against device-1 pointers."""
-    cur = torch.cuda.current_device()
+    cur = _get_device()
     if _last_dev >= 0 and _last_dev != cur:
         raise TtsbError(f'tensor lives on cuda:{_last_dev} but the current device is cuda:{cur}; '
                         f'wrap the call in torch.cuda.device({_last_dev})')
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(_get_raw_stream(cur))
+
+
+# torch.cuda.current_stream() builds a Stream object through several python layers (~5 us); a training step makes ~400
+# launches, so the raw C entry points are used when this torch build has them
+_get_device = getattr(torch._C, '_cuda_getDevice', None) or torch.cuda.current_device
+_get_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None) or (lambda dev: torch.cuda.current_stream(dev).cuda_stream)
 
 
 def launch_count() -> int:

@@ -133,7 +133,8 @@ class ForwardTransformer:
         if encoder_model_dimension != decoder_model_dimension:
             raise ValueError('Expand feeds the encoder output to the decoder: model dimensions must match')
         self.mel_channels = int(mel_channels)
-        self.vocab_size = int(kwargs.get('vocab_size', DEFAULT_VOCAB))
+        # reference tokenizer: 126 symbols + pad, one more id when model_breathing adds the breathing token (tokenizer.py:28-33)
+        self.vocab_size = int(kwargs.get('vocab_size', DEFAULT_VOCAB + (1 if model_breathing else 0)))
         self.alphabet = kwargs.get('alphabet')
         self.device = torch.device(kwargs.get('device', 'cuda:0'))
         # numerics of the tensor-core products: 'bf16x3' meets the 1e-3 mel parity gate, 'bf16' is the fast mode
@@ -350,7 +351,7 @@ class ForwardTransformer:
 
     def _gemm(self, pl: _PackedLinear, B, T, srcs, seg_src, seg_shift, relu=False, residual=None, ln=None, row_len=None,
               out_f32=None, out_hi=None, out_lo=None, ld_out=None, tag=None, out_fp16=False, out_preln=None,
-              dropout=None, dropout_post=None):
+              dropout=None, dropout_post=None, residual_pair=None):
         prof = self._prof
         if prof is not None and tag is not None:
             e0 = torch.cuda.Event(enable_timing=True)
@@ -375,6 +376,10 @@ class ForwardTransformer:
         if residual is not None:
             a.residual = residual.data_ptr()
             a.ld_res = residual.shape[-1]
+        elif residual_pair is not None:   # the bf16 hi/lo activation pair is the residual stream (bf16x3 inference)
+            a.residual_hi = residual_pair[0].data_ptr()
+            a.residual_lo = residual_pair[1].data_ptr()
+            a.ld_res = residual_pair[0].shape[-1]
         unfused_ln = None
         if ln is not None and pl.n_tiles > 1:
             # the row does not fit one accumulator tile: GEMM writes the pre-norm value, LayerNorm runs as a row kernel
@@ -416,11 +421,21 @@ class ForwardTransformer:
             e1.record()
             prof.setdefault(tag, []).append((e0, e1, 2.0 * B * T * pl.K * pl.N))
 
+    def _pair_stream(self, name: str) -> bool:
+        """bf16x3 + tcgen05 + LayerNorm fused in the GEMM epilogue (row fits one accumulator tile or a CTA pair): the hi/lo
+        pair is the residual stream and no fp32 activation plane is kept between blocks."""
+        d = self._stacks[name]['d']
+        return self._split and self.impl != 'simt' and _pick_block_n(d, True) >= d
+
     def _conv_shifts(self, k: int) -> List[int]:
         return [j - (k - 1) // 2 for j in range(k)]
 
-    def _block(self, P, name: str, i: int, x, lens, B: int, T: int, attn_out: Optional[dict], key: str):
-        """One SelfAttentionDenseBlock / SelfAttentionConvBlock (reference: model/layers.py:214-264)."""
+    def _block(self, P, name: str, i: int, x, lens, B: int, T: int, attn_out: Optional[dict], key: str, need_f32: bool = True):
+        """One SelfAttentionDenseBlock / SelfAttentionConvBlock (reference: model/layers.py:214-264).
+
+        In bf16x3 mode the hi/lo pair of an activation carries 16 mantissa bits and serves as the residual stream itself:
+        the LayerNorm GEMMs then write no fp32 copy (x[0] / the returned z[0] are None unless `need_f32`) -- 4 instead of
+        8 bytes stored per element by the epilogue that bounds those GEMMs."""
         st = self._stacks[name]
         d, H = st['d'], st['heads'][i]
         dh = d // H
@@ -461,15 +476,20 @@ class ForwardTransformer:
         if attn_out is not None:
             attn_out[key] = wts
         # --- output projection on concat([x, attn]) + residual + LayerNorm + row mask
-        y = self._act(B, T, d)
-        self._gemm(P[pre + 'wo'], B, T, [(x_hi, x_lo, d, 0), (at_hi, at_lo, d, 0)], [0, 1], [0, 0], residual=x_f,
+        pair_stream = self._pair_stream(name)
+        y = self._act(B, T, d, f32=not pair_stream)
+
+        def res(t):  # residual operand of a LayerNorm GEMM: fp32 plane if it exists, else the hi/lo pair
+            return dict(residual=t[0]) if t[0] is not None else dict(residual_pair=(t[1], t[2]))
+
+        self._gemm(P[pre + 'wo'], B, T, [(x_hi, x_lo, d, 0), (at_hi, at_lo, d, 0)], [0, 1], [0, 0], **res(x),
                    ln=(W[pre + 'ln1.gamma'], W[pre + 'ln1.beta']), row_len=lens, out_f32=y[0], out_hi=y[1], out_lo=y[2])
-        z = self._act(B, T, d)
+        z = self._act(B, T, d, f32=need_f32 or not pair_stream)
         if i < st['n_dense']:
             F = int(st['ffn'])
             _, h_hi, h_lo = self._act(B, T, P[pre + 'ffn1'].n_pad, f32=False)
             self._gemm(P[pre + 'ffn1'], B, T, [(y[1], y[2], d, 0)], [0], [0], relu=True, out_hi=h_hi, out_lo=h_lo)
-            self._gemm(P[pre + 'ffn2'], B, T, [(h_hi, h_lo, P[pre + 'ffn1'].n_pad, 0)], [0], [0], residual=y[0],
+            self._gemm(P[pre + 'ffn2'], B, T, [(h_hi, h_lo, P[pre + 'ffn1'].n_pad, 0)], [0], [0], **res(y),
                        ln=(W[pre + 'ln2.gamma'], W[pre + 'ln2.beta']), row_len=lens, out_f32=z[0], out_hi=z[1], out_lo=z[2])
         else:
             k = int(st['kernel'])
@@ -482,7 +502,7 @@ class ForwardTransformer:
                 self._gemm(pl, B, T, [(h_hi, h_lo, ld, 0)], [0] * k, shifts, relu=True, out_hi=o_hi, out_lo=o_lo,
                            tag=f'{name}.conv{j}')
                 h_hi, h_lo, ld = o_hi, o_lo, pl.n_pad
-            self._gemm(P[pre + f'conv{n - 1}'], B, T, [(h_hi, h_lo, ld, 0)], [0] * k, shifts, residual=y[0],
+            self._gemm(P[pre + f'conv{n - 1}'], B, T, [(h_hi, h_lo, ld, 0)], [0] * k, shifts, **res(y),
                        ln=(W[pre + 'ln2.gamma'], W[pre + 'ln2.beta']), row_len=lens, out_f32=z[0], out_hi=z[1], out_lo=z[2],
                        tag=f'{name}.conv{n - 1}')
         return z
@@ -519,12 +539,14 @@ class ForwardTransformer:
         d = self._stacks['encoder']['d']
         enc_len = torch.empty((B,), dtype=torch.int32, device=dev)
         lib.phoneme_lengths(x, 0, enc_len)
-        h = self._act(B, Tp, d)
+        pair_stream = self._pair_stream('encoder')
+        h = self._act(B, Tp, d, f32=not pair_stream)
         lib.embed_ln_pe_fwd(x, W['embedding'], W['encoder.ln.gamma'], W['encoder.ln.beta'], P['encoder.pe'],
                             W['encoder.pos_scalar'].reshape(1), LN_EPS, h[0], h[1], h[2])
         enc_attn = {}
-        for i in range(len(self._stacks['encoder']['heads'])):
-            h = self._block(P, 'encoder', i, h, enc_len, B, Tp, enc_attn, self._attn_key('encoder', i))
+        n_enc = len(self._stacks['encoder']['heads'])
+        for i in range(n_enc):   # the pitch embedding below reads the fp32 plane of the last block
+            h = self._block(P, 'encoder', i, h, enc_len, B, Tp, enc_attn, self._attn_key('encoder', i), need_f32=(i == n_enc - 1))
         durations = self._stat_predictor(P, 'dur_pred', h, enc_len, B, Tp, relu_head=True)
         pitch = self._stat_predictor(P, 'pitch_pred', h, enc_len, B, Tp, relu_head=False)
         src_pitch = tgt_pitch if tgt_pitch is not None else pitch
@@ -544,11 +566,11 @@ class ForwardTransformer:
         dec_attn = {}
         idx = torch.empty((B, Tm), dtype=torch.int32, device=dev)
         lib.expand_indices(st['dur_int'], Tm, idx)
-        m = self._act(B, Tm, dd)
+        m = self._act(B, Tm, dd, f32=not self._pair_stream('decoder'))
         lib.expand_ln_pe_fwd(st['h_pe'], idx, W['decoder.ln.gamma'], W['decoder.ln.beta'], P['decoder.pe'],
                              W['decoder.pos_scalar'].reshape(1), LN_EPS, m[0], m[1], m[2])
         for i in range(len(self._stacks['decoder']['heads'])):
-            m = self._block(P, 'decoder', i, m, st['dec_len'], B, Tm, dec_attn, self._attn_key('decoder', i))
+            m = self._block(P, 'decoder', i, m, st['dec_len'], B, Tm, dec_attn, self._attn_key('decoder', i), need_f32=False)
         mel = torch.empty((B, Tm, self.mel_channels), dtype=torch.float32, device=dev)
         self._gemm(P['out'], B, Tm, [(m[1], m[2], dd, 0)], [0], [0], out_f32=mel, ld_out=self.mel_channels)
         return mel, dec_attn
@@ -734,7 +756,11 @@ class ForwardTransformer:
     # ------------------------------------------------------------------------------------------------
     # persistence (reference: model/models.py:600-638 -- config.yaml + weights file in one directory)
     # ------------------------------------------------------------------------------------------------
-    def save_model(self, path: str):
+    def save_model(self, path: str, with_optimizer: bool = True):
+        """reference: model/models.py:600-619 (config.yaml with `step` + weights in one directory).  Besides the weights
+        the optimizer state is written (Adam moments, iterations, learning rate, dropout seed base), which is what the
+        reference's tf.train.Checkpoint(step, optimizer, net) holds (train_tts.py:121-131): a directory written here is
+        enough to resume training bit-for-bit."""
         import yaml
         path = Path(path)
         path.mkdir(parents=True, exist_ok=True)
@@ -744,18 +770,66 @@ class ForwardTransformer:
         cfg['step'] = self.step
         with open(path / 'config.yaml', 'w') as f:
             yaml.safe_dump(cfg, f)
-        torch.save({k: v.cpu() for k, v in self.weights.items()}, path / 'model_weights.pt')
+        torch.save({k: v.detach().cpu() for k, v in self.weights.items()}, path / 'model_weights.pt')
+        from .hdf5_weights import save_keras_hdf5
+        save_keras_hdf5(self, path / 'model_weights.hdf5')
+        if with_optimizer and self.optimizer is not None:
+            torch.save(self.optimizer_state(), path / 'optimizer.pt')
+
+    def optimizer_state(self) -> dict:
+        """Adam state keyed by parameter name (independent of the flat-buffer layout)."""
+        opt = self.optimizer
+        state = {'iterations': int(opt.iterations), 'lr': float(opt.lr), 'beta_1': opt.beta_1, 'beta_2': opt.beta_2,
+                 'epsilon': opt.epsilon, 'm': {}, 'v': {}}
+        if self._engine is not None:
+            state['base_seed'] = int(self._engine.base_seed)
+        if opt.m is not None:
+            eng = self._get_engine()
+            for name in eng.names:
+                off, _ = eng.offsets[name]
+                n = self.weights[name].numel()
+                state['m'][name] = opt.m[off:off + n].view(self.weights[name].shape).detach().cpu().clone()
+                state['v'][name] = opt.v[off:off + n].view(self.weights[name].shape).detach().cpu().clone()
+        return state
+
+    def load_optimizer_state(self, state: dict):
+        from .training import Adam
+        if self.optimizer is None:
+            self._compile(Adam(state['lr'], beta_1=state['beta_1'], beta_2=state['beta_2'], epsilon=state['epsilon']))
+        opt = self.optimizer
+        opt.lr, opt.iterations = float(state['lr']), int(state['iterations'])
+        opt.beta_1, opt.beta_2, opt.epsilon = state['beta_1'], state['beta_2'], state['epsilon']
+        eng = self._get_engine()
+        if 'base_seed' in state:
+            eng.base_seed = int(state['base_seed'])
+        if state['m']:
+            opt.m = torch.zeros_like(eng.flat_w)
+            opt.v = torch.zeros_like(eng.flat_w)
+            for name in eng.names:
+                off, _ = eng.offsets[name]
+                n = self.weights[name].numel()
+                opt.m[off:off + n].copy_(state['m'][name].reshape(-1))
+                opt.v[off:off + n].copy_(state['v'][name].reshape(-1))
 
     @classmethod
     def load_model(cls, path, **overrides):
-        """reference: model/models.py:621-638.  ``overrides`` (e.g. device=..., precision=...) update the stored config."""
+        """reference: model/models.py:621-638.  ``overrides`` (e.g. device=..., precision=...) update the stored config.
+        Weights come from model_weights.pt, or from a Keras model_weights.hdf5 written by the reference; when the
+        directory holds optimizer.pt (see save_model) the optimizer state and `step` are restored as well."""
         import yaml
         path = Path(path)
         with open(path / 'config.yaml', 'r') as f:
             config = yaml.safe_load(f)
+        config.pop('step', None)
         config.update(overrides)
         model = cls.from_config(config)
-        model.set_weights(torch.load(path / 'model_weights.pt', map_location='cpu'))
+        if (path / 'model_weights.pt').exists():
+            model.set_weights(torch.load(path / 'model_weights.pt', map_location='cpu'))
+        else:
+            from .hdf5_weights import load_keras_hdf5
+            model.set_weights(load_keras_hdf5(model, path / 'model_weights.hdf5'))
+        if (path / 'optimizer.pt').exists():
+            model.load_optimizer_state(torch.load(path / 'optimizer.pt', map_location='cpu'))
         return model
 
     @classmethod

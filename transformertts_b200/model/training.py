@@ -498,10 +498,11 @@ class TrainEngine:
             dur_int = torch.empty((B, Tp), dtype=torch.int32, device=dev)
             dec_len = torch.empty((B,), dtype=torch.int32, device=dev)
             lib.durations_to_int(dur_tgt.float(), 1.0, None, None, dur_int, dec_len)
-            Tm = int(dec_len.max().item())
             mel_len = mel_tgt.shape[1]
-            if Tm < mel_len:
-                raise ValueError(f'durations expand to {Tm} frames but the target has {mel_len}')
+            # decoder length = longest expanded row, but never shorter than the target: a data-parallel shard (or a batch
+            # padded to a bucket length) may hold only rows shorter than the padded target of the GLOBAL batch, which the
+            # reference would have processed at the global length (extra frames are padding rows, masked like any other)
+            Tm = max(int(dec_len.max().item()), mel_len)
             idx = torch.empty((B, Tm), dtype=torch.int32, device=dev)
             lib.expand_indices(dur_int, Tm, idx)
             dd = m._stacks['decoder']['d']
