@@ -306,7 +306,7 @@ def train_bench(args, rank, world, dev, cfg, params, steps=None):
     Bt = 32
     steps = steps or args.steps
     warm = max(args.warmup, 3)
-    model = ForwardTransformer(**cfg, device=str(dev), train_dropout=True)
+    model = ForwardTransformer(**cfg, device=str(dev), train_dropout=True, train_graphs=not args.no_graphs)
     model.set_weights(params)
     model._compile(Adam(1e-4))
     eng = model._get_engine()
@@ -393,6 +393,7 @@ def train_bench(args, rank, world, dev, cfg, params, steps=None):
             'config': {'workload': 'C3: LJ256 training step (fwd+bwd+Adam, dropout 0.1, MAE losses [1,1,3]), 32 rows/GPU, 128 phonemes -> 1000 frames',
                        'model': CFG_NAME, 'global_batch': Bt * world, 'seq_len': TM,
                        'parallelism': f'dp{world} (NCCL all-reduce of the flat fp32 gradient in 2 buckets, decoder bucket overlapped with the encoder backward)',
+                       'launch': 'eager' if args.no_graphs else 'CUDA graphs (forward + decoder backward | encoder backward), Adam and the NCCL all-reduces launched eagerly',
                        'l2': 'per-step working set exceeds the 126 MB L2'},
             'frames_per_sec': sps * Bt * TM * world,
             'ms_per_step_without_allreduce': ms_local, 'nccl_exposed_ms': max(0.0, ms_step - ms_local) if world > 1 else 0.0,

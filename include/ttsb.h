@@ -51,6 +51,13 @@ void ttsb_reset_launch_count(void);
  * "kernels of this library that ran" */
 void ttsb_add_launch_count(int64_t n);
 
+/* Dropout decisions are a stateless hash of (seed, site, element index); `seed` is a by-value argument of every kernel that
+ * draws them.  The 32-bit word *salt_dev (DEVICE memory) is XORed into that seed by all kernels launched afterwards on the
+ * stream (stream-ordered device-to-device copies into the library's constant memory; 0 after load).  A host that replays a
+ * captured training step puts this call at the head of the capture and rewrites *salt_dev before every replay, which gives
+ * each step its own masks although the captured `seed` arguments never change. */
+int ttsb_set_dropout_salt(const uint32_t* salt_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Weight / activation preparation
  * ------------------------------------------------------------------------------------------------------- */

@@ -158,8 +158,29 @@ def test_save_load_roundtrip_and_factory(tmp_path):
     m3, cfg = factory.tts_custom(str(tmp_path / 'step_1' / 'config.yaml'), str(tmp_path / 'step_1'))
     assert cfg['encoder_model_dimension'] == 128
     assert torch.equal(m3.call(tok, target_durations=dur, target_pitch=pit)['mel'], want)
-    with pytest.raises(NotImplementedError):
-        factory.tts_ljspeech()
+    # the published weights are a directory (zip) of config.yaml + Keras model_weights.hdf5: same layout, read by the
+    # pure-python HDF5 reader; without the file on disk (no network here) the factory says where it looked
+    pub = tmp_path / 'bdf06b9_ljspeech_step_95000'
+    pub.mkdir()
+    for f in ('config.yaml', 'model_weights.hdf5'):
+        (pub / f).write_bytes((tmp_path / 'step_1' / f).read_bytes())
+    m4 = factory.tts_ljspeech(path=str(pub))
+    assert torch.equal(m4.call(tok, target_durations=dur, target_pitch=pit)['mel'], want)
+    import shutil
+    import zipfile
+    with zipfile.ZipFile(tmp_path / 'w' / 'bdf06b9_ljspeech_step_90000.zip' if (tmp_path / 'w').mkdir() is None else None, 'w') as z:
+        for f in ('config.yaml', 'model_weights.hdf5'):
+            z.write(pub / f, f'bdf06b9_ljspeech_step_90000/{f}')
+    shutil.rmtree(pub)
+    import os
+    os.environ['TTSB_WEIGHTS_DIR'] = str(tmp_path / 'w')
+    try:
+        m5 = factory.tts_ljspeech(step='90000')
+        assert torch.equal(m5.call(tok, target_durations=dur, target_pitch=pit)['mel'], want)
+        with pytest.raises(FileNotFoundError):
+            factory.tts_ljspeech(step='12345')
+    finally:
+        del os.environ['TTSB_WEIGHTS_DIR']
 
 
 # ----------------------------------------------------------------------------------------------------------

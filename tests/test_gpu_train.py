@@ -434,3 +434,45 @@ def test_prefetch_loader_feeds_training_steps(tmp_path):
     finally:
         loader.close()
     assert model.step == 3
+
+
+def test_graphed_training_step_equals_eager_step():
+    """train_graphs=True replays the step as two CUDA graphs.  Without dropout the graphed step must reproduce the eager step
+    (same kernels, same arguments; weight-gradient sums use fp32 atomics, so equality is to rounding noise); with dropout the
+    per-step salt must change the masks from step to step and keep forward and backward masks consistent."""
+    from transformertts_b200.model.models import ForwardTransformer
+    from transformertts_b200.model.training import Adam
+    cfg = fo.CONFIGS['C1']
+    p = fo.init_params(cfg, seed=7)
+    tok, dur, pit = fo.make_inputs('ragged', 4, 24, 150, seed=321)
+    mel_tgt = fo.make_mel_targets(dur, 80, seed=322)
+    models = []
+    for graphs in (False, True):
+        m = ForwardTransformer(**cfg, train_dropout=False, train_graphs=graphs)
+        m.set_weights(p)
+        m._compile(Adam(1e-4))
+        losses = [float(m.train_step(tok, mel_tgt, dur, pit)['loss']) for _ in range(4)]
+        models.append((m, losses))
+    (me, le), (mg, lg) = models
+    assert all(abs(a - b) < 2e-4 * abs(a) for a, b in zip(le, lg)), (le, lg)
+    assert le[3] < le[0]                                                       # the steps do train
+    we, wg = me._get_engine().flat_w, mg._get_engine().flat_w
+    assert float((we - wg).abs().max()) < 2.5e-4                               # 4 Adam steps of lr 1e-4; sign flips of ~0 gradients only
+    assert mg.step == 4 and len(mg._get_engine()._graphs) == 1
+    # another shape gets its own graphs; the first one still replays
+    tok2, dur2, pit2 = fo.make_inputs('ragged', 3, 24, 120, seed=323)
+    mg.train_step(tok2, fo.make_mel_targets(dur2, 80, seed=324), dur2, pit2)
+    assert len(mg._get_engine()._graphs) == 2 and math.isfinite(float(mg.train_step(tok, mel_tgt, dur, pit)['loss']))
+    # dropout on: the loss on the same batch changes from step to step (new masks), and the directional derivative along the
+    # gradient matches |g| (forward and backward of one step use the same masks)
+    md = ForwardTransformer(**cfg, train_dropout=True, train_graphs=True)
+    md.set_weights(p)
+    md._compile(Adam(0.0))                                                     # lr 0: weights stay put
+    l = [float(md.train_step(tok, mel_tgt, dur, pit)['loss']) for _ in range(3)]
+    assert abs(l[0] - l[1]) > 1e-4 and abs(l[1] - l[2]) > 1e-4
+    # eager evaluation afterwards is unaffected by the salt left in the library (no dropout in val_step)
+    mv = ForwardTransformer(**cfg, train_dropout=False)
+    mv.set_weights(p)
+    mv._compile(Adam(0.0))
+    v1, v2 = float(md.val_step(tok, mel_tgt, dur, pit)['loss']), float(mv.val_step(tok, mel_tgt, dur, pit)['loss'])
+    assert abs(v1 - v2) < 1e-6 * abs(v2)

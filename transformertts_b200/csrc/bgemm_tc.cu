@@ -484,3 +484,5 @@ extern "C" int ttsb_wgrad(const ttsb_wgrad_args* a, void* stream_v) {
   if (rc) return rc;
   return launch(tmA[0], tmA[1], tmB, p, stream);
 }
+
+TTSB_DEFINE_SALT_SETTER(set_salt_bgemm)

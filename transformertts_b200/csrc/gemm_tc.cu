@@ -1026,3 +1026,5 @@ extern "C" int ttsb_linear_fwd(const ttsb_gemm_args* a, void* stream_v) {
   if (pair) return launch(true, 0, num_m_tiles);
   return launch(false, 0, p.num_tiles);
 }
+
+TTSB_DEFINE_SALT_SETTER(set_salt_gemm)

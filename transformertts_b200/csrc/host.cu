@@ -110,3 +110,13 @@ extern "C" int ttsb_abi_version(void) { return TTSB_ABI_VERSION; }
 extern "C" int64_t ttsb_launch_count(void) { return ttsb::g_launches.load(); }
 extern "C" void ttsb_reset_launch_count(void) { ttsb::g_launches.store(0); }
 extern "C" void ttsb_add_launch_count(int64_t n) { ttsb::g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" int ttsb_set_dropout_salt(const uint32_t* salt_dev, void* stream) {
+  if (!salt_dev) { ttsb::set_last_error("ttsb_set_dropout_salt: salt_dev is NULL"); return TTSB_ERR_INVALID_ARGUMENT; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = ttsb::set_salt_gemm(salt_dev, s);
+  if (!rc) rc = ttsb::set_salt_rowops(salt_dev, s);
+  if (!rc) rc = ttsb::set_salt_train_ops(salt_dev, s);
+  if (!rc) rc = ttsb::set_salt_bgemm(salt_dev, s);
+  return rc;
+}

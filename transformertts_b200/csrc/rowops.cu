@@ -479,3 +479,5 @@ extern "C" int ttsb_phoneme_lengths(const int32_t* phonemes, int B, int T, int32
   phoneme_lengths_kernel<<<B, 256, 0, STREAM(stream)>>>(phonemes, T, padding, out);
   LAUNCH_OK("phoneme_lengths_kernel");
 }
+
+TTSB_DEFINE_SALT_SETTER(set_salt_rowops)

@@ -684,3 +684,5 @@ extern "C" int ttsb_adam_tf_step(float* param, const float* grad, float* m, floa
   adam_tf_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM(stream)>>>(param, grad, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
   LAUNCH_OK("adam_tf_kernel");
 }
+
+TTSB_DEFINE_SALT_SETTER(set_salt_train_ops)

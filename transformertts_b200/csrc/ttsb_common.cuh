@@ -37,12 +37,26 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 
 // Stateless dropout decision shared by forward and backward kernels: keep element `idx` of dropout site `site` when the
 // 32-bit mix of (seed, site, idx) is >= thresh = p * 2^32 (keras Dropout semantics: kept values are scaled by 1/(1-p)).
+// c_drop_salt (one copy per translation unit, zero unless a host sets it with ttsb_set_dropout_salt) is XORed into the seed:
+// a training step captured as a CUDA graph has its `seed` arguments frozen at capture, so the per-step variation comes from
+// this device-resident word, refreshed by memcpy nodes at the head of the graph.
+static __constant__ uint32_t c_drop_salt = 0;
 __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t site, uint64_t idx, uint32_t thresh) {
+  seed ^= c_drop_salt;
   uint32_t x = (uint32_t)idx * 0x9E3779B1u ^ (uint32_t)(idx >> 32) * 0x85EBCA77u ^ seed * 0xC2B2AE3Du ^ site * 0x27D4EB2Fu;
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
   return x >= thresh;
 }
 __host__ __device__ __forceinline__ uint32_t dropout_thresh(float p) { return p > 0.f ? (uint32_t)((double)p * 4294967296.0) : 0u; }
+
+// Every translation unit that draws dropout decisions defines one of these (TTSB_DEFINE_SALT_SETTER(name)); host.cu calls
+// them all from ttsb_set_dropout_salt.
+#define TTSB_DEFINE_SALT_SETTER(name)                                                                           \
+  namespace ttsb {                                                                                              \
+  int name(const uint32_t* salt_dev, cudaStream_t stream) {                                                     \
+    return check_cuda(cudaMemcpyToSymbolAsync(c_drop_salt, salt_dev, sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, stream), #name); \
+  }                                                                                                             \
+  }
 
 // ------------------------------------------------------------------------------------------------
 // mbarrier

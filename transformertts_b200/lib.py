@@ -20,7 +20,7 @@ _LIB_PATH = Path(os.environ.get('TTSB_LIB') or Path(__file__).resolve().parent /
 _lib = None
 
 EXPORTS = [
-    'ttsb_last_error', 'ttsb_abi_version', 'ttsb_launch_count', 'ttsb_reset_launch_count', 'ttsb_add_launch_count', 'ttsb_pack_weight',
+    'ttsb_last_error', 'ttsb_abi_version', 'ttsb_launch_count', 'ttsb_reset_launch_count', 'ttsb_add_launch_count', 'ttsb_set_dropout_salt', 'ttsb_pack_weight',
     'ttsb_repack_batched',
     'ttsb_split_bf16', 'ttsb_embed_ln_pe_fwd', 'ttsb_linear_fwd', 'ttsb_layernorm_fwd', 'ttsb_mha_fwd', 'ttsb_statpred_head_fwd',
     'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
@@ -163,6 +163,11 @@ def reset_launch_count():
 
 def add_launch_count(n: int):
     load().ttsb_add_launch_count(int(n))
+
+
+def set_dropout_salt(salt_dev: torch.Tensor):
+    """salt_dev: int32/uint32 CUDA tensor with one element (see include/ttsb.h)."""
+    _check(load().ttsb_set_dropout_salt(ptr(salt_dev), _stream()), 'ttsb_set_dropout_salt')
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -167,6 +167,8 @@ class ForwardTransformer:
         self.optimizer = None
         self.loss_weights = [1., 1., 3.]
         self.train_dropout = bool(kwargs.get('train_dropout', True))  # False: deterministic training step (parity tests)
+        # training: replay the step as two CUDA graphs per input shape (training.TrainEngine.step_graphed)
+        self.train_graphs = bool(kwargs.get('train_graphs', False))
         self._engine = None
         self._drop_seed = 0
         self._init_weights(seed=int(kwargs.get('seed', 42)))
@@ -862,7 +864,10 @@ class ForwardTransformer:
         if data_parallel:
             from ..utils.data_parallel import GradSync
             sync = GradSync(eng.flat_g)
-        out = eng.forward_backward(input_sequence, target_sequence, target_durations, target_pitch, training=True, sync=sync)
+        if self.train_graphs:
+            out = eng.step_graphed(input_sequence, target_sequence, target_durations, target_pitch, sync=sync)
+        else:
+            out = eng.forward_backward(input_sequence, target_sequence, target_durations, target_pitch, training=True, sync=sync)
         scale = sync.finish() if sync is not None else 1.0
         eng.apply_adam(self.optimizer, grad_scale=scale)
         return out

@@ -60,6 +60,9 @@ class TrainEngine:
         self.seed = 1234
         self.rank = 0
         self.drop_sites = 0
+        self._salt_dev = None
+        self._graphs = {}
+        self._graph_pool = None
 
     # ------------------------------------------------------------------------------------------------
     # packed operands for the step (weights change every step)
@@ -460,16 +463,53 @@ class TrainEngine:
     # full step
     # ------------------------------------------------------------------------------------------------
     def forward_backward(self, phonemes, mel_tgt, dur_tgt, pitch_tgt, training=True, sync=None):
+        """Eager step: forward (+ backward when training).  `sync.bucket_ready` is called as soon as the decoder gradients
+        are final (the data-parallel all-reduce of that bucket then overlaps the encoder backward)."""
+        m = self.model
+        self._set_salt(0)
+        it = m.optimizer.iterations if m.optimizer else 0
+        self.seed = (self.base_seed * 2654435761 + it * 40503 + self.rank * 97) & 0x7fffffff
+        saved_precision = m.precision
+        m.precision = 'bf16'
+        try:
+            gen = self._fb_gen(phonemes, mel_tgt, dur_tgt, pitch_tgt, training)
+            out = next(gen)                 # forward (+ decoder backward)
+            if training:
+                if sync is not None:        # decoder gradients are final: start their all-reduce under the encoder backward
+                    sync.bucket_ready(*self.decoder_range)
+                next(gen, None)             # encoder-side backward
+            else:
+                gen.close()
+            return out
+        finally:
+            m.precision = saved_precision
+
+    def _set_salt(self, value: int):
+        """Device-resident word XORed into every dropout seed (include/ttsb.h: ttsb_set_dropout_salt): 0 in eager steps,
+        a per-step value under CUDA-graph replay (the captured seed arguments are frozen)."""
+        if self._salt_dev is None:
+            self._salt_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self._salt_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._salt_value = 0
+            self._salt_applied = 0      # what the library's constant memory currently holds
+        if value == 0 and self._salt_applied == 0:
+            return
+        self._salt_host[0] = value
+        self._salt_dev.copy_(self._salt_host, non_blocking=True)
+        if value == 0:                  # eager path after graphed steps: reset the library state once
+            lib.set_dropout_salt(self._salt_dev)
+            self._salt_applied = 0
+
+    def _fb_gen(self, phonemes, mel_tgt, dur_tgt, pitch_tgt, training=True, Tm_hint=None):
+        """The step as a generator: yields the output dictionary after the forward pass + decoder backward (decoder
+        gradients final), finishes with the encoder-side backward.  The caller owns m.precision / self.seed."""
         m, W, G = self.model, self.model.weights, self.g
         dev = self.dev
         self.use_dropout = training and m.train_dropout
         self.drop_rate = float(m.config.get('dropout_rate', 0.0)) if self.use_dropout else 0.0
         self.drop_sites = 0
-        self.seed = (self.base_seed * 2654435761 + (m.optimizer.iterations if m.optimizer else 0) * 40503 + self.rank * 97) & 0x7fffffff
         m._drop_seed = self.seed
-        saved_precision = m.precision
-        m.precision = 'bf16'
-        try:
+        if True:
             P = self._pack()
             x = torch.as_tensor(phonemes).to(device=dev, dtype=torch.int32).contiguous()
             mel_tgt = torch.as_tensor(mel_tgt).to(device=dev, dtype=torch.float32).contiguous()
@@ -502,7 +542,7 @@ class TrainEngine:
             # decoder length = longest expanded row, but never shorter than the target: a data-parallel shard (or a batch
             # padded to a bucket length) may hold only rows shorter than the padded target of the GLOBAL batch, which the
             # reference would have processed at the global length (extra frames are padding rows, masked like any other)
-            Tm = max(int(dec_len.max().item()), mel_len)
+            Tm = Tm_hint if Tm_hint is not None else max(int(dec_len.max().item()), mel_len)
             idx = torch.empty((B, Tm), dtype=torch.int32, device=dev)
             lib.expand_indices(dur_int, Tm, idx)
             dd = m._stacks['decoder']['d']
@@ -531,7 +571,8 @@ class TrainEngine:
                    'losses': {'mel': losses[0], 'duration': losses[1], 'pitch': losses[2]},
                    'loss': wts[0] * losses[0] + wts[1] * losses[1] + wts[2] * losses[2], 'mel_lengths': dec_len}
             if not training:
-                return out
+                yield out
+                return
             # =============================== backward ===============================
             self.flat_g.zero_()
             C = m.mel_channels
@@ -546,8 +587,7 @@ class TrainEngine:
                 dz = self._block_bwd('decoder', i, dec_ctx[i], dz, dec_len, B)
                 dec_ctx[i] = None
             d_exp = self._prologue_bwd('decoder', dz, expanded, dec_len, B, Tm, site_d)
-            if sync is not None:  # decoder gradients are final: start their all-reduce under the encoder backward
-                sync.bucket_ready(*self.decoder_range)
+            yield out             # decoder gradients are final
             dh_pe = self._f32(B, Tp, d)
             lib.expand_bwd(d_exp, dur_int, dh_pe)
             lib.pitch_embed_bwd(dh_pe, pitch_tgt, pw, W['pitch_embed.b'], G['pitch_embed.w'].view(-1), G['pitch_embed.b'])
@@ -560,9 +600,77 @@ class TrainEngine:
                 enc_ctx[i] = None
             de = self._prologue_bwd('encoder', dz, e_rows.view(B, Tp, d), enc_len, B, Tp, site_e)
             lib.embedding_bwd(de, x, G['embedding'])
-            return out
+
+    # ------------------------------------------------------------------------------------------------
+    # the training step as two CUDA graphs (forward + decoder backward | encoder-side backward), Adam launched eagerly
+    # ------------------------------------------------------------------------------------------------
+    def step_graphed(self, phonemes, mel_tgt, dur_tgt, pitch_tgt, sync=None):
+        """Replays the captured step for this input shape (captures it on first use).  ~400 launches, each with host-side
+        tensor-map encoding, become two graph launches: the eager step is host-launch bound (tools/step_cpu_time.py).
+        Per-step state that the captured kernel arguments cannot carry lives in device memory: the dropout salt (see
+        _set_salt); Adam's scalars are not captured (one eager launch).  Outputs are views of static buffers, valid until
+        the next step of the same shape (loss / losses are copied out)."""
+        m = self.model
+        phonemes, mel_tgt, dur_tgt, pitch_tgt = (torch.as_tensor(t) for t in (phonemes, mel_tgt, dur_tgt, pitch_tgt))
+        B, Tp = phonemes.shape
+        mel_len = mel_tgt.shape[1]
+        Tm = max(int(dur_tgt.sum(1).max()), mel_len)          # host sync only if the durations live on the device
+        key = (B, Tp, mel_len, Tm, bool(m.train_dropout), float(m.config.get('dropout_rate', 0.0)))
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._capture_step(key, phonemes, mel_tgt, dur_tgt, pitch_tgt, Tm)
+        else:
+            for dst, src in zip(ent['ins'], (phonemes, mel_tgt, dur_tgt, pitch_tgt)):
+                dst.copy_(src, non_blocking=True)
+        it = m.optimizer.iterations if m.optimizer else 0
+        self._set_salt(((it + 1) * 40503 + 12345) & 0x7fffffff)
+        self._salt_applied = 1
+        ent['g1'].replay()
+        lib.add_launch_count(ent['n1'])
+        if sync is not None:
+            sync.bucket_ready(*self.decoder_range)
+        ent['g2'].replay()
+        lib.add_launch_count(ent['n2'])
+        out = dict(ent['out'])
+        out['loss'] = out['loss'].clone()
+        out['losses'] = {k: v.clone() for k, v in out['losses'].items()}
+        return out
+
+    def _capture_step(self, key, phonemes, mel_tgt, dur_tgt, pitch_tgt, Tm):
+        m = self.model
+        dev = self.dev
+        ins = [phonemes.to(device=dev, dtype=torch.int32).contiguous().clone(), mel_tgt.to(device=dev, dtype=torch.float32).contiguous().clone(),
+               dur_tgt.to(device=dev, dtype=torch.int32).contiguous().clone(), pitch_tgt.to(device=dev, dtype=torch.float32).contiguous().clone()]
+        self.seed = (self.base_seed * 2654435761 + self.rank * 97) & 0x7fffffff    # frozen in the graph; the salt varies per step
+        saved_precision = m.precision
+        m.precision = 'bf16'
+        try:
+            self._set_salt(1)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # eager warm-up on the capture shapes (packs, function attributes, allocator)
+                for _ in self._fb_gen(*ins, training=True, Tm_hint=Tm):
+                    pass
+            torch.cuda.current_stream().wait_stream(side)
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            n0 = lib.launch_count()
+            with torch.cuda.graph(g1, pool=self._graph_pool):
+                lib.set_dropout_salt(self._salt_dev)
+                gen = self._fb_gen(*ins, training=True, Tm_hint=Tm)
+                out = next(gen)
+            n1 = lib.launch_count()
+            with torch.cuda.graph(g2, pool=self._graph_pool):
+                next(gen, None)
+            n2 = lib.launch_count()
         finally:
             m.precision = saved_precision
+        if len(self._graphs) >= 4:
+            self._graphs.pop(next(iter(self._graphs)))
+        ent = {'ins': ins, 'g1': g1, 'g2': g2, 'out': out, 'n1': n1 - n0, 'n2': n2 - n1}
+        self._graphs[key] = ent
+        return ent
 
     def _prologue_bwd(self, name, g, u, lens, B, T, site):
         m, W, G = self.model, self.model.weights, self.g
