@@ -275,7 +275,12 @@ int ttsb_layernorm_bwd(const float* dz, const float* u, const float* gamma, int 
                        void* stream);
 /* column sums of bf16 (rows, ld)[:, :C] accumulated into fp32 out[C] (bias gradients) */
 int ttsb_colsum_bf16(const void* x, int64_t rows, int C, int ld, float* out, void* stream);
+/* three adjacent column segments of width seg -> three outputs (the q / k / v bias gradients from the (rows, 3d) buffer) */
+int ttsb_colsum_bf16_x3(const void* x, int64_t rows, int seg, int ld, float* out0, float* out1, float* out2, void* stream);
 int ttsb_relu_bwd(void* dy_bf16, const void* h_bf16, int64_t n, void* stream);
+/* ttsb_relu_bwd plus the bias gradient of the layer that produced h, in the same pass: colsum[c] += sum_rows (masked dy)
+ * (dy, h bf16 (rows, C) contiguous). */
+int ttsb_relu_bwd_colsum(void* dy, const void* h, int64_t rows, int C, float* colsum, void* stream);
 /* fp32 (rows, C) -> bf16 (rows, ld_out >= C) with zero padding columns */
 int ttsb_cast_bf16_pad(const float* x, int64_t rows, int C, void* out_bf16, int ld_out, void* stream);
 /* mean |pred - target| over ALL elements of pred[:, :Tt] (utils/losses.py:41-49 as called with mask=None), added to

@@ -476,3 +476,44 @@ def test_graphed_training_step_equals_eager_step():
     mv._compile(Adam(0.0))
     v1, v2 = float(md.val_step(tok, mel_tgt, dur, pit)['loss']), float(mv.val_step(tok, mel_tgt, dur, pit)['loss'])
     assert abs(v1 - v2) < 1e-6 * abs(v2)
+
+
+@pytest.mark.parametrize('C', [128, 256, 384])
+def test_layernorm_bwd_vectorised_and_fused_column_sums(C):
+    """The vectorised persistent LayerNorm-backward kernel (C == ld, C % 128 == 0) against fp64 autograd, and the fused
+    ReLU-mask + bias-gradient pass / the three-output column sum against their two-step definitions."""
+    lib = _lib()
+    g = torch.Generator().manual_seed(5)
+    B, T = 5, 333
+    u = torch.randn(B, T, C, generator=g)
+    dz = torch.randn(B, T, C, generator=g)
+    gamma = 1 + 0.1 * torch.randn(C, generator=g)
+    lens = torch.tensor([333, 100, 0, 250, 333], dtype=torch.int32)
+    uu = u.double().requires_grad_(True)
+    gg = gamma.double().requires_grad_(True)
+    bb = torch.zeros(C, dtype=torch.float64, requires_grad=True)
+    keep = (torch.arange(T)[None] < lens[:, None])[..., None].double()
+    (fo.layer_norm(uu, gg, bb) * keep * dz.double()).sum().backward()
+    du = torch.full((B, T, C), float('nan'), device=DEV)
+    gb = torch.full((B, T, C), float('nan'), dtype=torch.bfloat16, device=DEV)
+    dg, db, dbias = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    lib.layernorm_bwd(dz.to(DEV), u.to(DEV), gamma.to(DEV), B, T, C, C, 1e-6, lens.to(DEV), False, du, gb, dg, db, dbias=dbias)
+    torch.cuda.synchronize()
+    assert _rel(du, uu.grad) < 1e-5
+    assert _rel(dg, gg.grad) < 1e-5 and _rel(db, bb.grad) < 1e-5
+    assert _rel(gb.float(), uu.grad) < 5e-3 and _rel(dbias, uu.grad.sum((0, 1))) < 1e-4
+    # relu mask + bias gradient in one pass
+    h = torch.randn(B, T, C, generator=g).bfloat16().to(DEV)
+    dy = torch.randn(B, T, C, generator=g).bfloat16().to(DEV)
+    want = dy.float() * (h.float() > 0)
+    cs = torch.zeros(C, device=DEV)
+    lib.relu_bwd_colsum(dy, h, cs)
+    torch.cuda.synchronize()
+    assert torch.equal(dy.float(), want) and _rel(cs, want.sum((0, 1))) < 1e-5
+    # q | k | v column sums of one (rows, 3C) buffer into three outputs
+    x = torch.randn(B * T, 3 * C, generator=g).bfloat16().to(DEV)
+    o = [torch.zeros(C, device=DEV) for _ in range(3)]
+    lib.colsum_bf16_x3(x, B * T, C, 3 * C, *o)
+    torch.cuda.synchronize()
+    for k in range(3):
+        assert _rel(o[k], x[:, k * C:(k + 1) * C].float().sum(0)) < 1e-5

@@ -15,6 +15,7 @@
 // the same row-major tensors read MN-major.  An MN-major tile is fetched as ceil(rows/64) TMA boxes of [64 k x 64 mn]
 // (8 KiB each, 128B swizzle) and described to the MMA with LBO = 8192 B (next 64-wide MN block), SBO = 1024 B (next 8 k).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "../../include/ttsb.h"
 #include "ttsb_common.cuh"
@@ -31,7 +32,11 @@ constexpr int BG_A_BYTES = BG_BM * BG_BK * 2;
 constexpr int BG_B_BYTES = BG_MAX_BN * BG_BK * 2;
 constexpr int BG_STAGE_BYTES = BG_A_BYTES + BG_B_BYTES;
 constexpr int BG_BAR_OFFSET = BG_STAGES * BG_STAGE_BYTES;
-constexpr int BG_SMEM_BYTES = BG_BAR_OFFSET + 256 + 1024;
+// bf16 outputs leave through shared staging boxes and TMA tile stores: 2 alternating boxes x 4 lane quarters of
+// [32 rows x 64 cols] (4 KiB, 128B swizzle) -- see the staged epilogue below
+constexpr int BG_STAGE_OUT_OFFSET = (BG_BAR_OFFSET + 256 + 1023) / 1024 * 1024;
+constexpr int BG_STAGE_OUT_BYTES = 2 * 4 * 4096;
+constexpr int BG_SMEM_BYTES = BG_STAGE_OUT_OFFSET + BG_STAGE_OUT_BYTES + 1024;
 constexpr int BG_MN_BOX_BYTES = 64 * 128;  // one [64 k x 64 mn] box
 
 struct BgOperand {
@@ -69,11 +74,12 @@ struct BgParams {
   float* dw;                  // fp32 (num_seg*Cin, N) accumulated with atomics
   // common
   int block_n, n_tiles, m_tiles, num_tiles;
+  int staged;  // 1: bf16 output through shared staging + TMA tile stores (batched mode, block_n % 64 == 0)
 };
 
 __global__ void __launch_bounds__(BG_THREADS, 1)
 bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmB, const BgParams p) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const BgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BG_BAR_OFFSET);
@@ -222,6 +228,7 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int ch_begin = half ? (nch + 1) >> 1 : 0;
     const int ch_end = half ? nch : (nch + 1) >> 1;
     uint32_t r[16];
+    uint32_t slab_ctr = 0;  // staged epilogue: slabs stored so far (selects the staging box)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       if (tile_kblocks(tile) == 0) continue;
       mbar_wait(tmem_full + acc, acc_phase);
@@ -238,7 +245,99 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const bool row_keep = row_ok && (p.row_len == nullptr || m < __ldg(p.row_len + b));
         const int clen = p.col_len ? __ldg(p.col_len + b) : p.N;
         const size_t o = (size_t)(p.out_by_b ? b : z) * (size_t)p.out_z_stride + (size_t)(row_ok ? m : 0) * p.ld_out + h * p.out_h_col + n0;
-        if (p.sm_P != nullptr) {
+        if (p.staged) {
+          // ---- bf16 output as TMA tile stores.  A thread owns one output ROW, so direct stores are 32-byte pieces of 32
+          //      different rows per warp instruction (request-rate bound: the fused dS epilogue ran at 240 us for 390 MB).
+          //      The two warps of a lane quarter fill a [32 rows x 64 cols] 128B-swizzled box (warp `half` writes column
+          //      chunks 2*half, 2*half+1 of the slab) and one lane hands it to the TMA unit; two boxes alternate, so only
+          //      the store issued two slabs ago must have been read out.  Rows >= M / columns past the tensor are clipped
+          //      by the tensor map.  With sm_P set the value is the fused softmax backward of the row (see below).
+          uint8_t* stage_out = smem + BG_STAGE_OUT_OFFSET;
+          const bool issuer = half == 0 && lane == 0;
+          const int lrow = row & 31;
+          const bool sm = p.sm_P != nullptr;
+          int len = p.N;
+          bool live = row_keep;
+          float dsum = 0.f;
+          if (sm) {
+            len = min(max(__ldg(p.sm_len + b), 0), p.N);
+            live = row_ok && ((p.sm_flags & 2) ? len > 0 : m < len);
+            if (p.sm_flags & 1) len = min(len, m + 1);
+            dsum = live ? __ldg(p.sm_D + (size_t)z * p.M + m) : 0.f;
+          }
+          const uint32_t thresh = dropout_thresh(p.sm_drop_p);
+          const float ks = p.sm_drop_p > 0.f ? 1.f / (1.f - p.sm_drop_p) : 1.f;
+          uint32_t qa[16], qb[16];
+          for (int s0 = 0; s0 < nch; s0 += 4) {
+            const int ca = s0 + 2 * half, cb = ca + 1;
+            uint4 pv[2][2], pd[2][2];
+            if (sm) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int c0 = (u ? cb : ca) << 4;
+                const bool need = live && n0 + c0 < len;
+                pv[u][0] = pv[u][1] = pd[u][0] = pd[u][1] = make_uint4(0, 0, 0, 0);
+                if (need) {
+                  const uint4* src = reinterpret_cast<const uint4*>(p.sm_P + o + c0);
+                  pv[u][0] = __ldg(src);
+                  pv[u][1] = __ldg(src + 1);
+                  if (p.sm_Pdrop != nullptr) {
+                    const uint4* sd = reinterpret_cast<const uint4*>(p.sm_Pdrop + o + c0);
+                    pd[u][0] = __ldg(sd);
+                    pd[u][1] = __ldg(sd + 1);
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            tmem_ld16(taddr + (ca << 4), qa);
+            tmem_ld16(taddr + (cb << 4), qb);
+            uint8_t* box = stage_out + ((slab_ctr & 1u) ? 4 * 4096 : 0) + quarter * 4096;
+            ++slab_ctr;
+            if (issuer) tma_store_wait_read_but_one();
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            tmem_wait_ld();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int c0 = (u ? cb : ca) << 4;
+              float y[16];
+              if (sm) {
+                const __nv_bfloat16* pp = reinterpret_cast<const __nv_bfloat16*>(pv[u]);
+                const uint16_t* dd = reinterpret_cast<const uint16_t*>(pd[u]);
+                const size_t e0 = o + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int k = n0 + c0 + j;
+                  bool keep = true;
+                  if (p.sm_drop_p > 0.f) keep = p.sm_Pdrop != nullptr ? (dd[j] & 0x7fffu) != 0 : dropout_keep(p.sm_seed, p.sm_site, e0 + j, thresh);
+                  const float g = keep ? __uint_as_float(u ? qb[j] : qa[j]) * ks : 0.f;
+                  y[j] = (live && k < len) ? p.sm_scale * __bfloat162float(pp[j]) * (g - dsum) : 0.f;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int n = n0 + c0 + j;
+                  y[j] = (row_keep && n < clen && n < p.N) ? __uint_as_float(u ? qb[j] : qa[j]) * p.alpha : 0.f;
+                }
+              }
+              uint32_t hh[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 v = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                hh[j] = *reinterpret_cast<const uint32_t*>(&v);
+              }
+              const int k0 = 2 * (2 * half + u);
+              const uint32_t o0 = lrow * 128 + (((k0) ^ (lrow & 7)) << 4), o1 = lrow * 128 + (((k0 + 1) ^ (lrow & 7)) << 4);
+              *reinterpret_cast<uint4*>(box + o0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              *reinterpret_cast<uint4*>(box + o1) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            if (issuer && n0 + (s0 << 4) < p.out_cols)
+              tma_store_3d(&tmO, box, h * p.out_h_col + n0 + (s0 << 4), m_tile * BG_BM + quarter * 32, p.out_by_b ? b : z);
+            if (issuer) tma_store_commit();
+          }
+        } else if (p.sm_P != nullptr) {
           // ---- softmax backward fused into the dP product (see ttsb_bgemm_args): this thread owns query row m of
           //      problem z.  The P_pre row segments of all its chunks are requested before the first TMEM load.
           int len = min(max(__ldg(p.sm_len + b), 0), p.N);
@@ -354,9 +453,17 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           tmem_ld16(taddr + c0, r);
           tmem_wait_ld();
           if (row_ok) {
+            if ((p.N & 3) == 0 && n0 + c0 + 16 <= p.N) {   // 16-byte aligned: four vector reductions instead of sixteen scalar ones
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + c0 + j < p.N) atomicAdd(dst + c0 + j, __uint_as_float(r[j]));
+              for (int j = 0; j < 16; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(r[j])),
+                             "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n0 + c0 + j < p.N) atomicAdd(dst + c0 + j, __uint_as_float(r[j]));
+            }
           }
         }
       }
@@ -365,6 +472,7 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       if (lane == 0) mbar_arrive(tmem_empty + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.staged && half == 0 && lane == 0) tma_store_wait_all();  // staged boxes fully written out before exit
   }
 
   tc_fence_before();
@@ -376,14 +484,14 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
 }
 
-static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const BgParams& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o, const BgParams& p, cudaStream_t stream) {
   static PerDevice<bool> attr_set;
   if (!attr_set.get()) {
     TTSB_CUDA_OK(cudaFuncSetAttribute(bgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMEM_BYTES));
     attr_set.get() = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  bgemm_tc_kernel<<<grid, BG_THREADS, BG_SMEM_BYTES, stream>>>(a0, a1, b, p);
+  bgemm_tc_kernel<<<grid, BG_THREADS, BG_SMEM_BYTES, stream>>>(a0, a1, b, o, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "bgemm_tc_kernel launch");
 }
@@ -440,7 +548,18 @@ extern "C" int ttsb_bgemm(const ttsb_bgemm_args* a, void* stream_v) {
   rc = make_tmap_bf16_3d(&tmB, a->b, (uint64_t)a->b_dim0, (uint64_t)a->b_dim1, (uint64_t)a->b_dim2, (uint64_t)a->b_stride1,
                          (uint64_t)a->b_stride2, BG_BK, a->b_mn_major ? 64 : p.block_n);
   if (rc) return rc;
-  return launch(tmA, tmA, tmB, p, stream);
+  // bf16-only outputs of a tile width that fills whole 64-column boxes go through shared staging + TMA tile stores
+  // (TTSB_NO_STAGED_STORE=1 keeps the direct thread-per-row stores)
+  static const bool no_staged = getenv("TTSB_NO_STAGED_STORE") != nullptr;
+  CUtensorMap tmO = tmB;
+  if (!no_staged && p.out_bf16 && !p.out_f32 && p.block_n % 64 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0) {
+    const uint64_t cols = p.out_by_b ? (uint64_t)p.H * p.out_h_col : (uint64_t)p.out_cols;
+    rc = make_tmap_bf16_3d(&tmO, p.out_bf16, cols, (uint64_t)p.M, (uint64_t)(p.out_by_b ? a->B : p.Z), (uint64_t)p.ld_out,
+                           (uint64_t)p.out_z_stride, 64, 32);
+    if (rc) return rc;
+    p.staged = 1;
+  }
+  return launch(tmA, tmA, tmB, tmO, p, stream);
 }
 
 extern "C" int ttsb_wgrad(const ttsb_wgrad_args* a, void* stream_v) {
@@ -482,7 +601,7 @@ extern "C" int ttsb_wgrad(const ttsb_wgrad_args* a, void* stream_v) {
   }
   int rc = make_tmap_bf16_3d(&tmB, a->g, (uint64_t)a->N, (uint64_t)a->T, (uint64_t)a->B, (uint64_t)a->ldg, (uint64_t)a->ldg * a->T, BG_BK, 64);
   if (rc) return rc;
-  return launch(tmA[0], tmA[1], tmB, p, stream);
+  return launch(tmA[0], tmA[1], tmB, tmB, p, stream);
 }
 
 TTSB_DEFINE_SALT_SETTER(set_salt_bgemm)

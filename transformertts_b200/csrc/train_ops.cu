@@ -193,9 +193,154 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dz, const float* 
   }
 }
 
+// Same contract for rows whose width fills whole 128-column groups (C == ld, C % 128 == 0: every block LayerNorm of the
+// model): a lane owns 4 consecutive columns per group (16-byte loads / stores, 8-byte bf16 stores), warps walk the rows with
+// a grid stride and fetch row r+1 while the shuffle reductions of row r are in flight, and the column partials
+// (dgamma, dbeta, dbias) stay in registers for the whole kernel: one shared-memory reduction and C*3 global atomics per block
+// instead of per 32 rows.
+template <int NG>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_vec_kernel(const float* __restrict__ dz, const float* __restrict__ u, const float* __restrict__ gamma, int M, int T,
+                         float eps, const int* __restrict__ row_len, int relu_mask, float pre_drop_p, uint32_t pre_site,
+                         float post_drop_p, uint32_t post_site, uint32_t seed, float* __restrict__ du,
+                         __nv_bfloat16* __restrict__ g_out, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         float* __restrict__ dbias) {
+  constexpr int C = NG * 128;
+  __shared__ float part[3 * C];
+  for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) part[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const uint32_t post_thresh = dropout_thresh(post_drop_p), pre_thresh = dropout_thresh(pre_drop_p);
+  const float post_scale = post_drop_p > 0.f ? 1.f / (1.f - post_drop_p) : 1.f;
+  const float pre_scale = pre_drop_p > 0.f ? 1.f / (1.f - pre_drop_p) : 1.f;
+  float4 gam[NG], acc_g[NG], acc_b[NG], acc_x[NG];
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    gam[i] = __ldg(reinterpret_cast<const float4*>(gamma + 4 * lane + 128 * i));
+    acc_g[i] = acc_b[i] = acc_x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 un[NG], gn[NG];
+  auto fetch = [&](int row) {
+    const size_t base = (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      un[i] = __ldcs(reinterpret_cast<const float4*>(u + base + 4 * lane + 128 * i));
+      gn[i] = __ldcs(reinterpret_cast<const float4*>(dz + base + 4 * lane + 128 * i));
+    }
+  };
+  int row = wid;
+  if (row < M) fetch(row);
+  for (; row < M; row += nwarps) {
+    float4 uv[NG], gz[NG];
+#pragma unroll
+    for (int i = 0; i < NG; ++i) { uv[i] = un[i]; gz[i] = gn[i]; }
+    if (row + nwarps < M) fetch(row + nwarps);
+    const int b = row / T, t = row % T;
+    const bool live = row_len == nullptr || t < __ldg(row_len + b);
+    const size_t base = (size_t)row * C;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      float* g4 = reinterpret_cast<float*>(&gz[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float g = live ? g4[j] : 0.f;
+        if (post_drop_p > 0.f) g = dropout_keep(seed, post_site, base + 4 * lane + 128 * i + j, post_thresh) ? g * post_scale : 0.f;
+        g4[j] = g;
+      }
+      s += (uv[i].x + uv[i].y) + (uv[i].z + uv[i].w);
+    }
+    const float mean = wsum(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      const float a = uv[i].x - mean, b2 = uv[i].y - mean, c2 = uv[i].z - mean, d2 = uv[i].w - mean;
+      q += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+    }
+    const float rstd = rsqrtf(wsum(q) * (1.f / C) + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      const float* u4 = reinterpret_cast<const float*>(&uv[i]);
+      const float* g4 = reinterpret_cast<const float*>(&gz[i]);
+      const float* m4 = reinterpret_cast<const float*>(&gam[i]);
+      float* ag = reinterpret_cast<float*>(&acc_g[i]);
+      float* ab = reinterpret_cast<float*>(&acc_b[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (u4[j] - mean) * rstd;
+        const float gg = g4[j] * m4[j];
+        sg += gg;
+        sgx = fmaf(gg, xh, sgx);
+        ag[j] = fmaf(g4[j], xh, ag[j]);
+        ab[j] += g4[j];
+      }
+    }
+    // two reductions in one pass over the shuffle network
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+    }
+    sg *= (1.f / C);
+    sgx *= (1.f / C);
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      const float* u4 = reinterpret_cast<const float*>(&uv[i]);
+      const float* g4 = reinterpret_cast<const float*>(&gz[i]);
+      const float* m4 = reinterpret_cast<const float*>(&gam[i]);
+      float* ax = reinterpret_cast<float*>(&acc_x[i]);
+      float d4[4], gv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (u4[j] - mean) * rstd;
+        d4[j] = rstd * (g4[j] * m4[j] - sg - xh * sgx);
+        float v = d4[j];
+        if (relu_mask && !(u4[j] > 0.f)) v = 0.f;
+        if (pre_drop_p > 0.f) v = dropout_keep(seed, pre_site, base + 4 * lane + 128 * i + j, pre_thresh) ? v * pre_scale : 0.f;
+        gv[j] = v;
+        ax[j] += v;
+      }
+      const size_t o = base + 4 * lane + 128 * i;
+      if (du) __stcs(reinterpret_cast<float4*>(du + o), make_float4(d4[0], d4[1], d4[2], d4[3]));
+      if (g_out) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(gv[0], gv[1]), hi = __floats2bfloat162_rn(gv[2], gv[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(g_out + o) = pk;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    const float* ag = reinterpret_cast<const float*>(&acc_g[i]);
+    const float* ab = reinterpret_cast<const float*>(&acc_b[i]);
+    const float* ax = reinterpret_cast<const float*>(&acc_x[i]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 4 * lane + 128 * i + j;
+      atomicAdd(part + c, ag[j]);
+      atomicAdd(part + C + c, ab[j]);
+      atomicAdd(part + 2 * C + c, ax[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(dgamma + c, part[c]);
+    atomicAdd(dbeta + c, part[C + c]);
+    if (dbias) atomicAdd(dbias + c, part[2 * C + c]);
+  }
+}
+
 // column sums of a bf16 matrix (rows, ld)[:, :C] -> fp32 [C] (accumulated): bias gradients.
 // Block = 8 warps x 128 rows; a warp reads 512 contiguous bytes of a row (32 lanes x 8 bf16), partials meet in smem.
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C, int ld, float* __restrict__ out) {
+// Columns [k*seg, (k+1)*seg) go to out_k (k = 0..2; seg >= C: a single output): the q/k/v bias gradients are three
+// separate parameters but one (rows, 3d) gradient buffer.
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C, int ld, float* __restrict__ out,
+                                   int seg, float* __restrict__ out1, float* __restrict__ out2) {
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + lane * 8;
@@ -219,7 +364,8 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t 
     float sum = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) sum += red[k][threadIdx.x];
-    atomicAdd(out + c, sum);
+    const int k = c / seg;
+    atomicAdd((k == 0 ? out : (k == 1 ? out1 : out2)) + (c - k * seg), sum);
   }
 }
 
@@ -235,6 +381,43 @@ __global__ void relu_bwd_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloa
   for (int j = 0; j < 8; ++j)
     if (!(__bfloat162float(hp[j]) > 0.f)) gp[j] = __float2bfloat16(0.f);
   *reinterpret_cast<uint4*>(dy + i) = g;
+}
+
+// The same with the bias gradient of the layer that produced h: colsum[c] += sum over rows of the masked dy (C == ld).
+// Block = 8 warps x 128 rows x 256 columns, like colsum_bf16_kernel: one pass over dy / h instead of two.
+__global__ void relu_bwd_colsum_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h, int64_t rows, int C,
+                                       float* __restrict__ colsum) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * 128;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < C) {
+    for (int64_t r = r0 + w; r < r0 + 128 && r < rows; r += 8) {
+      uint4 g = *reinterpret_cast<const uint4*>(dy + r * C + c0);
+      const uint4 hv = *reinterpret_cast<const uint4*>(h + r * C + c0);
+      __nv_bfloat16* gp = reinterpret_cast<__nv_bfloat16*>(&g);
+      const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!(__bfloat162float(hp[j]) > 0.f)) gp[j] = __float2bfloat16(0.f);
+        acc[j] += __bfloat162float(gp[j]);
+      }
+      *reinterpret_cast<uint4*>(dy + r * C + c0) = g;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[w][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += red[k][threadIdx.x];
+    atomicAdd(colsum + c, sum);
+  }
 }
 
 // fp32 (rows, C) -> bf16 (rows, ld_out >= C), zero in the padding columns (K of a GEMM must be a multiple of 64)
@@ -569,6 +752,17 @@ extern "C" int ttsb_layernorm_bwd(const float* dz, const float* u, const float* 
   if (!dz || !u || !gamma || !dgamma || !dbeta || B <= 0 || T <= 0 || C <= 0 || C > 512 || ld < C || ld > 512)
     return bad("ttsb_layernorm_bwd: bad arguments (C, ld <= 512)");
   const int rows = B * T;
+  if (C == ld && C % 128 == 0 && C <= 384) {   // every block LayerNorm of the model: vectorised persistent kernel
+    const int grid = min((rows + 7) / 8, 2 * num_sms());
+#define TTSB_LNV(NG)                                                                                                            \
+  layernorm_bwd_vec_kernel<NG><<<grid, 256, 0, STREAM(stream)>>>(dz, u, gamma, rows, T, eps, row_len, relu_mask, pre_drop_p, pre_site, \
+                                                                post_drop_p, post_site, seed, du, BF(g_bf16), dgamma, dbeta, dbias)
+    if (C == 128) TTSB_LNV(1);
+    else if (C == 256) TTSB_LNV(2);
+    else TTSB_LNV(3);
+#undef TTSB_LNV
+    LAUNCH_OK("layernorm_bwd_vec_kernel");
+  }
   const int blocks = (rows + 31) / 32;
   const size_t sm = 3 * C * sizeof(float);
 #define TTSB_LNB(NV)                                                                                                              \
@@ -585,7 +779,15 @@ extern "C" int ttsb_layernorm_bwd(const float* dz, const float* u, const float* 
 extern "C" int ttsb_colsum_bf16(const void* x, int64_t rows, int C, int ld, float* out, void* stream) {
   if (!x || !out || rows <= 0 || C <= 0 || ld < C || ld % 8 || (ld < ((C + 7) / 8) * 8)) return bad("ttsb_colsum_bf16: need ld % 8 == 0 and ld >= round_up(C, 8)");
   dim3 grid((C + 255) / 256, (unsigned)((rows + 127) / 128));
-  colsum_bf16_kernel<<<grid, 256, 0, STREAM(stream)>>>(CBF(x), rows, C, ld, out);
+  colsum_bf16_kernel<<<grid, 256, 0, STREAM(stream)>>>(CBF(x), rows, C, ld, out, C, nullptr, nullptr);
+  LAUNCH_OK("colsum_bf16_kernel");
+}
+
+extern "C" int ttsb_colsum_bf16_x3(const void* x, int64_t rows, int seg, int ld, float* out0, float* out1, float* out2, void* stream) {
+  if (!x || !out0 || !out1 || !out2 || rows <= 0 || seg <= 0 || seg % 8 || ld < 3 * seg || ld % 8)
+    return bad("ttsb_colsum_bf16_x3: need seg % 8 == 0 and ld >= 3 * seg, ld % 8 == 0");
+  dim3 grid((3 * seg + 255) / 256, (unsigned)((rows + 127) / 128));
+  colsum_bf16_kernel<<<grid, 256, 0, STREAM(stream)>>>(CBF(x), rows, 3 * seg, ld, out0, seg, out1, out2);
   LAUNCH_OK("colsum_bf16_kernel");
 }
 
@@ -593,6 +795,13 @@ extern "C" int ttsb_relu_bwd(void* dy, const void* h, int64_t n, void* stream) {
   if (!dy || !h || n <= 0 || n % 8) return bad("ttsb_relu_bwd: n must be a positive multiple of 8");
   relu_bwd_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, STREAM(stream)>>>(BF(dy), CBF(h), n);
   LAUNCH_OK("relu_bwd_kernel");
+}
+
+extern "C" int ttsb_relu_bwd_colsum(void* dy, const void* h, int64_t rows, int C, float* colsum, void* stream) {
+  if (!dy || !h || !colsum || rows <= 0 || C <= 0 || C % 8) return bad("ttsb_relu_bwd_colsum: C must be a positive multiple of 8");
+  dim3 grid((C + 255) / 256, (unsigned)((rows + 127) / 128));
+  relu_bwd_colsum_kernel<<<grid, 256, 0, STREAM(stream)>>>(BF(dy), CBF(h), rows, C, colsum);
+  LAUNCH_OK("relu_bwd_colsum_kernel");
 }
 
 extern "C" int ttsb_cast_bf16_pad(const float* x, int64_t rows, int C, void* out, int ld_out, void* stream) {

@@ -26,7 +26,7 @@ EXPORTS = [
     'ttsb_pitch_embed_add_fwd', 'ttsb_durations_to_int', 'ttsb_expand_indices', 'ttsb_length_regulate_fwd',
     'ttsb_expand_ln_pe_fwd', 'ttsb_mel_lengths', 'ttsb_phoneme_lengths', 'ttsb_stft_mel_log',
     'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_rowdot_heads', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
-    'ttsb_relu_bwd', 'ttsb_colsum_bf16', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_scaled_ce_loss', 'ttsb_diag_loss', 'ttsb_diag_loss_train', 'ttsb_attention_scores', 'ttsb_durations_from_attention', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
+    'ttsb_relu_bwd', 'ttsb_relu_bwd_colsum', 'ttsb_colsum_bf16', 'ttsb_colsum_bf16_x3', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_scaled_ce_loss', 'ttsb_diag_loss', 'ttsb_diag_loss_train', 'ttsb_attention_scores', 'ttsb_durations_from_attention', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
     'ttsb_pitch_embed_bwd', 'ttsb_statpred_head_bwd', 'ttsb_adam_tf_step', 'ttsb_embed_ln_pe_train_fwd',
     'ttsb_expand_ln_pe_train_fwd',
 ]
@@ -321,6 +321,16 @@ def colsum_bf16(x, rows, Cc, ld, out):
 
 def relu_bwd(dy, h):
     _check(load().ttsb_relu_bwd(ptr(dy), ptr(h), C.c_int64(dy.numel()), _stream()), 'ttsb_relu_bwd')
+
+
+def relu_bwd_colsum(dy, h, colsum):
+    """dy *= (h > 0) in place and colsum += column sums of the result (the bias gradient of the layer that produced h)."""
+    Cc = dy.shape[-1]
+    _check(load().ttsb_relu_bwd_colsum(ptr(dy), ptr(h), C.c_int64(dy.numel() // Cc), Cc, ptr(colsum), _stream()), 'ttsb_relu_bwd_colsum')
+
+
+def colsum_bf16_x3(x, rows, seg, ld, out0, out1, out2):
+    _check(load().ttsb_colsum_bf16_x3(ptr(x), C.c_int64(rows), seg, ld, ptr(out0), ptr(out1), ptr(out2), _stream()), 'ttsb_colsum_bf16_x3')
 
 
 def cast_bf16_pad(x, rows, Cc, out, ld_out):

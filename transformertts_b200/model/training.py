@@ -313,8 +313,7 @@ class TrainEngine:
             self._wgrad([(h, F)], g2, d, B, T, F, d, [(0, 0)], G[pre + 'ffn2.w'])
             dh_ = self._bf(B, T, F)
             m._gemm(P[pre + 'ffn2.d'], B, T, [(g2, None, d, 0)], [0], [0], out_hi=dh_, ld_out=F)
-            lib.relu_bwd(dh_, h)
-            lib.colsum_bf16(dh_, B * T, F, F, G[pre + 'ffn1.b'])
+            lib.relu_bwd_colsum(dh_, h, G[pre + 'ffn1.b'])     # ReLU mask + the bias gradient in one pass
             self._wgrad([(c['y_bf'], d)], dh_, F, B, T, d, F, [(0, 0)], G[pre + 'ffn1.w'])
             dy = self._f32(B, T, d)
             m._gemm(P[pre + 'ffn1.d'], B, T, [(dh_, None, F, 0)], [0], [0], residual=du2, out_f32=dy, ld_out=d)
@@ -328,15 +327,14 @@ class TrainEngine:
             g_cur, g_dim = g2, d
             for j in range(n - 1, -1, -1):
                 cin = in_dims[j]
-                if j < n - 1:  # (the last conv's bias gradient comes out of the LayerNorm backward kernel)
-                    lib.colsum_bf16(g_cur, B * T, g_dim, g_cur.shape[-1], G[pre + f'conv{j}.b'])
+                # bias gradients: the last conv's comes out of the LayerNorm backward kernel, the others out of the ReLU-mask pass
                 self._wgrad([(inputs[j], cin)], g_cur, g_cur.shape[-1], B, T, cin, g_dim, [(0, s_) for s_ in shifts], G[pre + f'conv{j}.w'])
                 kpad = _round_up(g_dim, 64)
                 assert g_cur.shape[-1] == kpad, 'gradient operand must be padded to the packed contraction width'
                 if j > 0:
                     dx_ = self._bf(B, T, cin)
                     m._gemm(P[pre + f'conv{j}.d'], B, T, [(g_cur, None, kpad, 0)], [0] * k, dshifts, out_hi=dx_, ld_out=cin)
-                    lib.relu_bwd(dx_, inputs[j])
+                    lib.relu_bwd_colsum(dx_, inputs[j], G[pre + f'conv{j - 1}.b'])
                     g_cur, g_dim = dx_, cin
                 else:
                     dy = self._f32(B, T, d)
@@ -382,10 +380,13 @@ class TrainEngine:
         self._bgemm(B, H, T, dh, T, c['P_drop'], (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0, 1), dattn, (d, T, B), (d, d * T),
                     (dh, 0, 0, 0, 1), out_ptr_off=2 * d, **common)
         # ---- q/k/v projections
-        for n_, nm in enumerate(('wq', 'wk', 'wv')):  # the three Dense layers own separate (d,d) kernels: one column slice each
-            gs = dqkv[..., n_ * d:]
-            lib.colsum_bf16(gs, B * T, d, 3 * d, G[pre + nm + '.b'])
-            self._wgrad([(c['x_bf'], d)], gs, 3 * d, B, T, d, d, [(0, 0)], G[pre + nm + '.w'])
+        # the three Dense layers own separate (d,d) kernels and biases but share the (B,T,3d) gradient buffer: one column-sum
+        # launch with three outputs, one weight-gradient GEMM of width 3d into a scratch matrix, three strided adds
+        lib.colsum_bf16_x3(dqkv, B * T, d, 3 * d, G[pre + 'wq.b'], G[pre + 'wk.b'], G[pre + 'wv.b'])
+        dw_qkv = torch.zeros((d, 3 * d), dtype=torch.float32, device=self.dev)
+        self._wgrad([(c['x_bf'], d)], dqkv, 3 * d, B, T, d, 3 * d, [(0, 0)], dw_qkv)
+        for n_, nm in enumerate(('wq', 'wk', 'wv')):
+            G[pre + nm + '.w'].add_(dw_qkv[:, n_ * d:(n_ + 1) * d])
         dx = self._f32(B, T, d)
         m._gemm(P[pre + 'qkv.d'], B, T, [(dqkv, None, 3 * d, 0)], [0], [0], residual=dx_acc, out_f32=dx, ld_out=d)
         return dx
