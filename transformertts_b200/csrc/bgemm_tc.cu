@@ -268,24 +268,41 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           const uint32_t thresh = dropout_thresh(p.sm_drop_p);
           const float ks = p.sm_drop_p > 0.f ? 1.f / (1.f - p.sm_drop_p) : 1.f;
           uint32_t qa[16], qb[16];
+          // fused softmax backward: the P_pre row segments of the NEXT slab are requested before the current slab is
+          // processed: the slab loop is a dependent chain (TMEM load -> math -> shared store -> barrier -> TMA store) with two
+          // warps per lane quarter and nothing else to hide a global load behind
+          uint4 pn00, pn01, pn10, pn11;   // next slab: [chunk u][16-byte half]
+          auto prefetch = [&](int s0n) {
+            pn00 = pn01 = pn10 = pn11 = make_uint4(0, 0, 0, 0);
+            if (sm && s0n < nch && live) {
+              const int ca_n = (s0n + 2 * half) << 4, cb_n = ca_n + 16;
+              if (n0 + ca_n < len) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.sm_P + o + ca_n);
+                pn00 = __ldg(src);
+                pn01 = __ldg(src + 1);
+              }
+              if (n0 + cb_n < len) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.sm_P + o + cb_n);
+                pn10 = __ldg(src);
+                pn11 = __ldg(src + 1);
+              }
+            }
+          };
+          prefetch(0);
           for (int s0 = 0; s0 < nch; s0 += 4) {
             const int ca = s0 + 2 * half, cb = ca + 1;
             uint4 pv[2][2], pd[2][2];
+            pv[0][0] = pn00; pv[0][1] = pn01; pv[1][0] = pn10; pv[1][1] = pn11;
+            prefetch(s0 + 4);
             if (sm) {
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
                 const int c0 = (u ? cb : ca) << 4;
-                const bool need = live && n0 + c0 < len;
-                pv[u][0] = pv[u][1] = pd[u][0] = pd[u][1] = make_uint4(0, 0, 0, 0);
-                if (need) {
-                  const uint4* src = reinterpret_cast<const uint4*>(p.sm_P + o + c0);
-                  pv[u][0] = __ldg(src);
-                  pv[u][1] = __ldg(src + 1);
-                  if (p.sm_Pdrop != nullptr) {
-                    const uint4* sd = reinterpret_cast<const uint4*>(p.sm_Pdrop + o + c0);
-                    pd[u][0] = __ldg(sd);
-                    pd[u][1] = __ldg(sd + 1);
-                  }
+                pd[u][0] = pd[u][1] = make_uint4(0, 0, 0, 0);
+                if (p.sm_Pdrop != nullptr && live && n0 + c0 < len) {
+                  const uint4* sd = reinterpret_cast<const uint4*>(p.sm_Pdrop + o + c0);
+                  pd[u][0] = __ldg(sd);
+                  pd[u][1] = __ldg(sd + 1);
                 }
               }
             }
