@@ -380,6 +380,23 @@ int ttsb_phoneme_lengths(const int32_t* phonemes, int B, int T, int32_t padding,
 int ttsb_stft_mel_log(const float* wav, int n_clips, int n_samples, const float* mel_basis, int n_mels,
                       int normalizer, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange (BASELINE.json: "NCCL allreduce over NVLink on gradient buckets only"; the reference has
+ * no distributed code).  One communicator per process / GPU.  NCCL is loaded at run time (libnccl.so.2 of the host
+ * process, or $TTSB_NCCL_LIB); without it these return TTSB_ERR_UNSUPPORTED.
+ *   ttsb_dp_unique_id       : rank 0 fills a 128-byte id that the host distributes to all ranks (any side channel)
+ *   ttsb_dp_init            : collective; binds to the calling thread's current CUDA device
+ *   ttsb_dp_allreduce_bucket: in-place SUM of buf[0:count] (fp32, device) across ranks, enqueued on `stream`; the 1/N
+ *                             factor is applied by ttsb_adam_tf_step(grad_scale).  Call it as soon as a contiguous slice of
+ *                             the flat gradient buffer is final, on a second stream, to overlap it with the remaining
+ *                             backward kernels.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct ttsb_dp_comm ttsb_dp_comm;
+int ttsb_dp_unique_id(void* id_out_128_bytes);
+int ttsb_dp_init(const void* unique_id_128_bytes, int rank, int world, ttsb_dp_comm** out);
+int ttsb_dp_allreduce_bucket(ttsb_dp_comm* comm, float* buf, int64_t count, void* stream);
+int ttsb_dp_destroy(ttsb_dp_comm* comm);
+
 #ifdef __cplusplus
 }
 #endif

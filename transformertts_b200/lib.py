@@ -28,7 +28,7 @@ EXPORTS = [
     'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_rowdot_heads', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
     'ttsb_relu_bwd', 'ttsb_relu_bwd_colsum', 'ttsb_colsum_bf16', 'ttsb_colsum_bf16_x3', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_scaled_ce_loss', 'ttsb_diag_loss', 'ttsb_diag_loss_train', 'ttsb_attention_scores', 'ttsb_durations_from_attention', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
     'ttsb_pitch_embed_bwd', 'ttsb_statpred_head_bwd', 'ttsb_adam_tf_step', 'ttsb_embed_ln_pe_train_fwd',
-    'ttsb_expand_ln_pe_train_fwd',
+    'ttsb_expand_ln_pe_train_fwd', 'ttsb_dp_unique_id', 'ttsb_dp_init', 'ttsb_dp_allreduce_bucket', 'ttsb_dp_destroy',
 ]
 
 
@@ -406,3 +406,27 @@ def adam_tf_step(param, grad, m, v, lr_t, beta1, beta2, eps, grad_scale=1.0):
     _check(load().ttsb_adam_tf_step(ptr(param), ptr(grad), ptr(m), ptr(v), C.c_int64(param.numel()), C.c_float(lr_t),
                                     C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(grad_scale), _stream()),
            'ttsb_adam_tf_step')
+
+
+# ------------------------------------------------------------------------------------------------------------
+# data-parallel gradient exchange (NCCL behind the C ABI)
+# ------------------------------------------------------------------------------------------------------------
+def dp_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(load().ttsb_dp_unique_id(buf), 'ttsb_dp_unique_id')
+    return buf.raw
+
+
+def dp_init(unique_id: bytes, rank: int, world: int):
+    comm = C.c_void_p()
+    _check(load().ttsb_dp_init(C.c_char_p(unique_id), int(rank), int(world), C.byref(comm)), 'ttsb_dp_init')
+    return comm
+
+
+def dp_allreduce_bucket(comm, buf: torch.Tensor, stream: int):
+    """In-place sum of the contiguous fp32 CUDA tensor `buf` across ranks on the raw stream handle `stream`."""
+    _check(load().ttsb_dp_allreduce_bucket(comm, ptr(buf), C.c_int64(buf.numel()), C.c_void_p(stream)), 'ttsb_dp_allreduce_bucket')
+
+
+def dp_destroy(comm):
+    _check(load().ttsb_dp_destroy(comm), 'ttsb_dp_destroy')

@@ -426,8 +426,8 @@ class Aligner(ForwardTransformer):
         eng = self._get_engine()
         sync = None
         if data_parallel:
-            from ..utils.data_parallel import GradSync
-            sync = GradSync(eng.flat_g)
+            from ..utils.data_parallel import make_grad_sync
+            sync = make_grad_sync(eng.flat_g)
         out = eng.forward_backward(inp, tar, stop_prob, training=True, sync=sync)
         scale = sync.finish() if sync is not None else 1.0
         eng.apply_adam(self.optimizer, grad_scale=scale)

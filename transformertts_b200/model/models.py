@@ -862,8 +862,8 @@ class ForwardTransformer:
         eng = self._get_engine()
         sync = None
         if data_parallel:
-            from ..utils.data_parallel import GradSync
-            sync = GradSync(eng.flat_g)
+            from ..utils.data_parallel import make_grad_sync
+            sync = make_grad_sync(eng.flat_g)
         if self.train_graphs:
             out = eng.step_graphed(input_sequence, target_sequence, target_durations, target_pitch, sync=sync)
         else:

@@ -68,6 +68,73 @@ class GradSync:
         return 1.0 / self.world
 
 
+class NativeGradSync:
+    """The same contract as GradSync with the exchange done by libttsb's own NCCL entry points (include/ttsb.h: ttsb_dp_*):
+    torch.distributed only carries the 128-byte NCCL id to the ranks once.  Buckets are reduced on a dedicated stream, ordered
+    against the compute stream with two events, so a bucket overlaps the backward kernels that follow it."""
+
+    _shared = {}   # device index -> (communicator, stream, world)
+
+    def __init__(self, flat: torch.Tensor, group=None):
+        from .. import lib
+        self.lib = lib
+        self.flat = flat
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._sent: List[Tuple[int, int]] = []
+        if self.world == 1:
+            return
+        dev = flat.device.index
+        if dev not in NativeGradSync._shared:
+            rank = dist.get_rank(group)
+            box = [lib.dp_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=group)
+            with torch.cuda.device(dev):
+                comm = lib.dp_init(box[0], rank, self.world)
+                NativeGradSync._shared[dev] = (comm, torch.cuda.Stream(device=dev), self.world)
+        self.comm, self.stream, _ = NativeGradSync._shared[dev]
+
+    def _reduce(self, lo: int, hi: int):
+        cur = torch.cuda.current_stream(self.flat.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.stream.wait_event(ev)          # the slice is final on the compute stream
+        self.lib.dp_allreduce_bucket(self.comm, self.flat[lo:hi], self.stream.cuda_stream)
+
+    def bucket_ready(self, lo: int, hi: int):
+        if self.world == 1 or hi <= lo:
+            return
+        self._reduce(lo, hi)
+        self._sent.append((lo, hi))
+
+    def finish(self) -> float:
+        if self.world == 1:
+            return 1.0
+        pos = 0
+        for lo, hi in sorted(self._sent):
+            if lo > pos:
+                self._reduce(pos, lo)
+            pos = max(pos, hi)
+        if pos < self.flat.numel():
+            self._reduce(pos, self.flat.numel())
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        torch.cuda.current_stream(self.flat.device).wait_event(done)   # Adam (compute stream) sees the reduced gradient
+        self._sent = []
+        return 1.0 / self.world
+
+
+def make_grad_sync(flat: torch.Tensor, group=None):
+    """GradSync implementation for this process: libttsb's NCCL path on CUDA (TTSB_DP_BACKEND=torch selects the
+    torch.distributed one), torch.distributed (gloo) for CPU tensors in the host-logic tests."""
+    backend = os.environ.get('TTSB_DP_BACKEND', 'native')
+    if flat.is_cuda and backend == 'native' and dist.is_initialized() and dist.get_world_size(group) > 1:
+        try:
+            return NativeGradSync(flat, group)
+        except Exception as e:   # NCCL not loadable: fall back, loudly
+            print(f'[transformertts_b200] native NCCL path unavailable ({e}); using torch.distributed', flush=True)
+    return GradSync(flat, group)
+
+
 def global_loss(local_loss: torch.Tensor, local_numel: int, group=None) -> torch.Tensor:
     """The reference loss is a mean over the padded batch tensor; the single-process equivalent of a sharded batch is the
     numel-weighted mean of the shard losses."""
