@@ -319,16 +319,33 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               const int c0 = (u ? cb : ca) << 4;
               float y[16];
               if (sm) {
-                const __nv_bfloat16* pp = reinterpret_cast<const __nv_bfloat16*>(pv[u]);
+                // dS[j] = scale * P[j] * (keep[j] * dP[j] / (1-p) - D)  as  fma(a, dP, -(ps * D)),  ps = scale * P,
+                // a = keep ? ps / (1-p) : 0; one mask hash per element pair; the key-length test only in the boundary chunk
+                const uint32_t* pw = reinterpret_cast<const uint32_t*>(pv[u]);
                 const uint16_t* dd = reinterpret_cast<const uint16_t*>(pd[u]);
                 const size_t e0 = o + c0;
+                const int kbase = n0 + c0;
+                const float sks = p.sm_scale * ks;
+                if (!live || kbase >= len) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int k = n0 + c0 + j;
-                  bool keep = true;
-                  if (p.sm_drop_p > 0.f) keep = p.sm_Pdrop != nullptr ? (dd[j] & 0x7fffu) != 0 : dropout_keep(p.sm_seed, p.sm_site, e0 + j, thresh);
-                  const float g = keep ? __uint_as_float(u ? qb[j] : qa[j]) * ks : 0.f;
-                  y[j] = (live && k < len) ? p.sm_scale * __bfloat162float(pp[j]) * (g - dsum) : 0.f;
+                  for (int j = 0; j < 16; ++j) y[j] = 0.f;
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; j += 2) {
+                    const float p0 = __uint_as_float(pw[j >> 1] << 16), p1 = __uint_as_float(pw[j >> 1] & 0xffff0000u);
+                    bool k0 = true, k1 = true;
+                    if (p.sm_drop_p > 0.f) {
+                      if (p.sm_Pdrop != nullptr) { k0 = (dd[j] & 0x7fffu) != 0; k1 = (dd[j + 1] & 0x7fffu) != 0; }
+                      else dropout_keep2(p.sm_seed, p.sm_site, e0 + j, thresh, k0, k1);
+                    }
+                    const float r0 = __uint_as_float(u ? qb[j] : qa[j]), r1 = __uint_as_float(u ? qb[j + 1] : qa[j + 1]);
+                    y[j] = fmaf(k0 ? p0 * sks : 0.f, r0, -(p0 * p.sm_scale) * dsum);
+                    y[j + 1] = fmaf(k1 ? p1 * sks : 0.f, r1, -(p1 * p.sm_scale) * dsum);
+                  }
+                  if (kbase + 16 > len) {   // the chunk that straddles the key length (P is zero there already; keep exact zeros)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = (kbase + j < len) ? y[j] : 0.f;
+                  }
                 }
               } else {
 #pragma unroll

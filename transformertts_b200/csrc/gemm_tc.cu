@@ -180,7 +180,12 @@ __device__ __forceinline__ void apply_dropout16(float (&y)[16], float p, uint32_
   const uint32_t thresh = dropout_thresh(p);
   const float ks = 1.f / (1.f - p);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) y[j] = dropout_keep(seed, site, elem0 + j, thresh) ? y[j] * ks : 0.f;
+  for (int j = 0; j < 16; j += 2) {   // elem0 is a multiple of 16 (ld_out % 16 == 0 for dropout outputs): one hash per pair
+    bool k0, k1;
+    dropout_keep2(seed, site, elem0 + j, thresh, k0, k1);
+    y[j] = k0 ? y[j] * ks : 0.f;
+    y[j + 1] = k1 ? y[j + 1] * ks : 0.f;
+  }
 }
 
 // exchange of per-row partial sums between the two warps that share a lane quarter

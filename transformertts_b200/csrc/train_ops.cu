@@ -59,6 +59,74 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ S, int Z, int H, in
   }
 }
 
+// The same for rows of up to 1024 padded keys (every attention of the model at T <= 1024) with the row held in registers:
+// ONE pass over S (16-byte loads, lane = 4 consecutive keys per 128-key group), exp evaluated once, 8-byte bf16 stores, one
+// dropout hash per key pair.  NG = number of 128-key groups.
+template <int NG>
+__global__ void __launch_bounds__(256)
+softmax_fwd_vec_kernel(const float* __restrict__ S, int Z, int H, int T, int Tk, int ld, const int* __restrict__ kv_len, float drop_p,
+                       uint32_t seed, uint32_t site, int flags, __nv_bfloat16* __restrict__ P_pre, __nv_bfloat16* __restrict__ P_drop) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= Z * T) return;
+  const int lane = threadIdx.x & 31;
+  const int z = row / T, t = row % T, b = z / H;
+  int len = min(max(__ldg(kv_len + b), 0), Tk);
+  const size_t base = (size_t)row * ld;
+  const bool live = (flags & 2) ? len > 0 : t < len;
+  if (flags & 1) len = min(len, t + 1);
+  if (!live) len = 0;
+  float4 v[NG];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    const int k = 4 * lane + 128 * i;
+    v[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (k < len) {   // (ld is a multiple of 16, so a started group of four is inside the padded row)
+      v[i] = __ldcs(reinterpret_cast<const float4*>(S + base + k));
+      if (k + 1 >= len) v[i].y = -INFINITY;
+      if (k + 2 >= len) v[i].z = -INFINITY;
+      if (k + 3 >= len) v[i].w = -INFINITY;
+      mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    }
+  }
+  mx = wmax(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    v[i].x = __expf(v[i].x - mx); v[i].y = __expf(v[i].y - mx); v[i].z = __expf(v[i].z - mx); v[i].w = __expf(v[i].w - mx);
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  sum = wsum(sum);
+  const float inv = len > 0 ? 1.f / sum : 0.f;
+  const uint32_t thresh = dropout_thresh(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    const int k = 4 * lane + 128 * i;
+    if (k < ld) {
+      float pv[4] = {v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv};
+      if (len == 0) pv[0] = pv[1] = pv[2] = pv[3] = 0.f;     // exp(-inf - (-inf)) is NaN on dead rows
+      const __nv_bfloat162 a = __floats2bfloat162_rn(pv[0], pv[1]), c = __floats2bfloat162_rn(pv[2], pv[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&a);
+      pk.y = *reinterpret_cast<const uint32_t*>(&c);
+      *reinterpret_cast<uint2*>(P_pre + base + k) = pk;
+      if (P_drop != P_pre) {
+        bool k0 = true, k1 = true, k2 = true, k3 = true;
+        if (drop_p > 0.f) {
+          dropout_keep2(seed, site, base + k, thresh, k0, k1);
+          dropout_keep2(seed, site, base + k + 2, thresh, k2, k3);
+        }
+        const __nv_bfloat162 d0 = __floats2bfloat162_rn(k0 ? pv[0] * keep_scale : 0.f, k1 ? pv[1] * keep_scale : 0.f);
+        const __nv_bfloat162 d1 = __floats2bfloat162_rn(k2 ? pv[2] * keep_scale : 0.f, k3 ? pv[3] * keep_scale : 0.f);
+        pk.x = *reinterpret_cast<const uint32_t*>(&d0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&d1);
+        *reinterpret_cast<uint2*>(P_drop + base + k) = pk;
+      }
+    }
+  }
+}
+
 // dS = scale * P_pre * (dPp - sum_k P_pre dPp),  dPp = dP * keep/(1-p).  Two light passes over the row (the second one
 // hits L2); keeping the row in registers instead was measured 2-4x slower (occupancy).
 __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P_pre, const float* __restrict__ dP, int Z, int H, int T, int Tk,
@@ -244,12 +312,13 @@ layernorm_bwd_vec_kernel(const float* __restrict__ dz, const float* __restrict__
 #pragma unroll
     for (int i = 0; i < NG; ++i) {
       float* g4 = reinterpret_cast<float*>(&gz[i]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float g = live ? g4[j] : 0.f;
-        if (post_drop_p > 0.f) g = dropout_keep(seed, post_site, base + 4 * lane + 128 * i + j, post_thresh) ? g * post_scale : 0.f;
-        g4[j] = g;
+      bool kk[4] = {true, true, true, true};
+      if (post_drop_p > 0.f) {
+        dropout_keep2(seed, post_site, base + 4 * lane + 128 * i, post_thresh, kk[0], kk[1]);
+        dropout_keep2(seed, post_site, base + 4 * lane + 128 * i + 2, post_thresh, kk[2], kk[3]);
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g4[j] = (live && kk[j]) ? g4[j] * post_scale : 0.f;
       s += (uv[i].x + uv[i].y) + (uv[i].z + uv[i].w);
     }
     const float mean = wsum(s) * (1.f / C);
@@ -293,13 +362,18 @@ layernorm_bwd_vec_kernel(const float* __restrict__ dz, const float* __restrict__
       const float* m4 = reinterpret_cast<const float*>(&gam[i]);
       float* ax = reinterpret_cast<float*>(&acc_x[i]);
       float d4[4], gv[4];
+      bool kp[4] = {true, true, true, true};
+      if (pre_drop_p > 0.f) {
+        dropout_keep2(seed, pre_site, base + 4 * lane + 128 * i, pre_thresh, kp[0], kp[1]);
+        dropout_keep2(seed, pre_site, base + 4 * lane + 128 * i + 2, pre_thresh, kp[2], kp[3]);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float xh = (u4[j] - mean) * rstd;
         d4[j] = rstd * (g4[j] * m4[j] - sg - xh * sgx);
         float v = d4[j];
         if (relu_mask && !(u4[j] > 0.f)) v = 0.f;
-        if (pre_drop_p > 0.f) v = dropout_keep(seed, pre_site, base + 4 * lane + 128 * i + j, pre_thresh) ? v * pre_scale : 0.f;
+        v = kp[j] ? v * pre_scale : 0.f;
         gv[j] = v;
         ax[j] += v;
       }
@@ -733,6 +807,18 @@ extern "C" int ttsb_softmax_fwd(const float* S, int B, int H, int T, int Tk, int
                                 uint32_t seed, uint32_t site, int flags, void* P_pre, void* P_drop, void* stream) {
   if (!S || !kv_len || !P_pre || !P_drop || B <= 0 || H <= 0 || T <= 0 || Tk <= 0 || ld < Tk) return bad("ttsb_softmax_fwd: bad arguments");
   const int rows = B * H * T;
+  if (ld % 4 == 0 && ld <= 1024 && (reinterpret_cast<uintptr_t>(S) & 15) == 0 && (reinterpret_cast<uintptr_t>(P_pre) & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(P_drop) & 7) == 0) {
+#define TTSB_SMV(NG)                                                                                                                  \
+  softmax_fwd_vec_kernel<NG><<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(S, B * H, H, T, Tk, ld, kv_len, drop_p, seed, site, flags, \
+                                                                          BF(P_pre), BF(P_drop))
+    if (ld <= 128) TTSB_SMV(1);
+    else if (ld <= 256) TTSB_SMV(2);
+    else if (ld <= 512) TTSB_SMV(4);
+    else TTSB_SMV(8);
+#undef TTSB_SMV
+    LAUNCH_OK("softmax_fwd_vec_kernel");
+  }
   softmax_fwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(S, B * H, H, T, Tk, ld, kv_len, drop_p, seed, site, flags, BF(P_pre), BF(P_drop));
   LAUNCH_OK("softmax_fwd_kernel");
 }

@@ -41,11 +41,24 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 // a training step captured as a CUDA graph has its `seed` arguments frozen at capture, so the per-step variation comes from
 // this device-resident word, refreshed by memcpy nodes at the head of the graph.
 static __constant__ uint32_t c_drop_salt = 0;
-__device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t site, uint64_t idx, uint32_t thresh) {
+// One 32-bit hash serves TWO consecutive elements (16 bits each; the rate is resolved to 2^-16): the per-element cost of the
+// mask is what bounds the attention-probability kernels of the training step (ncu: the fused dS epilogue issued ~42
+// instructions per element with a hash per element).
+__device__ __forceinline__ uint32_t dropout_hash(uint32_t seed, uint32_t site, uint64_t pair) {
   seed ^= c_drop_salt;
-  uint32_t x = (uint32_t)idx * 0x9E3779B1u ^ (uint32_t)(idx >> 32) * 0x85EBCA77u ^ seed * 0xC2B2AE3Du ^ site * 0x27D4EB2Fu;
+  uint32_t x = (uint32_t)pair * 0x9E3779B1u ^ (uint32_t)(pair >> 32) * 0x85EBCA77u ^ seed * 0xC2B2AE3Du ^ site * 0x27D4EB2Fu;
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-  return x >= thresh;
+  return x;
+}
+__device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t site, uint64_t idx, uint32_t thresh) {
+  const uint32_t h = dropout_hash(seed, site, idx >> 1);
+  return ((idx & 1) ? (h >> 16) : (h & 0xffffu)) >= (thresh >> 16);
+}
+// decisions for elements idx_even and idx_even + 1 (idx_even must be even) from one hash
+__device__ __forceinline__ void dropout_keep2(uint32_t seed, uint32_t site, uint64_t idx_even, uint32_t thresh, bool& k0, bool& k1) {
+  const uint32_t h = dropout_hash(seed, site, idx_even >> 1);
+  k0 = (h & 0xffffu) >= (thresh >> 16);
+  k1 = (h >> 16) >= (thresh >> 16);
 }
 __host__ __device__ __forceinline__ uint32_t dropout_thresh(float p) { return p > 0.f ? (uint32_t)((double)p * 4294967296.0) : 0u; }
 
