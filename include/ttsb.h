@@ -381,6 +381,27 @@ int ttsb_stft_mel_log(const float* wav, int n_clips, int n_samples, const float*
                       int normalizer, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * mel -> waveform  (Audio.reconstruct_waveform, data/audio.py:94-110: librosa mel_to_stft(power=1) + griffinlim(32, momentum .99))
+ *   n_fft 1024, hop 256, periodic Hann, centred frames with reflect padding (the reference configuration).
+ * ------------------------------------------------------------------------------------------------------- */
+/* mel amplitudes (n_frames, n_mels) -> non-negative linear magnitudes (n_frames, 513): per frame min_{x>=0} |A x - m|^2 for the
+ * mel basis A (n_mels, 513), from the start max(pinv(A) m, 0) that librosa's nnls uses, with n_iter FISTA steps of size `step`
+ * (1 / |A|_2^2).  band[2*j], band[2*j+1] = first / past-last non-zero bin of basis row j; bin_mels[2*k], [2*k+1] = first /
+ * past-last mel row that is non-zero at bin k.  basis_pinv is (513, n_mels). */
+int ttsb_mel_to_linear(const float* mel_amp, int n_frames, int n_mels, const float* mel_basis, const float* basis_pinv,
+                       const int32_t* band, const int32_t* bin_mels, float step, int n_iter, float* out, void* stream);
+/* librosa.stft: wav (n_samples) -> complex64 (1 + n_samples/256, 513) as interleaved (re, im) floats */
+int ttsb_stft_complex(const float* wav, int n_samples, float* spec_out, void* stream);
+/* librosa.istft: complex64 (n_frames, 513) -> wav (256 * (n_frames - 1)).  workspace: ttsb_istft_workspace_bytes(n_frames) bytes
+ * of device memory (the windowed time frames before the overlap-add). */
+int64_t ttsb_istft_workspace_bytes(int n_frames);
+int ttsb_istft(const float* spec, int n_frames, void* workspace, int64_t workspace_bytes, float* wav_out, void* stream);
+/* one phase update of fast Griffin-Lim over n complex bins: a = rebuilt - momentum/(1+momentum) * previous (previous may be
+ * NULL: first iteration); a /= |a| + 1e-16; projected_out = magnitude * a.  rebuilt / previous / projected_out are complex64. */
+int ttsb_griffinlim_update(const float* rebuilt, const float* previous, const float* magnitude, float momentum, int64_t n,
+                           float* projected_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange (BASELINE.json: "NCCL allreduce over NVLink on gradient buckets only"; the reference has
  * no distributed code).  One communicator per process / GPU.  NCCL is loaded at run time (libnccl.so.2 of the host
  * process, or $TTSB_NCCL_LIB); without it these return TTSB_ERR_UNSUPPORTED.

@@ -274,3 +274,39 @@ def test_golden_audio_vectors():
     mels = np.stack([ao.mel_spectrogram(c) for c in clips])
     assert mels.shape == g['mel'].shape == (2, 1 + 11008 // 256, 80)
     assert np.abs(mels - g['mel']).max() < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------------------
+# (e) mel -> waveform oracle (data/audio.py:94-110): istft against torch.istft, NNLS solvers against each other
+# ----------------------------------------------------------------------------------------------------------
+def test_istft_restatement_matches_torch_istft_and_inverts_stft():
+    y = ao.make_clips(1, 11008, seed=5)[0]
+    D = ao.stft(y)
+    yi = ao.istft(D)
+    assert yi.shape == (256 * (D.shape[1] - 1),)
+    assert np.abs(yi - y[:len(yi)]).max() < 1e-6                      # perfect reconstruction (Hann, hop = n_fft / 4)
+    yt = torch.istft(torch.from_numpy(D), 1024, 256, 1024, torch.hann_window(1024, periodic=True), center=True).numpy()
+    assert np.abs(yt - yi[:len(yt)]).max() < 1e-6
+    wss = ao.window_sumsquare(D.shape[1])
+    assert abs(wss[2048] - 1.5) < 1e-6                                # sum of four shifted squared Hann windows
+
+
+def test_nnls_solvers_agree_and_griffinlim_converges():
+    """librosa's nnls (L-BFGS-B from the clipped least-squares start) vs the fixed-count FISTA projected gradient the CUDA path
+    runs: same objective value (both essentially exact), solutions within 1 % of each other; Griffin-Lim with a shared
+    initial phase reproduces a spectrogram consistent with the target magnitudes."""
+    y = ao.make_clips(1, 11008, seed=6)[0]
+    mel = ao.mel_spectrogram(y).T
+    amp = np.exp(mel).astype(np.float32)
+    A = ao.mel_filterbank()
+    x1 = ao.mel_to_stft(amp, solver='lbfgsb')
+    x2 = ao.mel_to_stft(amp, solver='pg', n_iter=64)
+    assert x1.min() >= 0 and x2.min() >= 0
+    o1, o2 = 0.5 * np.sum((A @ x1 - amp) ** 2), 0.5 * np.sum((A @ x2 - amp) ** 2)
+    assert o2 <= o1 + 1e-6 and o2 < 1e-6 * 0.5 * np.sum(amp ** 2)
+    assert np.linalg.norm(x1 - x2) / np.linalg.norm(x1) < 1e-2
+    w = ao.griffinlim(x2, n_iter=16, seed=3)
+    assert w.shape == (256 * (x2.shape[1] - 1),) and np.isfinite(w).all()
+    err = np.linalg.norm(np.abs(ao.stft(w)) - x2) / np.linalg.norm(x2)   # spectral convergence after 16 iterations
+    err0 = np.linalg.norm(np.abs(ao.stft(ao.griffinlim(x2, n_iter=0, seed=3))) - x2) / np.linalg.norm(x2)
+    assert err < 0.5 * err0

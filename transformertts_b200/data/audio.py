@@ -95,6 +95,73 @@ class Audio:
         lib.stft_mel_log(wav.contiguous(), self._mel_basis(), self.normalizer.code, out)
         return out
 
+    # ---- mel -> waveform (data/audio.py:94-110)
+    def _inverse_tables(self):
+        """Host-side constants of the mel inversion: pinv(A) (the least-squares start librosa's nnls uses), 1/|A|_2^2, and the
+        sparsity pattern of the mel basis (rows are bands, every bin belongs to <= 2 rows)."""
+        if getattr(self, '_inv', None) is None:
+            A = slaney_mel_basis(self.sampling_rate, self.n_fft, self.mel_channels, self.f_min, self.f_max).astype(np.float64)
+            nz = A != 0
+            band = np.zeros((A.shape[0], 2), dtype=np.int32)
+            for j in range(A.shape[0]):
+                idx = np.nonzero(nz[j])[0]
+                band[j] = (idx[0], idx[-1] + 1) if len(idx) else (0, 0)
+            bins = np.zeros((A.shape[1], 2), dtype=np.int32)
+            for k in range(A.shape[1]):
+                idx = np.nonzero(nz[:, k])[0]
+                bins[k] = (idx[0], idx[-1] + 1) if len(idx) else (0, 0)
+            dev = self.device
+            self._inv = dict(pinv=torch.from_numpy(np.linalg.pinv(A).astype(np.float32)).to(dev).contiguous(),
+                             step=float(1.0 / np.linalg.norm(A, 2) ** 2), band=torch.from_numpy(band).to(dev).contiguous(),
+                             bins=torch.from_numpy(bins).to(dev).contiguous())
+        return self._inv
+
+    def mel_to_linear_device(self, mel_amp: torch.Tensor, n_iter: int = 64) -> torch.Tensor:
+        """mel amplitudes (T, n_mels) CUDA -> linear magnitudes (T, 513) CUDA (librosa mel_to_stft(power=1), see ttsb.h)."""
+        with torch.cuda.device(self.device):
+            inv = self._inverse_tables()
+            out = torch.empty((mel_amp.shape[0], self.n_fft // 2 + 1), dtype=torch.float32, device=self.device)
+            lib.mel_to_linear(mel_amp.contiguous(), self._mel_basis(), inv['pinv'], inv['band'], inv['bins'], inv['step'], n_iter, out)
+            return out
+
+    def griffinlim_device(self, S: torch.Tensor, n_iter: int = 32, momentum: float = 0.99, init_angles: torch.Tensor = None,
+                          seed: int = None) -> torch.Tensor:
+        """librosa.griffinlim on the GPU: S (T, 513) magnitudes -> waveform (256 (T-1)).  init_angles: unit-modulus complex64
+        (T, 513); default: exp(2 pi i u), u uniform (the reference draws it from numpy's global RNG)."""
+        with torch.cuda.device(self.device):
+            dev = self.device
+            T = S.shape[0]
+            if init_angles is None:
+                g = torch.Generator(device='cpu')
+                if seed is not None:
+                    g.manual_seed(seed)
+                ph = 2 * np.pi * torch.rand(S.shape, generator=g, dtype=torch.float64)
+                init_angles = torch.polar(torch.ones_like(ph), ph).to(torch.complex64)
+            proj = torch.view_as_real((S.to(torch.complex64) * init_angles.to(dev)).contiguous()).contiguous()
+            ws = torch.empty(lib.istft_workspace_bytes(T) // 4, dtype=torch.float32, device=dev)
+            wav = torch.empty(self.hop_length * (T - 1), dtype=torch.float32, device=dev)
+            rebuilt, prev = torch.empty_like(proj), None
+            S = S.contiguous()
+            for _ in range(n_iter):
+                lib.istft(proj, ws, wav)
+                spare = prev if prev is not None else torch.empty_like(proj)
+                lib.stft_complex(wav, spare)                    # `spare` becomes the new rebuilt spectrum
+                lib.griffinlim_update(spare, rebuilt if prev is not None else None, S, momentum, proj)
+                prev, rebuilt = rebuilt, spare
+            lib.istft(proj, ws, wav)
+            return wav
+
+    def reconstruct_waveform(self, mel: np.ndarray, n_iter: int = 32, nnls_iter: int = 64, init_angles=None, seed: int = None) -> np.ndarray:
+        """reference: data/audio.py:94-110.  mel: normalised (n_mels, T) as the reference passes it -> waveform float32."""
+        m = np.asarray(mel, dtype=np.float32)
+        amp = torch.from_numpy(np.ascontiguousarray(self._denormalize(m).T.astype(np.float32))).to(self.device)   # (T, n_mels)
+        S = self.mel_to_linear_device(amp, nnls_iter)
+        ia = None if init_angles is None else torch.as_tensor(np.ascontiguousarray(np.asarray(init_angles).T)).to(torch.complex64)
+        return self.griffinlim_device(S, n_iter=n_iter, init_angles=ia, seed=seed).cpu().numpy()
+
+    def _denormalize(self, S):
+        return self.normalizer.denormalize(S)
+
     def mel_spectrogram_batch(self, wavs: np.ndarray) -> np.ndarray:
         w = torch.from_numpy(np.ascontiguousarray(wavs, dtype=np.float32)).to(self.device)
         return self.mel_spectrogram_device(w).cpu().numpy()

@@ -28,7 +28,8 @@ EXPORTS = [
     'ttsb_bgemm', 'ttsb_wgrad', 'ttsb_rowdot_heads', 'ttsb_softmax_fwd', 'ttsb_softmax_bwd', 'ttsb_layernorm_bwd',
     'ttsb_relu_bwd', 'ttsb_relu_bwd_colsum', 'ttsb_colsum_bf16', 'ttsb_colsum_bf16_x3', 'ttsb_cast_bf16_pad', 'ttsb_mae_loss', 'ttsb_scaled_ce_loss', 'ttsb_diag_loss', 'ttsb_diag_loss_train', 'ttsb_attention_scores', 'ttsb_durations_from_attention', 'ttsb_expand_bwd', 'ttsb_embedding_bwd', 'ttsb_pe_scalar_bwd',
     'ttsb_pitch_embed_bwd', 'ttsb_statpred_head_bwd', 'ttsb_adam_tf_step', 'ttsb_embed_ln_pe_train_fwd',
-    'ttsb_expand_ln_pe_train_fwd', 'ttsb_dp_unique_id', 'ttsb_dp_init', 'ttsb_dp_allreduce_bucket', 'ttsb_dp_destroy',
+    'ttsb_expand_ln_pe_train_fwd', 'ttsb_mel_to_linear', 'ttsb_stft_complex', 'ttsb_istft_workspace_bytes', 'ttsb_istft', 'ttsb_griffinlim_update',
+    'ttsb_dp_unique_id', 'ttsb_dp_init', 'ttsb_dp_allreduce_bucket', 'ttsb_dp_destroy',
 ]
 
 
@@ -111,6 +112,7 @@ def load() -> C.CDLL:
     lib.ttsb_reset_launch_count.restype = None
     lib.ttsb_add_launch_count.restype = None
     lib.ttsb_add_launch_count.argtypes = [C.c_int64]
+    lib.ttsb_istft_workspace_bytes.restype = C.c_int64
     for name in EXPORTS:
         if not hasattr(lib, name):
             raise TtsbError(f'libttsb.so does not export {name}')
@@ -430,3 +432,31 @@ def dp_allreduce_bucket(comm, buf: torch.Tensor, stream: int):
 
 def dp_destroy(comm):
     _check(load().ttsb_dp_destroy(comm), 'ttsb_dp_destroy')
+
+
+# ------------------------------------------------------------------------------------------------------------
+# mel -> waveform (Griffin-Lim)
+# ------------------------------------------------------------------------------------------------------------
+def mel_to_linear(mel_amp, basis, pinv, band, bin_mels, step, n_iter, out):
+    T, n_mels = mel_amp.shape
+    _check(load().ttsb_mel_to_linear(ptr(mel_amp), T, n_mels, ptr(basis), ptr(pinv), ptr(band), ptr(bin_mels), C.c_float(step), int(n_iter),
+                                     ptr(out), _stream()), 'ttsb_mel_to_linear')
+
+
+def stft_complex(wav, spec_out):
+    _check(load().ttsb_stft_complex(ptr(wav), wav.numel(), ptr(spec_out), _stream()), 'ttsb_stft_complex')
+
+
+def istft(spec, workspace, wav_out):
+    T = spec.shape[0]
+    _check(load().ttsb_istft(ptr(spec), T, ptr(workspace), C.c_int64(workspace.numel() * workspace.element_size()), ptr(wav_out), _stream()),
+           'ttsb_istft')
+
+
+def istft_workspace_bytes(n_frames: int) -> int:
+    return int(load().ttsb_istft_workspace_bytes(int(n_frames)))
+
+
+def griffinlim_update(rebuilt, previous, magnitude, momentum, projected_out):
+    _check(load().ttsb_griffinlim_update(ptr(rebuilt), ptr(previous), ptr(magnitude), C.c_float(momentum), C.c_int64(magnitude.numel()),
+                                         ptr(projected_out), _stream()), 'ttsb_griffinlim_update')
