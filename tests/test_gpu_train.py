@@ -202,10 +202,32 @@ def test_layernorm_bwd_and_small_ops():
     assert (pd.cpu() - pr).abs().max() < 1e-7
 
 
-@pytest.mark.parametrize('cfg_name,B,Tp,Tm', [('C1', 3, 24, 150), ('LJ256', 2, 32, 260), ('REF384', 2, 24, 200)])
-def test_train_step_loss_grads_and_adam(cfg_name, B, Tp, Tm):
-    """One deterministic training step (dropout off): loss, every parameter gradient and the Adam update vs the
-    oracle (torch autograd on the restated fp32 graph).  The GPU forward/backward is single-pass bf16."""
+def _grad_report(eng, ref_g, zero_names, gscale):
+    rows = []
+    for name, gref in ref_g.items():
+        got = eng.g[name].detach().double().cpu()
+        if name in zero_names:
+            assert float(got.norm()) < 2e-3 * gscale, name        # analytically zero (key bias: softmax shift invariance)
+            continue
+        gr = gref.double()
+        if gr.dim() == 0:
+            rows.append((abs(float(got) - float(gr)) / abs(float(gr)), 1.0 if float(got) * float(gr) > 0 else -1.0, name))
+        else:
+            rows.append((_rel(got, gr), float((got * gr).sum() / (got.norm() * gr.norm())), name))
+    rows.sort(reverse=True)
+    return rows
+
+
+@pytest.mark.parametrize('cfg_name,B,Tp,Tm,tol_emu,cos_emu,tol_f32,cos_f32', [
+    ('C1', 16, 48, 400, 0.06, 0.998, 0.15, 0.99),          # shallow model, larger batch: bf16 noise averages out
+    ('LJ256', 8, 48, 400, 0.16, 0.99, 0.25, 0.975),        # 6+6 blocks: rounding differences decorrelate through the depth
+    ('REF384', 2, 24, 200, 0.30, 0.95, 0.35, 0.95)])
+def test_train_step_loss_grads_and_adam(cfg_name, B, Tp, Tm, tol_emu, cos_emu, tol_f32, cos_f32):
+    """One deterministic training step (dropout off): loss, every parameter gradient and the Adam update against torch
+    autograd on the restated graph -- once with the oracle's matrix products fed bf16-rounded operands like the tensor-core
+    path (forward_oracle.EMULATE_BF16: what remains is summation order and the decorrelation of individual roundings), once
+    against the plain fp32 oracle.  Gates come from tools/grad_noise.py measurements (profiles/r02_grad_noise.md) with ~1.5x
+    margin; the pos_encoding_scalar gradients (one number each, heavy cancellation) are gated on sign and a factor of two."""
     torch.set_num_threads(8)
     from transformertts_b200.model.models import ForwardTransformer
     from transformertts_b200.model.training import Adam
@@ -214,33 +236,27 @@ def test_train_step_loss_grads_and_adam(cfg_name, B, Tp, Tm):
     tok, dur, pit = fo.make_inputs('ragged', B, Tp, Tm, seed=301)
     mel_tgt = fo.make_mel_targets(dur, 80, seed=302)
     ref_out, ref_g = fo.loss_and_grads(p, cfg, tok, mel_tgt, dur, pit)
+    emu_out, emu_g = fo.loss_and_grads(p, cfg, tok, mel_tgt, dur, pit, emulate_bf16=True)
     model = ForwardTransformer(**cfg, train_dropout=False)
     model.set_weights(p)
     model._compile(Adam(1e-4))
     eng = model._get_engine()
     out = eng.forward_backward(tok, mel_tgt, dur, pit, training=True)
     torch.cuda.synchronize()
-    assert abs(out['loss'].item() - ref_out['loss'].item()) < 2e-2 * abs(ref_out['loss'].item())
+    assert abs(out['loss'].item() - float(ref_out['loss'])) < 2e-3 * abs(float(ref_out['loss']))
+    assert abs(out['loss'].item() - float(emu_out['loss'])) < 5e-4 * abs(float(emu_out['loss']))
     for k in ('mel', 'duration', 'pitch'):
-        assert abs(out['losses'][k].item() - ref_out['losses'][k].item()) < 2e-2 * abs(ref_out['losses'][k].item()) + 1e-4
-    worst = []
+        assert abs(out['losses'][k].item() - float(emu_out['losses'][k])) < 2e-3 * abs(float(emu_out['losses'][k])) + 1e-4
     gscale = max(float(g.norm()) for g in ref_g.values())
-    for name, gref in ref_g.items():
-        got = eng.g[name].detach().double().cpu()
-        if float(gref.norm()) < 1e-6 * gscale:
-            # analytically zero gradient (key bias: softmax is invariant to a per-query shift of the logits)
-            assert float(got.norm()) < 2e-3 * gscale, name
-            continue
-        if gref.dim() == 0:
-            # pos_encoding_scalar: one number summed over every activation with heavy cancellation
-            assert abs(float(got) - float(gref)) < 0.5 * abs(float(gref)) + 5e-3 * gscale, name
-            continue
-        cos = float((got * gref.double()).sum() / (got.norm() * gref.double().norm()))
-        worst.append((_rel(got, gref), cos, name))
-    worst.sort(reverse=True)
-    print('worst gradient relative errors:', worst[:6])
-    # single-pass bf16 forward+backward on a tiny batch: the q/k kernels of the first blocks are the noisiest tensors
-    assert worst[0][0] < 0.3 and min(w[1] for w in worst) > 0.95, worst[:6]
+    zero = {n for n, g in ref_g.items() if float(g.norm()) < 1e-6 * gscale}
+    for tag, oracle_g, tol, cmin in (('bf16-emulating oracle', emu_g, tol_emu, cos_emu), ('fp32 oracle', ref_g, tol_f32, cos_f32)):
+        rows = _grad_report(eng, oracle_g, zero, gscale)
+        print(f'{cfg_name} vs {tag}: worst', [(n, round(r, 4), round(c, 5)) for r, c, n in rows[:5]])
+        for r, c, n in rows:
+            if n.endswith('pos_scalar'):
+                assert c > 0 and r < 1.0, (tag, n, r)
+            else:
+                assert r < tol and c > cmin, (tag, n, r, c)
     # Adam: the update applied to the flat buffer equals the oracle formula on the same gradients
     w0 = eng.flat_w.clone()
     g0 = eng.flat_g.clone()
@@ -253,6 +269,46 @@ def test_train_step_loss_grads_and_adam(cfg_name, B, Tp, Tm):
     # a second full step runs (weights were re-packed) and lowers nothing to NaN
     out2 = model.train_step(tok, mel_tgt, dur, pit)
     assert math.isfinite(out2['loss'].item())
+
+
+def test_train_step_gradients_against_reference_code_golden():
+    """tests/golden/ref_train_c1.npz: loss and (sampled) gradients of one _train_step of the UNMODIFIED reference model
+    (run on tests/tf_shim by tests/golden/make_golden_ref.py) -- the CUDA step against numbers the reference's code produced."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent / 'golden'))
+    from make_golden_ref import grad_sample_index
+    from transformertts_b200.model.models import ForwardTransformer
+    from transformertts_b200.model.training import Adam
+    g = np.load(Path(__file__).resolve().parent / 'golden' / 'ref_train_c1.npz')
+    cfg = dict(fo.CONFIGS['C1'], dropout_rate=0.0, predictors_dropout=0.0)
+    p = fo.init_params(cfg, seed=7)
+    tok, dur, pit = fo.make_inputs('ragged', int(g['B']), int(g['Tp']), int(g['Tm']), seed=int(g['seed']))
+    mel_tgt = fo.make_mel_targets(dur, 80, seed=int(g['mel_seed']))
+    model = ForwardTransformer(**cfg, train_dropout=False)
+    model.set_weights(p)
+    model._compile(Adam(1e-4))
+    eng = model._get_engine()
+    out = eng.forward_backward(tok, mel_tgt, dur, pit, training=True)
+    torch.cuda.synchronize()
+    assert abs(out['loss'].item() - float(g['loss'])) < 2e-3 * float(g['loss'])
+    for k, key in (('mel', 'mel_loss'), ('duration', 'duration_loss'), ('pitch', 'pitch_loss')):
+        assert abs(out['losses'][k].item() - float(g[key])) < 5e-3 * float(g[key]) + 1e-4
+    gscale = max(float(g['n:' + n]) for n in eng.names)
+    worst = []
+    for n in eng.names:
+        want = torch.from_numpy(g['g:' + n]).double()
+        got = eng.g[n].detach().reshape(-1).cpu()[torch.from_numpy(grad_sample_index(n, eng.g[n].numel()))].double()
+        if float(g['n:' + n]) < 1e-6 * gscale:
+            assert float(got.norm()) < 2e-3 * gscale, n
+            continue
+        if want.numel() == 1:
+            assert float(got) * float(want) > 0 and abs(float(got) - float(want)) < abs(float(want)), n
+            continue
+        worst.append((_rel(got, want), n))
+    worst.sort(reverse=True)
+    print('vs reference-code gradients: worst', worst[:5])
+    assert worst[0][0] < 0.2, worst[:5]          # single-pass bf16 on a 3-row batch: ~0.11 measured (tools/grad_noise.py)
 
 
 def _directional_check(train_dropout, eps):
