@@ -19,6 +19,7 @@
 
 #include "../../include/ttsb.h"
 #include "ttsb_common.cuh"
+#include "fft32.cuh"
 #include "ttsb_host.h"
 
 namespace ttsb {
@@ -32,41 +33,6 @@ constexpr int WARPS = 4;
 __device__ float g_tw_re[NFFT];   // cos(2 pi i / 1024)
 __device__ float g_tw_im[NFFT];   // -sin(2 pi i / 1024)
 __device__ float g_window[NFFT];  // periodic Hann
-
-__device__ constexpr float C32[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
-                                      0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f,
-                                      0.0f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f,
-                                      -0.70710678118654746f, -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f};
-__device__ constexpr float S32[16] = {0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
-                                      0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
-                                      1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f,
-                                      0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f};
-
-__host__ __device__ constexpr int bitrev5(int i) {
-  return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
-}
-
-// decimation-in-frequency radix-2 FFT of 32 register-resident complex values; X[bitrev5(i)] is left in slot i
-__device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
-#pragma unroll
-  for (int len = 32; len >= 2; len >>= 1) {
-    const int half = len >> 1;
-    const int step = 32 / len;
-#pragma unroll
-    for (int start = 0; start < 32; start += len) {
-#pragma unroll
-      for (int j = 0; j < half; ++j) {
-        const int a = start + j, b = a + half;
-        const float tr = re[a] - re[b], ti = im[a] - im[b];
-        re[a] += re[b];
-        im[a] += im[b];
-        const float c = C32[j * step], s = S32[j * step];
-        re[b] = tr * c + ti * s;
-        im[b] = ti * c - tr * s;
-      }
-    }
-  }
-}
 
 // Forward 1024-point complex FFT by one warp.  In: lane n2 holds z[32*n1 + n2] in (re[n1], im[n1]).  Out: Z[k] in natural
 // order in bre[k], bim[k] (shared, >= 32*33 floats each, private to the warp).
