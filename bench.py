@@ -430,7 +430,7 @@ def aligner_bench(args, rank, world, dev):
     B, Tp, T = 16, 130, 800
     cfg = alo.ALIGNER_CONFIGS['A5']
     params = alo.init_aligner_params(cfg, seed=7)
-    model = Aligner.from_config(dict(cfg, device=str(dev)), max_r=cfg['max_r'])
+    model = Aligner.from_config(dict(cfg, device=str(dev), cuda_graphs=not args.no_graphs), max_r=cfg['max_r'])
     model.set_weights(params)
     model.set_constants(reduction_factor=1, force_decoder_diagonal=True)
     tok, mel, stop = alo.make_aligner_inputs(cfg, B, Tp, T + 1, seed=500 + rank, ragged=False)
@@ -471,7 +471,7 @@ def aligner_bench(args, rank, world, dev):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     # ---- the training step (models.py:212-216): forward with dropout 0.1 in single-pass bf16 + backward + Adam
     from transformertts_b200.model.training import Adam
-    tmodel = Aligner.from_config(dict(cfg, device=str(dev), train_dropout=True), max_r=cfg['max_r'])
+    tmodel = Aligner.from_config(dict(cfg, device=str(dev), train_dropout=True, train_graphs=not args.no_graphs), max_r=cfg['max_r'])
     tmodel.set_weights(params)
     tmodel._compile(cfg['stop_loss_scaling'], Adam(1e-4))
     tmodel.set_constants(reduction_factor=1, force_decoder_diagonal=True)

@@ -234,3 +234,33 @@ def test_durations_from_aligner_attention_match_reference_dijkstra():
             assert np.allclose(diag.cpu().numpy(), diag_r, rtol=1e-4)
             for a, b_ in zip(d_gpu, d_ref):
                 assert a.dtype == np.int32 and np.array_equal(a, b_)      # integer durations: bit-exact
+
+
+def test_aligner_cuda_graph_replay_equals_eager():
+    """cuda_graphs / train_graphs: the teacher-forced validation step and the training step replayed as CUDA graphs must give
+    the eager results (same kernels, same arguments; weight-gradient sums use fp32 atomics -> training equal to rounding noise)."""
+    from transformertts_b200.model.aligner import Aligner
+    from transformertts_b200.model.training import Adam
+    cfg = alo.ALIGNER_CONFIGS['A-small']
+    p = alo.init_aligner_params(cfg, seed=7)
+    tok, mel, stop = alo.make_aligner_inputs(cfg, 3, 20, 49, seed=505)
+    eager = Aligner.from_config(dict(cfg), max_r=cfg['max_r'])
+    graphed = Aligner.from_config(dict(cfg, cuda_graphs=True), max_r=cfg['max_r'])
+    for m in (eager, graphed):
+        m.set_weights(p)
+        m.set_constants(reduction_factor=1, force_decoder_diagonal=True)
+    for _ in range(2):
+        a, b = eager._val_step(tok, mel, stop), graphed._val_step(tok, mel, stop)
+        assert torch.equal(a['mel'], b['mel']) and torch.equal(a['stop_prob'], b['stop_prob'])
+        assert torch.equal(a['loss'], b['loss'])
+        for k in a['decoder_attention']:
+            assert torch.equal(a['decoder_attention'][k], b['decoder_attention'][k])
+    losses = []
+    for graphs in (False, True):
+        m = Aligner.from_config(dict(cfg, train_dropout=False, train_graphs=graphs), max_r=cfg['max_r'])
+        m.set_weights(p)
+        m._compile(cfg['stop_loss_scaling'], Adam(1e-4))
+        m.set_constants(reduction_factor=1, force_decoder_diagonal=True)
+        losses.append([float(m.train_step(tok, mel, stop)['loss']) for _ in range(4)])
+    assert all(abs(x - y) < 5e-4 * abs(x) for x, y in zip(*losses)), losses
+    assert losses[0][3] < losses[0][0]

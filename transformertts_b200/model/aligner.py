@@ -68,6 +68,12 @@ class Aligner(ForwardTransformer):
         self.debug = debug
         self.alphabet = kwargs.get('alphabet')
         self.train_dropout = bool(kwargs.get('train_dropout', True))  # False: deterministic training step (parity tests)
+        # replay the teacher-forced validation step / training step as CUDA graphs per input shape (the steps are ~90 / ~430
+        # dependent launches of small kernels: host-launch bound when issued eagerly)
+        self.cuda_graphs = bool(kwargs.get('cuda_graphs', False))
+        self.train_graphs = bool(kwargs.get('train_graphs', False))
+        self._val_graphs = {}
+        self._graph_pool = None
         self.max_r = int(max_r)
         self.r = int(max_r)                        # models.py:46 -- starts at max_r, lowered by the schedule via set_constants
         self.stop_prob_index = 2
@@ -407,7 +413,49 @@ class Aligner(ForwardTransformer):
         return out, None
 
     def _val_step(self, inp, tar, stop_prob):
+        if self.cuda_graphs:
+            return self._val_step_graphed(inp, tar, stop_prob)
         return self._gta_forward(inp, tar, stop_prob, training=False)[0]
+
+    @_on_device
+    def _val_step_graphed(self, inp, tar, stop_prob):
+        """The validation step captured once per (shapes, r, diagonal flags) and replayed; outputs are copied out of the
+        graph's static buffers."""
+        inp, tar, stop_prob = torch.as_tensor(inp), torch.as_tensor(tar), torch.as_tensor(stop_prob)
+        self._prepare()
+        key = (tuple(inp.shape), tuple(tar.shape), self.r, self.force_encoder_diagonal, self.force_decoder_diagonal, id(self._packed))
+        ent = self._val_graphs.get(key)
+        if ent is None:
+            dev = self.device
+            ins = [inp.to(device=dev, dtype=torch.int32).contiguous().clone(), tar.to(device=dev, dtype=torch.float32).contiguous().clone(),
+                   stop_prob.to(device=dev, dtype=torch.int32).contiguous().clone()]
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._gta_forward(*ins, training=False)
+            torch.cuda.current_stream().wait_stream(side)
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            g = torch.cuda.CUDAGraph()
+            n0 = lib.launch_count()
+            with torch.cuda.graph(g, pool=self._graph_pool):
+                out = self._gta_forward(*ins, training=False)[0]
+            if len(self._val_graphs) >= 4:
+                self._val_graphs.pop(next(iter(self._val_graphs)))
+            ent = self._val_graphs[key] = {'ins': ins, 'g': g, 'out': out, 'n': lib.launch_count() - n0}
+        else:
+            for dst, src in zip(ent['ins'], (inp, tar, stop_prob)):
+                dst.copy_(src, non_blocking=True)
+        ent['g'].replay()
+        lib.add_launch_count(ent['n'])
+
+        def cp(v):
+            if torch.is_tensor(v):
+                return v.clone()
+            if isinstance(v, dict):
+                return {k: cp(x) for k, x in v.items()}
+            return v
+        return cp(ent['out'])
 
     val_step = _val_step
 
@@ -428,7 +476,10 @@ class Aligner(ForwardTransformer):
         if data_parallel:
             from ..utils.data_parallel import make_grad_sync
             sync = make_grad_sync(eng.flat_g)
-        out = eng.forward_backward(inp, tar, stop_prob, training=True, sync=sync)
+        if self.train_graphs and sync is None:
+            out = eng.step_graphed(inp, tar, stop_prob)
+        else:
+            out = eng.forward_backward(inp, tar, stop_prob, training=True, sync=sync)
         scale = sync.finish() if sync is not None else 1.0
         eng.apply_adam(self.optimizer, grad_scale=scale)
         return out

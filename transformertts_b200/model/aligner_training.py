@@ -304,6 +304,47 @@ class AlignerTrainEngine(TrainEngine):
     # ------------------------------------------------------------------------------------------------
     # full step
     # ------------------------------------------------------------------------------------------------
+    def step_graphed(self, inp, tar, stop_prob):
+        """forward + backward of the teacher-forced step as ONE CUDA graph per input shape (single process; with a gradient
+        all-reduce in the middle the eager path is used).  Per-step dropout masks come from the device-resident salt
+        (TrainEngine._set_salt); Adam stays an eager launch."""
+        m = self.model
+        inp, tar, stop_prob = torch.as_tensor(inp), torch.as_tensor(tar), torch.as_tensor(stop_prob)
+        key = (tuple(inp.shape), tuple(tar.shape), int(m.r), m.force_encoder_diagonal, m.force_decoder_diagonal, bool(m.train_dropout))
+        ent = self._graphs.get(key)
+        if ent is None:
+            dev = self.dev
+            ins = [inp.to(device=dev, dtype=torch.int32).contiguous().clone(), tar.to(device=dev, dtype=torch.float32).contiguous().clone(),
+                   stop_prob.to(device=dev, dtype=torch.int32).contiguous().clone()]
+            self._set_salt(1)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.forward_backward(*ins, training=True)
+            torch.cuda.current_stream().wait_stream(side)
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            g = torch.cuda.CUDAGraph()
+            n0 = lib.launch_count()
+            with torch.cuda.graph(g, pool=self._graph_pool):
+                lib.set_dropout_salt(self._salt_dev)
+                out = self.forward_backward(*ins, training=True)
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = self._graphs[key] = {'ins': ins, 'g': g, 'out': out, 'n': lib.launch_count() - n0}
+        else:
+            for dst, src in zip(ent['ins'], (inp, tar, stop_prob)):
+                dst.copy_(src, non_blocking=True)
+        it = m.optimizer.iterations if m.optimizer else 0
+        self._set_salt(((it + 1) * 40503 + 12345) & 0x7fffffff)
+        self._salt_applied = 1
+        ent['g'].replay()
+        lib.add_launch_count(ent['n'])
+        out = dict(ent['out'])
+        out['loss'] = out['loss'].clone()
+        out['losses'] = {k: v.clone() for k, v in out['losses'].items()}
+        return out
+
     def forward_backward(self, inp, tar, stop_prob, training=True, sync=None):
         m, W, G = self.model, self.model.weights, self.g
         dev = self.dev
