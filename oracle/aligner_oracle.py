@@ -3,8 +3,10 @@
 TEST INFRASTRUCTURE ONLY -- same rules as oracle/forward_oracle.py: nothing under ``oracle/`` is imported by the
 product package; only tests/, __graft_entry__.smoke() and bench.py's CPU legs use it, as the checker.
 
-PARITY UNPINNED for the model arithmetic (TensorFlow/Keras is not installable here).  What IS pinned against the
-reference's own known answers:
+PARITY STATUS: pinned to the reference's own code like oracle/forward_oracle.py -- tests/test_reference_shim.py runs the
+unmodified reference ``Aligner`` (model/models.py:15-341) on tests/tf_shim and compares its validation step (mel, stop logits,
+all attention maps, the three losses; r = 1 and 2, diagonal losses on) with this file; tests/golden/aligner_small.npz is
+written by that reference-code run.  Pinned against the reference's own known answers in addition:
   * the stop-token cross entropy -- tests/test_loss.py:12-24 of the reference (2.3705523014068604 with scaling 5,
     0.7679619193077087 with scaling 1 / masked_crossentropy) -- see tests/test_aligner_oracle.py
   * the look-ahead mask against ``torch.triu`` and the block structure against an independent

@@ -155,3 +155,64 @@ def test_prefetch_loader_yields_the_same_stream(corpus):
             assert a['name'] == b['name'] and torch.equal(a['mel'], b['mel'])
     finally:
         loader.close()
+
+
+def test_data_parallel_shards_have_equal_shapes_and_cover_each_global_batch(tmp_path):
+    """Data-parallel batching: bucket sizes must be multiples of the world size, every rank walks the same stream
+    of global batches, shards are padded to the GLOBAL lengths (equal shapes -> the mean of the shard losses is the global
+    loss) and the remainder flush is cut identically on every rank."""
+    rng = np.random.default_rng(3)
+    samples = [f's{i}' for i in range(37)]
+    lens = {s: int(rng.integers(5, 60)) for s in samples}
+
+    def prep(name):
+        n = lens[name]
+        return np.full((n, 2), float(n), dtype=np.float32), list(range(1, 1 + n // 4 + 1)), name
+
+    def make(rank, world, sizes=(4, 2)):
+        return ds.Dataset(samples, prep, lambda m, *_: m.shape[0], ('mel', 'tokens', 'name'), (np.float32, np.int32, None), [30], list(sizes),
+                          shuffle=True, drop_remainder=False, seed=1, pin_memory=False, rank=rank, world_size=world)
+
+    with pytest.raises(ValueError):
+        make(0, 2, sizes=(5, 2))
+    assert ds.round_batch_sizes([64, 42, 25, 1], 8) == [64, 40, 24, 8]
+    single = list(make(0, 1).all_batches())
+    r0, r1 = list(make(0, 2).all_batches()), list(make(1, 2).all_batches())
+    assert len(r0) == len(r1)
+    seen = []
+    for a, b in zip(r0, r1):
+        assert a['mel'].shape == b['mel'].shape and a['tokens'].shape == b['tokens'].shape      # equal shapes on both ranks
+        assert len(a['name']) == len(b['name'])
+        seen += a['name'] + b['name']
+    full = [n for bt in single for n in bt['name']]
+    assert set(seen) <= set(full) and len(seen) >= len(full) - 2                                 # at most world_size - 1 rows cut per bucket tail
+
+
+def test_config_manager_paths_and_latest_checkpoint(tmp_path):
+    import yaml
+    from pathlib import Path
+    from transformertts_b200.utils.training_config_manager import TrainingConfigManager
+    root = Path(__file__).resolve().parent.parent
+    raw = yaml.safe_load((root / 'config' / 'training_config.yaml').read_text())
+    raw['paths']['log_directory'] = str(tmp_path / 'logs')
+    raw['paths']['train_data_directory'] = str(tmp_path / 'data')
+    cfg = tmp_path / 'c.yaml'
+    cfg.write_text(yaml.safe_dump(raw))
+    cm = TrainingConfigManager(str(cfg))
+    # the reference's naming scheme (utils/training_config_manager.py:23-44)
+    assert cm.weights_dir == tmp_path / 'logs' / 'ljspeech' / 'tts_swap_conv_dims.alinger_extralayer_layernorm' / 'weights'
+    assert cm.mel_dir.name == 'mels.MelGAN_default' and cm.data_dir.name == 'data.ljspeech'
+    assert cm.duration_dir.name == 'durations.alinger_extralayer_layernorm.Stress_NoBreathing.MelGAN_default'
+    assert cm.train_metadata_path.name == 'train_metadata.Stress_NoBreathing.txt'
+    cm.create_remove_dirs()
+    assert cm.latest_checkpoint() is None
+    for name in ('step_5', 'step_20', 'step_100'):
+        (cm.weights_dir / name).mkdir()
+        (cm.weights_dir / name / 'optimizer.pt').write_bytes(b'x')
+    (cm.weights_dir / 'step_300').mkdir()                        # weights only: cannot resume from it
+    assert cm.latest_checkpoint().name == 'step_100'
+    (cm.weights_dir / 'latest').mkdir()
+    (cm.weights_dir / 'latest' / 'optimizer.pt').write_bytes(b'x')
+    assert cm.latest_checkpoint().name == 'latest'
+    cm.create_remove_dirs(clear_weights=True)
+    assert cm.latest_checkpoint() is None

@@ -39,7 +39,12 @@ def get_durations_from_alignment(batch_alignments, mels, phonemes, weighted: boo
     """utils/alignments.py:103-143.  batch_alignments: (N, heads, mel, phonemes) attention weights of the last decoder block
     (``Decoder_LastBlock_CrossAttention``); mels with start/end vectors, phonemes with start/end tokens.
     Returns (durations [list of int32 arrays of length phon_len - 1], None, jumpiness, peakiness, diag_measure); the second
-    element is the reference's plotting matrix (best attention + binary alignment), which is not produced here."""
+    element is the reference's plotting matrix (best attention + binary alignment), which is not produced here.
+
+    Ties: the reference runs scipy's Dijkstra on an explicit graph; the CUDA kernel runs the equivalent dynamic programme over
+    anti-diagonals and breaks EXACT cost ties in a fixed order (left, up, diagonal), scipy by heap-pop order.  On generic
+    attention maps the shortest path is unique and the durations are bit-identical (tests); on plateaus of exactly equal cost
+    (saturated / all-zero attention regions) the two may pick different, equally short paths."""
     att = torch.as_tensor(batch_alignments)
     if not att.is_cuda:
         att = att.cuda()
