@@ -266,6 +266,16 @@ int ttsb_rowdot_heads(const void* x_bf16, const void* y_bf16, int B, int T, int 
  * (Aligner blocks); without it query rows >= kv_len[b] are written as zeros (they are masked downstream). */
 int ttsb_softmax_fwd(const float* S, int B, int H, int T, int Tk, int ld, const int32_t* kv_len, float drop_p,
                      uint32_t seed, uint32_t site, int flags, void* P_pre, void* P_drop, void* stream);
+/* The two calls above (logits GEMM + ttsb_softmax_fwd) fused for self-attention with flags == 0: P_pre = softmax(scale *
+ * Q K^T) over keys < kv_len[b], P_drop = dropout(P_pre), both bf16 (B*H, T, ld_p); the logits stay in tensor memory.
+ * qkv is a bf16 (B, T, ld) activation tensor holding head h of Q at columns q_col0 + h*dh and of K at k_col0 + h*dh.
+ * Needs dh in {64, 128} (ttsb_attn_probs_supported; wider heads use the two calls above); pass P_drop == P_pre when
+ * drop_p == 0.
+ * Same dropout element index as ttsb_softmax_fwd: (z*T + t)*ld_p + key. */
+int ttsb_attn_probs_supported(int dh, int ld_p);
+int ttsb_attn_probs_fwd(const void* qkv, int ld, int q_col0, int k_col0, int B, int H, int T, int dh, const int32_t* kv_len,
+                        float scale, float drop_p, uint32_t seed, uint32_t site, void* P_pre, void* P_drop, int ld_p,
+                        void* stream);
 int ttsb_softmax_bwd(const void* P_pre, const float* dP, int B, int H, int T, int Tk, int ld, const int32_t* kv_len,
                      float scale, float drop_p, uint32_t seed, uint32_t site, int flags, void* dS, void* stream);
 /* LayerNorm backward from the saved pre-norm values u (keras LayerNormalization, model/layers.py:27,96,207,295,508). */

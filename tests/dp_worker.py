@@ -49,9 +49,16 @@ def main():
         s = fresh()
         o1 = s.train_step(tok, mel, dur, pit)
         e1 = s._get_engine()
-        torch.save({'g_dp': g_dp.cpu(), 'w_dp': w_dp.cpu(), 'loss_dp': float(loss_dp), 'g_single': e1.flat_g.cpu(),
+        # the same two shards stepped one after the other in THIS process: what the all-reduce must reproduce exactly
+        g_seq = torch.zeros_like(g_dp)
+        for r in range(world):
+            t = fresh()
+            sr = slice(r, None, world)
+            t.train_step(tok[sr], mel[sr], dur[sr], pit[sr])
+            g_seq += t._get_engine().flat_g / world
+        torch.save({'g_dp': g_dp.cpu(), 'w_dp': w_dp.cpu(), 'loss_dp': float(loss_dp), 'g_single': e1.flat_g.cpu(), 'g_seq': g_seq.cpu(),
                     'w_single': e1.flat_w.cpu(), 'loss_single': float(o1['loss']), 'same_across_ranks': same_across_ranks,
-                    'w0': torch.cat([p[n].reshape(-1) for n in eng.names]).numel()}, out_path)
+                    'offsets': {n: (eng.offsets[n][0], p[n].numel()) for n in eng.names}}, out_path)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -22,11 +22,24 @@ def test_dp_step_equals_single_process_step(tmp_path):
     d = torch.load(out)
     assert d['same_across_ranks']
     assert abs(d['loss_dp'] - d['loss_single']) < 1e-5 * abs(d['loss_single'])
-    g1, g2 = d['g_single'].double(), d['g_dp'].double()
+    g1, g2, g3 = d['g_single'].double(), d['g_dp'].double(), d['g_seq'].double()
     gscale = float(g1.abs().max())
-    # same arithmetic on the same rows; only the order of the fp32 sums differs (atomics, two partial sums + all-reduce)
-    assert float((g1 - g2).abs().max()) < 2e-5 * gscale
-    assert float((g1 - g2).norm() / g1.norm()) < 1e-5
+
+    def worst(a, b):
+        rows = [(float((a[off:off + n] - b[off:off + n]).abs().max()), name) for name, (off, n) in d['offsets'].items()]
+        rows.sort(reverse=True)
+        return rows[:4]
+
+    # (1) the exchange itself: the all-reduced gradient is the sum of the two shard gradients computed one after the other
+    # in one process -- same kernels on the same shapes, so only the atomics' order inside a shard run differs
+    print('DP vs the same shards stepped sequentially:', worst(g2, g3), 'gscale', gscale)
+    assert float((g2 - g3).abs().max()) < 2e-6 * gscale, worst(g2, g3)
+    # (2) against ONE step on the whole 32-row batch.  The arithmetic per batch row is the same, but the encoder-side GEMMs
+    # (1536 vs 768 rows) are tiled differently, so fp32 partial sums differ in the last bit, a few bf16 roundings of the
+    # activations / upstream gradients flip, and the difference grows towards the embedding end of the backward chain.
+    print('DP vs single process on the whole batch:', worst(g1, g2))
+    assert float((g1 - g2).abs().max()) < 3e-4 * gscale, worst(g1, g2)
+    assert float((g1 - g2).norm() / g1.norm()) < 2e-4
     # weights after Adam: identical wherever the gradient is above rounding noise (Adam's first step is lr * g / |g|)
     live = g1.abs() > 1e-3 * gscale
     assert float(((d['w_single'] - d['w_dp']).abs() * live).max()) < 1e-6

@@ -573,3 +573,59 @@ def test_layernorm_bwd_vectorised_and_fused_column_sums(C):
     torch.cuda.synchronize()
     for k in range(3):
         assert _rel(o[k], x[:, k * C:(k + 1) * C].float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize('H,dh,T,rate', [(2, 128, 1000, 0.1), (2, 64, 333, 0.1), (2, 192, 200, 0.0), (1, 128, 130, 0.25)])
+def test_fused_attention_probabilities_match_two_kernel_path(H, dh, T, rate):
+    """ttsb_attn_probs_fwd (logits in TMEM, two passes) against the materialised path (ttsb_bgemm fp32 logits +
+    ttsb_softmax_fwd) and an fp64 softmax: same probabilities to bf16 rounding, identical dropout decisions, exact zeros on
+    masked keys and padded query rows, poisoned outputs fully overwritten."""
+    lib = _lib()
+    from transformertts_b200.model.training import TrainEngine
+    from transformertts_b200.model.models import _round_up
+    g = torch.Generator().manual_seed(5)
+    B, d = 4, H * dh
+    qkv = (torch.randn(B, T, 3 * d, generator=g) * 1.5).bfloat16()
+    lens = torch.tensor([T, max(T // 2, 1), min(70, T), 1], dtype=torch.int32)
+    qkv_d, lens_d = qkv.to(DEV), lens.to(DEV)
+    Z, ldp = B * H, _round_up(T, 16)
+    eng = TrainEngine.__new__(TrainEngine)
+    eng.dev = torch.device(DEV)
+    S = torch.empty(Z, T, ldp, device=DEV)
+    eng._bgemm(B, H, T, T, dh, qkv_d, (3 * d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 0), qkv_d, (2 * d, T, B), (3 * d, 3 * d * T),
+               (dh, 0, 0, d), alpha=1.0 / math.sqrt(dh), out_f32=S, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
+    seed, site = 77, 5
+    P0 = torch.full((Z, T, ldp), float('nan'), dtype=torch.bfloat16, device=DEV)
+    D0 = torch.full((Z, T, ldp), float('nan'), dtype=torch.bfloat16, device=DEV) if rate > 0 else P0
+    lib.softmax_fwd(S, B, H, T, T, ldp, lens_d, rate, seed, site, P0, D0)
+    P1 = torch.full((Z, T, ldp), float('nan'), dtype=torch.bfloat16, device=DEV)
+    D1 = torch.full((Z, T, ldp), float('nan'), dtype=torch.bfloat16, device=DEV) if rate > 0 else P1
+    if dh > 128:   # the Q tile + K ring + 16 staging boxes do not fit next to each other: the engine keeps the two-kernel path
+        assert not lib.attn_probs_supported(dh, ldp)
+        return
+    assert lib.attn_probs_supported(dh, ldp)
+    lib.attn_probs_fwd(qkv_d, 3 * d, 0, d, B, H, T, dh, lens_d, 1.0 / math.sqrt(dh), rate, seed, site, P1, D1, ldp)
+    torch.cuda.synchronize()
+    assert torch.isfinite(P1.float()).all() and torch.isfinite(D1.float()).all()
+    p0, p1, d0, d1 = P0.float().cpu(), P1.float().cpu(), D0.float().cpu(), D1.float().cpu()
+    # fp64 reference on the bf16 inputs
+    x = qkv.double()
+    q, k = [t.reshape(B, T, H, dh).permute(0, 2, 1, 3) for t in x.split(d, dim=-1)[:2]]
+    logits = q @ k.transpose(-1, -2) / math.sqrt(dh)
+    kmask = torch.arange(T)[None, :] >= lens[:, None]
+    w = torch.softmax(logits.masked_fill(kmask[:, None, None, :], float('-inf')), -1)
+    w = w * (torch.arange(T)[None, :] < lens[:, None])[:, None, :, None]           # padded query rows are written as zeros
+    w = w.reshape(Z, T, T)
+    assert (p1[:, :, T:] == 0).all() and (d1[:, :, T:] == 0).all()
+    assert (p1[:, :, :T][w == 0] == 0).all()
+    err = (p1[:, :, :T].double() - w).abs()
+    assert float((err / (w + 1e-6)).max()) < 6e-3                                  # bf16 rounding (2^-9) + ex2.approx
+    assert float((p1 - p0).abs().max()) <= float(p0.abs().max()) * 2 ** -7         # the two CUDA paths agree to one bf16 ulp
+    if rate > 0:
+        big = p1 > 1e-30
+        assert ((d1 != 0) == (d0 != 0))[big & (p0 > 1e-30)].all()                  # identical keep decisions
+        kept = (d1 != 0)
+        assert abs(float(kept[big].float().mean()) - (1 - rate)) < 0.01
+        ratio = d1[kept] / p1[kept]
+        assert float((ratio - 1 / (1 - rate)).abs().max()) < 0.01 / (1 - rate)
+        assert (d1[~big] == 0).all()

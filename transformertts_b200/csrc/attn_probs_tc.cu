@@ -1,0 +1,451 @@
+// Attention probabilities of the training step in ONE kernel:  P = softmax(scale * Q K^T + key mask), P_drop = dropout(P)
+// (model/layers.py:176-188: scaled_dot_product_attention up to the attention weights, and the Dropout on them at :189-191
+// of the MultiHeadAttention call).  The two-kernel path (ttsb_bgemm writing fp32 logits, ttsb_softmax_fwd reading them
+// back) moves 4*T*T bytes each way per (batch row, head); here the logits never leave TMEM.
+//
+// A work item is (z = b*H + h, 128 query rows).  A softmax row spans all keys but TMEM holds 512 fp32 columns, so the
+// logits are produced TWICE: pass 1 sweeps the live 64-key tiles and keeps the running row maximum and sum (online
+// rescaling), pass 2 recomputes every tile and writes the normalised probabilities.  The extra QK^T is cheap (contraction
+// over dh only) next to the 8*T*T bytes of fp32 round trip it replaces.
+//
+//   warp 0     TMA producer: Q tile of the item once (resident), K tiles (64 keys) through a ring
+//   warp 1     tcgen05.mma issuer: S tile j (128 x 64) -> one of eight 64-column TMEM buffers
+//   warps 2-17 four groups of four warps (one per TMEM lane quarter); group g takes tiles j with j % 4 == g, a thread owns
+//              one query row of the tile.  After pass 1 the groups merge their (max, sum) through shared memory.
+//              Pass 2 stages one bf16 [32 rows x 64 cols] box (128B swizzle) per output and warp and hands it to TMA.
+// The softmax side is latency bound (dependent ex2 / hash chains, TMEM and shared-memory round trips), hence sixteen
+// warps of it: the first version with eight ran at half the issue rate (ncu: 2.5 warps per scheduler, 50 % issue slots).
+//
+// Masks follow ttsb_softmax_fwd with flags == 0: keys >= len[b] get probability exactly 0, query rows >= len[b] are written
+// as zeros.  Dropout decisions come from the same stateless hash at the same element index ((z*T + m)*ld + k), so the
+// backward pass (fused dS epilogue of ttsb_bgemm) regenerates them.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "../../include/ttsb.h"
+#include "ttsb_common.cuh"
+#include "ttsb_host.h"
+
+namespace ttsb {
+
+constexpr int AP_BM = 128;
+constexpr int AP_BN = 64;
+constexpr int AP_GROUPS = 4;
+constexpr int AP_NBUF = 8;
+constexpr int AP_THREADS = 64 + AP_GROUPS * 128;
+constexpr int AP_QBOX_BYTES = 128 * 64 * 2;         // [128 query rows x 64 k] K-major box
+constexpr int AP_KBOX_BYTES = AP_BN * 64 * 2;       // [64 keys x 64 k]
+constexpr int AP_STAGING_BYTES = AP_GROUPS * 4 * 2 * 4096;   // per softmax warp: one [32 x 64] bf16 box per output
+constexpr int AP_STATS_BYTES = 2 * AP_GROUPS * 128 * 8;      // [item parity][group][row] (max, sum)
+constexpr int AP_BAR_BYTES = 512;
+constexpr int AP_MAX_SMEM = 227 * 1024;
+
+struct ApParams {
+  int Z, H, T, Tk, dh, kbs, nst;
+  int q_col0, k_col0;     // first column of head 0 of Q / K in the (B, T, ld) activation tensor
+  int m_tiles, n_tiles;   // query tiles per z, key tiles covering ld_p columns
+  int ld_p;
+  const int* kv_len;
+  float scale_log2e;
+  float drop_p;
+  uint32_t seed, site;
+  int two_outputs;
+};
+
+// shared-memory accesses by 32-bit shared address: through generic pointers derived from the dynamic-smem base the compiler
+// emits generic LD/ST (ncu: the statistics read-back alone took 5 % of the stall samples)
+__device__ __forceinline__ void ap_sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ap_sts64f(uint32_t saddr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(saddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float2 ap_lds64f(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr) : "memory");
+  return v;
+}
+// mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of spinning through issue slots the
+// softmax warps on the same scheduler need (ncu of the first version: 9 % of all issued instructions were wait loops)
+__device__ __forceinline__ void ap_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    if (++spins == 0x4000000u) { asm volatile("trap;"); }
+  }
+}
+
+__device__ __forceinline__ float ap_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(AP_THREADS, 1)
+attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmD, const ApParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int q_bytes = p.kbs * AP_QBOX_BYTES;
+  const int k_bytes = p.kbs * AP_KBOX_BYTES;
+  uint8_t* q_smem = smem;
+  uint8_t* k_smem = smem + q_bytes;
+  uint8_t* staging = k_smem + p.nst * k_bytes;
+  float2* stats = reinterpret_cast<float2*>(staging + AP_STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + AP_STAGING_BYTES + AP_STATS_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;
+  uint64_t* k_empty = bars + 6;
+  uint64_t* t_full = bars + 10;
+  uint64_t* t_empty = bars + 10 + AP_NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * AP_NBUF);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmP);
+    tma_prefetch_desc(&tmD);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(k_full + s, 1);
+      mbar_init(k_empty + s, 1);
+    }
+    for (int s = 0; s < AP_NBUF; ++s) {
+      mbar_init(t_full + s, 1);
+      mbar_init(t_empty + s, 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_items = p.Z * p.m_tiles;
+
+  // live key tiles of an item: none when every query row of the tile is padding
+  auto live_tiles = [&](int item, int& z, int& m0, int& len) -> int {
+    z = item / p.m_tiles;
+    m0 = (item % p.m_tiles) * AP_BM;
+    len = min(max(__ldg(p.kv_len + z / p.H), 0), p.Tk);
+    return m0 < len ? (len + AP_BN - 1) / AP_BN : 0;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const bool leader = elect_one();
+    uint32_t jc = 0, qc = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int z, m0, len;
+      const int nkl = live_tiles(item, z, m0, len);
+      if (nkl == 0) continue;
+      const int b = z / p.H, h = z % p.H;
+      ap_mbar_wait(q_empty, (qc & 1) ^ 1);
+      if (leader) {
+        mbar_arrive_expect_tx(q_full, (uint32_t)q_bytes);
+        for (int kb = 0; kb < p.kbs; ++kb) tma_load_3d(&tmQ, q_full, q_smem + kb * AP_QBOX_BYTES, p.q_col0 + h * p.dh + kb * 64, m0, b);
+      }
+      ++qc;
+      for (int job = 0; job < 2 * nkl; ++job) {
+        const int j = job < nkl ? job : job - nkl;
+        const int stage = jc % p.nst;
+        ap_mbar_wait(k_empty + stage, ((jc / p.nst) & 1) ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(k_full + stage, (uint32_t)k_bytes);
+          for (int kb = 0; kb < p.kbs; ++kb)
+            tma_load_3d(&tmK, k_full + stage, k_smem + stage * k_bytes + kb * AP_KBOX_BYTES, p.k_col0 + h * p.dh + kb * 64, j * AP_BN, b);
+        }
+        ++jc;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(AP_BM, AP_BN);
+    uint32_t jc = 0, qc = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int z, m0, len;
+      const int nkl = live_tiles(item, z, m0, len);
+      if (nkl == 0) continue;
+      ap_mbar_wait(q_full, qc & 1);
+      tc_fence_after();
+      const uint32_t qs = smem_u32(q_smem);
+      for (int job = 0; job < 2 * nkl; ++job) {
+        const int buf = jc & (AP_NBUF - 1);
+        const int stage = jc % p.nst;
+        ap_mbar_wait(t_empty + buf, ((jc / AP_NBUF) & 1) ^ 1);
+        ap_mbar_wait(k_full + stage, (jc / p.nst) & 1);
+        tc_fence_after();
+        const uint32_t ks = smem_u32(k_smem + stage * k_bytes);
+        if (leader) {
+          for (int kb = 0; kb < p.kbs; ++kb) {
+            const uint64_t a = make_smem_desc_sw128(qs + kb * AP_QBOX_BYTES);
+            const uint64_t bd = make_smem_desc_sw128(ks + kb * AP_KBOX_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base + buf * AP_BN, a + 2 * kk, bd + 2 * kk, idesc, (kb | kk) != 0);
+          }
+          umma_commit(k_empty + stage);
+          umma_commit(t_full + buf);
+        }
+        ++jc;
+      }
+      if (leader) umma_commit(q_empty);   // every MMA that reads this Q tile has completed when this arrives
+      ++qc;
+    }
+  } else {
+    // ===================== softmax warps =====================
+    const int quarter = warp & 3;
+    const int group = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    uint8_t* box0 = staging + (warp - 2) * 8192;
+    uint8_t* box1 = box0 + 4096;
+    const uint32_t box0_s = smem_u32(box0) + lane * 128, box1_s = box0_s + 4096;   // this lane's row of the two boxes
+    const uint32_t thresh16 = dropout_thresh(p.drop_p) >> 16;
+    const float ks = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const float c = p.scale_log2e;
+    const int sw = lane & 7;
+    const uint32_t hterm = dropout_hterm(p.seed, p.site, 0u);
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t jc = 0, it = 0;
+
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int z, m0, len;
+      const int nkl = live_tiles(item, z, m0, len);
+      const int m = m0 + row;
+      const bool live = m < len;
+      float mx = -INFINITY, l = 0.f;
+      // ---------------- pass 1: running maximum and sum over the live key tiles of this group
+      for (int j = 0; j < nkl; ++j, ++jc) {
+        if ((j & (AP_GROUPS - 1)) != group) continue;
+        const int buf = jc & (AP_NBUF - 1);
+        ap_mbar_wait(t_full + buf, (jc / AP_NBUF) & 1);
+        tc_fence_after();
+        const int n0 = j * AP_BN;
+        uint32_t ra[16], rb[16], rc[16], rd[16];
+        tmem_ld16(tlane + buf * AP_BN, ra);
+        tmem_ld16(tlane + buf * AP_BN + 16, rb);
+        tmem_ld16(tlane + buf * AP_BN + 32, rc);
+        tmem_ld16(tlane + buf * AP_BN + 48, rd);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + buf);     // the tile now lives in registers
+        float v[64];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] = __uint_as_float(ra[i]); v[16 + i] = __uint_as_float(rb[i]);
+          v[32 + i] = __uint_as_float(rc[i]); v[48 + i] = __uint_as_float(rd[i]);
+        }
+        if (n0 + AP_BN > len) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = (n0 + i < len) ? v[i] : -INFINITY;
+        }
+        float c0 = fmaxf(v[0], v[1]), c1 = fmaxf(v[2], v[3]), c2 = fmaxf(v[4], v[5]), c3 = fmaxf(v[6], v[7]);
+#pragma unroll
+        for (int i = 8; i < 64; i += 8) {
+          c0 = fmaxf(c0, fmaxf(v[i], v[i + 1])); c1 = fmaxf(c1, fmaxf(v[i + 2], v[i + 3]));
+          c2 = fmaxf(c2, fmaxf(v[i + 4], v[i + 5])); c3 = fmaxf(c3, fmaxf(v[i + 6], v[i + 7]));
+        }
+        const float cm = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));   // finite: key n0 of a live tile is < len
+        const float mnew = fmaxf(mx, cm * c);
+        const float neg = -mnew;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          a0 += ap_ex2(fmaf(v[i], c, neg)); a1 += ap_ex2(fmaf(v[i + 1], c, neg));
+          a2 += ap_ex2(fmaf(v[i + 2], c, neg)); a3 += ap_ex2(fmaf(v[i + 3], c, neg));
+        }
+        l = fmaf(l, ap_ex2(mx - mnew), (a0 + a1) + (a2 + a3));   // mx = -inf on the first tile: ex2(-inf) = 0
+        mx = mnew;
+      }
+      float inv = 0.f;
+      if (nkl > 0) {
+        // merge the groups' partial statistics (a group without a tile holds (-inf, 0); group 0 always has tile 0)
+        const uint32_t st = smem_u32(stats) + (it & 1) * (AP_GROUPS * 128 * 8);
+        ap_sts64f(st + (group * 128 + row) * 8, mx, l);
+        asm volatile("bar.sync 1, %0;" ::"n"(AP_GROUPS * 128) : "memory");
+        float2 o[AP_GROUPS];
+#pragma unroll
+        for (int g = 0; g < AP_GROUPS; ++g) o[g] = ap_lds64f(st + (g * 128 + row) * 8);
+        float mall = o[0].x;
+#pragma unroll
+        for (int g = 1; g < AP_GROUPS; ++g) mall = fmaxf(mall, o[g].x);
+        float lall = 0.f;
+#pragma unroll
+        for (int g = 0; g < AP_GROUPS; ++g) lall = fmaf(o[g].y, ap_ex2(o[g].x - mall), lall);
+        mx = live ? mall : INFINITY;      // dead query rows: ex2(x - inf) = 0
+        inv = live ? 1.f / lall : 0.f;
+        ++it;
+      }
+      // ---------------- pass 2: recomputed logits -> probabilities -> staged bf16 boxes -> TMA tile stores
+      const float neg = -mx;
+      for (int j = 0; j < p.n_tiles; ++j) {
+        const bool has_mma = j < nkl;
+        const bool mine = (j & (AP_GROUPS - 1)) == group;
+        const uint32_t my_jc = jc;
+        if (has_mma) ++jc;
+        if (!mine) continue;
+        const int buf = my_jc & (AP_NBUF - 1);
+        const int col0 = j * AP_BN;
+        // dropout hash of element pair k of this row segment: mix((x0 + k*C1) ^ hterm); the host admits tensors of
+        // < 2^33 elements only, so the pair index fits 32 bits and its high word is zero
+        const uint32_t x0 = (uint32_t)(((uint32_t)z * (uint32_t)p.T + (uint32_t)m) * (uint64_t)p.ld_p + (uint64_t)col0 >> 1) * DROPOUT_C1;
+        if (has_mma) {
+          ap_mbar_wait(t_full + buf, (my_jc / AP_NBUF) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float pv[32];
+          if (has_mma && col0 + 32 * hf < len) {      // warp-uniform
+            uint32_t ra[16], rb[16];
+            tmem_ld16(tlane + buf * AP_BN + 32 * hf, ra);
+            tmem_ld16(tlane + buf * AP_BN + 32 * hf + 16, rb);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              pv[i] = ap_ex2(fmaf(__uint_as_float(ra[i]), c, neg)) * inv;
+              pv[16 + i] = ap_ex2(fmaf(__uint_as_float(rb[i]), c, neg)) * inv;
+            }
+            if (col0 + 32 * hf + 32 > len) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) pv[i] = (col0 + 32 * hf + i < len) ? pv[i] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pv[i] = 0.f;
+          }
+          if (hf == 1 && has_mma) {   // last TMEM read of the tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + buf);
+          }
+          if (hf == 0) {              // the boxes of the previous job must have been read out by their TMA stores
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __nv_bfloat162 hv = __floats2bfloat162_rn(pv[8 * ch + 2 * i], pv[8 * ch + 2 * i + 1]);
+              w[i] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            ap_sts128(box0_s + (((4 * hf + ch) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+          }
+          if (p.two_outputs) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t w[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int k = 16 * hf + 4 * ch + i;   // pair index inside the 64-column segment
+                const uint32_t hsh = dropout_mix((x0 + (uint32_t)k * DROPOUT_C1) ^ hterm);
+                const float d0 = (hsh & 0xffffu) >= thresh16 ? pv[8 * ch + 2 * i] * ks : 0.f;
+                const float d1 = (hsh >> 16) >= thresh16 ? pv[8 * ch + 2 * i + 1] * ks : 0.f;
+                const __nv_bfloat162 hv = __floats2bfloat162_rn(d0, d1);
+                w[i] = *reinterpret_cast<const uint32_t*>(&hv);
+              }
+              ap_sts128(box1_s + (((4 * hf + ch) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmP, box0, col0, m0 + quarter * 32, z);
+          if (p.two_outputs) tma_store_3d(&tmD, box1, col0, m0 + quarter * 32, z);
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace ttsb
+
+using namespace ttsb;
+
+static int ap_ring_stages(int dh) {
+  const int kbs = dh / 64;
+  const int fixed = 1024 + AP_STAGING_BYTES + AP_STATS_BYTES + AP_BAR_BYTES + kbs * AP_QBOX_BYTES;
+  const int n = (AP_MAX_SMEM - fixed) / (kbs * AP_KBOX_BYTES);
+  return n > 4 ? 4 : n;
+}
+
+extern "C" int ttsb_attn_probs_supported(int dh, int ld_p) {
+  return dh > 0 && dh % 64 == 0 && ld_p > 0 && ld_p % 8 == 0 && ap_ring_stages(dh) >= 2;
+}
+
+extern "C" int ttsb_attn_probs_fwd(const void* qkv, int ld, int q_col0, int k_col0, int B, int H, int T, int dh,
+                                   const int32_t* kv_len, float scale, float drop_p, uint32_t seed, uint32_t site, void* P_pre,
+                                   void* P_drop, int ld_p, void* stream_v) {
+  if (!qkv || !kv_len || !P_pre || !P_drop || B <= 0 || H <= 0 || T <= 0) {
+    set_last_error("ttsb_attn_probs_fwd: NULL tensor or non-positive dimension");
+    return TTSB_ERR_INVALID_ARGUMENT;
+  }
+  if (!ttsb_attn_probs_supported(dh, ld_p) || ld_p < T || (uint64_t)B * H * T * (uint64_t)ld_p >= (1ull << 33) || ld % 8 || q_col0 % 8 || k_col0 % 8 || q_col0 + H * dh > ld || k_col0 + H * dh > ld ||
+      drop_p < 0.f || drop_p >= 1.f || (reinterpret_cast<uintptr_t>(P_pre) & 15) || (reinterpret_cast<uintptr_t>(P_drop) & 15) ||
+      (reinterpret_cast<uintptr_t>(qkv) & 15)) {
+    set_last_error("ttsb_attn_probs_fwd: need dh in {64,128}, ld_p >= T, ld_p % 8 == 0, 16-byte aligned tensors and column offsets");
+    return TTSB_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  ApParams p{};
+  p.Z = B * H; p.H = H; p.T = T; p.Tk = T; p.dh = dh; p.kbs = dh / 64;
+  p.q_col0 = q_col0; p.k_col0 = k_col0;
+  p.m_tiles = (T + AP_BM - 1) / AP_BM;
+  p.n_tiles = (ld_p + AP_BN - 1) / AP_BN;
+  p.ld_p = ld_p;
+  p.kv_len = kv_len;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.drop_p = drop_p; p.seed = seed; p.site = site;
+  p.two_outputs = (P_drop != P_pre) ? 1 : 0;
+  p.nst = ap_ring_stages(dh);
+  const int smem_bytes = 1024 + AP_STAGING_BYTES + AP_STATS_BYTES + AP_BAR_BYTES + p.kbs * AP_QBOX_BYTES + p.nst * p.kbs * AP_KBOX_BYTES;
+  CUtensorMap tmQ, tmK, tmP, tmD;
+  int rc = make_tmap_bf16_3d(&tmQ, qkv, (uint64_t)ld, (uint64_t)T, (uint64_t)B, (uint64_t)ld, (uint64_t)ld * T, 64, AP_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tmK, qkv, (uint64_t)ld, (uint64_t)T, (uint64_t)B, (uint64_t)ld, (uint64_t)ld * T, 64, AP_BN);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tmP, P_pre, (uint64_t)ld_p, (uint64_t)T, (uint64_t)p.Z, (uint64_t)ld_p, (uint64_t)ld_p * T, 64, 32);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tmD, P_drop, (uint64_t)ld_p, (uint64_t)T, (uint64_t)p.Z, (uint64_t)ld_p, (uint64_t)ld_p * T, 64, 32);
+  if (rc) return rc;
+  static PerDevice<bool> attr_set;
+  if (!attr_set.get()) {
+    TTSB_CUDA_OK(cudaFuncSetAttribute(attn_probs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_MAX_SMEM));
+    attr_set.get() = true;
+  }
+  const int items = p.Z * p.m_tiles;
+  const int grid = items < num_sms() ? items : num_sms();
+  attn_probs_tc_kernel<<<grid, AP_THREADS, smem_bytes, stream>>>(tmQ, tmK, tmP, tmD, p);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "attn_probs_tc_kernel launch");
+}
+
+TTSB_DEFINE_SALT_SETTER(set_salt_attn_probs)

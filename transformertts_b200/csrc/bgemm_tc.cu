@@ -326,6 +326,11 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const size_t e0 = o + c0;
                 const int kbase = n0 + c0;
                 const float sks = p.sm_scale * ks;
+                // mask hash of pair k of this chunk: mix((x0 + k*C1) ^ hterm) -- the host admits < 2^33 elements in this
+                // mode, so the pair index fits 32 bits (no 64-bit index arithmetic per pair)
+                const uint32_t hx0 = (uint32_t)(e0 >> 1) * DROPOUT_C1;
+                const uint32_t hterm = dropout_hterm(p.sm_seed, p.sm_site, 0u);
+                const uint32_t th16 = thresh >> 16;
                 if (!live || kbase >= len) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) y[j] = 0.f;
@@ -336,7 +341,11 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     bool k0 = true, k1 = true;
                     if (p.sm_drop_p > 0.f) {
                       if (p.sm_Pdrop != nullptr) { k0 = (dd[j] & 0x7fffu) != 0; k1 = (dd[j + 1] & 0x7fffu) != 0; }
-                      else dropout_keep2(p.sm_seed, p.sm_site, e0 + j, thresh, k0, k1);
+                      else {
+                        const uint32_t hsh = dropout_mix((hx0 + (uint32_t)(j >> 1) * DROPOUT_C1) ^ hterm);
+                        k0 = (hsh & 0xffffu) >= th16;
+                        k1 = (hsh >> 16) >= th16;
+                      }
                     }
                     const float r0 = __uint_as_float(u ? qb[j] : qa[j]), r1 = __uint_as_float(u ? qb[j + 1] : qa[j + 1]);
                     y[j] = fmaf(k0 ? p0 * sks : 0.f, r0, -(p0 * p.sm_scale) * dsum);
@@ -560,8 +569,8 @@ extern "C" int ttsb_bgemm(const ttsb_bgemm_args* a, void* stream_v) {
   p.row_len = a->row_len; p.col_len = a->col_len;
   if (a->sm_P) {
     if (!a->sm_D || !a->sm_len || !a->out_bf16 || a->out_by_b || a->out_h_col || a->out_batch_stride != (long long)a->M * a->ld_out ||
-        a->sm_drop_p < 0.f || a->sm_drop_p >= 1.f) {
-      set_last_error("ttsb_bgemm: the fused softmax backward needs sm_D, sm_len, out_bf16 and the (Z, M, ld_out) output layout");
+        a->sm_drop_p < 0.f || a->sm_drop_p >= 1.f || (unsigned long long)a->B * a->H * a->M * (unsigned long long)a->ld_out >= (1ull << 33)) {
+      set_last_error("ttsb_bgemm: the fused softmax backward needs sm_D, sm_len, out_bf16, the (Z, M, ld_out) output layout and < 2^33 elements");
       return TTSB_ERR_INVALID_ARGUMENT;
     }
     p.sm_P = static_cast<const __nv_bfloat16*>(a->sm_P);

@@ -118,5 +118,6 @@ extern "C" int ttsb_set_dropout_salt(const uint32_t* salt_dev, void* stream) {
   if (!rc) rc = ttsb::set_salt_rowops(salt_dev, s);
   if (!rc) rc = ttsb::set_salt_train_ops(salt_dev, s);
   if (!rc) rc = ttsb::set_salt_bgemm(salt_dev, s);
+  if (!rc) rc = ttsb::set_salt_attn_probs(salt_dev, s);
   return rc;
 }

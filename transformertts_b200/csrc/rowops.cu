@@ -331,15 +331,46 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int K, int N, in
 // bias and padded LayerNorm vector is described once (ttsb_pack_desc, device array) and refreshed by ONE launch per step.
 //   dst[r][c] = (r < R && c % cb < cb_valid) ? src[r*sr + (c / cb)*s_outer + (c % cb)*s_inner] : 0
 __global__ void repack_batched_kernel(const ttsb_pack_desc* __restrict__ descs) {
+  // 64x64 tiles staged through shared memory: the load runs along whichever source axis is contiguous (rows for the
+  // transposing forward packs of Keras (K,N) kernels, columns otherwise), the store always along destination columns.
+  __shared__ float tile[64][65];
   const ttsb_pack_desc d = descs[blockIdx.y];
-  const long long total = (long long)d.R_pad * d.C_cols;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / d.C_cols), c = (int)(i % d.C_cols);
-    const int blk = c / d.cb, ci = c % d.cb;
-    const float v = (r < d.R && ci < d.cb_valid) ? d.src[(long long)r * d.sr + (long long)blk * d.s_outer + (long long)ci * d.s_inner] : 0.f;
-    const long long o = (long long)r * d.dst_ld + c;
-    if (d.dst_f32) static_cast<float*>(d.dst)[o] = v;
-    else static_cast<__nv_bfloat16*>(d.dst)[o] = __float2bfloat16_rn(v);
+  const int tiles_c = (d.C_cols + 63) >> 6, tiles_r = (d.R_pad + 63) >> 6;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 256 threads: 64 x 4
+  const bool along_r = d.sr == 1 && d.s_inner != 1;
+  for (int tl = blockIdx.x; tl < tiles_r * tiles_c; tl += gridDim.x) {
+    const int r0 = (tl / tiles_c) << 6, c0 = (tl % tiles_c) << 6;
+    if (along_r) {
+      const int r = r0 + tx;
+#pragma unroll 4
+      for (int j = ty; j < 64; j += 4) {
+        const int c = c0 + j, blk = c / d.cb, ci = c % d.cb;
+        tile[tx][j] = (r < d.R && c < d.C_cols && ci < d.cb_valid)
+                          ? d.src[(long long)r * d.sr + (long long)blk * d.s_outer + (long long)ci * d.s_inner] : 0.f;
+      }
+    } else {
+      const int c = c0 + tx, blk = c / d.cb, ci = c % d.cb;
+      const bool cok = c < d.C_cols && ci < d.cb_valid;
+      const long long coff = (long long)blk * d.s_outer + (long long)ci * d.s_inner;
+#pragma unroll 4
+      for (int j = ty; j < 64; j += 4) {
+        const int r = r0 + j;
+        tile[j][tx] = (cok && r < d.R) ? d.src[(long long)r * d.sr + coff] : 0.f;
+      }
+    }
+    __syncthreads();
+    const int c = c0 + tx;
+    if (c < d.C_cols) {
+#pragma unroll 4
+      for (int j = ty; j < 64; j += 4) {
+        const int r = r0 + j;
+        if (r >= d.R_pad) break;
+        const long long o = (long long)r * d.dst_ld + c;
+        if (d.dst_f32) static_cast<float*>(d.dst)[o] = tile[j][tx];
+        else static_cast<__nv_bfloat16*>(d.dst)[o] = __float2bfloat16_rn(tile[j][tx]);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -367,7 +398,7 @@ extern "C" int ttsb_pack_weight(const float* w_kn, int K, int N, int n_pad, void
 
 extern "C" int ttsb_repack_batched(const ttsb_pack_desc* descs_device, int n, void* stream) {
   if (!descs_device || n <= 0) return bad("ttsb_repack_batched: bad arguments");
-  repack_batched_kernel<<<dim3(96, n), 256, 0, STREAM(stream)>>>(descs_device);
+  repack_batched_kernel<<<dim3(48, n), 256, 0, STREAM(stream)>>>(descs_device);
   LAUNCH_OK("repack_batched_kernel");
 }
 

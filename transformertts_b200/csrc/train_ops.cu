@@ -4,6 +4,7 @@
 // loss + its gradient, length-regulator / embedding / head backward, fused Adam.
 // All are coalesced row kernels; reductions across rows use shared-memory partials + fp32 atomics.
 #include <cuda_fp16.h>
+#include <algorithm>
 
 #include "../../include/ttsb.h"
 #include "ttsb_common.cuh"
@@ -673,18 +674,53 @@ __global__ void rowdot_heads_kernel(const __nv_bfloat16* __restrict__ x, const _
 // ------------------------------------------------------------------------------------------------
 __global__ void expand_bwd_kernel(const float* __restrict__ dm, const int* __restrict__ dur, int Tp, int Tm, int d,
                                   float* __restrict__ dx) {
+  // grid (B, chunks): every block rebuilds the row's exclusive prefix sum with a block scan, then its warps take the phoneme
+  // segments of its chunk; a lane owns float4 columns, the frame loop is unrolled by two for memory-level parallelism.
   extern __shared__ int cum[];  // exclusive starts, Tp+1
+  __shared__ int wtot[32];
   const int b = blockIdx.x;
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int i = 0; i < Tp; ++i) { cum[i] = run; run += max(dur[(size_t)b * Tp + i], 0); }
-    cum[Tp] = run;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  int carry = 0;
+  for (int base = 0; base < Tp; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < Tp ? max(dur[(size_t)b * Tp + i], 0) : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += wtot[w];
+    if (i < Tp) cum[i] = carry + woff + incl - v;
+    int tot = 0;
+    for (int w = 0; w < warps; ++w) tot += wtot[w];
+    carry += tot;
+    __syncthreads();
   }
+  if (threadIdx.x == 0) cum[Tp] = carry;
   __syncthreads();
-  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x >> 5; i < Tp; i += warps) {
-    const int s = cum[i], e = min(cum[i + 1], Tm);
-    for (int c = lane; c < d; c += 32) {
+  const int d4 = d >> 2;
+  for (int i = blockIdx.y * warps + warp; i < Tp; i += gridDim.y * warps) {
+    const int s = min(cum[i], Tm), e = min(cum[i + 1], Tm);
+    const float4* src = reinterpret_cast<const float4*>(dm + ((size_t)b * Tm) * d);
+    for (int c = lane; c < d4; c += 32) {
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+      int t = s;
+      for (; t + 1 < e; t += 2) {
+        const float4 u = src[(size_t)t * d4 + c], v = src[(size_t)(t + 1) * d4 + c];
+        a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+        a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+      }
+      if (t < e) {
+        const float4 u = src[(size_t)t * d4 + c];
+        a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+      }
+      reinterpret_cast<float4*>(dx + ((size_t)b * Tp + i) * d)[c] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+    }
+    for (int c = (d4 << 2) + lane; c < d; c += 32) {   // d % 4 tail
       float acc = 0.f;
       for (int t = s; t < e; ++t) acc += dm[((size_t)b * Tm + t) * d + c];
       dx[((size_t)b * Tp + i) * d + c] = acc;
@@ -701,9 +737,45 @@ __global__ void embedding_bwd_kernel(const float* __restrict__ dx, const int* __
   for (int c = threadIdx.x & 31; c < d; c += 32) atomicAdd(demb + (size_t)tok * d + c, dx[(size_t)row * d + c]);
 }
 
-// positional-encoding scalar gradient: sum_{row,c} g[row,c] * pe[t,c]
+// positional-encoding scalar gradient: sum_{row,c} g[row,c] * pe[t,c]   (d % 4 == 0: float4 columns, 32-bit index math)
 __global__ void pe_scalar_bwd_kernel(const float* __restrict__ g, const float* __restrict__ pe, int rows, int T, int d,
                                      float drop_p, uint32_t seed, uint32_t site, float* __restrict__ dscalar) {
+  const uint32_t thresh = dropout_thresh(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float local = 0.f;
+  const int d4 = d >> 2;
+  const int rpb = blockDim.x / d4 > 0 ? blockDim.x / d4 : 1;        // rows a block covers per sweep (d4 <= blockDim.x)
+  const int c4 = threadIdx.x % d4, rsub = threadIdx.x / d4;
+  if (rsub < rpb) {
+    for (int row = blockIdx.x * rpb + rsub; row < rows; row += gridDim.x * rpb) {
+      const int t = row % T;
+      float4 gv = reinterpret_cast<const float4*>(g + (size_t)row * d)[c4];
+      const float4 pv = __ldg(reinterpret_cast<const float4*>(pe + (size_t)t * d) + c4);
+      if (drop_p > 0.f) {
+        const uint64_t i0 = (uint64_t)row * d + 4 * c4;
+        bool k0, k1, k2, k3;
+        dropout_keep2(seed, site, i0, thresh, k0, k1);
+        dropout_keep2(seed, site, i0 + 2, thresh, k2, k3);
+        gv.x = k0 ? gv.x * keep_scale : 0.f; gv.y = k1 ? gv.y * keep_scale : 0.f;
+        gv.z = k2 ? gv.z * keep_scale : 0.f; gv.w = k3 ? gv.w * keep_scale : 0.f;
+      }
+      local = fmaf(gv.x, pv.x, fmaf(gv.y, pv.y, fmaf(gv.z, pv.z, fmaf(gv.w, pv.w, local))));
+    }
+  }
+  local = wsum(local);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    atomicAdd(dscalar, s);
+  }
+}
+
+// the same for widths that are not a multiple of four (or wider than a block)
+__global__ void pe_scalar_bwd_scalar_kernel(const float* __restrict__ g, const float* __restrict__ pe, int rows, int T, int d,
+                                            float drop_p, uint32_t seed, uint32_t site, float* __restrict__ dscalar) {
   const uint32_t thresh = dropout_thresh(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float local = 0.f;
@@ -726,24 +798,23 @@ __global__ void pe_scalar_bwd_kernel(const float* __restrict__ g, const float* _
   }
 }
 
-// pitch embedding Dense(1->d, relu) gradients w.r.t. its kernel and bias: pre = pitch*w + b
+// pitch embedding Dense(1->d, relu) gradients w.r.t. its kernel and bias: pre = pitch*w + b.  Threads run along the
+// channels (coalesced rows of g); a block takes a 64-row slab and folds its partial sums with one atomic per channel.
 __global__ void pitch_embed_bwd_kernel(const float* __restrict__ g, const float* __restrict__ pitch, const float* __restrict__ w,
                                        const float* __restrict__ bias, int rows, int d, float* __restrict__ dw, float* __restrict__ db) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
-  const int r0 = blockIdx.y * 256, r1 = min(r0 + 256, rows);
-  const float wc = w[c], bc = bias[c];
-  float sw = 0.f, sb = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    const float pv = pitch[r];
-    if (fmaf(pv, wc, bc) > 0.f) {
+  const int r0 = blockIdx.x * 64, r1 = min(r0 + 64, rows);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float wc = w[c], bc = bias[c];
+    float sw = 0.f, sb = 0.f;
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {
+      const float pv = __ldg(pitch + r);
       const float gv = g[(size_t)r * d + c];
-      sw += gv * pv;
-      sb += gv;
+      if (fmaf(pv, wc, bc) > 0.f) { sw = fmaf(gv, pv, sw); sb += gv; }
     }
+    atomicAdd(dw + c, sw);
+    atomicAdd(db + c, sb);
   }
-  atomicAdd(dw + c, sw);
-  atomicAdd(db + c, sb);
 }
 
 // StatPredictor head backward: out = act(h.w + b) * mask
@@ -938,7 +1009,8 @@ extern "C" int ttsb_rowdot_heads(const void* x, const void* y, int B, int T, int
 
 extern "C" int ttsb_expand_bwd(const float* dm, const int32_t* dur_int, int B, int Tp, int Tm, int d, float* dx, void* stream) {
   if (!dm || !dur_int || !dx || B <= 0 || Tp <= 0 || Tm <= 0 || d <= 0) return bad("ttsb_expand_bwd: bad arguments");
-  expand_bwd_kernel<<<B, 1024, (Tp + 1) * sizeof(int), STREAM(stream)>>>(dm, dur_int, Tp, Tm, d, dx);
+  const int chunks = std::min(32, (Tp + 7) / 8);
+  expand_bwd_kernel<<<dim3(B, chunks), 256, (Tp + 1) * sizeof(int), STREAM(stream)>>>(dm, dur_int, Tp, Tm, d, dx);
   LAUNCH_OK("expand_bwd_kernel");
 }
 
@@ -952,7 +1024,10 @@ extern "C" int ttsb_embedding_bwd(const float* dx, const int32_t* tokens, int B,
 extern "C" int ttsb_pe_scalar_bwd(const float* g, const float* pe, int B, int T, int d, float drop_p, uint32_t seed, uint32_t site,
                                   float* dscalar, void* stream) {
   if (!g || !pe || !dscalar || B <= 0 || T <= 0 || d <= 0) return bad("ttsb_pe_scalar_bwd: bad arguments");
-  pe_scalar_bwd_kernel<<<296, 256, 0, STREAM(stream)>>>(g, pe, B * T, T, d, drop_p, seed, site, dscalar);
+  if (d % 4 == 0 && d / 4 <= 384)
+    pe_scalar_bwd_kernel<<<592, 384, 0, STREAM(stream)>>>(g, pe, B * T, T, d, drop_p, seed, site, dscalar);
+  else
+    pe_scalar_bwd_scalar_kernel<<<296, 256, 0, STREAM(stream)>>>(g, pe, B * T, T, d, drop_p, seed, site, dscalar);
   LAUNCH_OK("pe_scalar_bwd_kernel");
 }
 
@@ -960,8 +1035,7 @@ extern "C" int ttsb_pitch_embed_bwd(const float* g, const float* pitch, const fl
                                     float* dw, float* db, void* stream) {
   if (!g || !pitch || !w || !bias || !dw || !db || B <= 0 || T <= 0 || d <= 0) return bad("ttsb_pitch_embed_bwd: bad arguments");
   const int rows = B * T;
-  dim3 grid((d + 127) / 128, (rows + 255) / 256);
-  pitch_embed_bwd_kernel<<<grid, 128, 0, STREAM(stream)>>>(g, pitch, w, bias, rows, d, dw, db);
+  pitch_embed_bwd_kernel<<<(rows + 63) / 64, std::min(512, ((d + 31) / 32) * 32), 0, STREAM(stream)>>>(g, pitch, w, bias, rows, d, dw, db);
   LAUNCH_OK("pitch_embed_bwd_kernel");
 }
 

@@ -44,11 +44,19 @@ static __constant__ uint32_t c_drop_salt = 0;
 // One 32-bit hash serves TWO consecutive elements (16 bits each; the rate is resolved to 2^-16): the per-element cost of the
 // mask is what bounds the attention-probability kernels of the training step (ncu: the fused dS epilogue issued ~42
 // instructions per element with a hash per element).
-__device__ __forceinline__ uint32_t dropout_hash(uint32_t seed, uint32_t site, uint64_t pair) {
+// hash(pair) = mix((uint32)pair * C1 ^ hterm(seed, site, pair >> 32)).  Kernels that walk consecutive pairs hoist hterm and
+// step the first term by C1 per pair (dropout_hterm / dropout_mix below) instead of redoing the 64-bit index arithmetic.
+constexpr uint32_t DROPOUT_C1 = 0x9E3779B1u;
+__device__ __forceinline__ uint32_t dropout_hterm(uint32_t seed, uint32_t site, uint32_t pair_hi) {
   seed ^= c_drop_salt;
-  uint32_t x = (uint32_t)pair * 0x9E3779B1u ^ (uint32_t)(pair >> 32) * 0x85EBCA77u ^ seed * 0xC2B2AE3Du ^ site * 0x27D4EB2Fu;
+  return pair_hi * 0x85EBCA77u ^ seed * 0xC2B2AE3Du ^ site * 0x27D4EB2Fu;
+}
+__device__ __forceinline__ uint32_t dropout_mix(uint32_t x) {
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
   return x;
+}
+__device__ __forceinline__ uint32_t dropout_hash(uint32_t seed, uint32_t site, uint64_t pair) {
+  return dropout_mix((uint32_t)pair * DROPOUT_C1 ^ dropout_hterm(seed, site, (uint32_t)(pair >> 32)));
 }
 __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t site, uint64_t idx, uint32_t thresh) {
   const uint32_t h = dropout_hash(seed, site, idx >> 1);

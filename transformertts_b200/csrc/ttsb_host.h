@@ -15,6 +15,7 @@ int set_salt_gemm(const uint32_t* salt_dev, cudaStream_t stream);
 int set_salt_rowops(const uint32_t* salt_dev, cudaStream_t stream);
 int set_salt_train_ops(const uint32_t* salt_dev, cudaStream_t stream);
 int set_salt_bgemm(const uint32_t* salt_dev, cudaStream_t stream);
+int set_salt_attn_probs(const uint32_t* salt_dev, cudaStream_t stream);
 
 // State that CUDA keeps PER DEVICE (cudaFuncSetAttribute, __constant__ uploads, the SM count) must be initialised once per
 // device, not once per process: a process that touches a second GPU would otherwise run there with default limits / zero tables.

@@ -10,6 +10,7 @@ fp32 buffers so that Adam is one launch and data-parallel all-reduce works on co
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict
 
 import torch
@@ -63,6 +64,7 @@ class TrainEngine:
         self._salt_dev = None
         self._graphs = {}
         self._graph_pool = None
+        self.fused_probs = os.environ.get('TTSB_NO_FUSED_PROBS') is None   # attn_probs_tc.cu instead of logits GEMM + softmax
 
     # ------------------------------------------------------------------------------------------------
     # packed operands for the step (weights change every step)
@@ -246,15 +248,19 @@ class TrainEngine:
         m._gemm(P[pre + 'qkv'], B, T, [(x_bf, None, d, 0)], [0], [0], out_hi=qkv, ld_out=3 * d)
         ldp = _round_up(T, 16)
         Z = B * H
-        S = self._f32(Z, T, ldp)
-        self._bgemm(B, H, T, T, dh, qkv, (3 * d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 0), qkv, (2 * d, T, B), (3 * d, 3 * d * T),
-                    (dh, 0, 0, d), alpha=1.0 / math.sqrt(dh), out_f32=S, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
         P_pre = self._bf(Z, T, ldp)
         rate = self.drop_rate
         P_drop = self._bf(Z, T, ldp) if rate > 0 else P_pre
         site_p = self._site()
-        lib.softmax_fwd(S, B, H, T, T, ldp, lens, rate, self.seed, site_p, P_pre, P_drop)
-        del S
+        if self.fused_probs and lib.attn_probs_supported(dh, ldp):
+            # logits, softmax and attention dropout in one kernel: the (Z, T, T) fp32 logits never reach HBM
+            lib.attn_probs_fwd(qkv, 3 * d, 0, d, B, H, T, dh, lens, 1.0 / math.sqrt(dh), rate, self.seed, site_p, P_pre, P_drop, ldp)
+        else:
+            S = self._f32(Z, T, ldp)
+            self._bgemm(B, H, T, T, dh, qkv, (3 * d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 0), qkv, (2 * d, T, B), (3 * d, 3 * d * T),
+                        (dh, 0, 0, d), alpha=1.0 / math.sqrt(dh), out_f32=S, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
+            lib.softmax_fwd(S, B, H, T, T, ldp, lens, rate, self.seed, site_p, P_pre, P_drop)
+            del S
         attn = self._bf(B, T, d)
         # O = P V: V is read MN-major straight from the QKV buffer (columns 2d + h*dh), no transposed copy
         self._bgemm(B, H, T, dh, T, P_drop, (T, T, Z), (ldp, T * ldp), (0, 0, 1, 0), qkv, (d, T, B), (3 * d, 3 * d * T),
