@@ -269,13 +269,20 @@ int ttsb_softmax_fwd(const float* S, int B, int H, int T, int Tk, int ld, const 
 /* The two calls above (logits GEMM + ttsb_softmax_fwd) fused for self-attention with flags == 0: P_pre = softmax(scale *
  * Q K^T) over keys < kv_len[b], P_drop = dropout(P_pre), both bf16 (B*H, T, ld_p); the logits stay in tensor memory.
  * qkv is a bf16 (B, T, ld) activation tensor holding head h of Q at columns q_col0 + h*dh and of K at k_col0 + h*dh.
- * Needs dh in {64, 128} (ttsb_attn_probs_supported; wider heads use the two calls above); pass P_drop == P_pre when
- * drop_p == 0.
+ * Needs dh in {64, 128, 192} and fewer than 2^33 probabilities (ttsb_attn_probs_supported; otherwise use the two calls
+ * above); pass P_drop == P_pre when drop_p == 0.
  * Same dropout element index as ttsb_softmax_fwd: (z*T + t)*ld_p + key. */
 int ttsb_attn_probs_supported(int dh, int ld_p);
 int ttsb_attn_probs_fwd(const void* qkv, int ld, int q_col0, int k_col0, int B, int H, int T, int dh, const int32_t* kv_len,
                         float scale, float drop_p, uint32_t seed, uint32_t site, void* P_pre, void* P_drop, int ld_p,
                         void* stream);
+/* Backward counterpart (the same kernel, one pass): dS = scale * P_pre * (dropout(dO V^T) - D) bf16 (B*H, T, ld_p), the
+ * softmax gradient of model/layers.py:186-192 fused into the dP product -- what ttsb_bgemm does with sm_P set, with sixteen
+ * epilogue warps and no fp32 dP in HBM.  dO bf16 (B, T, ld_do) holds head h at columns do_col0 + h*dh, v bf16 (B, T, ld_v)
+ * at v_col0 + h*dh; D fp32 (B*H*T) from ttsb_rowdot_heads; keys >= kv_len[b] and query rows >= kv_len[b] give zeros. */
+int ttsb_attn_ds_bwd(const void* dO, int ld_do, int do_col0, const void* v, int ld_v, int v_col0, int B, int H, int T, int dh,
+                     const int32_t* kv_len, const void* P_pre, const float* D, float scale, float drop_p, uint32_t seed,
+                     uint32_t site, void* dS, int ld_p, void* stream);
 int ttsb_softmax_bwd(const void* P_pre, const float* dP, int B, int H, int T, int Tk, int ld, const int32_t* kv_len,
                      float scale, float drop_p, uint32_t seed, uint32_t site, int flags, void* dS, void* stream);
 /* LayerNorm backward from the saved pre-norm values u (keras LayerNormalization, model/layers.py:27,96,207,295,508). */

@@ -600,9 +600,6 @@ def test_fused_attention_probabilities_match_two_kernel_path(H, dh, T, rate):
     lib.softmax_fwd(S, B, H, T, T, ldp, lens_d, rate, seed, site, P0, D0)
     P1 = torch.full((Z, T, ldp), float('nan'), dtype=torch.bfloat16, device=DEV)
     D1 = torch.full((Z, T, ldp), float('nan'), dtype=torch.bfloat16, device=DEV) if rate > 0 else P1
-    if dh > 128:   # the Q tile + K ring + 16 staging boxes do not fit next to each other: the engine keeps the two-kernel path
-        assert not lib.attn_probs_supported(dh, ldp)
-        return
     assert lib.attn_probs_supported(dh, ldp)
     lib.attn_probs_fwd(qkv_d, 3 * d, 0, d, B, H, T, dh, lens_d, 1.0 / math.sqrt(dh), rate, seed, site, P1, D1, ldp)
     torch.cuda.synchronize()
@@ -629,3 +626,54 @@ def test_fused_attention_probabilities_match_two_kernel_path(H, dh, T, rate):
         ratio = d1[kept] / p1[kept]
         assert float((ratio - 1 / (1 - rate)).abs().max()) < 0.01 / (1 - rate)
         assert (d1[~big] == 0).all()
+
+
+@pytest.mark.parametrize('H,dh,T,rate', [(2, 128, 1000, 0.1), (2, 64, 333, 0.1), (2, 192, 200, 0.0), (1, 128, 130, 0.25)])
+def test_fused_attention_ds_matches_bgemm_epilogue_and_fp64(H, dh, T, rate):
+    """ttsb_attn_ds_bwd against the fused dS epilogue of ttsb_bgemm (same formula, same dropout hash) and against an fp64
+    evaluation of scale * P * (mask * dP / (1-p) - D) on the same bf16 inputs and the same mask."""
+    lib = _lib()
+    from transformertts_b200.model.training import TrainEngine
+    from transformertts_b200.model.models import _round_up
+    g = torch.Generator().manual_seed(9)
+    B, d = 4, H * dh
+    qkv = torch.randn(B, T, 3 * d, generator=g).bfloat16()
+    dO = torch.randn(B, T, d, generator=g).bfloat16()
+    lens = torch.tensor([T, max(T // 2, 1), min(70, T), 1], dtype=torch.int32)
+    Z, ldp = B * H, _round_up(T, 16)
+    Pm = torch.rand(Z, T, ldp, generator=g)
+    kmask = (torch.arange(ldp)[None, :] < lens[:, None]).repeat_interleave(H, 0)[:, None, :]
+    qmask = (torch.arange(T)[None, :] < lens[:, None]).repeat_interleave(H, 0)[:, :, None]
+    Pm = (Pm * kmask * qmask / Pm.sum(-1, keepdim=True).clamp_min(1e-3)).bfloat16()
+    D = torch.randn(Z * T, generator=g) * 0.1
+    qkv_d, dO_d, lens_d, P_d, D_d = qkv.to(DEV), dO.to(DEV), lens.to(DEV), Pm.to(DEV), D.to(DEV)
+    eng = TrainEngine.__new__(TrainEngine)
+    eng.dev = torch.device(DEV)
+    seed, site, scale = 31, 4, 1.0 / math.sqrt(dh)
+    dS0 = torch.full((Z, T, ldp), float('nan'), dtype=torch.bfloat16, device=DEV)
+    eng._bgemm(B, H, T, T, dh, dO_d, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv_d, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
+               out_bf16=dS0, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp,
+               softmax_bwd=(P_d, D_d, scale, rate, seed, site, 0, lens_d, None))
+    dS1 = torch.full((Z, T, ldp), float('nan'), dtype=torch.bfloat16, device=DEV)
+    assert lib.attn_probs_supported(dh, ldp)
+    lib.attn_ds_bwd(dO_d, d, 0, qkv_d, 3 * d, 2 * d, B, H, T, dh, lens_d, P_d, D_d, scale, rate, seed, site, dS1, ldp)
+    torch.cuda.synchronize()
+    a, b = dS0.float().cpu(), dS1.float().cpu()
+    assert torch.isfinite(b).all()
+    assert float((a - b).abs().max()) <= 2 ** -7 * float(a.abs().max()) + 1e-6       # same arithmetic up to fma contraction
+    assert ((b == 0) | (kmask & qmask).expand_as(b)).all()                            # zeros on masked keys / padded rows
+    # fp64 with the mask read back from the forward kernel's P_drop (same hash, same element index)
+    if rate > 0:
+        Pd = torch.empty(Z, T, ldp, dtype=torch.bfloat16, device=DEV)
+        S = torch.zeros(Z, T, ldp, device=DEV)
+        lib.softmax_fwd(S, B, H, T, T, ldp, lens_d, rate, seed, site, torch.empty_like(Pd), Pd)   # uniform rows: P > 0 on live keys
+        keep = (Pd.float().cpu() != 0).double()
+    else:
+        keep = torch.ones(Z, T, ldp, dtype=torch.float64)
+    v = qkv.double()[..., 2 * d:].reshape(B, T, H, dh).permute(0, 2, 1, 3).reshape(Z, T, dh)
+    do = dO.double().reshape(B, T, H, dh).permute(0, 2, 1, 3).reshape(Z, T, dh)
+    dP = torch.zeros(Z, T, ldp, dtype=torch.float64)
+    dP[:, :, :T] = do @ v.transpose(-1, -2)
+    ref = scale * Pm.double() * (keep * dP / (1 - rate) - D.double().reshape(Z, T, 1)) * (kmask & qmask)
+    err = (b.double() - ref).abs()
+    assert float(err.max()) < 8e-3 * float(ref.abs().max()) + 1e-6, float(err.max())

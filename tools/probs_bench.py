@@ -38,7 +38,20 @@ def main():
                    (dh, 0, 0, d), alpha=1.0 / math.sqrt(dh), out_f32=S, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp)
         lib.softmax_fwd(S, B, H, T, T, ldp, lens, rate, 7, 3, P, D)
 
-    for name, fn in (('fused', fused), ('two-kernel', two)):
+    dO = torch.randn(B, T, d, generator=g).bfloat16().to(dev)
+    Dv = (torch.randn(Z * T, generator=g) * 0.1).to(dev)
+    dS = torch.empty(Z, T, ldp, dtype=torch.bfloat16, device=dev)
+    fused()
+    scale = 1.0 / math.sqrt(dh)
+
+    def ds_fused():
+        lib.attn_ds_bwd(dO, d, 0, qkv, 3 * d, 2 * d, B, H, T, dh, lens, P, Dv, scale, rate, 7, 3, dS, ldp)
+
+    def ds_bgemm():
+        eng._bgemm(B, H, T, T, dh, dO, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
+                   out_bf16=dS, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp, softmax_bwd=(P, Dv, scale, rate, 7, 3, 0, lens, None))
+
+    for name, fn in (('fused', fused), ('two-kernel', two), ('dS fused', ds_fused), ('dS bgemm epilogue', ds_bgemm)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()

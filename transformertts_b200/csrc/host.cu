@@ -59,7 +59,7 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -77,7 +77,7 @@ static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t
   }
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
@@ -93,6 +93,14 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
   const cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};
   const cuuint32_t box[3] = {box0, box1, 1};
   return encode(out, base, 3, dims, strides, box);
+}
+
+int make_tmap_bf16_3d_sw64(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1,
+                           uint64_t stride2, uint32_t box0, uint32_t box1) {
+  const cuuint64_t dims[3] = {dim0, dim1, dim2};
+  const cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};
+  const cuuint32_t box[3] = {box0, box1, 1};
+  return encode(out, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1, uint32_t box0,

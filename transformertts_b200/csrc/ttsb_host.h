@@ -28,6 +28,9 @@ struct PerDevice {
 // bf16 tensor (dim0 contiguous, dim1 rows, dim2 batches); strides in ELEMENTS; 128-byte swizzle; OOB reads give zeros.
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1,
                       uint64_t stride2, uint32_t box0, uint32_t box1);
+// the same with the 64-byte swizzle (boxes of 32 bf16 columns: row stride 64 B, 16-byte chunk index ^= (row >> 1) & 3)
+int make_tmap_bf16_3d_sw64(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1,
+                           uint64_t stride2, uint32_t box0, uint32_t box1);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1, uint32_t box0,
                       uint32_t box1);
 }  // namespace ttsb

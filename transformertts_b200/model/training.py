@@ -370,9 +370,14 @@ class TrainEngine:
             # matrix (Z*T*T*4 bytes) is never written or re-read
             D = self._f32(Z * T)
             lib.rowdot_heads(dattn, c['attn'], H, dh, D)
-            self._bgemm(B, H, T, T, dh, dattn, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
-                        out_bf16=dS, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp,
-                        softmax_bwd=(c['P_pre'], D, 1.0 / math.sqrt(dh), rate, self.seed, site_p, 0, lens, None))  # dropout decisions re-drawn from the hash (no P_drop re-read)
+            if self.fused_probs and lib.attn_probs_supported(dh, ldp):
+                # sixteen-warp epilogue twin of the forward probability kernel (dropout decisions re-drawn from the hash)
+                lib.attn_ds_bwd(dattn, d, 0, qkv, 3 * d, 2 * d, B, H, T, dh, lens, c['P_pre'], D, 1.0 / math.sqrt(dh), rate, self.seed,
+                                site_p, dS, ldp)
+            else:
+                self._bgemm(B, H, T, T, dh, dattn, (d, T, B), (d, d * T), (dh, 0, 0, 0), qkv, (d, T, B), (3 * d, 3 * d * T), (dh, 0, 0, 2 * d),
+                            out_bf16=dS, ld_out=ldp, out_batch_stride=T * ldp, out_cols=ldp,
+                            softmax_bwd=(c['P_pre'], D, 1.0 / math.sqrt(dh), rate, self.seed, site_p, 0, lens, None))  # (no P_drop re-read)
         dqkv = self._bf(B, T, 3 * d)
         common = dict(out_bf16=dqkv, ld_out=3 * d, out_batch_stride=T * 3 * d, out_h_col=dh, out_by_b=1, out_cols=dh)
         qkv_dims, qkv_str = (d, T, B), (3 * d, 3 * d * T)
