@@ -72,6 +72,11 @@ __device__ __forceinline__ void ap_sts128(uint32_t saddr, uint32_t a, uint32_t b
 __device__ __forceinline__ void ap_sts64f(uint32_t saddr, float a, float b) {
   asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(saddr), "f"(a), "f"(b) : "memory");
 }
+__device__ __forceinline__ uint4 ap_lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float2 ap_lds64f(uint32_t saddr) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr) : "memory");
@@ -120,7 +125,8 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* k_empty = k_full + AP_MAX_STAGES;
   uint64_t* t_full = k_empty + AP_MAX_STAGES;
   uint64_t* t_empty = t_full + AP_NBUF;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + AP_NBUF);
+  uint64_t* p_full = t_empty + AP_NBUF;          // MODE 1: one per softmax warp, the P box of its next half tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + AP_GROUPS * 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -138,6 +144,7 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(t_full + s, 1);
       mbar_init(t_empty + s, 4);
     }
+    for (int s = 0; s < AP_GROUPS * 4; ++s) mbar_init(p_full + s, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -236,7 +243,7 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int sw = (lane >> 1) & 3;   // 64B swizzle: 16-byte chunk index ^= bits 7-8 of the address = (row >> 1) & 3
     const uint32_t hterm = dropout_hterm(p.seed, p.site, 0u);
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t jc = 0, it = 0;
+    uint32_t jc = 0, it = 0, pcount = 0;
 
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int z, m0, len;
@@ -248,31 +255,49 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float dsum = live ? __ldg(p.sm_D + (size_t)z * p.T + m) : 0.f;
         const bool any_dead = __any_sync(0xffffffffu, !live);
         const float sc = p.scale, sks = p.scale * ks;
-        const __nv_bfloat16* prow = p.sm_P + ((size_t)z * p.T + (live ? m : 0)) * p.ld_p;
         const int n_t = max(p.n_tiles, nkl);
-        for (int j = 0; j < n_t; ++j) {
+        const uint32_t jc_base = jc;
+        jc += nkl;
+        // The saved P box of a half tile ([32 rows x 32 cols], the layout of the output boxes) is fetched by TMA into this
+        // warp's second staging box one half tile ahead of its use.  Per-thread global loads next to their use left the
+        // kernel on the loads (ncu: 4.5 long-scoreboard stalls per issued instruction); holding the next segment in
+        // registers instead spilled inside the loop.
+        uint64_t* pbar = p_full + (warp - 2);
+        auto want_p = [&](int j, int hf) { return j < nkl && j * AP_BN + 32 * hf < len; };     // warp-uniform
+        auto issue_p = [&](int j, int hf) {
+          if (lane == 0) {
+            mbar_arrive_expect_tx(pbar, 2048u);
+            tma_load_3d(&tmD, pbar, box1, j * AP_BN + 32 * hf, m0 + quarter * 32, z);
+          }
+        };
+        if (want_p(group, 0)) issue_p(group, 0);
+        for (int j = group; j < n_t; j += AP_GROUPS) {
           const bool has_mma = j < nkl;
-          const bool mine = (j & (AP_GROUPS - 1)) == group;
-          const uint32_t my_jc = jc;
-          if (has_mma) ++jc;
-          if (!mine) continue;
+          const uint32_t my_jc = jc_base + j;
           const int buf = my_jc & (AP_NBUF - 1);
           const int col0 = j * AP_BN;
           const uint32_t x0 = (uint32_t)(((uint32_t)z * (uint32_t)p.T + (uint32_t)m) * (uint64_t)p.ld_p + (uint64_t)col0 >> 1) * DROPOUT_C1;
-          // the saved P row segment of this tile (64 bf16) is requested before the wait on the product
-          const bool need = has_mma && live && col0 < len;
-          uint4 pq[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            pq[q] = make_uint4(0, 0, 0, 0);
-            if (need && col0 + 8 * q < len) pq[q] = __ldg(reinterpret_cast<const uint4*>(prow + col0) + q);
-          }
           if (has_mma) {
             ap_mbar_wait(t_full + buf, (my_jc / AP_NBUF) & 1);
             tc_fence_after();
           }
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
+            uint4 cur[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cur[q] = make_uint4(0, 0, 0, 0);
+            if (want_p(j, hf)) {
+              ap_mbar_wait(pbar, pcount & 1);
+              ++pcount;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) cur[q] = ap_lds128(box1_s + ((q ^ sw) << 4));
+              fence_proxy_async_smem();    // the box is overwritten by the next TMA load (async proxy) after these reads
+              __syncwarp();
+            }
+            {
+              const int nj = hf == 0 ? j : j + AP_GROUPS, nhf = hf ^ 1;
+              if (want_p(nj, nhf)) issue_p(nj, nhf);
+            }
             float y[32];
             if (has_mma && col0 + 32 * hf < len) {      // warp-uniform (tcgen05.ld is .sync.aligned); dead rows carry P = 0
               uint32_t ra[16], rb[16];
@@ -281,7 +306,7 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               tmem_wait_ld();
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const uint4 qv = pq[4 * hf + (i >> 2)];
+                const uint4 qv = cur[i >> 2];
                 const uint32_t w = (i & 3) == 0 ? qv.x : (i & 3) == 1 ? qv.y : (i & 3) == 2 ? qv.z : qv.w;
                 const float p0 = __uint_as_float(w << 16), p1 = __uint_as_float(w & 0xffff0000u);
                 const uint32_t hsh = dropout_mix((x0 + (uint32_t)(16 * hf + i) * DROPOUT_C1) ^ hterm);
@@ -575,7 +600,7 @@ extern "C" int ttsb_attn_ds_bwd(const void* dO, int ld_do, int do_col0, const vo
   p.drop_p = drop_p; p.seed = seed; p.site = site;
   p.sm_P = static_cast<const __nv_bfloat16*>(P_pre);
   p.sm_D = D;
-  return ap_launch<1>(dO, ld_do, do_col0, v, ld_v, v_col0, B, H, T, dh, p, dS, dS, ld_p, static_cast<cudaStream_t>(stream_v));
+  return ap_launch<1>(dO, ld_do, do_col0, v, ld_v, v_col0, B, H, T, dh, p, dS, P_pre, ld_p, static_cast<cudaStream_t>(stream_v));   // second map: P loads
 }
 
 TTSB_DEFINE_SALT_SETTER(set_salt_attn_probs)
