@@ -252,7 +252,8 @@ def test_aligner_cuda_graph_replay_equals_eager():
     for _ in range(2):
         a, b = eager._val_step(tok, mel, stop), graphed._val_step(tok, mel, stop)
         assert torch.equal(a['mel'], b['mel']) and torch.equal(a['stop_prob'], b['stop_prob'])
-        assert torch.equal(a['loss'], b['loss'])
+        # the loss kernels fold block partials with fp32 atomics: equal up to the order of those additions
+        assert abs(float(a['loss']) - float(b['loss'])) <= 2e-6 * abs(float(a['loss']))
         for k in a['decoder_attention']:
             assert torch.equal(a['decoder_attention'][k], b['decoder_attention'][k])
     losses = []

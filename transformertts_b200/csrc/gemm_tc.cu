@@ -177,14 +177,18 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, size_t orow, i
 }
 
 __device__ __forceinline__ void apply_dropout16(float (&y)[16], float p, uint32_t seed, uint32_t site, uint64_t elem0) {
-  const uint32_t thresh = dropout_thresh(p);
+  const uint32_t t16 = dropout_thresh(p) >> 16;
   const float ks = 1.f / (1.f - p);
+  // elem0 is a multiple of 16 (ld_out % 16 == 0 for dropout outputs): the eight pair indices share their high word and the
+  // low word cannot wrap, so the 64-bit part of the hash is done once per chunk (exact for any tensor size)
+  const uint64_t pair0 = elem0 >> 1;
+  const uint32_t hterm = dropout_hterm(seed, site, (uint32_t)(pair0 >> 32));
+  const uint32_t x0 = (uint32_t)pair0 * DROPOUT_C1;
 #pragma unroll
-  for (int j = 0; j < 16; j += 2) {   // elem0 is a multiple of 16 (ld_out % 16 == 0 for dropout outputs): one hash per pair
-    bool k0, k1;
-    dropout_keep2(seed, site, elem0 + j, thresh, k0, k1);
-    y[j] = k0 ? y[j] * ks : 0.f;
-    y[j + 1] = k1 ? y[j + 1] * ks : 0.f;
+  for (int j = 0; j < 16; j += 2) {
+    const uint32_t h = dropout_mix((x0 + (uint32_t)(j >> 1) * DROPOUT_C1) ^ hterm);
+    y[j] = (h & 0xffffu) >= t16 ? y[j] * ks : 0.f;
+    y[j + 1] = (h >> 16) >= t16 ? y[j + 1] * ks : 0.f;
   }
 }
 

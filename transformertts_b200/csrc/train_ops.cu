@@ -290,6 +290,10 @@ layernorm_bwd_vec_kernel(const float* __restrict__ dz, const float* __restrict__
     gam[i] = __ldg(reinterpret_cast<const float4*>(gamma + 4 * lane + 128 * i));
     acc_g[i] = acc_b[i] = acc_x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  // mask hash of element pair k of a row: mix((xrow + k*C1) ^ hterm); the host routes tensors of >= 2^33 elements to the
+  // scalar kernel, so the pair index fits 32 bits (no 64-bit index arithmetic per pair)
+  const uint32_t hterm_post = dropout_hterm(seed, post_site, 0u), hterm_pre = dropout_hterm(seed, pre_site, 0u);
+  const uint32_t post_t16 = post_thresh >> 16, pre_t16 = pre_thresh >> 16;
   float4 un[NG], gn[NG];
   auto fetch = [&](int row) {
     const size_t base = (size_t)row * C;
@@ -309,14 +313,17 @@ layernorm_bwd_vec_kernel(const float* __restrict__ dz, const float* __restrict__
     const int b = row / T, t = row % T;
     const bool live = row_len == nullptr || t < __ldg(row_len + b);
     const size_t base = (size_t)row * C;
+    const uint32_t xl = ((uint32_t)(base >> 1) + 2u * lane) * DROPOUT_C1;   // pair of elements 4*lane, 4*lane+1 of the row
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NG; ++i) {
       float* g4 = reinterpret_cast<float*>(&gz[i]);
       bool kk[4] = {true, true, true, true};
       if (post_drop_p > 0.f) {
-        dropout_keep2(seed, post_site, base + 4 * lane + 128 * i, post_thresh, kk[0], kk[1]);
-        dropout_keep2(seed, post_site, base + 4 * lane + 128 * i + 2, post_thresh, kk[2], kk[3]);
+        const uint32_t h0 = dropout_mix((xl + (uint32_t)(64 * i) * DROPOUT_C1) ^ hterm_post);
+        const uint32_t h1 = dropout_mix((xl + (uint32_t)(64 * i + 1) * DROPOUT_C1) ^ hterm_post);
+        kk[0] = (h0 & 0xffffu) >= post_t16; kk[1] = (h0 >> 16) >= post_t16;
+        kk[2] = (h1 & 0xffffu) >= post_t16; kk[3] = (h1 >> 16) >= post_t16;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) g4[j] = (live && kk[j]) ? g4[j] * post_scale : 0.f;
@@ -365,8 +372,10 @@ layernorm_bwd_vec_kernel(const float* __restrict__ dz, const float* __restrict__
       float d4[4], gv[4];
       bool kp[4] = {true, true, true, true};
       if (pre_drop_p > 0.f) {
-        dropout_keep2(seed, pre_site, base + 4 * lane + 128 * i, pre_thresh, kp[0], kp[1]);
-        dropout_keep2(seed, pre_site, base + 4 * lane + 128 * i + 2, pre_thresh, kp[2], kp[3]);
+        const uint32_t h0 = dropout_mix((xl + (uint32_t)(64 * i) * DROPOUT_C1) ^ hterm_pre);
+        const uint32_t h1 = dropout_mix((xl + (uint32_t)(64 * i + 1) * DROPOUT_C1) ^ hterm_pre);
+        kp[0] = (h0 & 0xffffu) >= pre_t16; kp[1] = (h0 >> 16) >= pre_t16;
+        kp[2] = (h1 & 0xffffu) >= pre_t16; kp[3] = (h1 >> 16) >= pre_t16;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -909,7 +918,7 @@ extern "C" int ttsb_layernorm_bwd(const float* dz, const float* u, const float* 
   if (!dz || !u || !gamma || !dgamma || !dbeta || B <= 0 || T <= 0 || C <= 0 || C > 512 || ld < C || ld > 512)
     return bad("ttsb_layernorm_bwd: bad arguments (C, ld <= 512)");
   const int rows = B * T;
-  if (C == ld && C % 128 == 0 && C <= 384) {   // every block LayerNorm of the model: vectorised persistent kernel
+  if (C == ld && C % 128 == 0 && C <= 384 && (long long)rows * C < (1ll << 33)) {   // every block LayerNorm of the model: vectorised persistent kernel
     const int grid = min((rows + 7) / 8, 2 * num_sms());
 #define TTSB_LNV(NG)                                                                                                            \
   layernorm_bwd_vec_kernel<NG><<<grid, 256, 0, STREAM(stream)>>>(dz, u, gamma, rows, T, eps, row_len, relu_mask, pre_drop_p, pre_site, \
