@@ -513,7 +513,10 @@ def test_graphed_training_step_equals_eager_step():
     assert all(abs(a - b) < 2e-4 * abs(a) for a, b in zip(le, lg)), (le, lg)
     assert le[3] < le[0]                                                       # the steps do train
     we, wg = me._get_engine().flat_w, mg._get_engine().flat_w
-    assert float((we - wg).abs().max()) < 2.5e-4                               # 4 Adam steps of lr 1e-4; sign flips of ~0 gradients only
+    # 4 Adam steps of lr 1e-4: a parameter whose gradient is rounding noise around zero (key biases) moves by +-lr per step with
+    # a sign set by the order of fp32 atomics, so two runs may drift apart by up to 2*lr per step there; everything else agrees
+    assert float((we - wg).abs().max()) < 8.5e-4
+    assert float((we - wg).abs().mean()) < 2e-6
     assert mg.step == 4 and len(mg._get_engine()._graphs) == 1
     # another shape gets its own graphs; the first one still replays
     tok2, dur2, pit2 = fo.make_inputs('ragged', 3, 24, 120, seed=323)
