@@ -115,7 +115,7 @@ def jline(fn):
 
 def main():
     md = ['# Round 2 profile summary', '',
-          'Sources: `tools/_final_n1.sh` under gpurun on one B200 (files named below live in gpurun_out/, which is scratch; this file and',
+          'Sources: `tools/gpu_evidence_n1.sh` under gpurun on one B200 (files named below live in gpurun_out/, which is scratch; this file and',
           '`traffic.json` are the committed digests).  Peaks: MEASURED_PEAKS.json (6585 GB/s HBM copy, 1415.6 TFLOP/s sustained bf16).', '']
     b = jline(OUT / 'r02_bench_n1.json')
     if b:
@@ -145,7 +145,9 @@ def main():
     md += ['## ncu --set full captures', '']
     for rep, title in (('r02_gemm.ncu-rep', 'inference GEMMs of a decoder block (bf16x3)'), ('r02_mha.ncu-rep', 'fused attention (fp16, decoder)'),
                        ('r02_stft_v2.ncu-rep', 'STFT->mel v2'), ('r2f_stft.ncu-rep', 'STFT->mel v1 (round-1 kernel)'), ('r02_rowk.ncu-rep', 'training row kernels'),
-                       ('r02_ds.ncu-rep', 'fused dP -> dS batched GEMM (training)'), ('r2f_ds.ncu-rep', 'the same before the epilogue work'),
+                       ('r02_probs.ncu-rep', 'attention probabilities, training forward: QK^T + softmax + dropout in one kernel (C3 decoder shape, tools/probs_bench.py)'),
+                       ('r02_ds16.ncu-rep', 'attention dS, training backward: dO V^T + softmax gradient in one kernel (same shape)'),
+                       ('r02_ds.ncu-rep', 'the dS product as an epilogue of the generic batched GEMM (what the kernel above replaced)'), ('r2f_ds.ncu-rep', 'the same before its epilogue work'),
                        ('r02_expand_ln_pe.ncu-rep', 'length regulator gather + LayerNorm + PE (fused, real path)'),
                        ('r2f_expand.ncu-rep', 'length regulator kernels alone')):
         if (OUT / rep).exists():
