@@ -377,8 +377,8 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ 
           }
         }
         const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(sP + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (kSplit) *reinterpret_cast<uint4*>(sP + Cfg::P_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        st_shared_v4(sP + off, hi[0], hi[1], hi[2], hi[3]);
+        if (kSplit) st_shared_v4(sP + Cfg::P_BYTES + off, lo[0], lo[1], lo[2], lo[3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();

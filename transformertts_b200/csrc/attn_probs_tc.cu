@@ -82,24 +82,6 @@ __device__ __forceinline__ float2 ap_lds64f(uint32_t saddr) {
   asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr) : "memory");
   return v;
 }
-// mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of spinning through issue slots the
-// softmax warps on the same scheduler need (ncu of the first version: 9 % of all issued instructions were wait loops)
-__device__ __forceinline__ void ap_mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        "selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
-        : "memory");
-    if (ok) return;
-    if (++spins == 0x4000000u) { asm volatile("trap;"); }
-  }
-}
-
 __device__ __forceinline__ float ap_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -174,7 +156,7 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int nkl = live_tiles(item, z, m0, len);
       if (nkl == 0) continue;
       const int b = z / p.H, h = z % p.H;
-      ap_mbar_wait(q_empty, (qc & 1) ^ 1);
+      mbar_wait_parked(q_empty, (qc & 1) ^ 1);
       if (leader) {
         mbar_arrive_expect_tx(q_full, (uint32_t)q_bytes);
         for (int kb = 0; kb < p.kbs; ++kb) tma_load_3d(&tmQ, q_full, q_smem + kb * AP_QBOX_BYTES, p.q_col0 + h * p.dh + kb * 64, m0, b);
@@ -184,7 +166,7 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int job = 0; job < (MODE == 0 ? 2 : 1) * njobs; ++job) {       // probabilities: pass 1, then pass 2
         const int j = job < njobs ? job : job - njobs;
         const int stage = jc % p.nst;
-        ap_mbar_wait(k_empty + stage, ((jc / p.nst) & 1) ^ 1);
+        mbar_wait_parked(k_empty + stage, ((jc / p.nst) & 1) ^ 1);
         if (leader) {
           mbar_arrive_expect_tx(k_full + stage, (uint32_t)k_bytes);
           for (int kb = 0; kb < p.kbs; ++kb)
@@ -202,15 +184,15 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       int z, m0, len;
       const int nkl = live_tiles(item, z, m0, len);
       if (nkl == 0) continue;
-      ap_mbar_wait(q_full, qc & 1);
+      mbar_wait_parked(q_full, qc & 1);
       tc_fence_after();
       const uint32_t qs = smem_u32(q_smem);
       for (int job = 0; job < (MODE == 0 ? nkl : nkl / 2); ++job) {   // nkl/2 jobs per pass
         const int buf = (2 * jc) & (AP_NBUF - 1);      // tiles 2*jc, 2*jc + 1 -> buffers buf, buf + 1 (adjacent columns)
         const int stage = jc % p.nst;
-        ap_mbar_wait(t_empty + buf, (((2 * jc) / AP_NBUF) & 1) ^ 1);
-        ap_mbar_wait(t_empty + buf + 1, (((2 * jc) / AP_NBUF) & 1) ^ 1);
-        ap_mbar_wait(k_full + stage, (jc / p.nst) & 1);
+        mbar_wait_parked(t_empty + buf, (((2 * jc) / AP_NBUF) & 1) ^ 1);
+        mbar_wait_parked(t_empty + buf + 1, (((2 * jc) / AP_NBUF) & 1) ^ 1);
+        mbar_wait_parked(k_full + stage, (jc / p.nst) & 1);
         tc_fence_after();
         const uint32_t ks = smem_u32(k_smem + stage * k_bytes);
         if (leader) {
@@ -278,7 +260,7 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const int col0 = j * AP_BN;
           const uint32_t x0 = (uint32_t)(((uint32_t)z * (uint32_t)p.T + (uint32_t)m) * (uint64_t)p.ld_p + (uint64_t)col0 >> 1) * DROPOUT_C1;
           if (has_mma) {
-            ap_mbar_wait(t_full + buf, (my_jc / AP_NBUF) & 1);
+            mbar_wait_parked(t_full + buf, (my_jc / AP_NBUF) & 1);
             tc_fence_after();
           }
 #pragma unroll
@@ -287,7 +269,7 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
             for (int q = 0; q < 4; ++q) cur[q] = make_uint4(0, 0, 0, 0);
             if (want_p(j, hf)) {
-              ap_mbar_wait(pbar, pcount & 1);
+              mbar_wait_parked(pbar, pcount & 1);
               ++pcount;
 #pragma unroll
               for (int q = 0; q < 4; ++q) cur[q] = ap_lds128(box1_s + ((q ^ sw) << 4));
@@ -354,7 +336,7 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int j = 0; j < nkl; ++j, ++jc) {
         if ((j & (AP_GROUPS - 1)) != group) continue;
         const int buf = jc & (AP_NBUF - 1);
-        ap_mbar_wait(t_full + buf, (jc / AP_NBUF) & 1);
+        mbar_wait_parked(t_full + buf, (jc / AP_NBUF) & 1);
         tc_fence_after();
         const int n0 = j * AP_BN;
         uint32_t ra[16], rb[16], rc[16], rd[16];
@@ -429,7 +411,7 @@ attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // < 2^33 elements only, so the pair index fits 32 bits and its high word is zero
         const uint32_t x0 = (uint32_t)(((uint32_t)z * (uint32_t)p.T + (uint32_t)m) * (uint64_t)p.ld_p + (uint64_t)col0 >> 1) * DROPOUT_C1;
         if (has_mma) {
-          ap_mbar_wait(t_full + buf, (my_jc / AP_NBUF) & 1);
+          mbar_wait_parked(t_full + buf, (my_jc / AP_NBUF) & 1);
           tc_fence_after();
         }
 #pragma unroll

@@ -371,8 +371,8 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               }
               const int k0 = 2 * (2 * half + u);
               const uint32_t o0 = lrow * 128 + (((k0) ^ (lrow & 7)) << 4), o1 = lrow * 128 + (((k0 + 1) ^ (lrow & 7)) << 4);
-              *reinterpret_cast<uint4*>(box + o0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-              *reinterpret_cast<uint4*>(box + o1) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+              st_shared_v4(box + o0, hh[0], hh[1], hh[2], hh[3]);
+              st_shared_v4(box + o1, hh[4], hh[5], hh[6], hh[7]);
             }
             fence_proxy_async_smem();
             asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");

@@ -289,11 +289,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
           // 16-byte chunk ids of this 16-column chunk inside the 128-byte box row: 2*(2*half+u), +1; swizzle ^= row & 7
           const int k0 = 2 * (2 * half + u);
           const uint32_t o0 = lrow * 128 + (((k0) ^ (lrow & 7)) << 4), o1 = lrow * 128 + (((k0 + 1) ^ (lrow & 7)) << 4);
-          *reinterpret_cast<uint4*>(box_hi + o0) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(box_hi + o1) = make_uint4(h[4], h[5], h[6], h[7]);
+          st_shared_v4(box_hi + o0, h[0], h[1], h[2], h[3]);
+          st_shared_v4(box_hi + o1, h[4], h[5], h[6], h[7]);
           if (two) {
-            *reinterpret_cast<uint4*>(box_lo + o0) = make_uint4(l[0], l[1], l[2], l[3]);
-            *reinterpret_cast<uint4*>(box_lo + o1) = make_uint4(l[4], l[5], l[6], l[7]);
+            st_shared_v4(box_lo + o0, l[0], l[1], l[2], l[3]);
+            st_shared_v4(box_lo + o1, l[4], l[5], l[6], l[7]);
           }
         }
         fence_proxy_async_smem();
