@@ -105,6 +105,28 @@ def aligner_call(p: Dict[str, Tensor], cfg: dict, inputs: Tensor, targets: Tenso
             'mel_mask': dec_target_padding_mask, 'encoder_attention': enc_attn, 'text_mask': padding_mask}
 
 
+def aligner_predict(p: Dict[str, Tensor], cfg: dict, inp: Tensor, start_value: float, max_length: int = 1000, r: int = 1,
+                    stop_prob_index: int = 2) -> dict:
+    """Aligner.predict models.py:271-292 (encode=False): autoregressive decoding of ONE token row.  The decoder is re-run on
+    the whole prefix every iteration (as the reference does); the prefix grows by the LAST predicted frame (one per iteration,
+    also for r > 1, :280), the returned mel by the last r frames (:281-282); decoding stops when the arg-max of the last stop
+    distribution is `stop_prob_index` (:287) or after max_length // r + 1 iterations."""
+    mel_ch = int(cfg['mel_channels'])
+    inp = inp.reshape(1, -1)
+    output = torch.full((1, 1, mel_ch), float(start_value), dtype=p['embedding'].dtype)
+    output_concat = output.clone()
+    out = {}
+    for _ in range(int(max_length // r) + 1):
+        mo = aligner_call(p, cfg, inp, output, r=r, training=False)
+        output = torch.cat([output, mo['mel'][:1, -1:, :]], dim=-2)
+        output_concat = torch.cat([output_concat, mo['mel'][:1, -r:, :]], dim=-2)
+        out = {'mel': output_concat[0, 1:, :], 'decoder_attention': mo['decoder_attention'],
+               'encoder_attention': mo['encoder_attention'], 'stop_prob': mo['stop_prob']}
+        if int(torch.argmax(mo['stop_prob'][:, -1], dim=-1)) == stop_prob_index:
+            break
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # utils/losses.py, utils/metrics.py
 # ----------------------------------------------------------------------------------------

@@ -265,3 +265,25 @@ def test_aligner_cuda_graph_replay_equals_eager():
         losses.append([float(m.train_step(tok, mel, stop)['loss']) for _ in range(4)])
     assert all(abs(x - y) < 5e-4 * abs(x) for x, y in zip(*losses)), losses
     assert losses[0][3] < losses[0][0]
+
+
+@pytest.mark.parametrize('r,stop_bias', [(1, (6.0, 0.0, -6.0)), (2, (6.0, 0.0, -6.0)), (2, (-6.0, 0.0, 6.0))])
+def test_aligner_autoregressive_predict(r, stop_bias):
+    """Aligner.predict (models.py:271-292) on the GPU against the oracle loop (itself pinned to the reference's predict in
+    tests/test_reference_shim.py).  The stop head is biased so the stop decision does not hang on a near-tie: either the loop
+    runs to max_length (the prefix is fed back 13 / 7 times) or it stops after the first iteration."""
+    cfg = alo.ALIGNER_CONFIGS['A-small']
+    p = dict(alo.init_aligner_params(cfg, seed=7))
+    p['postnet.stop.b'] = torch.tensor(stop_bias)
+    tok, _, _ = alo.make_aligner_inputs(cfg, 2, 12, 21, seed=3)
+    m = _model('A-small', p)
+    m.set_constants(reduction_factor=r)
+    out = m.predict(tok[0], max_length=12, encode=False, verbose=False)
+    ref = alo.aligner_predict(p, dict(cfg, dropout_rate=0.0, decoder_prenet_dropout=0.0), tok[0], float(m.start_vec[0, 0]), max_length=12, r=r,
+                              stop_prob_index=m.stop_prob_index)
+    a, b = out['mel'].float().cpu(), ref['mel']
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert a.shape[0] == ((12 // r + 1) * r if stop_bias[0] > 0 else r)
+    assert float((a - b).abs().max()) < 5e-3 * max(1.0, float(b.abs().max())), float((a - b).abs().max())
+    with pytest.raises(NotImplementedError):
+        m.predict('text', max_length=4)      # encode=True needs the external phonemizer

@@ -301,3 +301,28 @@ def test_keras_weight_order_of_the_aligner():
     got = [[ident.get(id(v)) for v in layer.variables] for layer in ref.layers]
     assert got == want          # includes DecoderPrenet's non-trainable rate variable (None) in last position
     assert [layer.name for layer in ref.layers] == ['Embedding', 'Encoder', 'DecoderPrenet', 'Decoder', 'FinalProj', 'Postnet']
+
+
+@pytest.mark.parametrize('r,force_long', [(4, False), (1, False), (2, True)])
+def test_aligner_autoregressive_predict_matches_oracle(r, force_long):
+    """Aligner.predict (models.py:271-292, encode=False) of the UNMODIFIED reference against oracle.aligner_predict: same number
+    of iterations (stop decision) and the same frames.  force_long biases the stop head so the loop runs to max_length."""
+    cfg = alo.ALIGNER_CONFIGS['A-small']
+    p = alo.init_aligner_params(cfg, seed=7)
+    if force_long:
+        p = dict(p)
+        p['postnet.stop.b'] = torch.tensor([6.0, 0.0, -6.0])
+    tok, mel, _ = alo.make_aligner_inputs(cfg, 2, 12, 21, seed=3)
+    c0 = dict(cfg, dropout_rate=0.0, decoder_prenet_dropout=0.0)
+    ref = ref_shim.reference_aligner(c0, p, (tok, mel[:, :-1]))
+    ref._set_r(r)
+    with torch.no_grad():
+        o_ref = ref.predict(tok[0], max_length=10, encode=False, verbose=False)
+    o = alo.aligner_predict(p, c0, tok[0], float(ref.start_vec[0, 0]), max_length=10, r=r, stop_prob_index=ref.stop_prob_index)
+    a, b = torch.as_tensor(o_ref['mel']), o['mel']
+    assert a.shape == b.shape
+    if force_long:
+        assert a.shape[0] == (10 // r + 1) * r
+    assert float((a - b).abs().max()) < 1e-5
+    k = 'Decoder_LastBlock_CrossAttention'
+    assert float((torch.as_tensor(o_ref['decoder_attention'][k]) - o['decoder_attention'][k]).abs().max()) < 1e-5

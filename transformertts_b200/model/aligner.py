@@ -4,7 +4,7 @@ that produces the attention maps durations are extracted from (SURVEY.md section
 Built here: the teacher-forced forward (``call`` / ``_forward`` / ``_forward_encoder`` / ``_forward_decoder``) and the
 validation step with its losses (``_val_step`` = ``_gta_forward(training=False)``, models.py:168-220), every layer
 through libttsb.so; ``_train_step`` (teacher-forced forward with dropout in single-pass bf16, hand-written backward,
-Keras-form Adam) lives in aligner_training.py.  Not built: the autoregressive ``predict`` (raises TtsbError).
+Keras-form Adam) lives in aligner_training.py; ``predict`` is the reference's autoregressive loop over the same decoder call.
 
 Parameter names (flat dict, Keras layouts):
   embedding; encoder.* exactly as ForwardTransformer dense blocks (models.py docstring);
@@ -486,8 +486,39 @@ class Aligner(ForwardTransformer):
 
     train_step = _train_step
 
-    def predict(self, *a, **k):
-        raise lib.TtsbError('Aligner.predict (autoregressive decoding, models.py:271-292) is outside the built rows')
+    def encode_text(self, text):
+        """models.py:338-340: text -> token ids through the attached text pipeline (the espeak phonemizer is external)."""
+        tp = getattr(self, 'text_pipeline', None)
+        if tp is None:
+            raise NotImplementedError('text encoding needs the espeak phonemizer, which is outside the built path; '
+                                      'pass token ids with encode=False or attach a text_pipeline')
+        return tp(text)
+
+    @_on_device
+    def predict(self, inp, max_length=1000, encode=True, verbose=True):
+        """models.py:271-292: autoregressive decoding of one token row.  As in the reference the encoder runs once and the
+        decoder is re-run on the whole prefix every iteration; the prefix grows by the last predicted frame, the returned mel
+        by the last r frames, and decoding stops when the arg-max of the last stop distribution is `stop_prob_index`.
+        One host read per iteration (the stop decision), as `int(tf.argmax(...))` is in the reference."""
+        if encode:
+            inp = self.encode_text(inp)
+        dev = self.device
+        inp = torch.as_tensor(inp).to(device=dev, dtype=torch.int32).reshape(1, -1)
+        output = self.start_vec.to(device=dev, dtype=torch.float32).reshape(1, 1, self.mel_channels)
+        output_concat = output.clone()
+        out_dict = {}
+        enc, padding_mask, enc_attn, enc_len = self._call_encoder(inp, training=False)
+        r = int(self.r)
+        for _ in range(int(max_length // r) + 1):
+            mo = self._call_decoder(enc, output, padding_mask, training=False, enc_len=enc_len)
+            output = torch.cat([output, mo['mel'][:1, -1:, :]], dim=-2)
+            output_concat = torch.cat([output_concat, mo['mel'][:1, -r:, :]], dim=-2)
+            out_dict = {'mel': output_concat[0, 1:, :], 'decoder_attention': mo['decoder_attention'], 'encoder_attention': enc_attn}
+            if int(torch.argmax(mo['stop_prob'][:, -1], dim=-1)) == self.stop_prob_index:
+                if verbose:
+                    print('Stopping')
+                break
+        return out_dict
 
     def _compile(self, stop_scaling=8.0, optimizer=None):
         """models.py:222-227."""
