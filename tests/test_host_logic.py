@@ -66,8 +66,8 @@ def test_aligner_host_mirror_parameters_and_persistence(tmp_path):
     m2.set_constants(reduction_factor=2, force_decoder_diagonal=True)
     assert m2.r == 2 and m2.force_decoder_diagonal and not m2.force_encoder_diagonal
     import pytest
-    with pytest.raises(lib.TtsbError):
-        m2.predict(None)
+    with pytest.raises(NotImplementedError):
+        m2.predict('text')          # encode=True needs the external phonemizer (no text_pipeline attached)
 
 
 def test_duration_to_alignment_matrix():

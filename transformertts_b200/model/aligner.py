@@ -494,7 +494,6 @@ class Aligner(ForwardTransformer):
                                       'pass token ids with encode=False or attach a text_pipeline')
         return tp(text)
 
-    @_on_device
     def predict(self, inp, max_length=1000, encode=True, verbose=True):
         """models.py:271-292: autoregressive decoding of one token row.  As in the reference the encoder runs once and the
         decoder is re-run on the whole prefix every iteration; the prefix grows by the last predicted frame, the returned mel
@@ -502,6 +501,10 @@ class Aligner(ForwardTransformer):
         One host read per iteration (the stop decision), as `int(tf.argmax(...))` is in the reference."""
         if encode:
             inp = self.encode_text(inp)
+        return self._predict_tokens(inp, max_length, verbose)
+
+    @_on_device
+    def _predict_tokens(self, inp, max_length, verbose):
         dev = self.device
         inp = torch.as_tensor(inp).to(device=dev, dtype=torch.int32).reshape(1, -1)
         output = self.start_vec.to(device=dev, dtype=torch.float32).reshape(1, 1, self.mel_channels)
