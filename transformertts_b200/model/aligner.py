@@ -286,7 +286,7 @@ class Aligner(ForwardTransformer):
     def _call_encoder(self, inputs, training=False):
         """models.py:127-133 -> (encoder output triple, padding mask, attention weights, lengths)."""
         if training:
-            raise lib.TtsbError('Aligner: training=True (dropout + backward) is not built yet; use training=False')
+            raise lib.TtsbError('Aligner.call runs the inference path (training=False); dropout + backward live in train_step (aligner_training.AlignerTrainEngine)')
         P, W, dev = self._prepare(), self.weights, self.device
         x = torch.as_tensor(inputs).to(device=dev, dtype=torch.int32).contiguous()
         if x.dim() != 2:
@@ -306,7 +306,7 @@ class Aligner(ForwardTransformer):
     def _call_decoder(self, encoder_output, targets, encoder_padding_mask, training=False, enc_len=None):
         """models.py:135-154.  encoder_output: the activation triple returned by _call_encoder."""
         if training:
-            raise lib.TtsbError('Aligner: training=True (dropout + backward) is not built yet; use training=False')
+            raise lib.TtsbError('Aligner.call runs the inference path (training=False); dropout + backward live in train_step (aligner_training.AlignerTrainEngine)')
         P, W, dev = self._prepare(), self.weights, self.device
         tgt = torch.as_tensor(targets).to(device=dev, dtype=torch.float32).contiguous()
         B, T, mel = tgt.shape
