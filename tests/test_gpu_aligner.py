@@ -118,8 +118,8 @@ def test_aligner_unbuilt_paths_fail_loudly():
     cfg = alo.ALIGNER_CONFIGS['A-small']
     m = _model('A-small', alo.init_aligner_params(cfg, seed=7))
     tokens, mel, stop = alo.make_aligner_inputs(cfg, 2, 12, 20, seed=1)
-    with pytest.raises(lib.TtsbError):
-        m.predict(tokens)
+    with pytest.raises(NotImplementedError):
+        m.predict('some text')               # encode=True needs the external phonemizer (no text_pipeline attached)
     with pytest.raises(lib.TtsbError):
         m.call(tokens, mel, training=True)   # training goes through _train_step (dropout + backward)
 
