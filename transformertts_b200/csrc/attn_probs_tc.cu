@@ -14,17 +14,17 @@
 //   warps 2-17 four groups of four warps (one per TMEM lane quarter); group g takes tiles j with j % 4 == g, a thread owns
 //              one query row of the tile.  After pass 1 the groups merge their (max, sum) through shared memory.
 //              Pass 2 stages one bf16 [32 rows x 32 cols] box (64B swizzle) per output and warp and hands it to TMA;
-//              small boxes leave the shared memory to the K ring (7 stages at dh = 128: a 3-stage ring starved the MMAs).
+//              small boxes leave the shared memory to the K ring (three 128-key stages at dh = 128, two at dh = 192).
 // The softmax side is latency bound (dependent ex2 / hash chains, TMEM and shared-memory round trips), hence sixteen
 // warps of it: the first version with eight ran at half the issue rate (ncu: 2.5 warps per scheduler, 50 % issue slots).
 //
 // Masks follow ttsb_softmax_fwd with flags == 0: keys >= len[b] get probability exactly 0, query rows >= len[b] are written
 // as zeros.  Dropout decisions come from the same stateless hash at the same element index ((z*T + m)*ld + k), so the
-// backward pass (fused dS epilogue of ttsb_bgemm) regenerates them.
+// backward pass (MODE 1 below, or the dS epilogue of ttsb_bgemm) regenerates them.
 //
 // MODE 1 of the same kernel is the backward counterpart (softmax gradient fused into the dP product, what ttsb_bgemm does
-// with sm_P set): the MMA is dP = dO V^T (one pass), the epilogue reads the saved P row segment from global memory and
-// writes dS = scale * P * (dropout(dP) - D) through the same staged stores.
+// with sm_P set): the MMA is dP = dO V^T (one pass); the saved P box of a warp's next half tile arrives by TMA in its second
+// staging box while the current one is processed, and dS = scale * P * (dropout(dP) - D) leaves through the first.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -65,7 +65,7 @@ struct ApParams {
 };
 
 // shared-memory accesses by 32-bit shared address: through generic pointers derived from the dynamic-smem base the compiler
-// emits generic LD/ST (ncu: the statistics read-back alone took 5 % of the stall samples)
+// emits generic LD / ST.E instead of LDS / STS
 __device__ __forceinline__ void ap_sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
